@@ -1,0 +1,190 @@
+/* nsx.h -- C ABI of the B200-native neXtSIM explicit momentum / rheology solver (libnsx.so).
+ *
+ * This is the drop-in boundary for ONE hot path of nansencenter/nextsim:
+ *   FiniteElement::explicitSolve()      model/finiteelement.cpp:10182-10643
+ *   FiniteElement::updateSigmaDamage()  model/finiteelement.cpp:4137-4260   (BBM)
+ *   FiniteElement::updateSigmaEVP/MEVP  model/finiteelement.cpp:10649-10726
+ *   FiniteElement::updateGhosts()       model/finiteelement.cpp:13963-13996
+ *   FiniteElement::update()             model/finiteelement.cpp:3919-4132
+ * The reference has no FFI layer: the path is a set of member functions of FiniteElement working on
+ * its std::vector<double> members (declared model/finiteelement.hpp:166-169, 298-303, 521-522).
+ * Each entry point below names the member function or member set it replaces.  Host code keeps
+ * ownership of every array; the handle owns device memory only.  Plain pointers and sizes, no C++
+ * or torch types.  All functions return 0 on success, non-zero on error (see nsx_last_error);
+ * the host shim turns a non-zero status into the std::runtime_error the reference would throw.
+ *
+ * Layout conventions (identical to the reference):
+ *   - element arrays: [num_elements], owned elements first, ghost elements after
+ *   - nodal scalars:  [num_nodes], owned nodes first (local_ndof), ghost nodes after
+ *   - nodal vectors:  [2*num_nodes] split storage  u[0..N) | v[0..N)   (FE.cpp:10331-10332)
+ *   - indices[]: 1-based local node ids, 3 per element (GmshMesh::indexTr(), gmshmesh.cpp:1544)
+ */
+#ifndef NSX_H
+#define NSX_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NSX_VERSION 1
+
+typedef struct nsx_solver* nsx_handle;
+
+/* setup::DynamicsType (model/enums.hpp:142-149) */
+enum { NSX_DYN_BBM = 0, NSX_DYN_EVP = 3, NSX_DYN_MEVP = 4 };
+/* setup::BasalStressType (enums.hpp:86-90), setup::IceCategoryType (enums.hpp:92-97) */
+enum { NSX_BASAL_NONE = 0, NSX_BASAL_LEMIEUX = 1 };
+enum { NSX_ICECAT_CLASSIC = 0, NSX_ICECAT_YOUNG_ICE = 1 };
+
+/* Options read by the path; names and defaults follow model/options.cpp:43,109,111,309-376,397,545-547.
+ * Filled by nsx_params_defaults()/nsx_params_from_cfg() or by the host from its own vm[...] map. */
+typedef struct NsxDynParams {
+    int dynamics_type;              /* setup.dynamics-type           (bbm)      */
+    int basal_stress_type;          /* setup.basal_stress-type       (lemieux)  */
+    int ice_cat_type;               /* thermo.newice_type==4 -> YOUNG_ICE (FE.cpp:1212-1215) */
+    int substeps;                   /* dynamics.substeps             (120)      */
+    int equal_ridging;              /* age.equal_ridging             (false)    */
+    int newice_type;                /* thermo.newice_type            (4)        */
+    int use_young_ice_in_myi_reset; /* age.include_young_ice         (true)     */
+    int stop_after_substeps;        /* debug: run only the first k sub-cycles (0 = all)           */
+    int skip_ow_smoother;           /* debug: skip the open-water smoother (FE.cpp:10578-10611)   */
+    int use_coriolis;               /* dynamics.use_coriolis (only zeroes the turning angle, Q3)  */
+    double dtime_step;              /* simul.timestep                (200 s)    */
+    double ocean_turning_angle_rad; /* dynamics.oceanic_turning_angle (25 deg) * pi/180, FE.cpp:1167-1172 */
+    double min_h, min_c;            /* dynamics.min_h (0.05), dynamics.min_c (0.01) */
+    double young, nu0, tan_phi;     /* 5.9605e8, 1/3, 0.7 */
+    double compr_strength;          /* dynamics.compr_strength (1e10) ALREADY times scale_coef (FE.cpp:6998) */
+    double compaction_param;        /* -20 */
+    double undamaged_time_relaxation_sigma, exponent_relaxation_sigma;   /* 1e7, 5 */
+    double compression_factor, exponent_compression_factor;             /* 10e3, 1.5 */
+    double quad_drag_coef_water;    /* 0.0055 */
+    double evp_e, evp_Pstar, evp_C, evp_dmin;    /* 2, 27.5e3, 20, 1e-9 */
+    double mevp_alpha, mevp_beta;   /* 500, 500 */
+    double basal_k1, basal_k2, basal_Cb, basal_u0;   /* 10, 15, 20, 5e-5 */
+    /* host-side only (not used by kernels): cohesion recipe, FE.cpp:6995-6999 */
+    double C_lab, alea_factor, time_relaxation_damage_days;
+} NsxDynParams;
+
+/* One rank's mesh after FiniteElement::distributedMeshProcessing() (FE.cpp:50-143).  Replaces the reads of
+ * M_mesh / M_elements / bamgmesh / M_mask_dirichlet / M_neumann_flags inside the path. */
+typedef struct NsxMesh {
+    int num_nodes;          /* M_num_nodes  (owned + ghost)         FE.cpp:91 */
+    int local_ndof;         /* M_local_ndof (owned)                 FE.cpp:87 */
+    int num_elements;       /* M_num_elements (owned + ghost)       FE.cpp:84 */
+    int local_nelements;    /* M_local_nelements                    FE.cpp:90 */
+    const double* coord_x;  /* M_mesh.coordX()  [num_nodes] */
+    const double* coord_y;  /* M_mesh.coordY()  [num_nodes] */
+    const int* indices;     /* M_mesh.indexTr() [3*num_elements], 1-based local node ids */
+    const unsigned char* ghost_nodes;     /* GMSHElement::ghostNodes [3*num_elements]; NULL = derive (id > local_ndof) */
+    const unsigned char* mask_dirichlet;  /* M_mask_dirichlet [num_nodes] (owned nodes only, FE.cpp:228-234) */
+    const int* neumann_flags;             /* M_neumann_flags, sorted 0-based local node ids */
+    int n_neumann_flags;
+    const double* nodal_element_connectivity;  /* bamgmesh->NodalElementConnectivity, NaN padded, 1-based */
+    int nec_width;                              /* bamgmesh->NodalElementConnectivitySize[1] */
+    const double* nodal_connectivity;          /* bamgmesh->NodalConnectivity, last column = count */
+    int nc_width;                               /* bamgmesh->NodalConnectivitySize[1] */
+    const double* lat;      /* M_mesh.lat() [num_nodes], degrees */
+} NsxMesh;
+
+/* Products of FiniteElement::initUpdateGhosts() (FE.cpp:14003-14088) as CSR lists.  NULL for one rank. */
+typedef struct NsxHalo {
+    int rank, nranks;
+    int n_send_peers;       /* M_recipients_proc_id.size() */
+    const int* send_peer;   /* M_recipients_proc_id */
+    const int* send_ptr;    /* [n_send_peers+1] offsets into send_idx */
+    const int* send_idx;    /* M_extract_local_index[peer][:] concatenated (0-based local node ids) */
+    int n_recv_peers;       /* M_local_ghosts_proc_id.size() */
+    const int* recv_peer;   /* M_local_ghosts_proc_id */
+    const int* recv_ptr;
+    const int* recv_idx;    /* M_local_ghosts_local_index[peer][:] concatenated */
+} NsxHalo;
+
+/* Host arrays named after the FiniteElement members they mirror.  A NULL pointer means "not transferred".
+ * nsx_upload copies host -> device, nsx_download device -> host, for every non-NULL member. */
+typedef struct NsxFields {
+    /* nodal, [2*num_nodes] */
+    double* M_VT; double* M_UM; double* M_UT;
+    double* M_wind; double* M_ocean;            /* ExternalData::getVector() of M_wind / M_ocean */
+    double* M_tau_wi;                           /* optional OASIS wave stress (FE.cpp:10408-10415) */
+    double* D_tau_a; double* D_tau_w;           /* outputs */
+    /* nodal, [num_nodes] */
+    double* M_ssh;
+    /* element, [num_elements] */
+    double* M_sigma[3]; double* M_damage;
+    double* M_conc; double* M_thick; double* M_snow_thick;
+    double* M_conc_young; double* M_h_young; double* M_hs_young;
+    double* M_thick_myi; double* M_conc_myi; double* M_ridge_ratio;
+    double* M_element_depth; double* M_drag_ui; double* M_drag_ui_young;
+    double* M_Cohesion; double* M_time_relaxation_damage;
+    double* M_surface; double* M_delta_x;       /* outputs of the prep loop (FE.cpp:10239-10240) */
+    double* M_shape_coeff;                      /* output, [6*num_elements] element-major like M_shape_coeff[cpt][k] */
+    double* D_del_ci_ridge_myi;                 /* output of update() */
+} NsxFields;
+
+/* checkFieldsFast()-style summary computed on the device (FE.cpp:14536-14655). */
+typedef struct NsxCheck {
+    int n_nan;              /* non-finite entries in VT, sigma, damage, conc, thick */
+    int n_speed;            /* owned nodes with |u| > 5 m/s */
+    int n_range;            /* elements with damage or conc outside [0,1] or thick < 0 */
+    int pad_;
+    double max_speed;
+} NsxCheck;
+
+/* Device times (ms, CUDA events on the handle's stream) of the last nsx_explicit_solve / nsx_update,
+ * named after the reference's Timer rows (FE.cpp:10217-10642, 8205-8212). */
+typedef struct NsxTiming {
+    float prep_ms;          /* "prep elements" + "prep nodes" */
+    float subcycle_ms;      /* "sub-time stepping" */
+    float ow_smoother_ms;   /* "OW smoother" (incl. tau_w diagnostic) */
+    float update_ms;        /* "update" */
+    int   n_launches;       /* kernels launched by the last nsx_explicit_solve */
+    int   n_substeps;       /* sub-cycles executed */
+} NsxTiming;
+
+/* ---- life cycle (replaces the member allocation in distributedMeshProcessing / initVariables) ---- */
+int nsx_create(const NsxMesh* mesh, const NsxHalo* halo, int device, nsx_handle* out);
+int nsx_destroy(nsx_handle h);
+const char* nsx_last_error(nsx_handle h);      /* h may be NULL: error of the last failed nsx_create */
+int nsx_version(void);
+
+/* ---- options ---- */
+void nsx_params_defaults(NsxDynParams* p);                     /* model/options.cpp defaults */
+int  nsx_params_from_cfg(const char* path, NsxDynParams* p);    /* nextsim.cfg INI reader, unknown [dynamics] keys rejected */
+int  nsx_set_params(nsx_handle h, const NsxDynParams* p);
+
+/* ---- state transfer ---- */
+int nsx_upload(nsx_handle h, const NsxFields* f);
+int nsx_download(nsx_handle h, NsxFields* f);
+
+/* ---- the path ---- */
+int nsx_explicit_solve(nsx_handle h);   /* FiniteElement::explicitSolve()   FE.cpp:10182 */
+int nsx_update(nsx_handle h);           /* FiniteElement::update(UM_P)      FE.cpp:3919  */
+int nsx_update_ghosts(nsx_handle h);    /* FiniteElement::updateGhosts(M_VT) FE.cpp:13963 */
+int nsx_check(nsx_handle h, NsxCheck* out);
+int nsx_synchronize(nsx_handle h);
+int nsx_get_timing(nsx_handle h, NsxTiming* out);
+void* nsx_get_stream(nsx_handle h);     /* cudaStream_t the handle launches on */
+
+/* ---- multi-GPU halo wiring (replaces the Boost.MPI p2p of updateGhosts) ----
+ * One process per GPU: every rank exports a 64-byte CUDA IPC handle of its halo window, the host
+ * all-gathers them (MPI / torch.distributed, plumbing only) and connects each peer.  Several ranks
+ * inside one process (tests, one GPU): nsx_halo_connect_local(). */
+#define NSX_IPC_HANDLE_BYTES 64
+/* blob for `peer_rank` = [64-byte CUDA IPC handle of my halo window | int num_nodes | int n | n ghost ids
+ * (my M_local_ghosts_local_index[peer_rank])]; the peer needs it to store straight into my ghost slots. */
+int nsx_halo_blob_size(nsx_handle h, int peer_rank);
+int nsx_halo_blob(nsx_handle h, int peer_rank, unsigned char* out);
+int nsx_halo_connect_blob(nsx_handle h, int peer_rank, const unsigned char* blob_from_peer);
+int nsx_halo_connect_local(nsx_handle h, int peer_rank, nsx_handle peer);
+int nsx_halo_finalize(nsx_handle h);
+/* lock-step explicitSolve of several ranks that live in this process (one stream-ordered device) */
+int nsx_group_explicit_solve(int n, nsx_handle* handles);
+
+/* ---- pinned host memory for the per-step transfers (cudaHostRegister on the caller's vectors) ---- */
+int nsx_host_register(void* p, unsigned long bytes);
+int nsx_host_unregister(void* p);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NSX_H */

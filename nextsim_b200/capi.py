@@ -1,0 +1,313 @@
+"""ctypes binding of the C ABI in include/nsx.h (libnsx.so).
+
+This is the binding a Python harness uses; a C++ host (the reference) would include nsx.h directly
+(see INTEGRATION.md).  There is no CPU fallback: if libnsx.so is missing it is built with nvcc, and
+every compute entry point needs a CUDA device.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import build as _build
+
+c_double_p = C.POINTER(C.c_double)
+c_int_p = C.POINTER(C.c_int)
+c_ubyte_p = C.POINTER(C.c_ubyte)
+
+DYN = {"bbm": 0, "evp": 3, "mevp": 4}
+
+
+class NsxDynParams(C.Structure):
+    _fields_ = [
+        ("dynamics_type", C.c_int), ("basal_stress_type", C.c_int), ("ice_cat_type", C.c_int),
+        ("substeps", C.c_int), ("equal_ridging", C.c_int), ("newice_type", C.c_int),
+        ("use_young_ice_in_myi_reset", C.c_int), ("stop_after_substeps", C.c_int),
+        ("skip_ow_smoother", C.c_int), ("use_coriolis", C.c_int),
+        ("dtime_step", C.c_double), ("ocean_turning_angle_rad", C.c_double),
+        ("min_h", C.c_double), ("min_c", C.c_double),
+        ("young", C.c_double), ("nu0", C.c_double), ("tan_phi", C.c_double),
+        ("compr_strength", C.c_double), ("compaction_param", C.c_double),
+        ("undamaged_time_relaxation_sigma", C.c_double), ("exponent_relaxation_sigma", C.c_double),
+        ("compression_factor", C.c_double), ("exponent_compression_factor", C.c_double),
+        ("quad_drag_coef_water", C.c_double),
+        ("evp_e", C.c_double), ("evp_Pstar", C.c_double), ("evp_C", C.c_double), ("evp_dmin", C.c_double),
+        ("mevp_alpha", C.c_double), ("mevp_beta", C.c_double),
+        ("basal_k1", C.c_double), ("basal_k2", C.c_double), ("basal_Cb", C.c_double), ("basal_u0", C.c_double),
+        ("C_lab", C.c_double), ("alea_factor", C.c_double), ("time_relaxation_damage_days", C.c_double),
+    ]
+
+
+class NsxMesh(C.Structure):
+    _fields_ = [
+        ("num_nodes", C.c_int), ("local_ndof", C.c_int), ("num_elements", C.c_int), ("local_nelements", C.c_int),
+        ("coord_x", c_double_p), ("coord_y", c_double_p), ("indices", c_int_p),
+        ("ghost_nodes", c_ubyte_p), ("mask_dirichlet", c_ubyte_p),
+        ("neumann_flags", c_int_p), ("n_neumann_flags", C.c_int),
+        ("nodal_element_connectivity", c_double_p), ("nec_width", C.c_int),
+        ("nodal_connectivity", c_double_p), ("nc_width", C.c_int),
+        ("lat", c_double_p),
+    ]
+
+
+class NsxHalo(C.Structure):
+    _fields_ = [
+        ("rank", C.c_int), ("nranks", C.c_int),
+        ("n_send_peers", C.c_int), ("send_peer", c_int_p), ("send_ptr", c_int_p), ("send_idx", c_int_p),
+        ("n_recv_peers", C.c_int), ("recv_peer", c_int_p), ("recv_ptr", c_int_p), ("recv_idx", c_int_p),
+    ]
+
+
+NODAL2 = ("M_VT", "M_UM", "M_UT", "M_wind", "M_ocean", "M_tau_wi", "D_tau_a", "D_tau_w")
+NODAL1 = ("M_ssh",)
+ELEM = ("M_damage", "M_conc", "M_thick", "M_snow_thick", "M_conc_young", "M_h_young", "M_hs_young",
+        "M_thick_myi", "M_conc_myi", "M_ridge_ratio", "M_element_depth", "M_drag_ui", "M_drag_ui_young",
+        "M_Cohesion", "M_time_relaxation_damage", "M_surface", "M_delta_x")
+
+
+class NsxFields(C.Structure):
+    _fields_ = (
+        [(n, c_double_p) for n in ("M_VT", "M_UM", "M_UT", "M_wind", "M_ocean", "M_tau_wi", "D_tau_a", "D_tau_w")]
+        + [("M_ssh", c_double_p)]
+        + [("M_sigma", c_double_p * 3), ("M_damage", c_double_p)]
+        + [(n, c_double_p) for n in ("M_conc", "M_thick", "M_snow_thick", "M_conc_young", "M_h_young", "M_hs_young",
+                                     "M_thick_myi", "M_conc_myi", "M_ridge_ratio", "M_element_depth", "M_drag_ui",
+                                     "M_drag_ui_young", "M_Cohesion", "M_time_relaxation_damage", "M_surface",
+                                     "M_delta_x", "M_shape_coeff", "D_del_ci_ridge_myi")]
+    )
+
+
+class NsxCheck(C.Structure):
+    _fields_ = [("n_nan", C.c_int), ("n_speed", C.c_int), ("n_range", C.c_int), ("pad_", C.c_int),
+                ("max_speed", C.c_double)]
+
+
+class NsxTiming(C.Structure):
+    _fields_ = [("prep_ms", C.c_float), ("subcycle_ms", C.c_float), ("ow_smoother_ms", C.c_float),
+                ("update_ms", C.c_float), ("n_launches", C.c_int), ("n_substeps", C.c_int)]
+
+
+EXPORTS = (
+    "nsx_create", "nsx_destroy", "nsx_last_error", "nsx_version", "nsx_params_defaults", "nsx_params_from_cfg",
+    "nsx_set_params", "nsx_upload", "nsx_download", "nsx_explicit_solve", "nsx_update", "nsx_update_ghosts",
+    "nsx_check", "nsx_synchronize", "nsx_get_timing", "nsx_get_stream", "nsx_halo_blob_size", "nsx_halo_blob",
+    "nsx_halo_connect_blob", "nsx_halo_connect_local", "nsx_halo_finalize", "nsx_group_explicit_solve",
+    "nsx_host_register", "nsx_host_unregister",
+)
+
+_lib = None
+
+
+def lib():
+    """Load (building first if needed) libnsx.so.  Raises if it cannot be built: no fallback."""
+    global _lib
+    if _lib is None:
+        path = _build.build()
+        L = C.CDLL(path)
+        L.nsx_last_error.restype = C.c_char_p
+        L.nsx_last_error.argtypes = [C.c_void_p]
+        L.nsx_cfg_last_error.restype = C.c_char_p
+        L.nsx_get_stream.restype = C.c_void_p
+        L.nsx_get_stream.argtypes = [C.c_void_p]
+        L.nsx_params_defaults.restype = None
+        L.nsx_host_register.argtypes = [C.c_void_p, C.c_ulong]
+        L.nsx_host_unregister.argtypes = [C.c_void_p]
+        for f in ("nsx_destroy", "nsx_set_params", "nsx_upload", "nsx_download", "nsx_explicit_solve", "nsx_update",
+                  "nsx_update_ghosts", "nsx_check", "nsx_synchronize", "nsx_get_timing", "nsx_halo_finalize"):
+            getattr(L, f).argtypes = [C.c_void_p] + ([C.c_void_p] if f in (
+                "nsx_set_params", "nsx_upload", "nsx_download", "nsx_check", "nsx_get_timing") else [])
+        L.nsx_halo_blob_size.argtypes = [C.c_void_p, C.c_int]
+        L.nsx_halo_blob.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        L.nsx_halo_connect_blob.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        L.nsx_halo_connect_local.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        _lib = L
+    return _lib
+
+
+def default_params():
+    p = NsxDynParams()
+    lib().nsx_params_defaults(C.byref(p))
+    return p
+
+
+def params_from_cfg(path):
+    p = NsxDynParams()
+    rc = lib().nsx_params_from_cfg(str(path).encode(), C.byref(p))
+    if rc != 0:
+        raise RuntimeError("nsx_params_from_cfg: " + lib().nsx_cfg_last_error().decode())
+    return p
+
+
+def _f64(a):
+    a = np.ascontiguousarray(a, np.float64)
+    return a, a.ctypes.data_as(c_double_p)
+
+
+def _i32(a):
+    a = np.ascontiguousarray(a, np.int32)
+    return a, a.ctypes.data_as(c_int_p)
+
+
+def _u8(a):
+    a = np.ascontiguousarray(a, np.uint8)
+    return a, a.ctypes.data_as(c_ubyte_p)
+
+
+class Solver:
+    """Thin owner of one nsx_handle.  Methods map 1:1 on the C ABI."""
+
+    def __init__(self, lm, device=0):
+        """lm: partition.LocalMesh with bamg tables, BC masks and lat filled in."""
+        self.L = lib()
+        self.lm = lm
+        self.nn, self.ne = lm.num_nodes, lm.num_elements
+        keep = []
+        M = NsxMesh()
+        M.num_nodes, M.local_ndof = lm.num_nodes, lm.local_ndof
+        M.num_elements, M.local_nelements = lm.num_elements, lm.local_nelements
+        a, M.coord_x = _f64(lm.x); keep.append(a)
+        a, M.coord_y = _f64(lm.y); keep.append(a)
+        a, M.indices = _i32(lm.indices.reshape(-1)); keep.append(a)
+        a, M.ghost_nodes = _u8(lm.ghostNodes.reshape(-1)); keep.append(a)
+        a, M.mask_dirichlet = _u8(lm.mask_dirichlet); keep.append(a)
+        a, M.neumann_flags = _i32(lm.neumann_flags); keep.append(a)
+        M.n_neumann_flags = int(lm.neumann_flags.size)
+        a, M.nodal_element_connectivity = _f64(lm.nodal_element_connectivity.reshape(-1)); keep.append(a)
+        M.nec_width = int(lm.nodal_element_connectivity.shape[1])
+        a, M.nodal_connectivity = _f64(lm.nodal_connectivity.reshape(-1)); keep.append(a)
+        M.nc_width = int(lm.nodal_connectivity.shape[1])
+        a, M.lat = _f64(lm.lat); keep.append(a)
+        H = None
+        if lm.nranks > 1:
+            H = NsxHalo()
+            H.rank, H.nranks = lm.rank, lm.nranks
+            sp = sorted(lm.send_to)
+            rp = sorted(lm.recv_from)
+            H.n_send_peers, H.n_recv_peers = len(sp), len(rp)
+            a, H.send_peer = _i32(np.array(sp, np.int32)); keep.append(a)
+            a, H.recv_peer = _i32(np.array(rp, np.int32)); keep.append(a)
+            sptr = np.cumsum([0] + [lm.send_to[p].size for p in sp])
+            rptr = np.cumsum([0] + [lm.recv_from[p].size for p in rp])
+            a, H.send_ptr = _i32(sptr); keep.append(a)
+            a, H.recv_ptr = _i32(rptr); keep.append(a)
+            a, H.send_idx = _i32(np.concatenate([lm.send_to[p] for p in sp]) if sp else np.zeros(0)); keep.append(a)
+            a, H.recv_idx = _i32(np.concatenate([lm.recv_from[p] for p in rp]) if rp else np.zeros(0)); keep.append(a)
+        h = C.c_void_p()
+        rc = self.L.nsx_create(C.byref(M), C.byref(H) if H is not None else None, int(device), C.byref(h))
+        if rc != 0:
+            raise RuntimeError("nsx_create: " + self.L.nsx_last_error(None).decode())
+        self.h = h
+        self.peers = sorted(set(lm.send_to) | set(lm.recv_from)) if lm.nranks > 1 else []
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.nsx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _chk(self, rc, what):
+        if rc != 0:
+            raise RuntimeError("%s: %s" % (what, self.L.nsx_last_error(self.h).decode()))
+
+    def set_params(self, p):
+        self._chk(self.L.nsx_set_params(self.h, C.byref(p)), "nsx_set_params")
+
+    def _fields(self, d):
+        F = NsxFields()
+        keep = []
+        for k, v in d.items():
+            if k == "M_sigma":
+                for i in range(3):
+                    a = v[i]
+                    assert a.dtype == np.float64 and a.flags.c_contiguous and a.size == self.ne
+                    F.M_sigma[i] = a.ctypes.data_as(c_double_p)
+                    keep.append(a)
+                continue
+            assert v.dtype == np.float64 and v.flags.c_contiguous, k
+            n = 2 * self.nn if k in NODAL2 else self.nn if k in NODAL1 else 6 * self.ne if k == "M_shape_coeff" else self.ne
+            assert v.size == n, (k, v.size, n)
+            setattr(F, k, v.ctypes.data_as(c_double_p))
+            keep.append(v)
+        return F, keep
+
+    def upload(self, **arrays):
+        arrays = {k: np.ascontiguousarray(v, np.float64) if k != "M_sigma" else
+                  [np.ascontiguousarray(s, np.float64) for s in v] for k, v in arrays.items()}
+        F, keep = self._fields(arrays)
+        self._chk(self.L.nsx_upload(self.h, C.byref(F)), "nsx_upload")
+
+    def download(self, *names, out=None):
+        out = {} if out is None else out
+        for k in names:
+            if k in out:
+                continue
+            if k == "M_sigma":
+                out[k] = [np.empty(self.ne) for _ in range(3)]
+            else:
+                n = 2 * self.nn if k in NODAL2 else self.nn if k in NODAL1 else 6 * self.ne if k == "M_shape_coeff" else self.ne
+                out[k] = np.empty(n)
+        F, keep = self._fields({k: out[k] for k in names})
+        self._chk(self.L.nsx_download(self.h, C.byref(F)), "nsx_download")
+        return out
+
+    def explicit_solve(self):
+        self._chk(self.L.nsx_explicit_solve(self.h), "nsx_explicit_solve")
+
+    def update(self):
+        self._chk(self.L.nsx_update(self.h), "nsx_update")
+
+    def update_ghosts(self):
+        self._chk(self.L.nsx_update_ghosts(self.h), "nsx_update_ghosts")
+
+    def synchronize(self):
+        self._chk(self.L.nsx_synchronize(self.h), "nsx_synchronize")
+
+    def check(self):
+        c = NsxCheck()
+        self._chk(self.L.nsx_check(self.h, C.byref(c)), "nsx_check")
+        return c
+
+    def timing(self):
+        t = NsxTiming()
+        self._chk(self.L.nsx_get_timing(self.h, C.byref(t)), "nsx_get_timing")
+        return t
+
+    # ---- halo wiring ----
+    def halo_blob(self, peer):
+        n = self.L.nsx_halo_blob_size(self.h, int(peer))
+        buf = (C.c_ubyte * n)()
+        self._chk(self.L.nsx_halo_blob(self.h, int(peer), buf), "nsx_halo_blob")
+        return bytes(buf)
+
+    def halo_connect_blob(self, peer, blob):
+        buf = (C.c_ubyte * len(blob)).from_buffer_copy(blob)
+        self._chk(self.L.nsx_halo_connect_blob(self.h, int(peer), buf), "nsx_halo_connect_blob")
+
+    def halo_connect_local(self, peer, other):
+        self._chk(self.L.nsx_halo_connect_local(self.h, int(peer), other.h), "nsx_halo_connect_local")
+
+    def halo_finalize(self):
+        self._chk(self.L.nsx_halo_finalize(self.h), "nsx_halo_finalize")
+
+
+def group_explicit_solve(solvers):
+    L = lib()
+    hs = (C.c_void_p * len(solvers))(*[s.h for s in solvers])
+    rc = L.nsx_group_explicit_solve(len(solvers), hs)
+    if rc != 0:
+        raise RuntimeError("nsx_group_explicit_solve: " + L.nsx_last_error(solvers[0].h).decode())
+
+
+def connect_local_group(solvers):
+    """Wire the halos of ranks that all live in this process (tests / single-GPU emulation)."""
+    by_rank = {s.lm.rank: s for s in solvers}
+    for s in solvers:
+        for p in s.peers:
+            s.halo_connect_local(p, by_rank[p])
+    for s in solvers:
+        s.halo_finalize()

@@ -1,0 +1,716 @@
+// nsx_api.cu -- C ABI (include/nsx.h) over the CUDA kernels: handle life cycle, transfers, the
+// explicitSolve()/update() launch sequences and the NVLink halo wiring.  No CPU fallback: every entry
+// point that computes launches CUDA kernels and returns an error if the device is unavailable.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <mutex>
+
+#include "nsx_kernels.cuh"
+
+using namespace nsx;
+
+static std::string g_create_err;
+
+#define NSX_API_BEGIN(h)                                   \
+    if (!(h)) return 1;                                    \
+    try {                                                  \
+        NSX_CUDA(cudaSetDevice((h)->device));
+#define NSX_API_END(h)                                     \
+    }                                                      \
+    catch (std::exception const& e) {                      \
+        (h)->err = e.what();                               \
+        return 2;                                          \
+    }                                                      \
+    return 0;
+
+static inline int nblk(long n) { return (int)((n + TPB - 1) / TPB); }
+
+// ---------------------------------------------------------------------------------------------------
+// life cycle
+// ---------------------------------------------------------------------------------------------------
+static void build_mesh(nsx_solver* S, const NsxMesh* M)
+{
+    int const nn = M->num_nodes, ne = M->num_elements, ndof = M->local_ndof;
+    if (nn <= 0 || ne <= 0 || ndof <= 0 || ndof > nn || M->local_nelements > ne)
+        throw std::invalid_argument("nsx_create: inconsistent mesh sizes");
+    if (!M->coord_x || !M->coord_y || !M->indices || !M->lat || !M->nodal_element_connectivity || !M->nodal_connectivity)
+        throw std::invalid_argument("nsx_create: NULL mesh array");
+    if ((long)3 * ne >= (1L << 31)) throw std::invalid_argument("nsx_create: mesh too large for 32-bit staging slots");
+    S->nn = nn; S->ndof = ndof; S->ne = ne; S->ne_local = M->local_nelements;
+    cudaStream_t st = S->stream;
+
+    S->x.alloc(nn); S->y.alloc(nn); S->lat.alloc(nn);
+    NSX_CUDA(cudaMemcpyAsync(S->x.p, M->coord_x, nn * sizeof(double), cudaMemcpyHostToDevice, st));
+    NSX_CUDA(cudaMemcpyAsync(S->y.p, M->coord_y, nn * sizeof(double), cudaMemcpyHostToDevice, st));
+    NSX_CUDA(cudaMemcpyAsync(S->lat.p, M->lat, nn * sizeof(double), cudaMemcpyHostToDevice, st));
+
+    // element -> node planes (0-based) and the ascending node -> element ELL table
+    std::vector<int> e0(ne), e1(ne), e2(ne), deg(nn, 0);
+    for (int e = 0; e < ne; ++e) {
+        int const a = M->indices[3 * (size_t)e] - 1, b = M->indices[3 * (size_t)e + 1] - 1, c = M->indices[3 * (size_t)e + 2] - 1;
+        if (a < 0 || b < 0 || c < 0 || a >= nn || b >= nn || c >= nn)
+            throw std::invalid_argument("nsx_create: element index out of range");
+        if (M->ghost_nodes) {
+            // GMSHElement::ghostNodes must agree with "local id >= local_ndof" (gmshmesh.cpp:1298-1301)
+            const unsigned char* g = M->ghost_nodes + 3 * (size_t)e;
+            if ((g[0] != 0) != (a >= ndof) || (g[1] != 0) != (b >= ndof) || (g[2] != 0) != (c >= ndof))
+                throw std::invalid_argument("nsx_create: ghost_nodes disagrees with the owned-first node numbering");
+        }
+        e0[e] = a; e1[e] = b; e2[e] = c;
+        deg[a]++; deg[b]++; deg[c]++;
+    }
+    int w = 0;
+    for (int n = 0; n < nn; ++n) {
+        if (deg[n] == 0) throw std::invalid_argument("nsx_create: orphan node");
+        w = std::max(w, deg[n]);
+    }
+    S->ell_w = w;
+    std::vector<int> ell((size_t)w * nn, -1), fill(nn, 0);
+    for (int e = 0; e < ne; ++e) {               // ascending e: each row ends up in ascending element order
+        int const v[3] = {e0[e], e1[e], e2[e]};
+        for (int i = 0; i < 3; ++i) {
+            int const n = v[i];
+            ell[(size_t)fill[n] * nn + n] = i * ne + e;
+            fill[n]++;
+        }
+    }
+    S->en0.alloc(ne); S->en1.alloc(ne); S->en2.alloc(ne);
+    S->n2e.alloc(ell.size()); S->n2e_deg.alloc(nn);
+    NSX_CUDA(cudaMemcpyAsync(S->en0.p, e0.data(), ne * sizeof(int), cudaMemcpyHostToDevice, st));
+    NSX_CUDA(cudaMemcpyAsync(S->en1.p, e1.data(), ne * sizeof(int), cudaMemcpyHostToDevice, st));
+    NSX_CUDA(cudaMemcpyAsync(S->en2.p, e2.data(), ne * sizeof(int), cudaMemcpyHostToDevice, st));
+    NSX_CUDA(cudaMemcpyAsync(S->n2e.p, ell.data(), ell.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+    NSX_CUDA(cudaMemcpyAsync(S->n2e_deg.p, deg.data(), nn * sizeof(int), cudaMemcpyHostToDevice, st));
+
+    // bamg NodalElementConnectivity (double, NaN padded, 1-based; quirk Q6) -> int ELL, -1 padded, same order
+    int const nw = M->nec_width;
+    std::vector<int> nec((size_t)nw * nn, -1);
+    for (int n = 0; n < nn; ++n)
+        for (int j = 0; j < nw; ++j) {
+            double const raw = M->nodal_element_connectivity[(size_t)nw * n + j];
+            int e = -1;
+            if (!std::isnan(raw)) e = (int)raw - 1;
+            if (e >= ne) throw std::invalid_argument("nsx_create: NodalElementConnectivity entry out of range");
+            nec[(size_t)j * nn + n] = e < 0 ? -1 : e;
+        }
+    S->nec_w = nw;
+    S->nec.alloc(nec.size());
+    NSX_CUDA(cudaMemcpyAsync(S->nec.p, nec.data(), nec.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+
+    // bamg NodalConnectivity (last column = neighbour count, FE.cpp:10597) -> int ELL
+    int const cw = M->nc_width;
+    std::vector<int> n2n((size_t)std::max(cw - 1, 1) * nn, 0), ndeg(nn, 0);
+    for (int n = 0; n < nn; ++n) {
+        int const cnt = (int)M->nodal_connectivity[(size_t)cw * (n + 1) - 1];
+        if (cnt < 0 || cnt > cw - 1) throw std::invalid_argument("nsx_create: bad NodalConnectivity count");
+        ndeg[n] = cnt;
+        for (int j = 0; j < cnt; ++j) {
+            int const q = (int)M->nodal_connectivity[(size_t)cw * n + j] - 1;
+            if (q < 0 || q >= nn) throw std::invalid_argument("nsx_create: NodalConnectivity entry out of range");
+            n2n[(size_t)j * nn + n] = q;
+        }
+    }
+    S->nc_w = cw - 1;
+    S->n2n.alloc(n2n.size()); S->n2n_deg.alloc(nn);
+    NSX_CUDA(cudaMemcpyAsync(S->n2n.p, n2n.data(), n2n.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+    NSX_CUDA(cudaMemcpyAsync(S->n2n_deg.p, ndeg.data(), nn * sizeof(int), cudaMemcpyHostToDevice, st));
+
+    // node flags
+    std::vector<uint8_t> fl(nn, 0);
+    for (int n = 0; n < nn; ++n) {
+        if (M->mask_dirichlet && M->mask_dirichlet[n]) fl[n] |= NF_DIRICHLET;
+        if (n >= ndof) fl[n] |= NF_GHOST;
+        if (std::signbit(M->lat[n])) fl[n] |= NF_LATNEG;
+    }
+    for (int k = 0; k < M->n_neumann_flags; ++k) {
+        int const n = M->neumann_flags[k];
+        if (n < 0 || n >= nn) throw std::invalid_argument("nsx_create: neumann flag out of range");
+        fl[n] |= NF_NEUMANN;
+    }
+    S->nflags.alloc(nn);
+    NSX_CUDA(cudaMemcpyAsync(S->nflags.p, fl.data(), nn, cudaMemcpyHostToDevice, st));
+    NSX_CUDA(cudaStreamSynchronize(st));      // host vectors go out of scope
+}
+
+static void alloc_fields(nsx_solver* S)
+{
+    size_t const nn = S->nn, ne = S->ne;
+    cudaStream_t st = S->stream;
+    // halo window: [VT0 | VT1 | flags]
+    size_t const vt_bytes = 2 * nn * sizeof(double);
+    size_t const flag_bytes = 256 * sizeof(unsigned long long);
+    S->window_bytes = 2 * vt_bytes + flag_bytes;
+    NSX_CUDA(cudaMalloc(&S->window, S->window_bytes));
+    NSX_CUDA(cudaMemsetAsync(S->window, 0, S->window_bytes, st));
+    S->VT[0] = (double*)S->window;
+    S->VT[1] = S->VT[0] + 2 * nn;
+    S->flags = (unsigned long long*)(S->VT[1] + 2 * nn);
+
+    DBuf<double>* nodal2[] = {&S->UM, &S->UT, &S->wind, &S->ocean, &S->tau_wi, &S->tau_a, &S->tau_w, &S->VTM, &S->grad_ssh};
+    for (auto* b : nodal2) { b->alloc(2 * nn); b->zero(st); }
+    DBuf<double>* nodal1[] = {&S->ssh, &S->node_mass, &S->rlmass, &S->cbu, &S->fcor};
+    for (auto* b : nodal1) { b->alloc(nn); b->zero(st); }
+    DBuf<double>* elem[] = {&S->sig0, &S->sig1, &S->sig2, &S->damage, &S->conc, &S->thick, &S->snow, &S->conc_young,
+                            &S->h_young, &S->hs_young, &S->thick_myi, &S->conc_myi, &S->ridge_ratio, &S->depth,
+                            &S->drag_ui, &S->drag_ui_young, &S->cohesion, &S->t_heal, &S->surface, &S->delta_x,
+                            &S->del_ci_ridge_myi, &S->emass, &S->ecbu};
+    for (auto* b : elem) { b->alloc(ne); b->zero(st); }
+    S->shape.alloc(6 * ne); S->shape.zero(st);
+    S->ec.alloc(6 * ne); S->ec.zero(st);
+    S->contrib.alloc(6 * ne); S->contrib.zero(st);
+    S->ow_list.alloc(S->ndof); S->ow_count.alloc(1); S->ow_count.zero(st);
+    S->check_i.alloc(4); S->check_d.alloc(1);
+    S->halo_err.alloc(1); S->halo_err.zero(st);
+    for (auto& e : S->ev) NSX_CUDA(cudaEventCreate(&e));
+}
+
+static void build_halo(nsx_solver* S, const NsxHalo* H)
+{
+    S->rank = 0; S->nranks = 1;
+    if (!H) return;
+    S->rank = H->rank; S->nranks = H->nranks;
+    if (H->nranks > 256) throw std::invalid_argument("nsx_create: at most 256 ranks");
+    auto link = [&](int r) -> PeerLink& {
+        for (auto& p : S->peers) if (p.rank == r) return p;
+        S->peers.emplace_back();
+        S->peers.back().rank = r;
+        return S->peers.back();
+    };
+    for (int k = 0; k < H->n_send_peers; ++k) {
+        PeerLink& p = link(H->send_peer[k]);
+        p.h_send_idx.assign(H->send_idx + H->send_ptr[k], H->send_idx + H->send_ptr[k + 1]);
+        for (int v : p.h_send_idx) if (v < 0 || v >= S->ndof) throw std::invalid_argument("nsx_create: send index is not an owned node");
+    }
+    for (int k = 0; k < H->n_recv_peers; ++k) {
+        PeerLink& p = link(H->recv_peer[k]);
+        p.h_recv_idx.assign(H->recv_idx + H->recv_ptr[k], H->recv_idx + H->recv_ptr[k + 1]);
+        for (int v : p.h_recv_idx) if (v < S->ndof || v >= S->nn) throw std::invalid_argument("nsx_create: recv index is not a ghost node");
+    }
+    if (S->peers.size() > 32) throw std::invalid_argument("nsx_create: at most 32 neighbour ranks");
+}
+
+extern "C" int nsx_version(void) { return NSX_VERSION; }
+
+extern "C" int nsx_create(const NsxMesh* mesh, const NsxHalo* halo, int device, nsx_handle* out)
+{
+    if (!mesh || !out) { g_create_err = "nsx_create: NULL argument"; return 1; }
+    *out = nullptr;
+    nsx_solver* S = new nsx_solver();
+    try {
+        int ndev = 0;
+        NSX_CUDA(cudaGetDeviceCount(&ndev));
+        if (device < 0 || device >= ndev) throw std::invalid_argument("nsx_create: no such CUDA device");
+        S->device = device;
+        NSX_CUDA(cudaSetDevice(device));
+        NSX_CUDA(cudaStreamCreateWithFlags(&S->stream, cudaStreamNonBlocking));
+        build_mesh(S, mesh);
+        alloc_fields(S);
+        build_halo(S, halo);
+        NSX_CUDA(cudaStreamSynchronize(S->stream));
+    } catch (std::exception const& e) {
+        g_create_err = e.what();
+        nsx_destroy(S);
+        return 2;
+    }
+    *out = S;
+    return 0;
+}
+
+extern "C" int nsx_destroy(nsx_handle S)
+{
+    if (!S) return 0;
+    cudaSetDevice(S->device);
+    if (S->stream) cudaStreamSynchronize(S->stream);
+    for (auto& p : S->peers) if (p.ipc_base) cudaIpcCloseMemHandle(p.ipc_base);
+    if (S->graph_exec) cudaGraphExecDestroy(S->graph_exec);
+    for (auto& e : S->ev) if (e) cudaEventDestroy(e);
+    if (S->window) cudaFree(S->window);
+    if (S->stream) cudaStreamDestroy(S->stream);
+    delete S;
+    return 0;
+}
+
+extern "C" const char* nsx_last_error(nsx_handle h) { return h ? h->err.c_str() : g_create_err.c_str(); }
+extern "C" void* nsx_get_stream(nsx_handle h) { return h ? (void*)h->stream : nullptr; }
+
+// ---------------------------------------------------------------------------------------------------
+// options -> kernel scalars
+// ---------------------------------------------------------------------------------------------------
+static KParams derive(nsx_solver const* S, NsxDynParams const& P)
+{
+    KParams K{};
+    K.dynamics_type = P.dynamics_type;
+    K.basal_stress_type = P.basal_stress_type;
+    K.young_ice = (P.ice_cat_type == NSX_ICECAT_YOUNG_ICE);
+    K.nn = S->nn; K.ndof = S->ndof; K.ne = S->ne;
+    K.dtime_step = P.dtime_step;
+    K.dte = P.dtime_step / double(P.substeps);                 // FE.cpp:10185
+    K.cos_ota = std::cos(P.ocean_turning_angle_rad);           // FE.cpp:10187-10188
+    K.sin_ota_abs = std::fabs(std::sin(P.ocean_turning_angle_rad));
+    K.min_m = RHOI * P.min_h;                                  // FE.cpp:10191
+    K.young = P.young;
+    K.compaction_param = P.compaction_param;
+    K.lambda0 = P.undamaged_time_relaxation_sigma;
+    K.exp_relax_m1 = P.exponent_relaxation_sigma - 1.;
+    K.relax_int_pow = -1;
+    for (int k = 0; k <= 4; ++k) if (K.exp_relax_m1 == (double)k) K.relax_int_pow = k;
+    K.compression_factor = P.compression_factor;
+    K.exp_compression = P.exponent_compression_factor;
+    K.compr_strength = P.compr_strength;
+    K.tan_phi = P.tan_phi;
+    K.sqrt_nu_rhoi = std::sqrt(2. * (1. + P.nu0) * RHOI);      // FE.cpp:4140
+    double const Dunit_factor = 1. / (1. - P.nu0 * P.nu0);     // FE.cpp:1495-1505
+    K.D00 = Dunit_factor * 1.;
+    K.D01 = Dunit_factor * P.nu0;
+    K.D22 = Dunit_factor * (1. - P.nu0) / 2.;
+    K.evp_e = P.evp_e; K.evp_Pstar = P.evp_Pstar; K.evp_C = P.evp_C; K.evp_dmin = P.evp_dmin;
+    K.re2 = 1. / (P.evp_e * P.evp_e);
+    if (P.dynamics_type == NSX_DYN_EVP) {                      // FE.cpp:10708-10711
+        double const T = P.dtime_step / 3.;
+        K.ralpha1 = 0.5 * K.dte / T;
+        K.ralpha2 = 0.5 * K.dte / T * P.evp_e * P.evp_e;
+    } else {                                                   // FE.cpp:10724
+        K.ralpha1 = 1. / P.mevp_alpha;
+        K.ralpha2 = 1. / P.mevp_alpha;
+    }
+    K.mevp_b = P.mevp_beta + 1.;
+    K.rhow_cdw = RHOW * P.quad_drag_coef_water;
+    K.u0 = P.basal_u0;
+    K.k1 = P.basal_k1; K.k2 = P.basal_k2; K.Cb = P.basal_Cb;
+    K.min_c = P.min_c; K.min_h = P.min_h;
+    K.equal_ridging = P.equal_ridging;
+    K.myi_with_young = (P.newice_type == 4 && P.use_young_ice_in_myi_reset);
+    return K;
+}
+
+extern "C" int nsx_set_params(nsx_handle S, const NsxDynParams* p)
+{
+    NSX_API_BEGIN(S)
+    if (!p) throw std::invalid_argument("nsx_set_params: NULL");
+    if (p->dynamics_type != NSX_DYN_BBM && p->dynamics_type != NSX_DYN_EVP && p->dynamics_type != NSX_DYN_MEVP)
+        throw std::invalid_argument("nsx_set_params: dynamics_type must be bbm, evp or mevp");
+    if (p->substeps <= 0 || !(p->dtime_step > 0.)) throw std::invalid_argument("nsx_set_params: substeps and dtime_step must be positive");
+    S->P = *p;
+    S->K = derive(S, *p);
+    S->have_params = true;
+    S->graph_valid = false;
+    NSX_API_END(S)
+}
+
+// ---------------------------------------------------------------------------------------------------
+// transfers
+// ---------------------------------------------------------------------------------------------------
+namespace {
+struct FieldMap { double* host; double* dev; size_t n; };
+}
+static void field_table(nsx_solver* S, const NsxFields* f, std::vector<FieldMap>& t, bool upload)
+{
+    size_t const nn = S->nn, ne = S->ne;
+    auto add = [&](double* h, double* d, size_t n) { if (h) t.push_back({h, d, n}); };
+    add(f->M_VT, S->VT[S->cur], 2 * nn);
+    add(f->M_UM, S->UM.p, 2 * nn);
+    add(f->M_UT, S->UT.p, 2 * nn);
+    add(f->M_wind, S->wind.p, 2 * nn);
+    add(f->M_ocean, S->ocean.p, 2 * nn);
+    add(f->M_tau_wi, S->tau_wi.p, 2 * nn);
+    add(f->D_tau_a, S->tau_a.p, 2 * nn);
+    add(f->D_tau_w, S->tau_w.p, 2 * nn);
+    add(f->M_ssh, S->ssh.p, nn);
+    add(f->M_sigma[0], S->sig0.p, ne);
+    add(f->M_sigma[1], S->sig1.p, ne);
+    add(f->M_sigma[2], S->sig2.p, ne);
+    add(f->M_damage, S->damage.p, ne);
+    add(f->M_conc, S->conc.p, ne);
+    add(f->M_thick, S->thick.p, ne);
+    add(f->M_snow_thick, S->snow.p, ne);
+    add(f->M_conc_young, S->conc_young.p, ne);
+    add(f->M_h_young, S->h_young.p, ne);
+    add(f->M_hs_young, S->hs_young.p, ne);
+    add(f->M_thick_myi, S->thick_myi.p, ne);
+    add(f->M_conc_myi, S->conc_myi.p, ne);
+    add(f->M_ridge_ratio, S->ridge_ratio.p, ne);
+    add(f->M_element_depth, S->depth.p, ne);
+    add(f->M_drag_ui, S->drag_ui.p, ne);
+    add(f->M_drag_ui_young, S->drag_ui_young.p, ne);
+    add(f->M_Cohesion, S->cohesion.p, ne);
+    add(f->M_time_relaxation_damage, S->t_heal.p, ne);
+    add(f->M_surface, S->surface.p, ne);
+    add(f->M_delta_x, S->delta_x.p, ne);
+    add(f->D_del_ci_ridge_myi, S->del_ci_ridge_myi.p, ne);
+    (void)upload;
+}
+
+extern "C" int nsx_upload(nsx_handle S, const NsxFields* f)
+{
+    NSX_API_BEGIN(S)
+    if (!f) throw std::invalid_argument("nsx_upload: NULL");
+    std::vector<FieldMap> t;
+    field_table(S, f, t, true);
+    for (auto& m : t)
+        NSX_CUDA(cudaMemcpyAsync(m.dev, m.host, m.n * sizeof(double), cudaMemcpyHostToDevice, S->stream));
+    if (f->M_tau_wi) S->have_tau_wi = true;
+    if (f->M_shape_coeff) throw std::invalid_argument("nsx_upload: M_shape_coeff is an output");
+    NSX_CUDA(cudaStreamSynchronize(S->stream));
+    NSX_API_END(S)
+}
+
+extern "C" int nsx_download(nsx_handle S, NsxFields* f)
+{
+    NSX_API_BEGIN(S)
+    if (!f) throw std::invalid_argument("nsx_download: NULL");
+    std::vector<FieldMap> t;
+    field_table(S, f, t, false);
+    for (auto& m : t)
+        NSX_CUDA(cudaMemcpyAsync(m.host, m.dev, m.n * sizeof(double), cudaMemcpyDeviceToHost, S->stream));
+    if (f->M_shape_coeff) {
+        // device SoA planes -> M_shape_coeff[cpt][k]; contrib is free between solves and reused as scratch
+        k_shape_to_aos<<<nblk(6L * S->ne), TPB, 0, S->stream>>>(S->ne, S->shape.p, S->contrib.p);
+        NSX_CUDA(cudaGetLastError());
+        NSX_CUDA(cudaMemcpyAsync(f->M_shape_coeff, S->contrib.p, 6 * (size_t)S->ne * sizeof(double), cudaMemcpyDeviceToHost, S->stream));
+    }
+    NSX_CUDA(cudaStreamSynchronize(S->stream));
+    int herr = 0;
+    NSX_CUDA(cudaMemcpy(&herr, S->halo_err.p, sizeof(int), cudaMemcpyDeviceToHost));
+    if (herr) throw std::runtime_error("halo exchange timed out waiting for rank " + std::to_string(herr - 1));
+    NSX_API_END(S)
+}
+
+extern "C" int nsx_host_register(void* p, size_t bytes)
+{
+    return cudaHostRegister(p, bytes, cudaHostRegisterDefault) == cudaSuccess ? 0 : 2;
+}
+extern "C" int nsx_host_unregister(void* p) { return cudaHostUnregister(p) == cudaSuccess ? 0 : 2; }
+
+extern "C" int nsx_synchronize(nsx_handle S)
+{
+    NSX_API_BEGIN(S)
+    NSX_CUDA(cudaStreamSynchronize(S->stream));
+    NSX_API_END(S)
+}
+
+// ---------------------------------------------------------------------------------------------------
+// halo wiring
+// ---------------------------------------------------------------------------------------------------
+static_assert(sizeof(cudaIpcMemHandle_t) == NSX_IPC_HANDLE_BYTES, "ipc handle size");
+
+static void finish_link(nsx_solver* S, PeerLink& p, double* base, int peer_nn, const int* peer_recv_idx_for_me, size_t n)
+{
+    if (n != p.h_send_idx.size()) throw std::runtime_error("halo: peer ghost list length differs from my send list");
+    p.peer_nn = peer_nn;
+    p.peer_vt[0] = base;
+    p.peer_vt[1] = base + 2 * (size_t)peer_nn;
+    p.peer_flags = (unsigned long long*)(base + 4 * (size_t)peer_nn);
+    p.d_send_src.alloc(n); p.d_send_dst.alloc(n);
+    if (n) {
+        NSX_CUDA(cudaMemcpy(p.d_send_src.p, p.h_send_idx.data(), n * sizeof(int), cudaMemcpyHostToDevice));
+        NSX_CUDA(cudaMemcpy(p.d_send_dst.p, peer_recv_idx_for_me, n * sizeof(int), cudaMemcpyHostToDevice));
+    }
+    p.connected = true;
+}
+
+extern "C" int nsx_halo_connect_local(nsx_handle S, int peer_rank, nsx_handle Q)
+{
+    NSX_API_BEGIN(S)
+    if (!Q) throw std::invalid_argument("nsx_halo_connect_local: NULL peer");
+    PeerLink* mine = nullptr;
+    for (auto& p : S->peers) if (p.rank == peer_rank) mine = &p;
+    if (!mine) throw std::invalid_argument("nsx_halo_connect_local: not a neighbour rank");
+    const PeerLink* theirs = nullptr;
+    for (auto& p : Q->peers) if (p.rank == S->rank) theirs = &p;
+    static const std::vector<int> empty;
+    auto const& ridx = theirs ? theirs->h_recv_idx : empty;
+    if (Q->device != S->device) {
+        int can = 0;
+        NSX_CUDA(cudaDeviceCanAccessPeer(&can, S->device, Q->device));
+        if (!can) throw std::runtime_error("nsx_halo_connect_local: no peer access between the two devices");
+        cudaError_t e = cudaDeviceEnablePeerAccess(Q->device, 0);
+        if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) NSX_CUDA(e);
+        (void)cudaGetLastError();
+    }
+    finish_link(S, *mine, Q->VT[0], Q->nn, ridx.data(), ridx.size());
+    NSX_API_END(S)
+}
+
+// The peer's ghost index list for me travels with the IPC handle: [64 B handle | int nn | int n | n ints]
+extern "C" int nsx_halo_blob_size(nsx_handle S, int peer_rank)
+{
+    if (!S) return -1;
+    for (auto& p : S->peers) if (p.rank == peer_rank) return NSX_IPC_HANDLE_BYTES + 8 + 4 * (int)p.h_recv_idx.size();
+    return NSX_IPC_HANDLE_BYTES + 8;
+}
+extern "C" int nsx_halo_blob(nsx_handle S, int peer_rank, unsigned char* out)
+{
+    NSX_API_BEGIN(S)
+    NSX_CUDA(cudaIpcGetMemHandle(&S->ipc, S->window));
+    std::memcpy(out, &S->ipc, NSX_IPC_HANDLE_BYTES);
+    int hdr[2] = {S->nn, 0};
+    const PeerLink* pl = nullptr;
+    for (auto& p : S->peers) if (p.rank == peer_rank) pl = &p;
+    if (pl) hdr[1] = (int)pl->h_recv_idx.size();
+    std::memcpy(out + NSX_IPC_HANDLE_BYTES, hdr, 8);
+    if (pl && hdr[1]) std::memcpy(out + NSX_IPC_HANDLE_BYTES + 8, pl->h_recv_idx.data(), 4 * (size_t)hdr[1]);
+    NSX_API_END(S)
+}
+extern "C" int nsx_halo_connect_blob(nsx_handle S, int peer_rank, const unsigned char* blob)
+{
+    NSX_API_BEGIN(S)
+    PeerLink* mine = nullptr;
+    for (auto& p : S->peers) if (p.rank == peer_rank) mine = &p;
+    if (!mine) throw std::invalid_argument("nsx_halo_connect_blob: not a neighbour rank");
+    cudaIpcMemHandle_t hdl;
+    std::memcpy(&hdl, blob, NSX_IPC_HANDLE_BYTES);
+    int hdr[2];
+    std::memcpy(hdr, blob + NSX_IPC_HANDLE_BYTES, 8);
+    void* base = nullptr;
+    NSX_CUDA(cudaIpcOpenMemHandle(&base, hdl, cudaIpcMemLazyEnablePeerAccess));
+    mine->ipc_base = base;
+    finish_link(S, *mine, (double*)base, hdr[0], (const int*)(blob + NSX_IPC_HANDLE_BYTES + 8), (size_t)hdr[1]);
+    NSX_API_END(S)
+}
+
+extern "C" int nsx_halo_finalize(nsx_handle S)
+{
+    NSX_API_BEGIN(S)
+    for (auto& p : S->peers) if (!p.connected) throw std::runtime_error("nsx_halo_finalize: rank " + std::to_string(p.rank) + " not connected");
+    S->halo_ready = true;
+    S->graph_valid = false;
+    NSX_API_END(S)
+}
+
+// One ghost exchange of VT[cur]: push my owned values into every holder, publish the epoch, then wait
+// for every owner of my ghosts.  `wait` is false for lock-step groups that share one stream.
+static void halo_exchange(nsx_solver* S, bool wait)
+{
+    if (S->peers.empty()) return;
+    if (!S->halo_ready) throw std::runtime_error("halo exchange before nsx_halo_finalize");
+    cudaStream_t st = S->stream;
+    S->epoch++;
+    SignalArgs sa{}; WaitArgs wa{};
+    for (auto& p : S->peers) {
+        int const n = (int)p.d_send_src.n;
+        if (n) {
+            k_halo_push<<<nblk(n), TPB, 0, st>>>(n, S->nn, p.peer_nn, p.d_send_src.p, p.d_send_dst.p,
+                                                 S->VT[S->cur], p.peer_vt[S->cur]);
+            sa.flag[sa.n++] = p.peer_flags + S->rank;
+        }
+        if (!p.h_recv_idx.empty()) wa.slot[wa.n++] = p.rank;
+    }
+    S->n_launch += (int)S->peers.size();
+    if (wait) {
+        if (sa.n) { k_halo_signal<<<1, 32, 0, st>>>(sa, S->epoch); S->n_launch++; }
+        if (wa.n) { k_halo_wait<<<1, 32, 0, st>>>(wa, S->flags, S->epoch, 20000000LL, S->halo_err.p); S->n_launch++; }
+    }
+    NSX_CUDA(cudaGetLastError());
+}
+
+extern "C" int nsx_update_ghosts(nsx_handle S)
+{
+    NSX_API_BEGIN(S)
+    halo_exchange(S, !S->halo_local);
+    NSX_API_END(S)
+}
+
+// ---------------------------------------------------------------------------------------------------
+// explicitSolve()  FE.cpp:10182-10643 as a launch sequence (phases split so that several ranks living
+// in one process can be stepped in lock-step on one device: nsx_group_explicit_solve)
+// ---------------------------------------------------------------------------------------------------
+static void phase_prep(nsx_solver* S)
+{
+    cudaStream_t st = S->stream;
+    KParams const& K = S->K;
+    S->ow_count.zero(st);
+    k_prep_elements<<<nblk(S->ne), TPB, 0, st>>>(K, S->en0.p, S->en1.p, S->en2.p, S->x.p, S->y.p, S->UM.p,
+        S->conc.p, S->thick.p, S->snow.p, S->conc_young.p, S->h_young.p, S->hs_young.p, S->depth.p, S->ssh.p,
+        S->cohesion.p, S->t_heal.p, S->surface.p, S->delta_x.p, S->shape.p, S->emass.p, S->ecbu.p, S->ec.p);
+    k_prep_nodes<<<nblk(S->nn), TPB, 0, st>>>(K, S->nflags.p, S->n2e.p, S->n2e_deg.p, S->nec.p, S->nec_w,
+        S->en0.p, S->en1.p, S->en2.p, S->surface.p, S->emass.p, S->ecbu.p, S->shape.p, S->ssh.p,
+        S->drag_ui.p, S->drag_ui_young.p, S->conc.p, S->conc_young.p, S->wind.p, S->lat.p,
+        S->VT[S->cur], S->VTM.p, S->node_mass.p, S->rlmass.p, S->cbu.p, S->fcor.p, S->grad_ssh.p, S->tau_a.p,
+        S->ow_list.p, S->ow_count.p);
+    S->n_launch += 2;
+    NSX_CUDA(cudaGetLastError());
+}
+
+// one sub-cycle up to (not including) the ghost exchange; flips S->cur
+static void phase_substep(nsx_solver* S, int s)
+{
+    cudaStream_t st = S->stream;
+    KParams const& K = S->K;
+    const double* VTc = S->VT[S->cur];
+    double* VTn = S->VT[S->cur ^ 1];
+    if (K.dynamics_type == NSX_DYN_BBM)
+        k_element_bbm<<<nblk(S->ne), TPB, 0, st>>>(K, S->en0.p, S->en1.p, S->en2.p, VTc, S->shape.p, S->ec.p,
+                                                   S->sig0.p, S->sig1.p, S->sig2.p, S->damage.p, S->contrib.p);
+    else
+        k_element_vp<<<nblk(S->ne), TPB, 0, st>>>(K, S->en0.p, S->en1.p, S->en2.p, VTc, S->shape.p, S->ec.p,
+                                                  S->sig0.p, S->sig1.p, S->sig2.p, S->contrib.p);
+    int const move = (K.dynamics_type != NSX_DYN_MEVP);
+    k_node_solve<<<nblk(S->nn), TPB, 0, st>>>(K, move, move && s > 0, S->nflags.p, S->n2e.p, S->n2e_deg.p,
+        S->contrib.p, S->grad_ssh.p, S->node_mass.p, S->rlmass.p, S->cbu.p, S->fcor.p, S->tau_a.p,
+        S->have_tau_wi ? S->tau_wi.p : nullptr, S->ocean.p, S->VTM.p, VTc, VTn, S->UM.p, S->UT.p);
+    S->n_launch += 2;
+    S->cur ^= 1;
+    NSX_CUDA(cudaGetLastError());
+}
+
+// mesh moves that follow the loop: mEVP's single move (FE.cpp:10559-10573) or the ghosts' lagged last move
+static void phase_post_move(nsx_solver* S, int nrun)
+{
+    cudaStream_t st = S->stream;
+    KParams const& K = S->K;
+    if (K.dynamics_type == NSX_DYN_MEVP) {
+        k_move_mesh<<<nblk(S->nn), TPB, 0, st>>>(S->nn, 0, S->nn, K.dtime_step, S->nflags.p, S->VT[S->cur], S->UM.p, S->UT.p);
+        S->n_launch++;
+    } else if (S->nn > S->ndof && nrun > 0) {
+        k_move_mesh<<<nblk(S->nn - S->ndof), TPB, 0, st>>>(S->nn, S->ndof, S->nn, K.dte, S->nflags.p, S->VT[S->cur], S->UM.p, S->UT.p);
+        S->n_launch++;
+    }
+    NSX_CUDA(cudaGetLastError());
+}
+
+// Both ping-pong buffers must agree on the nodes a sweep does not write.  Only OWNED entries are copied:
+// ghost slots of the other buffer belong to the owners' pushes (a faster peer may already be writing them).
+static void phase_ow_begin(nsx_solver* S)
+{
+    size_t const nn = S->nn, nd = S->ndof;
+    NSX_CUDA(cudaMemcpyAsync(S->VT[S->cur ^ 1], S->VT[S->cur], nd * sizeof(double), cudaMemcpyDeviceToDevice, S->stream));
+    NSX_CUDA(cudaMemcpyAsync(S->VT[S->cur ^ 1] + nn, S->VT[S->cur] + nn, nd * sizeof(double), cudaMemcpyDeviceToDevice, S->stream));
+}
+static void phase_ow_sweep(nsx_solver* S)
+{
+    int const grid = std::min(nblk(S->ndof), 148 * 4);
+    k_ow_sweep<<<grid, TPB, 0, S->stream>>>(S->nn, S->ow_list.p, S->ow_count.p, S->n2n.p, S->n2n_deg.p,
+                                             S->VT[S->cur], S->VT[S->cur ^ 1]);
+    S->n_launch++;
+    S->cur ^= 1;
+    NSX_CUDA(cudaGetLastError());
+}
+static void phase_tauw(nsx_solver* S)
+{
+    k_tauw_owmove<<<nblk(S->nn), TPB, 0, S->stream>>>(S->K, S->nflags.p, S->node_mass.p, S->VT[S->cur], S->VTM.p,
+                                                      S->ocean.p, S->tau_w.p, S->UM.p, S->UT.p);
+    S->n_launch++;
+    NSX_CUDA(cudaGetLastError());
+}
+
+static int substeps_to_run(nsx_solver const* S)
+{
+    int const steps = S->P.substeps;
+    return (S->P.stop_after_substeps > 0) ? std::min(steps, S->P.stop_after_substeps) : steps;
+}
+
+static void solve_group(int n, nsx_solver** W)
+{
+    // lock-step over ranks; for n == 1 this is the plain single-rank sequence.  Ranks in a group share a
+    // device and are serialised on their own streams through events only at exchange points; with one
+    // process per GPU (n == 1, peers remote) the exchange waits on NVLink flags instead.
+    for (int r = 0; r < n; ++r) {
+        nsx_solver* S = W[r];
+        if (!S->have_params) throw std::runtime_error("nsx_explicit_solve before nsx_set_params");
+        NSX_CUDA(cudaSetDevice(S->device));
+        S->n_launch = 0;
+        NSX_CUDA(cudaEventRecord(S->ev[0], S->stream));
+        phase_prep(S);
+        NSX_CUDA(cudaEventRecord(S->ev[1], S->stream));
+    }
+    int const nrun = substeps_to_run(W[0]);
+    bool const remote = (n == 1) && !W[0]->halo_local;
+    auto exchange = [&]() {
+        if (n == 1) { halo_exchange(W[0], remote); return; }
+        // in-process group: all pushes, then a cross-stream join so nobody reads ghosts too early
+        for (int r = 0; r < n; ++r) { NSX_CUDA(cudaSetDevice(W[r]->device)); halo_exchange(W[r], false); NSX_CUDA(cudaEventRecord(W[r]->ev[5], W[r]->stream)); }
+        for (int r = 0; r < n; ++r)
+            for (int q = 0; q < n; ++q)
+                if (q != r) NSX_CUDA(cudaStreamWaitEvent(W[r]->stream, W[q]->ev[5], 0));
+    };
+    for (int s = 0; s < nrun; ++s) {
+        for (int r = 0; r < n; ++r) { NSX_CUDA(cudaSetDevice(W[r]->device)); phase_substep(W[r], s); }
+        exchange();
+    }
+    for (int r = 0; r < n; ++r) {
+        NSX_CUDA(cudaSetDevice(W[r]->device));
+        NSX_CUDA(cudaEventRecord(W[r]->ev[2], W[r]->stream));
+        phase_post_move(W[r], nrun);
+    }
+    if (!W[0]->P.skip_ow_smoother) {
+        for (int r = 0; r < n; ++r) { NSX_CUDA(cudaSetDevice(W[r]->device)); phase_ow_begin(W[r]); }
+        for (int nit = 0; nit < 50; ++nit) {       // hard-coded 50 sweeps, FE.cpp:10580
+            for (int r = 0; r < n; ++r) { NSX_CUDA(cudaSetDevice(W[r]->device)); phase_ow_sweep(W[r]); }
+            exchange();
+        }
+    }
+    for (int r = 0; r < n; ++r) {
+        nsx_solver* S = W[r];
+        NSX_CUDA(cudaSetDevice(S->device));
+        phase_tauw(S);
+        NSX_CUDA(cudaEventRecord(S->ev[3], S->stream));
+        S->timing.n_launches = S->n_launch;
+        S->timing.n_substeps = nrun;
+        S->timing_valid = true;
+    }
+}
+
+extern "C" int nsx_explicit_solve(nsx_handle S)
+{
+    NSX_API_BEGIN(S)
+    nsx_solver* W[1] = {S};
+    solve_group(1, W);
+    NSX_API_END(S)
+}
+
+extern "C" int nsx_group_explicit_solve(int n, nsx_handle* hs)
+{
+    if (n <= 0 || !hs || !hs[0]) return 1;
+    try {
+        for (int r = 0; r < n; ++r) hs[r]->halo_local = true;
+        solve_group(n, hs);
+    } catch (std::exception const& e) { hs[0]->err = e.what(); return 2; }
+    return 0;
+}
+
+extern "C" int nsx_update(nsx_handle S)
+{
+    NSX_API_BEGIN(S)
+    if (!S->have_params) throw std::runtime_error("nsx_update before nsx_set_params");
+    NSX_CUDA(cudaEventRecord(S->ev[3], S->stream));
+    k_update<<<nblk(S->ne), TPB, 0, S->stream>>>(S->K, S->nflags.p, S->en0.p, S->en1.p, S->en2.p, S->x.p, S->y.p, S->UM.p,
+        S->surface.p, S->conc.p, S->thick.p, S->snow.p, S->thick_myi.p, S->conc_myi.p, S->ridge_ratio.p,
+        S->conc_young.p, S->h_young.p, S->hs_young.p, S->sig0.p, S->sig1.p, S->sig2.p, S->del_ci_ridge_myi.p);
+    NSX_CUDA(cudaGetLastError());
+    NSX_CUDA(cudaEventRecord(S->ev[4], S->stream));
+    S->update_timed = true;
+    NSX_API_END(S)
+}
+
+extern "C" int nsx_get_timing(nsx_handle S, NsxTiming* out)
+{
+    NSX_API_BEGIN(S)
+    if (!out) throw std::invalid_argument("nsx_get_timing: NULL");
+    NSX_CUDA(cudaStreamSynchronize(S->stream));
+    if (S->timing_valid) {
+        NSX_CUDA(cudaEventElapsedTime(&S->timing.prep_ms, S->ev[0], S->ev[1]));
+        NSX_CUDA(cudaEventElapsedTime(&S->timing.subcycle_ms, S->ev[1], S->ev[2]));
+        NSX_CUDA(cudaEventElapsedTime(&S->timing.ow_smoother_ms, S->ev[2], S->ev[3]));
+    }
+    if (S->update_timed) NSX_CUDA(cudaEventElapsedTime(&S->timing.update_ms, S->ev[3], S->ev[4]));
+    *out = S->timing;
+    NSX_API_END(S)
+}
+
+extern "C" int nsx_check(nsx_handle S, NsxCheck* out)
+{
+    NSX_API_BEGIN(S)
+    if (!out) throw std::invalid_argument("nsx_check: NULL");
+    S->check_i.zero(S->stream); S->check_d.zero(S->stream);
+    int const n = std::max(S->nn, S->ne);
+    k_check<<<nblk(n), TPB, 0, S->stream>>>(S->nn, S->ndof, S->ne, S->VT[S->cur], S->sig0.p, S->sig1.p, S->sig2.p,
+                                            S->damage.p, S->conc.p, S->thick.p, S->check_i.p, (unsigned long long*)S->check_d.p);
+    NSX_CUDA(cudaGetLastError());
+    int hi[4]; double hd;
+    NSX_CUDA(cudaMemcpyAsync(hi, S->check_i.p, sizeof(hi), cudaMemcpyDeviceToHost, S->stream));
+    NSX_CUDA(cudaMemcpyAsync(&hd, S->check_d.p, sizeof(hd), cudaMemcpyDeviceToHost, S->stream));
+    NSX_CUDA(cudaStreamSynchronize(S->stream));
+    out->n_nan = hi[0]; out->n_speed = hi[1]; out->n_range = hi[2]; out->pad_ = 0; out->max_speed = hd;
+    NSX_API_END(S)
+}

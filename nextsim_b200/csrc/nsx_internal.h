@@ -1,0 +1,161 @@
+// nsx_internal.h -- private state of one solver handle (one rank == one GPU).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <stdexcept>
+#include <string>
+#include <vector>
+#include <deque>
+
+#include "../../include/nsx.h"
+
+namespace nsx {
+
+struct CudaError : std::runtime_error { using std::runtime_error::runtime_error; };
+
+#define NSX_CUDA(call)                                                                         \
+    do {                                                                                       \
+        cudaError_t e_ = (call);                                                               \
+        if (e_ != cudaSuccess)                                                                 \
+            throw nsx::CudaError(std::string(#call) + " failed: " + cudaGetErrorString(e_) +   \
+                                 " (" __FILE__ ":" + std::to_string(__LINE__) + ")");          \
+    } while (0)
+
+// physical constants, model/constants.hpp:56-86
+constexpr double RHOI = 917., RHOW = 1025., RHOS = 330., GRAVITY = 9.80616, OMEGA = 7.292e-5, RHOA = 1.22;
+constexpr double PI_ = 3.14159265358979323846;
+constexpr double DAYS_IN_SEC = 86400.;
+
+// node flag bits
+enum : uint8_t { NF_DIRICHLET = 1, NF_NEUMANN = 2, NF_GHOST = 4, NF_LATNEG = 8 };
+
+template <class T>
+struct DBuf {
+    T* p = nullptr;
+    size_t n = 0;
+    void alloc(size_t n_) {
+        release();
+        n = n_;
+        if (n) NSX_CUDA(cudaMalloc(&p, n * sizeof(T)));
+    }
+    void zero(cudaStream_t s) { if (n) NSX_CUDA(cudaMemsetAsync(p, 0, n * sizeof(T), s)); }
+    void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+    ~DBuf() { release(); }
+    DBuf() = default;
+    DBuf(const DBuf&) = delete;
+    DBuf& operator=(const DBuf&) = delete;
+};
+
+// Scalars the kernels need, derived once from NsxDynParams (passed by value to kernels).
+struct KParams {
+    int dynamics_type, basal_stress_type, young_ice;
+    int nn, ndof, ne;
+    double dte, dtime_step;
+    double cos_ota, sin_ota_abs, min_m;
+    // BBM
+    double young, compaction_param, lambda0, exp_relax_m1, compression_factor, exp_compression;
+    double compr_strength, tan_phi, sqrt_nu_rhoi;
+    double D00, D01, D22;                  // M_Dunit non-zeros (FE.cpp:1491-1507)
+    int    relax_int_pow;                  // exponent_relaxation_sigma-1 if a small integer, else -1
+    // EVP / mEVP
+    double evp_e, evp_Pstar, evp_C, evp_dmin, ralpha1, ralpha2, re2;
+    double mevp_b;                         // beta+1
+    // nodal solve
+    double rhow_cdw, u0;
+    // basal
+    double k1, k2, Cb;
+    // update()
+    double min_c, min_h;
+    int equal_ridging, myi_with_young;
+};
+
+struct PeerLink {
+    int rank = -1;
+    std::vector<int> h_send_idx;           // my local node ids to send (M_extract_local_index[peer])
+    std::vector<int> h_recv_idx;           // my ghost ids filled by that peer (M_local_ghosts_local_index[peer])
+    // device-side push tables
+    DBuf<int> d_send_src;                  // my local node id
+    DBuf<int> d_send_dst;                  // peer's local ghost id
+    double* peer_vt[2] = {nullptr, nullptr};   // peer's VT ping-pong buffers (mapped)
+    unsigned long long* peer_flags = nullptr;  // peer's flag array (mapped); I write slot [my rank]
+    int peer_nn = 0;
+    void* ipc_base = nullptr;              // cudaIpcOpenMemHandle result (to close)
+    bool connected = false;
+};
+
+} // namespace nsx
+
+struct nsx_solver {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    std::string err;
+
+    int nn = 0, ndof = 0, ne = 0, ne_local = 0;
+    int rank = 0, nranks = 1;
+    NsxDynParams P{};
+    bool have_params = false;
+    nsx::KParams K{};
+
+    // ---- mesh (device) ----
+    nsx::DBuf<double> x, y, lat;
+    nsx::DBuf<uint8_t> nflags;
+    nsx::DBuf<int> en0, en1, en2;              // element -> node, 0-based
+    int ell_w = 0;                             // node -> (element,local vertex) ascending element id
+    nsx::DBuf<int> n2e;                        // [ell_w * nn] column-major, value = 3*e + i
+    nsx::DBuf<int> n2e_deg;
+    int nc_w = 0;                              // node -> node, bamg order
+    nsx::DBuf<int> n2n;                        // [nc_w * nn] column-major
+    nsx::DBuf<int> n2n_deg;
+    int nec_w = 0;                             // bamg NodalElementConnectivity as int ELL (-1 padded), bamg order
+    nsx::DBuf<int> nec;
+
+    // ---- fields (device) ----
+    // halo window: VT ping-pong buffers + flags live in ONE allocation so it can be IPC-exported
+    void* window = nullptr;
+    size_t window_bytes = 0;
+    double* VT[2] = {nullptr, nullptr};        // [2*nn] each
+    unsigned long long* flags = nullptr;       // [nranks] arrival epochs written by peers
+    int cur = 0;                               // which VT buffer holds the current velocity
+    unsigned long long epoch = 0;              // halo exchange counter
+
+    nsx::DBuf<double> UM, UT, wind, ocean, tau_wi, tau_a, tau_w, ssh, VTM;
+    bool have_tau_wi = false;
+    nsx::DBuf<double> sig0, sig1, sig2, damage;
+    nsx::DBuf<double> conc, thick, snow, conc_young, h_young, hs_young, thick_myi, conc_myi, ridge_ratio;
+    nsx::DBuf<double> depth, drag_ui, drag_ui_young, cohesion, t_heal;
+    nsx::DBuf<double> surface, delta_x, shape;   // shape: 6 SoA planes [6*ne]
+    nsx::DBuf<double> del_ci_ridge_myi;
+    // prep products
+    nsx::DBuf<double> emass, ecbu;               // element mass, element C_bu
+    nsx::DBuf<double> node_mass, rlmass, cbu, fcor, grad_ssh;
+    nsx::DBuf<double> ec;                        // hoisted per-element constants [6*ne] (meaning depends on rheology)
+    nsx::DBuf<double> contrib;                   // element -> node stress contributions [6*ne]
+    nsx::DBuf<int> ow_list;                      // open-water nodes to smooth
+    nsx::DBuf<int> ow_count;
+    nsx::DBuf<int> check_i; nsx::DBuf<double> check_d;
+
+    // ---- halo ----
+    std::deque<nsx::PeerLink> peers;             // union of send/recv peers
+    nsx::DBuf<int> ghost_ids;                    // all ghost node ids [nn-ndof]
+    nsx::DBuf<int> halo_err;                     // device error word (timeouts)
+    bool halo_ready = false;
+    bool halo_local = false;                     // all peers live in this process on this device
+    cudaIpcMemHandle_t ipc{};
+
+    // ---- timing ----
+    cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    NsxTiming timing{};
+    bool timing_valid = false;
+    bool update_timed = false;
+    int n_launch = 0;
+
+    // CUDA graph of one explicitSolve (built lazily, invalidated by nsx_set_params / halo changes)
+    cudaGraphExec_t graph_exec = nullptr;
+    bool graph_valid = false;
+    int graph_cur_in = -1;
+
+    // pinned staging for transfers
+    void* pinned = nullptr;
+    size_t pinned_bytes = 0;
+};

@@ -1,0 +1,646 @@
+// nsx_kernels.cuh -- hand-written FP64 CUDA kernels (sm_100a) for the explicit sub-cycled momentum solve.
+//
+// Layout: every field is a flat SoA plane in HBM.  Element planes are indexed by local element id
+// (owned first, ghosts after), node planes by local node id (owned first); nodal 2-vectors are stored
+// split [u | v] exactly like the reference (FE.cpp:10331-10332).  Element->node connectivity is three
+// int32 planes; the node->element incidence needed for the fixed-order reduction of FE.cpp:10445-10467
+// is a column-major ELL table (coalesced per column) of staging-slot ids in ASCENDING element order.
+//
+// No float atomics anywhere: element kernels write their three nodal stress contributions to a staging
+// plane, node kernels subtract them in the reference's order starting from grad_ssh.
+#pragma once
+#include "nsx_internal.h"
+
+namespace nsx {
+
+constexpr int TPB = 256;
+
+__device__ __forceinline__ double ld_nc(const double* p) { return __ldg(p); }
+
+// ---------------------------------------------------------------------------------------------------
+// prep elements  (FE.cpp:10235-10341 minus the nodal scatters, which k_prep_nodes gathers)
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(TPB)
+k_prep_elements(KParams K,
+                const int* __restrict__ en0, const int* __restrict__ en1, const int* __restrict__ en2,
+                const double* __restrict__ x, const double* __restrict__ y, const double* __restrict__ UM,
+                const double* __restrict__ conc, const double* __restrict__ thick, const double* __restrict__ snow,
+                const double* __restrict__ conc_y, const double* __restrict__ h_y, const double* __restrict__ hs_y,
+                const double* __restrict__ depth, const double* __restrict__ ssh,
+                const double* __restrict__ cohesion, const double* __restrict__ t_heal,
+                double* __restrict__ surface, double* __restrict__ delta_x, double* __restrict__ shape,
+                double* __restrict__ emass, double* __restrict__ ecbu, double* __restrict__ ec)
+{
+    int const e = blockIdx.x * blockDim.x + threadIdx.x;
+    int const ne = K.ne, nn = K.nn;
+    if (e >= ne) return;
+    int const a = en0[e], b = en1[e], c = en2[e];
+    // GmshMesh::vertices(indices, um, 1.)  gmshmesh.cpp:1929-1939
+    double const xa = x[a] + 1. * UM[a], ya = y[a] + 1. * UM[a + nn];
+    double const xb = x[b] + 1. * UM[b], yb = y[b] + 1. * UM[b + nn];
+    double const xc = x[c] + 1. * UM[c], yc = y[c] + 1. * UM[c + nn];
+
+    // sides() FE.cpp:1642-1663 and the integer-truncated mean (quirk Q1, FE.cpp:10239)
+    double const s0 = hypot(xb - xa, yb - ya);
+    double const s1 = hypot(xc - xb, yc - yb);
+    double const s2 = hypot(xc - xa, yc - ya);
+    int acc = 0;
+    acc = __double2int_rz((double)acc + s0);
+    acc = __double2int_rz((double)acc + s1);
+    acc = __double2int_rz((double)acc + s2);
+    double const dx = (double)(acc / 3);
+    delta_x[e] = dx;
+
+    // jacobian / measure / shapeCoeff  FE.cpp:1613-1618, 1929-1933, 1951-1964
+    double jac = (xb - xa) * (yc - ya);
+    jac -= (xc - xa) * (yb - ya);
+    double const A = 0.5 * fabs(jac);
+    surface[e] = A;
+    shape[0 * (size_t)ne + e] = (yb - yc) / jac;
+    shape[1 * (size_t)ne + e] = (yc - ya) / jac;
+    shape[2 * (size_t)ne + e] = (ya - yb) / jac;
+    shape[3 * (size_t)ne + e] = (xc - xb) / jac;
+    shape[4 * (size_t)ne + e] = (xa - xc) / jac;
+    shape[5 * (size_t)ne + e] = (xb - xa) / jac;
+
+    // slab mass FE.cpp:10255-10269
+    double const cc = conc[e], hh = thick[e];
+    double tc = cc, tt = hh, ts = snow[e];
+    if (K.young_ice) { tc += conc_y[e]; tt += h_y[e]; ts += hs_y[e]; }
+    double const m = (tc > 0.) ? (RHOI * tt + RHOS * ts) / tc : 0.;
+    emass[e] = m;
+
+    // Lemieux basal stress numerator FE.cpp:10273-10308
+    double element_ssh = 0.;
+    element_ssh += ssh[a]; element_ssh += ssh[b]; element_ssh += ssh[c];
+    element_ssh /= 3.;
+    double const depth_eff = fmax(0., element_ssh + fmax(2., depth[e]));
+    double critical_h = 0., critical_h_mod = 0.;
+    if (K.basal_stress_type == NSX_BASAL_LEMIEUX) {
+        double mean_keel_depth = K.k1 * hh;
+        mean_keel_depth = fmin(mean_keel_depth, cc * 28.);
+        critical_h = cc * depth_eff / K.k1;
+        critical_h_mod = mean_keel_depth / K.k1;
+    }
+    ecbu[e] = K.k2 * fmax(0., critical_h_mod - critical_h) * exp(-K.Cb * (1. - cc));
+
+    // per-step constants of the rheology, hoisted out of the sub-cycle loop
+    double const vol = hh * A;                                 // FE.cpp:10450
+    if (K.dynamics_type == NSX_DYN_BBM) {
+        bool const ice = !(cc <= 0.1);                         // quirk Q4 (FE.cpp:4146-4151)
+        double const expC = exp(K.compaction_param * (1. - cc));
+        ec[0 * (size_t)ne + e] = ice ? expC : 0.;              // 0 marks "no ice" (expC > 0 always)
+        ec[1 * (size_t)ne + e] = pow(hh, K.exp_compression) * K.compression_factor * expC;   // Pmax FE.cpp:4192
+        ec[2 * (size_t)ne + e] = cohesion[e];
+        ec[3 * (size_t)ne + e] = 1. / (dx * K.sqrt_nu_rhoi);   // FE.cpp:4232
+        ec[4 * (size_t)ne + e] = K.dte / t_heal[e] * expC;     // FE.cpp:4256-4257
+        ec[5 * (size_t)ne + e] = vol;
+    } else {
+        // P = Pstar*exp(-C(1-c)) FE.cpp:10684 ; negative marks thick==0 (quirk Q5, FE.cpp:10656)
+        ec[0 * (size_t)ne + e] = (hh == 0.) ? -1. : K.evp_Pstar * exp(-K.evp_C * (1. - cc));
+        ec[5 * (size_t)ne + e] = vol;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// prep nodes  (nodal scatters of FE.cpp:10309-10340 as ordered gathers + FE.cpp:10356-10416)
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(TPB)
+k_prep_nodes(KParams K, const uint8_t* __restrict__ nflags,
+             const int* __restrict__ n2e, const int* __restrict__ n2e_deg,
+             const int* __restrict__ nec, int nec_w,
+             const int* __restrict__ en0, const int* __restrict__ en1, const int* __restrict__ en2,
+             const double* __restrict__ surface, const double* __restrict__ emass, const double* __restrict__ ecbu,
+             const double* __restrict__ shape, const double* __restrict__ ssh,
+             const double* __restrict__ drag_ui, const double* __restrict__ drag_ui_y,
+             const double* __restrict__ conc, const double* __restrict__ conc_y,
+             const double* __restrict__ wind, const double* __restrict__ lat,
+             double* __restrict__ VT, double* __restrict__ VTM,
+             double* __restrict__ node_mass, double* __restrict__ rlmass, double* __restrict__ cbu,
+             double* __restrict__ fcor, double* __restrict__ grad_ssh, double* __restrict__ tau_a,
+             int* __restrict__ ow_list, int* __restrict__ ow_count)
+{
+    int const n = blockIdx.x * blockDim.x + threadIdx.x;
+    int const nn = K.nn, ne = K.ne;
+    if (n >= nn) return;
+    uint8_t const fl = nflags[n];
+    bool const skip_static = (fl & (NF_DIRICHLET | NF_GHOST)) != 0;
+    double const g3rd = GRAVITY / 3.;
+
+    double sumA = 0., sumMA = 0., cb = 0., gu = 0., gv = 0.;
+    int const deg = n2e_deg[n];
+    for (int k = 0; k < deg; ++k) {                       // ascending element id == reference loop order
+        int const s = n2e[(size_t)k * nn + n];
+        int const i = s / ne;
+        int const e = s - i * ne;
+        (void)i;
+        double const A = surface[e], m = emass[e];
+        sumA += A;
+        sumMA += m * A;
+        cb = fmax(cb, ecbu[e]);
+        // FE.cpp:10328 tests the RUNNING nodal mass (this element already added)
+        if (!skip_static && sumMA != 0.) {
+            double const mgA = m * A * g3rd;
+            int const nj0 = en0[e], nj1 = en1[e], nj2 = en2[e];
+            double const h0 = ssh[nj0], h1 = ssh[nj1], h2 = ssh[nj2];
+            gu -= shape[0 * (size_t)ne + e] * mgA * h0;  gv -= shape[3 * (size_t)ne + e] * mgA * h0;
+            gu -= shape[1 * (size_t)ne + e] * mgA * h1;  gv -= shape[4 * (size_t)ne + e] * mgA * h1;
+            gu -= shape[2 * (size_t)ne + e] * mgA * h2;  gv -= shape[5 * (size_t)ne + e] * mgA * h2;
+        }
+    }
+    grad_ssh[n] = gu;
+    grad_ssh[n + nn] = gv;
+    cbu[n] = cb;
+
+    // open-water nodes: zero the velocity (FE.cpp:10366-10370) and remember them for the smoother
+    if (sumMA == 0.) {
+        VT[n] = 0.;
+        VT[n + nn] = 0.;
+        if (n < K.ndof && !(fl & NF_DIRICHLET)) {
+            int const slot = atomicAdd(ow_count, 1);
+            ow_list[slot] = n;
+        }
+    }
+
+    // atmospheric drag, surface-weighted over bamg's NodalElementConnectivity order (FE.cpp:10374-10394)
+    double drag = 0., surf = 0.;
+    for (int j = 0; j < nec_w; ++j) {
+        int const e = nec[(size_t)j * nn + n];
+        if (e < 0) continue;
+        double dragp = drag_ui[e];
+        if (K.young_ice) {
+            double const c0 = conc[e], c1 = conc_y[e];
+            if (c0 + c1 > 0.) dragp = (drag_ui[e] * c0 + drag_ui_y[e] * c1) / (c0 + c1);
+        }
+        drag += dragp * surface[e];
+        surf += surface[e];
+    }
+    double const wu = wind[n], wv = wind[n + nn];
+    drag *= RHOA * hypot(wu, wv) / surf;
+    tau_a[n] = drag * wu;
+    tau_a[n + nn] = drag * wv;
+
+    fcor[n] = 2 * OMEGA * sin(lat[n] * PI_ / 180.);
+
+    double rl = 1. / sumA;                                  // FE.cpp:10400-10402
+    node_mass[n] = sumMA * rl;
+    rl *= 3.;
+    rlmass[n] = rl;
+
+    VTM[n] = VT[n];
+    VTM[n + nn] = VT[n + nn];
+}
+
+// ---------------------------------------------------------------------------------------------------
+// BBM element update  (FE.cpp:4137-4260) + element part of the stress-gradient assembly (10449-10465)
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double pow_relax(double q, KParams const& K)
+{
+    switch (K.relax_int_pow) {
+        case 0: return 1.;
+        case 1: return q;
+        case 2: return q * q;
+        case 3: return q * q * q;
+        case 4: { double const q2 = q * q; return q2 * q2; }
+        default: return pow(q, K.exp_relax_m1);
+    }
+}
+
+__global__ void __launch_bounds__(TPB)
+k_element_bbm(KParams K,
+              const int* __restrict__ en0, const int* __restrict__ en1, const int* __restrict__ en2,
+              const double* __restrict__ VT, const double* __restrict__ shape, const double* __restrict__ ec,
+              double* __restrict__ sig0, double* __restrict__ sig1, double* __restrict__ sig2,
+              double* __restrict__ damage, double* __restrict__ contrib)
+{
+    int const e = blockIdx.x * blockDim.x + threadIdx.x;
+    int const ne = K.ne, nn = K.nn;
+    if (e >= ne) return;
+    double const expC = ec[e];
+    double const vol = ec[5 * (size_t)ne + e];
+    double const dx0 = shape[e], dx1 = shape[(size_t)ne + e], dx2 = shape[2 * (size_t)ne + e];
+    double const dy0 = shape[3 * (size_t)ne + e], dy1 = shape[4 * (size_t)ne + e], dy2 = shape[5 * (size_t)ne + e];
+    double s0, s1, s2, d;
+    if (expC == 0.) {                   // conc <= 0.1 : no ice (FE.cpp:4151-4159)
+        s0 = s1 = s2 = 0.;
+        d = 0.;
+    } else {
+        int const a = en0[e], b = en1[e], c = en2[e];
+        double const ua = VT[a], va = VT[a + nn], ub = VT[b], vb = VT[b + nn], uc = VT[c], vc = VT[c + nn];
+        // epsilon_veloc = B0T * u  (FE.cpp:4167-4176; B0T rows: [dxN 0], [0 dyN], [dyN dxN])
+        double e0 = dx0 * ua; e0 += dx1 * ub; e0 += dx2 * uc;
+        double e1 = dy0 * va; e1 += dy1 * vb; e1 += dy2 * vc;
+        double e2 = dy0 * ua; e2 += dx0 * va; e2 += dy1 * ub; e2 += dx1 * vb; e2 += dy2 * uc; e2 += dx2 * vc;
+
+        s0 = sig0[e]; s1 = sig1[e]; s2 = sig2[e]; d = damage[e];
+        double const dt = K.dte;
+        double sigma_n = (s0 + s1) * 0.5;
+        double const omd = 1. - d;
+        double const time_viscous = K.lambda0 * pow_relax(omd * expC, K);
+        double tildeP = 0.;
+        if (sigma_n < 0.) {
+            double const Pmax = ec[(size_t)ne + e];
+            tildeP = fmin(1., -Pmax / sigma_n);
+        }
+        double const mult = fmin(1. - 1e-12, time_viscous / (time_viscous + dt * (1. - tildeP)));
+        double const elasticity = K.young * omd * expC;
+        double const dtE = dt * elasticity;
+        s0 += dtE * K.D00 * e0;  s0 += dtE * K.D01 * e1;  s0 *= mult;
+        s1 += dtE * K.D01 * e0;  s1 += dtE * K.D00 * e1;  s1 *= mult;
+        s2 += dtE * K.D22 * e2;                           s2 *= mult;
+
+        double const sigma_s = hypot((s0 - s1) / 2., s2);
+        sigma_n = (s0 + s1) * 0.5;
+        double dcrit;
+        if (sigma_n < -K.compr_strength) dcrit = -K.compr_strength / sigma_n;
+        else dcrit = ec[2 * (size_t)ne + e] / (sigma_s + K.tan_phi * sigma_n);
+        if ((0. < dcrit) && (dcrit < 1.)) {
+            double const rtd = sqrt(elasticity) * ec[3 * (size_t)ne + e];
+            double const f = (1. - dcrit) * dt * rtd;
+            d += omd * f;
+            s0 -= s0 * f;  s1 -= s1 * f;  s2 -= s2 * f;
+        }
+        d = fmax(0., d - ec[4 * (size_t)ne + e]);
+    }
+    sig0[e] = s0; sig1[e] = s1; sig2[e] = s2; damage[e] = d;
+    // nodal contributions V*(sigma . grad N_i)  (FE.cpp:10464-10465)
+    contrib[0 * (size_t)ne + e] = vol * (s0 * dx0 + s2 * dy0);
+    contrib[1 * (size_t)ne + e] = vol * (s0 * dx1 + s2 * dy1);
+    contrib[2 * (size_t)ne + e] = vol * (s0 * dx2 + s2 * dy2);
+    contrib[3 * (size_t)ne + e] = vol * (s2 * dx0 + s1 * dy0);
+    contrib[4 * (size_t)ne + e] = vol * (s2 * dx1 + s1 * dy1);
+    contrib[5 * (size_t)ne + e] = vol * (s2 * dx2 + s1 * dy2);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// EVP / mEVP element update  (FE.cpp:10649-10726)
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(TPB)
+k_element_vp(KParams K,
+             const int* __restrict__ en0, const int* __restrict__ en1, const int* __restrict__ en2,
+             const double* __restrict__ VT, const double* __restrict__ shape, const double* __restrict__ ec,
+             double* __restrict__ sig0, double* __restrict__ sig1, double* __restrict__ sig2,
+             double* __restrict__ contrib)
+{
+    int const e = blockIdx.x * blockDim.x + threadIdx.x;
+    int const ne = K.ne, nn = K.nn;
+    if (e >= ne) return;
+    double const Pp = ec[e];
+    double const vol = ec[5 * (size_t)ne + e];
+    double const dx0 = shape[e], dx1 = shape[(size_t)ne + e], dx2 = shape[2 * (size_t)ne + e];
+    double const dy0 = shape[3 * (size_t)ne + e], dy1 = shape[4 * (size_t)ne + e], dy2 = shape[5 * (size_t)ne + e];
+    double s0, s1, s2;
+    if (Pp < 0.) {
+        s0 = s1 = s2 = 0.;
+    } else {
+        int const a = en0[e], b = en1[e], c = en2[e];
+        double const ua = VT[a], va = VT[a + nn], ub = VT[b], vb = VT[b + nn], uc = VT[c], vc = VT[c + nn];
+        double eps11 = dx0 * ua; eps11 += dx1 * ub; eps11 += dx2 * uc;
+        double eps22 = dy0 * va; eps22 += dy1 * vb; eps22 += dy2 * vc;
+        double eps12 = 0.5 * (dx0 * va + dy0 * ua); eps12 += 0.5 * (dx1 * vb + dy1 * ub); eps12 += 0.5 * (dx2 * vc + dy2 * uc);
+        double const eps1 = eps11 + eps22, eps2 = eps11 - eps22;
+        double const delta = sqrt(eps1 * eps1 + (eps2 * eps2 + 4 * eps12 * eps12) * K.re2);
+        double const zeta = Pp / (delta + K.evp_dmin);
+        s0 = sig0[e]; s1 = sig1[e]; s2 = sig2[e];
+        double sigma1 = s0 + s1, sigma2 = s0 - s1;
+        sigma1 += K.ralpha1 * (zeta * (eps1 - delta) - sigma1);
+        sigma2 += K.ralpha2 * (zeta * eps2 * K.re2 - sigma2);
+        s2 += K.ralpha2 * (zeta * eps12 * K.re2 - s2);
+        s0 = 0.5 * (sigma1 + sigma2);
+        s1 = 0.5 * (sigma1 - sigma2);
+    }
+    sig0[e] = s0; sig1[e] = s1; sig2[e] = s2;
+    contrib[0 * (size_t)ne + e] = vol * (s0 * dx0 + s2 * dy0);
+    contrib[1 * (size_t)ne + e] = vol * (s0 * dx1 + s2 * dy1);
+    contrib[2 * (size_t)ne + e] = vol * (s0 * dx2 + s2 * dy2);
+    contrib[3 * (size_t)ne + e] = vol * (s2 * dx0 + s1 * dy0);
+    contrib[4 * (size_t)ne + e] = vol * (s2 * dx1 + s1 * dy1);
+    contrib[5 * (size_t)ne + e] = vol * (s2 * dx2 + s1 * dy2);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// nodal solve: ordered gather of the stress gradient (10445-10467), implicit drag/Coriolis 2x2 solve
+// (10472-10529) and the Lagrangian mesh move (10539-10553).  Reads VTc, writes VTn (ping-pong).
+// Ghost nodes are written by their owner (halo push); their mesh move uses the received value and is
+// therefore applied one kernel later (`lag_ghost_move`), which is the same arithmetic sequence.
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(TPB)
+k_node_solve(KParams K, int move_mesh, int lag_ghost_move,
+             const uint8_t* __restrict__ nflags, const int* __restrict__ n2e, const int* __restrict__ n2e_deg,
+             const double* __restrict__ contrib, const double* __restrict__ grad_ssh,
+             const double* __restrict__ node_mass, const double* __restrict__ rlmass,
+             const double* __restrict__ cbu, const double* __restrict__ fcor,
+             const double* __restrict__ tau_a, const double* __restrict__ tau_wi,
+             const double* __restrict__ ocean, const double* __restrict__ VTM,
+             const double* __restrict__ VTc, double* __restrict__ VTn,
+             double* __restrict__ UM, double* __restrict__ UT)
+{
+    int const n = blockIdx.x * blockDim.x + threadIdx.x;
+    int const nn = K.nn, ne = K.ne;
+    if (n >= nn) return;
+    uint8_t const fl = nflags[n];
+    double const uice = VTc[n], vice = VTc[n + nn];
+    if (fl & NF_GHOST) {
+        if (lag_ghost_move) {
+            UT[n] += K.dte * uice;  UT[n + nn] += K.dte * vice;
+            if (!(fl & NF_NEUMANN)) { UM[n] += K.dte * uice;  UM[n + nn] += K.dte * vice; }
+        }
+        return;
+    }
+    double un = uice, vn = vice;
+    double const nm = node_mass[n];
+    if (!(fl & NF_DIRICHLET) && nm != 0.) {
+        double gu = grad_ssh[n], gv = grad_ssh[n + nn];
+        int const deg = n2e_deg[n];
+        for (int k = 0; k < deg; ++k) {
+            int const s = n2e[(size_t)k * nn + n];
+            gu -= contrib[s];
+            gv -= contrib[s + 3 * (size_t)ne];
+        }
+        double dtep = K.dte, delu = 0., delv = 0.;
+        if (K.dynamics_type == NSX_DYN_MEVP) {
+            delu = (VTM[n] - uice) / K.mevp_b;
+            delv = (VTM[n + nn] - vice) / K.mevp_b;
+            dtep = K.dte / K.mevp_b;
+        }
+        double const dte_over_mass = dtep / fmax(K.min_m, nm);
+        double const ou = ocean[n], ov = ocean[n + nn];
+        double const c_prime = K.rhow_cdw * hypot(ou - uice, ov - vice);
+        double const tau_b = cbu[n] / (hypot(uice, vice) + K.u0);
+        double const sin_s = (fl & NF_LATNEG) ? -K.sin_ota_abs : K.sin_ota_abs;   // std::copysign(sin, lat[i])
+        double const alpha = 1. + dte_over_mass * (c_prime * K.cos_ota + tau_b);
+        double const beta = dtep * fcor[n] + dte_over_mass * c_prime * sin_s;
+        double const rdenom = 1. / (alpha * alpha + beta * beta);
+        double tau_x = tau_a[n], tau_y = tau_a[n + nn];
+        if (tau_wi) { tau_x = tau_x + tau_wi[n]; tau_y = tau_y + tau_wi[n + nn]; }
+        tau_x = tau_x + c_prime * (ou * K.cos_ota - ov * sin_s);
+        tau_y = tau_y + c_prime * (ov * K.cos_ota + ou * sin_s);
+        double const rl = rlmass[n];
+        double const grad_x = gu * rl, grad_y = gv * rl;
+        un = alpha * uice + beta * vice + dte_over_mass * (alpha * (grad_x + tau_x) + beta * (grad_y + tau_y)) + alpha * delu + beta * delv;
+        un *= rdenom;
+        vn = alpha * vice - beta * uice + dte_over_mass * (alpha * (grad_y + tau_y) - beta * (grad_x + tau_x)) + alpha * delv - beta * delu;
+        vn *= rdenom;
+    }
+    VTn[n] = un;
+    VTn[n + nn] = vn;
+    if (move_mesh) {
+        UT[n] += K.dte * un;  UT[n + nn] += K.dte * vn;
+        if (!(fl & NF_NEUMANN)) { UM[n] += K.dte * un;  UM[n + nn] += K.dte * vn; }
+    }
+}
+
+// mesh move over an explicit node range with an explicit time increment:
+//   mEVP: once after the loop with dtime_step (FE.cpp:10559-10573); ghosts: final lagged move.
+__global__ void __launch_bounds__(TPB)
+k_move_mesh(int nn, int n_begin, int n_end, double dt, const uint8_t* __restrict__ nflags,
+            const double* __restrict__ VT, double* __restrict__ UM, double* __restrict__ UT)
+{
+    int const n = n_begin + blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= n_end) return;
+    double const u = VT[n], v = VT[n + nn];
+    UT[n] += dt * u;  UT[n + nn] += dt * v;
+    if (!(nflags[n] & NF_NEUMANN)) { UM[n] += dt * u;  UM[n + nn] += dt * v; }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// open-water smoother, one Jacobi sweep over the compacted list (FE.cpp:10580-10608)
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(TPB)
+k_ow_sweep(int nn, const int* __restrict__ ow_list, const int* __restrict__ ow_count,
+           const int* __restrict__ n2n, const int* __restrict__ n2n_deg,
+           const double* __restrict__ VTin, double* __restrict__ VTout)
+{
+    int const cnt = *ow_count;
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < cnt; t += gridDim.x * blockDim.x) {
+        int const n = ow_list[t];
+        int const deg = n2n_deg[n];
+        double su = 0., sv = 0.;
+        for (int j = 0; j < deg; ++j) {
+            int const q = n2n[(size_t)j * nn + n];
+            su += VTin[q];
+            sv += VTin[q + nn];
+        }
+        VTout[n] = su / deg;
+        VTout[n + nn] = sv / deg;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// ice-ocean stress diagnostic + open-water mesh move  (FE.cpp:10615-10640)
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(TPB)
+k_tauw_owmove(KParams K, const uint8_t* __restrict__ nflags, const double* __restrict__ node_mass,
+              const double* __restrict__ VT, const double* __restrict__ VTM, const double* __restrict__ ocean,
+              double* __restrict__ tau_w, double* __restrict__ UM, double* __restrict__ UT)
+{
+    int const n = blockIdx.x * blockDim.x + threadIdx.x;
+    int const nn = K.nn;
+    if (n >= nn) return;
+    double const u = VT[n], v = VT[n + nn];
+    double const uice = 0.5 * (u + VTM[n]);
+    double const vice = 0.5 * (v + VTM[n + nn]);
+    double const ou = ocean[n], ov = ocean[n + nn];
+    double const c_prime = K.rhow_cdw * hypot(ou - uice, ov - vice);
+    tau_w[n] = c_prime * (uice - ou);
+    tau_w[n + nn] = c_prime * (vice - ov);
+    uint8_t const fl = nflags[n];
+    if ((fl & NF_DIRICHLET) || node_mass[n] != 0.) return;
+    UT[n] += K.dtime_step * u;  UT[n + nn] += K.dtime_step * v;
+    if (!(fl & NF_NEUMANN)) { UM[n] += K.dtime_step * u;  UM[n + nn] += K.dtime_step * v; }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// update()  (FE.cpp:3946-4131): Lagrangian area change, ridging, mechanical redistribution, clamps
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(TPB)
+k_update(KParams K, const uint8_t* __restrict__ nflags,
+         const int* __restrict__ en0, const int* __restrict__ en1, const int* __restrict__ en2,
+         const double* __restrict__ x, const double* __restrict__ y, const double* __restrict__ UM,
+         double* __restrict__ surface, double* __restrict__ conc, double* __restrict__ thick, double* __restrict__ snow,
+         double* __restrict__ thick_myi, double* __restrict__ conc_myi, double* __restrict__ ridge_ratio,
+         double* __restrict__ conc_y, double* __restrict__ h_y, double* __restrict__ hs_y,
+         double* __restrict__ sig0, double* __restrict__ sig1, double* __restrict__ sig2,
+         double* __restrict__ del_ci_ridge_myi)
+{
+    int const e = blockIdx.x * blockDim.x + threadIdx.x;
+    int const nn = K.nn;
+    if (e >= K.ne) return;
+    int const a = en0[e], b = en1[e], c = en2[e];
+    bool const to_be_updated = !((nflags[a] | nflags[b] | nflags[c]) & NF_NEUMANN);
+
+    double const xa = x[a] + 1. * UM[a], ya = y[a] + 1. * UM[a + nn];
+    double const xb = x[b] + 1. * UM[b], yb = y[b] + 1. * UM[b + nn];
+    double const xc = x[c] + 1. * UM[c], yc = y[c] + 1. * UM[c + nn];
+    double jac = (xb - xa) * (yc - ya);
+    jac -= (xc - xa) * (yb - ya);
+
+    double del_ci = 0.;
+    double const surface_old = surface[e];
+    double const surface_new = 0.5 * fabs(jac);
+    surface[e] = surface_new;
+    double cc = conc[e], hh = thick[e], hs = snow[e], hmyi = thick_myi[e], cmyi = conc_myi[e], rr = ridge_ratio[e];
+    double cy = 0., hy = 0., hsy = 0.;
+    bool const young = K.young_ice != 0;
+    if (young) { cy = conc_y[e]; hy = h_y[e]; hsy = hs_y[e]; }
+    double const old_conc = cc;
+    if ((cc > 0.) && to_be_updated) {
+        double const surf_ratio = surface_old / surface_new;
+        cc *= surf_ratio;  hh *= surf_ratio;  hs *= surf_ratio;  hmyi *= surf_ratio;
+        sig0[e] *= surf_ratio;  sig1[e] *= surf_ratio;  sig2[e] *= surf_ratio;
+        rr = 1. - (1. - rr) * fmin(1., cc) / (old_conc * surf_ratio);
+        if (young) { hy *= surf_ratio;  cy *= surf_ratio;  hsy *= surf_ratio; }
+        if (K.equal_ridging) {
+            double const conc_ratio = fmin(1., cc) / old_conc;
+            cmyi *= conc_ratio;
+            del_ci = 0.;
+        } else {
+            cmyi *= surf_ratio;
+            del_ci = -cmyi;
+            cmyi = fmin(cmyi, 1.);
+            del_ci += cmyi;
+        }
+        del_ci *= DAYS_IN_SEC / K.dtime_step;
+    }
+    double open_water = 1. - cc;
+    if (young) open_water -= cy;
+    open_water = (open_water < 0.) ? 0. : open_water;
+    open_water = (open_water > 1.) ? 1. : open_water;
+
+    double new_conc_young = 0., del_c = 0.;
+    if (young) {
+        if (cy > 0.) {
+            new_conc_young = fmin(1., fmax(0., 1. - cc - open_water));
+            if ((cc > K.min_c) && (hh > K.min_h) && (new_conc_young < cy)) {
+                double const new_h_young = new_conc_young * hy / cy;
+                double const new_hs_young = new_conc_young * hsy / cy;
+                double const newice = hy - new_h_young;
+                del_c = (cy - new_conc_young) / 10.;
+                double const newsnow = hsy - new_hs_young;
+                hy = new_h_young;
+                hsy = new_hs_young;
+                rr = 1. - (1. - rr) * hh / (hh + newice);
+                hh += newice;
+                hs += newsnow;
+            }
+        } else {
+            hy = 0.;
+            hsy = 0.;
+        }
+    }
+    cc = fmin(1., fmax(0., 1. - new_conc_young - open_water + del_c));
+    if (young) {
+        new_conc_young = fmax(0., fmin(new_conc_young, 1. - cc));
+        cy = new_conc_young;
+    }
+    if (cc > 0.) {
+        double test_h_thick = hh / cc;
+        test_h_thick = (test_h_thick > 50.) ? 50. : test_h_thick;
+        cc = fmin(1. - new_conc_young, hh / test_h_thick);
+    } else {
+        rr = 0.;  hh = 0.;  hs = 0.;
+    }
+    cc = (cc > 0.) ? cc : 0.;
+    hh = (hh > 0.) ? hh : 0.;
+    hmyi = (hmyi > 0.) ? hmyi : 0.;
+    hs = (hs > 0.) ? hs : 0.;
+    del_ci = -cmyi;
+    if (K.myi_with_young) cmyi = fmax(0., fmin(cmyi, cc + cy));
+    else cmyi = fmax(0., fmin(cmyi, cc));
+    del_ci += cmyi;
+
+    conc[e] = cc;  thick[e] = hh;  snow[e] = hs;  thick_myi[e] = hmyi;  conc_myi[e] = cmyi;  ridge_ratio[e] = rr;
+    if (young) { conc_y[e] = cy;  h_y[e] = hy;  hs_y[e] = hsy; }
+    del_ci_ridge_myi[e] = del_ci;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// checkFieldsFast-style device reduction (FE.cpp:14536-14655)
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(TPB)
+k_check(int nn, int ndof, int ne, const double* __restrict__ VT,
+        const double* __restrict__ sig0, const double* __restrict__ sig1, const double* __restrict__ sig2,
+        const double* __restrict__ damage, const double* __restrict__ conc, const double* __restrict__ thick,
+        int* __restrict__ out_i, unsigned long long* __restrict__ out_maxspeed_bits)
+{
+    int const t = blockIdx.x * blockDim.x + threadIdx.x;
+    int n_nan = 0, n_speed = 0, n_range = 0;
+    double sp = 0.;
+    if (t < nn) {
+        double const u = VT[t], v = VT[t + nn];
+        if (!isfinite(u) || !isfinite(v)) n_nan++;
+        else if (t < ndof) { sp = hypot(u, v); if (sp > 5.) n_speed++; }
+    }
+    if (t < ne) {
+        double const d = damage[t], c = conc[t], h = thick[t];
+        if (!isfinite(sig0[t]) || !isfinite(sig1[t]) || !isfinite(sig2[t]) || !isfinite(d) || !isfinite(c) || !isfinite(h)) n_nan++;
+        else if (d < 0. || d > 1. || c < 0. || c > 1. || h < 0.) n_range++;
+    }
+    // warp reduce then one atomic per warp (integers and a non-negative double compared as bits)
+    for (int o = 16; o > 0; o >>= 1) {
+        n_nan += __shfl_down_sync(0xffffffffu, n_nan, o);
+        n_speed += __shfl_down_sync(0xffffffffu, n_speed, o);
+        n_range += __shfl_down_sync(0xffffffffu, n_range, o);
+        sp = fmax(sp, __shfl_down_sync(0xffffffffu, sp, o));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (n_nan) atomicAdd(&out_i[0], n_nan);
+        if (n_speed) atomicAdd(&out_i[1], n_speed);
+        if (n_range) atomicAdd(&out_i[2], n_range);
+        atomicMax(out_maxspeed_bits, (unsigned long long)__double_as_longlong(sp));
+    }
+}
+
+// element-major <-> SoA transposes for M_shape_coeff[cpt][k]
+__global__ void k_shape_to_aos(int ne, const double* __restrict__ soa, double* __restrict__ aos)
+{
+    int const t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= 6 * ne) return;
+    int const e = t / 6, k = t - 6 * e;
+    aos[t] = soa[(size_t)k * ne + e];
+}
+
+// ---------------------------------------------------------------------------------------------------
+// halo exchange (replaces FE.cpp:13963-13996): the owner stores (u,v) straight into the holder's ghost
+// slots of the holder's VT buffer (local memory, or NVLink peer memory mapped through CUDA IPC).
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(TPB)
+k_halo_push(int n, int nn_src, int nn_dst, const int* __restrict__ src_idx, const int* __restrict__ dst_idx,
+            const double* __restrict__ VTsrc, double* __restrict__ VTdst)
+{
+    int const t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    int const s = src_idx[t], d = dst_idx[t];
+    VTdst[d] = VTsrc[s];
+    VTdst[d + nn_dst] = VTsrc[s + nn_src];
+}
+
+// after all pushes of this exchange: publish the epoch in every holder's flag slot (release, system scope)
+struct SignalArgs { unsigned long long* flag[32]; int n; };
+__global__ void k_halo_signal(SignalArgs a, unsigned long long epoch)
+{
+    int const t = threadIdx.x;
+    if (t >= a.n) return;
+    __threadfence_system();
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(a.flag[t]), "l"(epoch) : "memory");
+}
+
+// wait until every owner that fills my ghosts has published `epoch`; bounded spin -> error word
+struct WaitArgs { int slot[32]; int n; };
+__global__ void k_halo_wait(WaitArgs a, const unsigned long long* flags, unsigned long long epoch,
+                            long long max_spins, int* err)
+{
+    int const t = threadIdx.x;
+    if (t >= a.n) return;
+    const unsigned long long* f = flags + a.slot[t];
+    long long spins = 0;
+    for (;;) {
+        unsigned long long v;
+        asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(f) : "memory");
+        if (v >= epoch) break;
+        if (++spins > max_spins) { atomicExch(err, 1 + a.slot[t]); break; }
+        __nanosleep(100);
+    }
+}
+
+} // namespace nsx
