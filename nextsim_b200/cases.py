@@ -21,6 +21,7 @@ NODAL1_FIELDS = ("M_ssh",)
 CONFIGS = {
     "toy": dict(mesh="toy", kind="toy", dt=300.0, C_lab=1.5e6, alea_factor=0.33, use_coriolis=False),
     "10km": dict(mesh="10km", kind="large", dt=200.0, alea_factor=0.33),
+    "10km_stable": dict(mesh="10km", kind="stable", dt=200.0, alea_factor=0.33),
     "3km": dict(mesh="3km", kind="large", dt=200.0, alea_factor=0.33),
     "1km": dict(mesh="1km", kind="large", dt=200.0, alea_factor=0.33),
 }

@@ -143,7 +143,12 @@ def minstd_uniform01_fast(n):
 
 
 def make_state(m, kind="large", seed=SEED, young=True):
-    """Global element/node fields.  kind: 'toy' (nextsim.toy.cfg semantics) or 'large'."""
+    """Global element/node fields.  kind: 'toy' (nextsim.toy.cfg semantics), 'large' (BASELINE.md section 4:
+    conc~U(0.85,1), damage~U(0,0.8)) or 'stable' (conc~U(0.95,1), damage~U(0,0.5)).  The 'large' state holds
+    very weak elements (viscous relaxation time << sub-cycle) in which the reference's BBM update runs into a
+    growing period-2 oscillation of sigma_n around -Pmax; a 1e-15 input perturbation then grows to 1e-7 within
+    one model step in the reference algorithm itself ("Conditioning").  'stable' avoids that regime
+    and is what the strict 1e-9 full-step parity tests use."""
     rng = np.random.default_rng(seed + 1)
     ne, nn = m.ne, m.nn
     L = m.nx * m.h
@@ -166,7 +171,7 @@ def make_state(m, kind="large", seed=SEED, young=True):
         S["M_hs_young"] = z_e.copy()
         S["M_sigma"] = np.zeros((3, ne))
     else:
-        conc = rng.uniform(0.85, 1.0, ne)
+        conc = rng.uniform(0.85, 1.0, ne) if kind == "large" else rng.uniform(0.95, 1.0, ne)
         # ~8 % of the elements in smooth ice-free patches
         patch = (np.sin(2 * np.pi * 3.0 * cx / L + 0.7) * np.sin(2 * np.pi * 2.0 * cy / L + 1.9)
                  + 0.35 * np.sin(2 * np.pi * 7.0 * (cx + cy) / L))
@@ -178,7 +183,7 @@ def make_state(m, kind="large", seed=SEED, young=True):
         S["M_conc"] = conc
         S["M_thick"] = thick
         S["M_snow_thick"] = snow
-        S["M_damage"] = np.where(water, 0.0, rng.uniform(0.0, 0.8, ne))
+        S["M_damage"] = np.where(water, 0.0, rng.uniform(0.0, 0.8 if kind == "large" else 0.5, ne))
         xn, yn = m.x / L - 0.5, m.y / L - 0.5
         S["M_VT"] = np.concatenate([-0.6 * yn, 0.6 * xn]) * np.tile(np.exp(-4 * (xn ** 2 + yn ** 2)), 2)
         # translating cyclone 5..20 m/s
