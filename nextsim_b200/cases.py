@@ -48,7 +48,8 @@ def make_params(cfg, dyn, gm, substeps=120):
     return p, C_fix, C_alea
 
 
-def make_case(name="toy", nranks=1, dyn="bbm", open_east=False, substeps=120, nx=None, young=True, seed=syn.SEED):
+def make_case(name="toy", nranks=1, dyn="bbm", open_east=False, substeps=120, nx=None, young=True, seed=syn.SEED,
+              only_rank=None):
     cfg = dict(CONFIGS[name])
     mnx, h = syn.SIZES[cfg["mesh"]]
     if nx is not None:
@@ -72,7 +73,7 @@ def make_case(name="toy", nranks=1, dyn="bbm", open_east=False, substeps=120, nx
         pt.bc_marked_nodes(lm, gm.dirichlet_flags_root, gm.neumann_flags_root)
         lm.nodal_element_connectivity, lm.nodal_connectivity = pt.bamg_tables(lm.indices, lm.num_nodes)
         lm.lat = pt.scatter_nodal1(lm, gm.lat)
-    c.local = [local_fields(c, lm) for lm in c.lms]
+    c.local = [local_fields(c, lm) if only_rank in (None, lm.rank) else None for lm in c.lms]
     return c
 
 
