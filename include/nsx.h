@@ -146,6 +146,8 @@ int nsx_create(const NsxMesh* mesh, const NsxHalo* halo, int device, nsx_handle*
 int nsx_destroy(nsx_handle h);
 const char* nsx_last_error(nsx_handle h);      /* h may be NULL: error of the last failed nsx_create */
 int nsx_version(void);
+int nsx_abi_sizes(int* out, int n);          /* sizeof NsxDynParams, NsxMesh, NsxHalo, NsxFields, NsxCheck, NsxTiming */
+const char* nsx_cfg_last_error(void);         /* message of the last failed nsx_params_from_cfg */
 
 /* ---- options ---- */
 void nsx_params_defaults(NsxDynParams* p);                     /* model/options.cpp defaults */

@@ -714,3 +714,12 @@ extern "C" int nsx_check(nsx_handle S, NsxCheck* out)
     out->n_nan = hi[0]; out->n_speed = hi[1]; out->n_range = hi[2]; out->pad_ = 0; out->max_speed = hd;
     NSX_API_END(S)
 }
+
+// sizeof() of every struct that crosses the ABI, so a binding can detect layout drift
+extern "C" int nsx_abi_sizes(int* out, int n)
+{
+    int const s[6] = {(int)sizeof(NsxDynParams), (int)sizeof(NsxMesh), (int)sizeof(NsxHalo),
+                      (int)sizeof(NsxFields), (int)sizeof(NsxCheck), (int)sizeof(NsxTiming)};
+    for (int i = 0; i < n && i < 6; ++i) out[i] = s[i];
+    return 6;
+}

@@ -1,0 +1,114 @@
+"""The C-ABI library loads, exports every symbol include/nsx.h declares, and its structs match the binding.
+No compute calls here (no GPU in this suite); nsx_create must fail loudly, not fall back."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from nextsim_b200 import capi, cases
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_functions():
+    src = open(os.path.join(ROOT, "include", "nsx.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    names = re.findall(r"\b(nsx_[a-z_0-9]+)\s*\(", src)
+    return sorted(set(names))
+
+
+def test_header_symbols_exported():
+    L = capi.lib()
+    names = declared_functions()
+    assert len(names) >= 20
+    for n in names:
+        assert hasattr(L, n), "libnsx.so does not export %s" % n
+    assert set(capi.EXPORTS) <= set(names)
+    assert L.nsx_version() == 1
+
+
+def test_struct_layouts_match_ctypes():
+    L = capi.lib()
+    out = (C.c_int * 6)()
+    assert L.nsx_abi_sizes(out, 6) == 6
+    expect = [C.sizeof(capi.NsxDynParams), C.sizeof(capi.NsxMesh), C.sizeof(capi.NsxHalo),
+              C.sizeof(capi.NsxFields), C.sizeof(capi.NsxCheck), C.sizeof(capi.NsxTiming)]
+    assert list(out) == expect
+
+
+def test_defaults_follow_options_cpp():
+    p = capi.default_params()
+    assert p.substeps == 120 and p.dtime_step == 200.0
+    assert p.dynamics_type == 0 and p.basal_stress_type == 1 and p.ice_cat_type == 1
+    assert p.young == 5.9605e8 and p.nu0 == pytest.approx(1 / 3) and p.tan_phi == 0.7
+    assert p.compaction_param == -20.0 and p.exponent_relaxation_sigma == 5.0
+    assert p.ocean_turning_angle_rad == pytest.approx(np.deg2rad(25.0))
+    assert (p.evp_e, p.evp_Pstar, p.evp_C, p.evp_dmin) == (2.0, 27.5e3, 20.0, 1e-9)
+    assert (p.mevp_alpha, p.mevp_beta) == (500.0, 500.0)
+
+
+TOY_CFG = """
+[setup]
+ice-type=constant_partial
+[mesh]
+filename=square_with_point.msh
+[simul]
+timestep=300
+duration=1
+[debugging]
+log-level=debug#info
+[thermo]
+use_thermo_forcing=false
+newice_type=4
+[dynamics]
+use_coriolis=false
+alea_factor=.33
+#compression_factor=0
+C_lab=1.5e6
+"""
+
+
+def test_cfg_reader(tmp_path):
+    f = tmp_path / "toy.cfg"
+    f.write_text(TOY_CFG)
+    p = capi.params_from_cfg(f)
+    assert p.dtime_step == 300.0 and p.C_lab == 1.5e6 and p.alea_factor == 0.33
+    assert p.use_coriolis == 0 and p.ocean_turning_angle_rad == 0.0       # FE.cpp:1167-1172
+    assert p.compression_factor == 10e3                                    # commented line ignored
+    assert p.ice_cat_type == 1
+    f.write_text("[setup]\ndynamics-type=mevp\n[dynamics]\nmevp.alpha=300\nsubsteps=200\n[thermo]\nnewice_type=1\n")
+    p = capi.params_from_cfg(f)
+    assert p.dynamics_type == 4 and p.mevp_alpha == 300.0 and p.substeps == 200 and p.ice_cat_type == 0
+    f.write_text("[dynamics]\nnot_an_option=1\n")
+    with pytest.raises(RuntimeError, match="unrecognised option"):
+        capi.params_from_cfg(f)
+    f.write_text("[setup]\ndynamics-type=free_drift\n")
+    with pytest.raises(RuntimeError, match="outside the accelerated path"):
+        capi.params_from_cfg(f)
+    with pytest.raises(RuntimeError, match="cannot open"):
+        capi.params_from_cfg(tmp_path / "missing.cfg")
+
+
+def test_create_fails_loudly_without_gpu():
+    try:
+        import torch
+        if torch.cuda.is_available():
+            pytest.skip("a GPU is present")
+    except ImportError:
+        pass
+    c = cases.make_case("toy")
+    with pytest.raises(RuntimeError, match="nsx_create"):
+        capi.Solver(c.lms[0], 0)
+
+
+def test_product_never_imports_oracle():
+    """Only tests/, __graft_entry__.smoke() and bench.py's CPU legs may touch oracle/."""
+    pkg = os.path.join(ROOT, "nextsim_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for fn in files:
+            if fn.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
+                txt = open(os.path.join(dirpath, fn)).read()
+                for needle in ("import oracle", "from oracle", "liboracle", "orc_", "oracle_bridge"):
+                    assert needle not in txt, "%s references the oracle (%s)" % (fn, needle)
