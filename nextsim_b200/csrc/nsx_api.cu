@@ -3,6 +3,7 @@
 // point that computes launches CUDA kernels and returns an error if the device is unavailable.
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 
@@ -223,7 +224,7 @@ extern "C" int nsx_destroy(nsx_handle S)
     cudaSetDevice(S->device);
     if (S->stream) cudaStreamSynchronize(S->stream);
     for (auto& p : S->peers) if (p.ipc_base) cudaIpcCloseMemHandle(p.ipc_base);
-    if (S->graph_exec) cudaGraphExecDestroy(S->graph_exec);
+    for (auto& g : S->graph_exec) if (g) cudaGraphExecDestroy(g);
     for (auto& e : S->ev) if (e) cudaEventDestroy(e);
     if (S->window) cudaFree(S->window);
     if (S->stream) cudaStreamDestroy(S->stream);
@@ -349,7 +350,7 @@ extern "C" int nsx_upload(nsx_handle S, const NsxFields* f)
     field_table(S, f, t, true);
     for (auto& m : t)
         NSX_CUDA(cudaMemcpyAsync(m.dev, m.host, m.n * sizeof(double), cudaMemcpyHostToDevice, S->stream));
-    if (f->M_tau_wi) S->have_tau_wi = true;
+    if (f->M_tau_wi && !S->have_tau_wi) { S->have_tau_wi = true; S->graph_valid = false; }
     if (f->M_shape_coeff) throw std::invalid_argument("nsx_upload: M_shape_coeff is an output");
     NSX_CUDA(cudaStreamSynchronize(S->stream));
     NSX_API_END(S)
@@ -401,11 +402,7 @@ static void finish_link(nsx_solver* S, PeerLink& p, double* base, int peer_nn, c
     p.peer_vt[0] = base;
     p.peer_vt[1] = base + 2 * (size_t)peer_nn;
     p.peer_flags = (unsigned long long*)(base + 4 * (size_t)peer_nn);
-    p.d_send_src.alloc(n); p.d_send_dst.alloc(n);
-    if (n) {
-        NSX_CUDA(cudaMemcpy(p.d_send_src.p, p.h_send_idx.data(), n * sizeof(int), cudaMemcpyHostToDevice));
-        NSX_CUDA(cudaMemcpy(p.d_send_dst.p, peer_recv_idx_for_me, n * sizeof(int), cudaMemcpyHostToDevice));
-    }
+    p.h_send_dst.assign(peer_recv_idx_for_me, peer_recv_idx_for_me + n);
     p.connected = true;
 }
 
@@ -473,34 +470,51 @@ extern "C" int nsx_halo_finalize(nsx_handle S)
 {
     NSX_API_BEGIN(S)
     for (auto& p : S->peers) if (!p.connected) throw std::runtime_error("nsx_halo_finalize: rank " + std::to_string(p.rank) + " not connected");
+    // concatenated push tables (entry -> my node id, holder's ghost id), peers in link order
+    std::vector<int> src, dst;
+    for (auto& p : S->peers) {
+        src.insert(src.end(), p.h_send_idx.begin(), p.h_send_idx.end());
+        dst.insert(dst.end(), p.h_send_dst.begin(), p.h_send_dst.end());
+    }
+    S->n_send_total = (int)src.size();
+    S->d_send_src.alloc(src.size()); S->d_send_dst.alloc(dst.size());
+    if (!src.empty()) {
+        NSX_CUDA(cudaMemcpy(S->d_send_src.p, src.data(), src.size() * sizeof(int), cudaMemcpyHostToDevice));
+        NSX_CUDA(cudaMemcpy(S->d_send_dst.p, dst.data(), dst.size() * sizeof(int), cudaMemcpyHostToDevice));
+    }
+    S->d_epoch.alloc(1); S->d_done.alloc(1);
+    NSX_CUDA(cudaMemset(S->d_epoch.p, 0, sizeof(unsigned long long)));
+    NSX_CUDA(cudaMemset(S->d_done.p, 0, sizeof(unsigned int)));
     S->halo_ready = true;
     S->graph_valid = false;
     NSX_API_END(S)
 }
 
-// One ghost exchange of VT[cur]: push my owned values into every holder, publish the epoch, then wait
-// for every owner of my ghosts.  `wait` is false for lock-step groups that share one stream.
-static void halo_exchange(nsx_solver* S, bool wait)
+// One ghost exchange of VT[cur] as a single kernel: push my owned values into every holder, publish the
+// epoch, wait for every owner of my ghosts.  `sync` is false for lock-step groups ordered by streams/events.
+static void halo_exchange(nsx_solver* S, bool sync)
 {
     if (S->peers.empty()) return;
     if (!S->halo_ready) throw std::runtime_error("halo exchange before nsx_halo_finalize");
-    cudaStream_t st = S->stream;
-    S->epoch++;
-    SignalArgs sa{}; WaitArgs wa{};
+    HaloArgs a{};
+    a.sync = sync ? 1 : 0;
+    int off = 0;
     for (auto& p : S->peers) {
-        int const n = (int)p.d_send_src.n;
-        if (n) {
-            k_halo_push<<<nblk(n), TPB, 0, st>>>(n, S->nn, p.peer_nn, p.d_send_src.p, p.d_send_dst.p,
-                                                 S->VT[S->cur], p.peer_vt[S->cur]);
-            sa.flag[sa.n++] = p.peer_flags + S->rank;
+        if (!p.h_send_idx.empty()) {
+            a.peer_begin[a.n_peers] = off;
+            a.peer_vt[a.n_peers] = p.peer_vt[S->cur];
+            a.peer_nn[a.n_peers] = p.peer_nn;
+            a.peer_flag[a.n_peers] = p.peer_flags + S->rank;
+            off += (int)p.h_send_idx.size();
+            a.n_peers++;
         }
-        if (!p.h_recv_idx.empty()) wa.slot[wa.n++] = p.rank;
+        if (!p.h_recv_idx.empty()) a.wait_slot[a.n_wait++] = p.rank;
     }
-    S->n_launch += (int)S->peers.size();
-    if (wait) {
-        if (sa.n) { k_halo_signal<<<1, 32, 0, st>>>(sa, S->epoch); S->n_launch++; }
-        if (wa.n) { k_halo_wait<<<1, 32, 0, st>>>(wa, S->flags, S->epoch, 20000000LL, S->halo_err.p); S->n_launch++; }
-    }
+    a.peer_begin[a.n_peers] = off;
+    a.n_total = off;
+    k_halo_exchange<<<std::max(1, nblk(off)), TPB, 0, S->stream>>>(a, S->nn, S->d_send_src.p, S->d_send_dst.p,
+        S->VT[S->cur], S->flags, S->d_epoch.p, S->d_done.p, 40000000LL, S->halo_err.p);
+    S->n_launch++;
     NSX_CUDA(cudaGetLastError());
 }
 
@@ -600,6 +614,13 @@ static int substeps_to_run(nsx_solver const* S)
     return (S->P.stop_after_substeps > 0) ? std::min(steps, S->P.stop_after_substeps) : steps;
 }
 
+// timing events: inside a stream capture they must be recorded as external event nodes
+static void record(nsx_solver* S, int i)
+{
+    if (S->capturing) NSX_CUDA(cudaEventRecordWithFlags(S->ev[i], S->stream, cudaEventRecordExternal));
+    else NSX_CUDA(cudaEventRecord(S->ev[i], S->stream));
+}
+
 static void solve_group(int n, nsx_solver** W)
 {
     // lock-step over ranks; for n == 1 this is the plain single-rank sequence.  Ranks in a group share a
@@ -610,9 +631,9 @@ static void solve_group(int n, nsx_solver** W)
         if (!S->have_params) throw std::runtime_error("nsx_explicit_solve before nsx_set_params");
         NSX_CUDA(cudaSetDevice(S->device));
         S->n_launch = 0;
-        NSX_CUDA(cudaEventRecord(S->ev[0], S->stream));
+        record(S, 0);
         phase_prep(S);
-        NSX_CUDA(cudaEventRecord(S->ev[1], S->stream));
+        record(S, 1);
     }
     int const nrun = substeps_to_run(W[0]);
     bool const remote = (n == 1) && !W[0]->halo_local;
@@ -630,7 +651,7 @@ static void solve_group(int n, nsx_solver** W)
     }
     for (int r = 0; r < n; ++r) {
         NSX_CUDA(cudaSetDevice(W[r]->device));
-        NSX_CUDA(cudaEventRecord(W[r]->ev[2], W[r]->stream));
+        record(W[r], 2);
         phase_post_move(W[r], nrun);
     }
     if (!W[0]->P.skip_ow_smoother) {
@@ -644,18 +665,60 @@ static void solve_group(int n, nsx_solver** W)
         nsx_solver* S = W[r];
         NSX_CUDA(cudaSetDevice(S->device));
         phase_tauw(S);
-        NSX_CUDA(cudaEventRecord(S->ev[3], S->stream));
+        record(S, 3);
         S->timing.n_launches = S->n_launch;
         S->timing.n_substeps = nrun;
         S->timing_valid = true;
     }
 }
 
+// explicitSolve() of one rank.  The whole launch sequence (2 prep kernels, `substeps` x {element, node[, halo]},
+// 50 smoother sweeps, tau_w) is captured once into a CUDA graph per entry parity of the VT ping-pong and
+// replayed afterwards: at 2e5 elements a sub-cycle is ~10 us of device work, less than the host cost of
+// launching its kernels one by one.  NSX_NO_GRAPH=1 disables this (debugging).
 extern "C" int nsx_explicit_solve(nsx_handle S)
 {
     NSX_API_BEGIN(S)
     nsx_solver* W[1] = {S};
-    solve_group(1, W);
+    static const bool no_graph = (getenv("NSX_NO_GRAPH") != nullptr);
+    if (no_graph) {
+        solve_group(1, W);
+    } else {
+        if (!S->graph_valid) {
+            for (auto& g : S->graph_exec) if (g) { cudaGraphExecDestroy(g); g = nullptr; }
+            S->graph_valid = true;
+        }
+        int const slot = S->cur;
+        if (!S->graph_exec[slot]) {
+            if (!S->have_params) throw std::runtime_error("nsx_explicit_solve before nsx_set_params");
+            cudaGraph_t graph = nullptr;
+            NSX_CUDA(cudaStreamBeginCapture(S->stream, cudaStreamCaptureModeThreadLocal));
+            S->capturing = true;
+            try {
+                solve_group(1, W);
+            } catch (...) {
+                S->capturing = false;
+                cudaStreamEndCapture(S->stream, &graph);
+                if (graph) cudaGraphDestroy(graph);
+                S->cur = slot;
+                throw;
+            }
+            S->capturing = false;
+            NSX_CUDA(cudaStreamEndCapture(S->stream, &graph));
+            cudaError_t e = cudaGraphInstantiate(&S->graph_exec[slot], graph, 0);
+            cudaGraphDestroy(graph);
+            NSX_CUDA(e);
+            S->graph_cur_out[slot] = S->cur;
+            S->graph_launches[slot] = S->timing.n_launches;
+            S->graph_nsub[slot] = S->timing.n_substeps;
+            S->cur = slot;
+        }
+        NSX_CUDA(cudaGraphLaunch(S->graph_exec[slot], S->stream));
+        S->cur = S->graph_cur_out[slot];
+        S->timing.n_launches = S->graph_launches[slot];
+        S->timing.n_substeps = S->graph_nsub[slot];
+        S->timing_valid = true;
+    }
     NSX_API_END(S)
 }
 

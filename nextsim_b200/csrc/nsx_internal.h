@@ -75,8 +75,7 @@ struct PeerLink {
     std::vector<int> h_send_idx;           // my local node ids to send (M_extract_local_index[peer])
     std::vector<int> h_recv_idx;           // my ghost ids filled by that peer (M_local_ghosts_local_index[peer])
     // device-side push tables
-    DBuf<int> d_send_src;                  // my local node id
-    DBuf<int> d_send_dst;                  // peer's local ghost id
+    std::vector<int> h_send_dst;           // the peer's local ghost ids for my send list (same order)
     double* peer_vt[2] = {nullptr, nullptr};   // peer's VT ping-pong buffers (mapped)
     unsigned long long* peer_flags = nullptr;  // peer's flag array (mapped); I write slot [my rank]
     int peer_nn = 0;
@@ -117,7 +116,6 @@ struct nsx_solver {
     double* VT[2] = {nullptr, nullptr};        // [2*nn] each
     unsigned long long* flags = nullptr;       // [nranks] arrival epochs written by peers
     int cur = 0;                               // which VT buffer holds the current velocity
-    unsigned long long epoch = 0;              // halo exchange counter
 
     nsx::DBuf<double> UM, UT, wind, ocean, tau_wi, tau_a, tau_w, ssh, VTM;
     bool have_tau_wi = false;
@@ -137,7 +135,10 @@ struct nsx_solver {
 
     // ---- halo ----
     std::deque<nsx::PeerLink> peers;             // union of send/recv peers
-    nsx::DBuf<int> ghost_ids;                    // all ghost node ids [nn-ndof]
+    nsx::DBuf<int> d_send_src, d_send_dst;       // concatenated push tables over all send peers
+    nsx::DBuf<unsigned long long> d_epoch;       // device-resident exchange counter (graph replay safe)
+    nsx::DBuf<unsigned int> d_done;              // block completion counter of k_halo_exchange
+    int n_send_total = 0;
     nsx::DBuf<int> halo_err;                     // device error word (timeouts)
     bool halo_ready = false;
     bool halo_local = false;                     // all peers live in this process on this device
@@ -151,9 +152,10 @@ struct nsx_solver {
     int n_launch = 0;
 
     // CUDA graph of one explicitSolve (built lazily, invalidated by nsx_set_params / halo changes)
-    cudaGraphExec_t graph_exec = nullptr;
+    cudaGraphExec_t graph_exec[2] = {nullptr, nullptr};   // indexed by the VT parity at entry
+    int graph_cur_out[2] = {0, 0}, graph_launches[2] = {0, 0}, graph_nsub[2] = {0, 0};
     bool graph_valid = false;
-    int graph_cur_in = -1;
+    bool capturing = false;
 
     // pinned staging for transfers
     void* pinned = nullptr;

@@ -601,46 +601,63 @@ __global__ void k_shape_to_aos(int ne, const double* __restrict__ soa, double* _
 }
 
 // ---------------------------------------------------------------------------------------------------
-// halo exchange (replaces FE.cpp:13963-13996): the owner stores (u,v) straight into the holder's ghost
-// slots of the holder's VT buffer (local memory, or NVLink peer memory mapped through CUDA IPC).
+// halo exchange (replaces FE.cpp:13963-13996).  ONE kernel per exchange:
+//   1. every owner stores (u,v) of its shared nodes straight into the holders' ghost slots of the holders'
+//      VT buffer (local memory for in-process groups, NVLink peer memory mapped through CUDA IPC otherwise);
+//   2. the last block to finish publishes the new epoch in every holder's flag slot (release, system scope)
+//   3. and then waits (bounded spin) until every owner of MY ghosts has published the same epoch.
+// The epoch lives in device memory so a captured CUDA graph can be replayed.
 // ---------------------------------------------------------------------------------------------------
+struct HaloArgs {
+    int n_total;                        // send entries over all peers
+    int n_peers;                        // peers I send to
+    int peer_begin[33];                 // entry ranges per send peer
+    double* peer_vt[32];                // holder's VT buffer (current parity)
+    int peer_nn[32];
+    unsigned long long* peer_flag[32];  // holder's flag slot for me
+    int n_wait;                         // owners I wait for
+    int wait_slot[32];
+    int sync;                           // 0: stream-ordered group on one device, no flags
+};
+
 __global__ void __launch_bounds__(TPB)
-k_halo_push(int n, int nn_src, int nn_dst, const int* __restrict__ src_idx, const int* __restrict__ dst_idx,
-            const double* __restrict__ VTsrc, double* __restrict__ VTdst)
+k_halo_exchange(HaloArgs a, int nn_src, const int* __restrict__ src_idx, const int* __restrict__ dst_idx,
+                const double* __restrict__ VTsrc, const unsigned long long* my_flags,
+                unsigned long long* epoch_ctr, unsigned int* done_ctr, long long max_spins, int* err)
 {
     int const t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= n) return;
-    int const s = src_idx[t], d = dst_idx[t];
-    VTdst[d] = VTsrc[s];
-    VTdst[d + nn_dst] = VTsrc[s + nn_src];
-}
-
-// after all pushes of this exchange: publish the epoch in every holder's flag slot (release, system scope)
-struct SignalArgs { unsigned long long* flag[32]; int n; };
-__global__ void k_halo_signal(SignalArgs a, unsigned long long epoch)
-{
-    int const t = threadIdx.x;
-    if (t >= a.n) return;
-    __threadfence_system();
-    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(a.flag[t]), "l"(epoch) : "memory");
-}
-
-// wait until every owner that fills my ghosts has published `epoch`; bounded spin -> error word
-struct WaitArgs { int slot[32]; int n; };
-__global__ void k_halo_wait(WaitArgs a, const unsigned long long* flags, unsigned long long epoch,
-                            long long max_spins, int* err)
-{
-    int const t = threadIdx.x;
-    if (t >= a.n) return;
-    const unsigned long long* f = flags + a.slot[t];
-    long long spins = 0;
-    for (;;) {
-        unsigned long long v;
-        asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(f) : "memory");
-        if (v >= epoch) break;
-        if (++spins > max_spins) { atomicExch(err, 1 + a.slot[t]); break; }
-        __nanosleep(100);
+    if (t < a.n_total) {
+        int p = 0;
+        while (t >= a.peer_begin[p + 1]) ++p;
+        int const s = src_idx[t], d = dst_idx[t];
+        double* dst = a.peer_vt[p];
+        dst[d] = VTsrc[s];
+        dst[d + a.peer_nn[p]] = VTsrc[s + nn_src];
     }
+    if (!a.sync) return;
+    __shared__ bool last;
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) last = (atomicAdd(done_ctr, 1u) == gridDim.x - 1);
+    __syncthreads();
+    if (!last) return;
+    __threadfence_system();
+    unsigned long long const epoch = *((volatile unsigned long long*)epoch_ctr) + 1ULL;
+    if ((int)threadIdx.x < a.n_peers)
+        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(a.peer_flag[threadIdx.x]), "l"(epoch) : "memory");
+    if ((int)threadIdx.x < a.n_wait) {
+        const unsigned long long* f = my_flags + a.wait_slot[threadIdx.x];
+        long long spins = 0;
+        for (;;) {
+            unsigned long long v;
+            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(f) : "memory");
+            if (v >= epoch) break;
+            if (++spins > max_spins) { atomicExch(err, 1 + a.wait_slot[threadIdx.x]); break; }
+            __nanosleep(64);
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) { *epoch_ctr = epoch; *done_ctr = 0u; }
 }
 
 } // namespace nsx
