@@ -147,7 +147,10 @@ int nsx_destroy(nsx_handle h);
 const char* nsx_last_error(nsx_handle h);      /* h may be NULL: error of the last failed nsx_create */
 int nsx_version(void);
 int nsx_abi_sizes(int* out, int n);          /* sizeof NsxDynParams, NsxMesh, NsxHalo, NsxFields, NsxCheck, NsxTiming */
-const char* nsx_cfg_last_error(void);         /* message of the last failed nsx_params_from_cfg */
+/* tile decomposition of the sub-cycle kernel: ntiles, nodes/tile, slots, max local nodes, max slots,
+ * boundary tiles, dynamic shared memory bytes */
+int nsx_tile_info(nsx_handle h, int* out, int n);
+const char* nsx_cfg_last_error(void);        /* message of the last failed nsx_params_from_cfg */
 
 /* ---- options ---- */
 void nsx_params_defaults(NsxDynParams* p);                     /* model/options.cpp defaults */

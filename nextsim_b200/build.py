@@ -6,8 +6,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libnsx.so")
-SOURCES = ["nsx_api.cu", "nsx_cfg.cpp"]
-HEADERS = ["nsx_kernels.cuh", "nsx_internal.h", os.path.join("..", "..", "include", "nsx.h")]
+SOURCES = ["nsx_api.cu", "nsx_mesh.cpp", "nsx_cfg.cpp"]
+HEADERS = ["nsx_kernels.cuh", "nsx_internal.h", "nsx_mesh.h", os.path.join("..", "..", "include", "nsx.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

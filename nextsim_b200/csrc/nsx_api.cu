@@ -5,7 +5,6 @@
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
-#include <mutex>
 
 #include "nsx_kernels.cuh"
 
@@ -27,116 +26,42 @@ static std::string g_create_err;
 
 static inline int nblk(long n) { return (int)((n + TPB - 1) / TPB); }
 
+static int env_int(const char* name, int dflt)
+{
+    const char* v = getenv(name);
+    return (v && *v) ? atoi(v) : dflt;
+}
+
 // ---------------------------------------------------------------------------------------------------
 // life cycle
 // ---------------------------------------------------------------------------------------------------
-static void build_mesh(nsx_solver* S, const NsxMesh* M)
+static void upload_plan(nsx_solver* S)
 {
-    int const nn = M->num_nodes, ne = M->num_elements, ndof = M->local_ndof;
-    if (nn <= 0 || ne <= 0 || ndof <= 0 || ndof > nn || M->local_nelements > ne)
-        throw std::invalid_argument("nsx_create: inconsistent mesh sizes");
-    if (!M->coord_x || !M->coord_y || !M->indices || !M->lat || !M->nodal_element_connectivity || !M->nodal_connectivity)
-        throw std::invalid_argument("nsx_create: NULL mesh array");
-    if ((long)3 * ne >= (1L << 31)) throw std::invalid_argument("nsx_create: mesh too large for 32-bit staging slots");
-    S->nn = nn; S->ndof = ndof; S->ne = ne; S->ne_local = M->local_nelements;
+    MeshPlan& P = S->plan;
     cudaStream_t st = S->stream;
-
-    S->x.alloc(nn); S->y.alloc(nn); S->lat.alloc(nn);
-    NSX_CUDA(cudaMemcpyAsync(S->x.p, M->coord_x, nn * sizeof(double), cudaMemcpyHostToDevice, st));
-    NSX_CUDA(cudaMemcpyAsync(S->y.p, M->coord_y, nn * sizeof(double), cudaMemcpyHostToDevice, st));
-    NSX_CUDA(cudaMemcpyAsync(S->lat.p, M->lat, nn * sizeof(double), cudaMemcpyHostToDevice, st));
-
-    // element -> node planes (0-based) and the ascending node -> element ELL table
-    std::vector<int> e0(ne), e1(ne), e2(ne), deg(nn, 0);
-    for (int e = 0; e < ne; ++e) {
-        int const a = M->indices[3 * (size_t)e] - 1, b = M->indices[3 * (size_t)e + 1] - 1, c = M->indices[3 * (size_t)e + 2] - 1;
-        if (a < 0 || b < 0 || c < 0 || a >= nn || b >= nn || c >= nn)
-            throw std::invalid_argument("nsx_create: element index out of range");
-        if (M->ghost_nodes) {
-            // GMSHElement::ghostNodes must agree with "local id >= local_ndof" (gmshmesh.cpp:1298-1301)
-            const unsigned char* g = M->ghost_nodes + 3 * (size_t)e;
-            if ((g[0] != 0) != (a >= ndof) || (g[1] != 0) != (b >= ndof) || (g[2] != 0) != (c >= ndof))
-                throw std::invalid_argument("nsx_create: ghost_nodes disagrees with the owned-first node numbering");
-        }
-        e0[e] = a; e1[e] = b; e2[e] = c;
-        deg[a]++; deg[b]++; deg[c]++;
-    }
-    int w = 0;
-    for (int n = 0; n < nn; ++n) {
-        if (deg[n] == 0) throw std::invalid_argument("nsx_create: orphan node");
-        w = std::max(w, deg[n]);
-    }
-    S->ell_w = w;
-    std::vector<int> ell((size_t)w * nn, -1), fill(nn, 0);
-    for (int e = 0; e < ne; ++e) {               // ascending e: each row ends up in ascending element order
-        int const v[3] = {e0[e], e1[e], e2[e]};
-        for (int i = 0; i < 3; ++i) {
-            int const n = v[i];
-            ell[(size_t)fill[n] * nn + n] = i * ne + e;
-            fill[n]++;
-        }
-    }
-    S->en0.alloc(ne); S->en1.alloc(ne); S->en2.alloc(ne);
-    S->n2e.alloc(ell.size()); S->n2e_deg.alloc(nn);
-    NSX_CUDA(cudaMemcpyAsync(S->en0.p, e0.data(), ne * sizeof(int), cudaMemcpyHostToDevice, st));
-    NSX_CUDA(cudaMemcpyAsync(S->en1.p, e1.data(), ne * sizeof(int), cudaMemcpyHostToDevice, st));
-    NSX_CUDA(cudaMemcpyAsync(S->en2.p, e2.data(), ne * sizeof(int), cudaMemcpyHostToDevice, st));
-    NSX_CUDA(cudaMemcpyAsync(S->n2e.p, ell.data(), ell.size() * sizeof(int), cudaMemcpyHostToDevice, st));
-    NSX_CUDA(cudaMemcpyAsync(S->n2e_deg.p, deg.data(), nn * sizeof(int), cudaMemcpyHostToDevice, st));
-
-    // bamg NodalElementConnectivity (double, NaN padded, 1-based; quirk Q6) -> int ELL, -1 padded, same order
-    int const nw = M->nec_width;
-    std::vector<int> nec((size_t)nw * nn, -1);
-    for (int n = 0; n < nn; ++n)
-        for (int j = 0; j < nw; ++j) {
-            double const raw = M->nodal_element_connectivity[(size_t)nw * n + j];
-            int e = -1;
-            if (!std::isnan(raw)) e = (int)raw - 1;
-            if (e >= ne) throw std::invalid_argument("nsx_create: NodalElementConnectivity entry out of range");
-            nec[(size_t)j * nn + n] = e < 0 ? -1 : e;
-        }
-    S->nec_w = nw;
-    S->nec.alloc(nec.size());
-    NSX_CUDA(cudaMemcpyAsync(S->nec.p, nec.data(), nec.size() * sizeof(int), cudaMemcpyHostToDevice, st));
-
-    // bamg NodalConnectivity (last column = neighbour count, FE.cpp:10597) -> int ELL
-    int const cw = M->nc_width;
-    std::vector<int> n2n((size_t)std::max(cw - 1, 1) * nn, 0), ndeg(nn, 0);
-    for (int n = 0; n < nn; ++n) {
-        int const cnt = (int)M->nodal_connectivity[(size_t)cw * (n + 1) - 1];
-        if (cnt < 0 || cnt > cw - 1) throw std::invalid_argument("nsx_create: bad NodalConnectivity count");
-        ndeg[n] = cnt;
-        for (int j = 0; j < cnt; ++j) {
-            int const q = (int)M->nodal_connectivity[(size_t)cw * n + j] - 1;
-            if (q < 0 || q >= nn) throw std::invalid_argument("nsx_create: NodalConnectivity entry out of range");
-            n2n[(size_t)j * nn + n] = q;
-        }
-    }
-    S->nc_w = cw - 1;
-    S->n2n.alloc(n2n.size()); S->n2n_deg.alloc(nn);
-    NSX_CUDA(cudaMemcpyAsync(S->n2n.p, n2n.data(), n2n.size() * sizeof(int), cudaMemcpyHostToDevice, st));
-    NSX_CUDA(cudaMemcpyAsync(S->n2n_deg.p, ndeg.data(), nn * sizeof(int), cudaMemcpyHostToDevice, st));
-
-    // node flags
-    std::vector<uint8_t> fl(nn, 0);
-    for (int n = 0; n < nn; ++n) {
-        if (M->mask_dirichlet && M->mask_dirichlet[n]) fl[n] |= NF_DIRICHLET;
-        if (n >= ndof) fl[n] |= NF_GHOST;
-        if (std::signbit(M->lat[n])) fl[n] |= NF_LATNEG;
-    }
-    for (int k = 0; k < M->n_neumann_flags; ++k) {
-        int const n = M->neumann_flags[k];
-        if (n < 0 || n >= nn) throw std::invalid_argument("nsx_create: neumann flag out of range");
-        fl[n] |= NF_NEUMANN;
-    }
-    S->nflags.alloc(nn);
-    NSX_CUDA(cudaMemcpyAsync(S->nflags.p, fl.data(), nn, cudaMemcpyHostToDevice, st));
-    NSX_CUDA(cudaStreamSynchronize(st));      // host vectors go out of scope
+    S->nn = P.nn; S->ndof = P.ndof; S->ne = P.ne; S->ne_local = P.ne_local;
+    S->node_perm.upload(P.node_perm, st); S->elem_perm.upload(P.elem_perm, st);
+    S->x.upload(P.x, st); S->y.upload(P.y, st); S->lat.upload(P.lat, st);
+    S->nflags.upload(P.nflags, st);
+    S->en0.upload(P.en[0], st); S->en1.upload(P.en[1], st); S->en2.upload(P.en[2], st);
+    S->n2e.upload(P.n2e, st); S->n2e_deg.upload(P.n2e_deg, st);
+    S->nec.upload(P.nec, st);
+    S->n2n.upload(P.n2n, st); S->n2n_deg.upload(P.n2n_deg, st);
+    S->tiles.upload(P.tiles, st);
+    S->halo_nodes.upload(P.halo_nodes, st); S->halo_elems.upload(P.halo_elems, st);
+    S->slot_elem.upload(P.slot_elem, st); S->slot_conn.upload(P.slot_conn, st);
+    S->inc.upload(P.inc, st);
+    S->sub_smem = (2 * (size_t)P.max_local_nodes + 6 * (size_t)P.max_slots) * sizeof(double);
+    if (S->sub_smem > 200 * 1024) throw std::invalid_argument("nsx_create: tile does not fit in shared memory");
+    // the attribute is per function and device, shared by every handle: always ask for the cap
+    NSX_CUDA(cudaFuncSetAttribute(k_subcycle<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    NSX_CUDA(cudaFuncSetAttribute(k_subcycle<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    NSX_CUDA(cudaStreamSynchronize(st));
 }
 
 static void alloc_fields(nsx_solver* S)
 {
-    size_t const nn = S->nn, ne = S->ne;
+    size_t const nn = S->nn, ne = S->ne, ns = S->plan.nslots;
     cudaStream_t st = S->stream;
     // halo window: [VT0 | VT1 | flags]
     size_t const vt_bytes = 2 * nn * sizeof(double);
@@ -152,43 +77,87 @@ static void alloc_fields(nsx_solver* S)
     for (auto* b : nodal2) { b->alloc(2 * nn); b->zero(st); }
     DBuf<double>* nodal1[] = {&S->ssh, &S->node_mass, &S->rlmass, &S->cbu, &S->fcor};
     for (auto* b : nodal1) { b->alloc(nn); b->zero(st); }
-    DBuf<double>* elem[] = {&S->sig0, &S->sig1, &S->sig2, &S->damage, &S->conc, &S->thick, &S->snow, &S->conc_young,
+    DBuf<double>* elem[] = {&S->sig[0][0], &S->sig[0][1], &S->sig[0][2], &S->sig[1][0], &S->sig[1][1], &S->sig[1][2],
+                            &S->dmg[0], &S->dmg[1], &S->conc, &S->thick, &S->snow, &S->conc_young,
                             &S->h_young, &S->hs_young, &S->thick_myi, &S->conc_myi, &S->ridge_ratio, &S->depth,
                             &S->drag_ui, &S->drag_ui_young, &S->cohesion, &S->t_heal, &S->surface, &S->delta_x,
                             &S->del_ci_ridge_myi, &S->emass, &S->ecbu};
     for (auto* b : elem) { b->alloc(ne); b->zero(st); }
     S->shape.alloc(6 * ne); S->shape.zero(st);
-    S->ec.alloc(6 * ne); S->ec.zero(st);
-    S->contrib.alloc(6 * ne); S->contrib.zero(st);
+    S->slot_shape.alloc(6 * ns); S->slot_shape.zero(st);
+    S->slot_ec.alloc(6 * ns); S->slot_ec.zero(st);
+    S->stage.alloc(std::max(2 * nn, 6 * ne));
     S->ow_list.alloc(S->ndof); S->ow_count.alloc(1); S->ow_count.zero(st);
     S->check_i.alloc(4); S->check_d.alloc(1);
     S->halo_err.alloc(1); S->halo_err.zero(st);
+    S->d_epoch.alloc(1); S->d_done.alloc(1);
+    S->d_epoch.zero(st); S->d_done.zero(st);
     for (auto& e : S->ev) NSX_CUDA(cudaEventCreate(&e));
+    NSX_CUDA(cudaEventCreateWithFlags(&S->ev_fork, cudaEventDisableTiming));
+    NSX_CUDA(cudaEventCreateWithFlags(&S->ev_join, cudaEventDisableTiming));
 }
 
 static void build_halo(nsx_solver* S, const NsxHalo* H)
 {
     S->rank = 0; S->nranks = 1;
-    if (!H) return;
-    S->rank = H->rank; S->nranks = H->nranks;
-    if (H->nranks > 256) throw std::invalid_argument("nsx_create: at most 256 ranks");
-    auto link = [&](int r) -> PeerLink& {
-        for (auto& p : S->peers) if (p.rank == r) return p;
-        S->peers.emplace_back();
-        S->peers.back().rank = r;
-        return S->peers.back();
-    };
-    for (int k = 0; k < H->n_send_peers; ++k) {
-        PeerLink& p = link(H->send_peer[k]);
-        p.h_send_idx.assign(H->send_idx + H->send_ptr[k], H->send_idx + H->send_ptr[k + 1]);
-        for (int v : p.h_send_idx) if (v < 0 || v >= S->ndof) throw std::invalid_argument("nsx_create: send index is not an owned node");
+    std::vector<int> order(S->plan.ntiles);
+    for (int t = 0; t < S->plan.ntiles; ++t) order[t] = t;
+    if (H) {
+        S->rank = H->rank; S->nranks = H->nranks;
+        if (H->nranks > 256) throw std::invalid_argument("nsx_create: at most 256 ranks");
+        auto link = [&](int r) -> PeerLink& {
+            for (auto& p : S->peers) if (p.rank == r) return p;
+            S->peers.emplace_back();
+            S->peers.back().rank = r;
+            return S->peers.back();
+        };
+        std::vector<int> const& perm = S->plan.node_perm;
+        for (int k = 0; k < H->n_send_peers; ++k) {
+            PeerLink& p = link(H->send_peer[k]);
+            for (int q = H->send_ptr[k]; q < H->send_ptr[k + 1]; ++q) {
+                int const v = H->send_idx[q];
+                if (v < 0 || v >= S->ndof) throw std::invalid_argument("nsx_create: send index is not an owned node");
+                p.h_send_idx.push_back(perm[v]);
+                S->plan.tiles[perm[v] / S->plan.tile_nodes].boundary = 1;
+            }
+        }
+        for (int k = 0; k < H->n_recv_peers; ++k) {
+            PeerLink& p = link(H->recv_peer[k]);
+            for (int q = H->recv_ptr[k]; q < H->recv_ptr[k + 1]; ++q) {
+                int const v = H->recv_idx[q];
+                if (v < S->ndof || v >= S->nn) throw std::invalid_argument("nsx_create: recv index is not a ghost node");
+                p.h_recv_idx.push_back(perm[v]);
+            }
+        }
+        if (S->peers.size() > 32) throw std::invalid_argument("nsx_create: at most 32 neighbour ranks");
+        std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
+            return S->plan.tiles[a].boundary > S->plan.tiles[b].boundary; });
     }
-    for (int k = 0; k < H->n_recv_peers; ++k) {
-        PeerLink& p = link(H->recv_peer[k]);
-        p.h_recv_idx.assign(H->recv_idx + H->recv_ptr[k], H->recv_idx + H->recv_ptr[k + 1]);
-        for (int v : p.h_recv_idx) if (v < S->ndof || v >= S->nn) throw std::invalid_argument("nsx_create: recv index is not a ghost node");
+    // Every reader of a ghost slot must run BEFORE this rank publishes its epoch (a faster peer may overwrite the
+    // slot for the sub-cycle after next as soon as it sees the flag): tiles that read ghost nodes are boundary
+    // tiles too (flagged by build_mesh_plan), and the lagged ghost mesh move is spread over boundary tiles only.
+    S->n_boundary_tiles = 0;
+    for (auto const& td : S->plan.tiles) S->n_boundary_tiles += td.boundary;
+    int const nghost = S->nn - S->ndof;
+    if (nghost > 0) {
+        int const nb = std::max(1, S->n_boundary_tiles);
+        int const G = (nghost + nb - 1) / nb;
+        int k = 0;
+        for (int t : order) {
+            nsx::TileDesc& td = S->plan.tiles[t];
+            bool const take = (S->n_boundary_tiles == 0) ? (k == 0 && t == order[0]) : (td.boundary != 0);
+            if (take) {
+                td.ghost_begin = S->ndof + std::min(nghost, k * G);
+                td.n_ghost = std::min(nghost, (k + 1) * G) - std::min(nghost, k * G);
+                ++k;
+            } else {
+                td.ghost_begin = S->ndof; td.n_ghost = 0;
+            }
+        }
+        S->tiles.upload(S->plan.tiles, S->stream);
     }
-    if (S->peers.size() > 32) throw std::invalid_argument("nsx_create: at most 32 neighbour ranks");
+    S->tile_order.upload(order, S->stream);
+    NSX_CUDA(cudaStreamSynchronize(S->stream));
 }
 
 extern "C" int nsx_version(void) { return NSX_VERSION; }
@@ -204,8 +173,12 @@ extern "C" int nsx_create(const NsxMesh* mesh, const NsxHalo* halo, int device, 
         if (device < 0 || device >= ndev) throw std::invalid_argument("nsx_create: no such CUDA device");
         S->device = device;
         NSX_CUDA(cudaSetDevice(device));
+        NSX_CUDA(cudaDeviceGetAttribute(&S->sm_count, cudaDevAttrMultiProcessorCount, device));
         NSX_CUDA(cudaStreamCreateWithFlags(&S->stream, cudaStreamNonBlocking));
-        build_mesh(S, mesh);
+        NSX_CUDA(cudaStreamCreateWithFlags(&S->stream2, cudaStreamNonBlocking));
+        // one wave of the sub-cycle kernel = SMs x resident CTAs (3 by its launch bounds)
+        build_mesh_plan(mesh, S->plan, env_int("NSX_TILE_NODES", 224), S->sm_count * env_int("NSX_SUB_OCC", 3));
+        upload_plan(S);
         alloc_fields(S);
         build_halo(S, halo);
         NSX_CUDA(cudaStreamSynchronize(S->stream));
@@ -223,10 +196,14 @@ extern "C" int nsx_destroy(nsx_handle S)
     if (!S) return 0;
     cudaSetDevice(S->device);
     if (S->stream) cudaStreamSynchronize(S->stream);
+    if (S->stream2) cudaStreamSynchronize(S->stream2);
     for (auto& p : S->peers) if (p.ipc_base) cudaIpcCloseMemHandle(p.ipc_base);
     for (auto& g : S->graph_exec) if (g) cudaGraphExecDestroy(g);
     for (auto& e : S->ev) if (e) cudaEventDestroy(e);
+    if (S->ev_fork) cudaEventDestroy(S->ev_fork);
+    if (S->ev_join) cudaEventDestroy(S->ev_join);
     if (S->window) cudaFree(S->window);
+    if (S->stream2) cudaStreamDestroy(S->stream2);
     if (S->stream) cudaStreamDestroy(S->stream);
     delete S;
     return 0;
@@ -234,6 +211,25 @@ extern "C" int nsx_destroy(nsx_handle S)
 
 extern "C" const char* nsx_last_error(nsx_handle h) { return h ? h->err.c_str() : g_create_err.c_str(); }
 extern "C" void* nsx_get_stream(nsx_handle h) { return h ? (void*)h->stream : nullptr; }
+
+// sizeof() of every struct that crosses the ABI, so a binding can detect layout drift
+extern "C" int nsx_abi_sizes(int* out, int n)
+{
+    int const s[6] = {(int)sizeof(NsxDynParams), (int)sizeof(NsxMesh), (int)sizeof(NsxHalo),
+                      (int)sizeof(NsxFields), (int)sizeof(NsxCheck), (int)sizeof(NsxTiming)};
+    for (int i = 0; i < n && i < 6; ++i) out[i] = s[i];
+    return 6;
+}
+
+// tile decomposition summary: ntiles, nodes per tile, slots, max local nodes, max slots, boundary tiles, smem bytes
+extern "C" int nsx_tile_info(nsx_handle S, int* out, int n)
+{
+    if (!S) return 0;
+    int const v[7] = {S->plan.ntiles, S->plan.tile_nodes, S->plan.nslots, S->plan.max_local_nodes, S->plan.max_slots,
+                      S->n_boundary_tiles, (int)S->sub_smem};
+    for (int i = 0; i < n && i < 7; ++i) out[i] = v[i];
+    return 7;
+}
 
 // ---------------------------------------------------------------------------------------------------
 // options -> kernel scalars
@@ -300,59 +296,65 @@ extern "C" int nsx_set_params(nsx_handle S, const NsxDynParams* p)
 }
 
 // ---------------------------------------------------------------------------------------------------
-// transfers
+// transfers: the host speaks the reference's local numbering, the device an internal one; every field goes
+// through a device staging buffer and a permutation kernel (stream ordered, no extra synchronisation).
 // ---------------------------------------------------------------------------------------------------
 namespace {
-struct FieldMap { double* host; double* dev; size_t n; };
+enum Kind { NODAL2, NODAL1, ELEM };
+struct FieldMap { double* host; double* dev; Kind kind; };
 }
-static void field_table(nsx_solver* S, const NsxFields* f, std::vector<FieldMap>& t, bool upload)
+static void field_table(nsx_solver* S, const NsxFields* f, std::vector<FieldMap>& t)
 {
-    size_t const nn = S->nn, ne = S->ne;
-    auto add = [&](double* h, double* d, size_t n) { if (h) t.push_back({h, d, n}); };
-    add(f->M_VT, S->VT[S->cur], 2 * nn);
-    add(f->M_UM, S->UM.p, 2 * nn);
-    add(f->M_UT, S->UT.p, 2 * nn);
-    add(f->M_wind, S->wind.p, 2 * nn);
-    add(f->M_ocean, S->ocean.p, 2 * nn);
-    add(f->M_tau_wi, S->tau_wi.p, 2 * nn);
-    add(f->D_tau_a, S->tau_a.p, 2 * nn);
-    add(f->D_tau_w, S->tau_w.p, 2 * nn);
-    add(f->M_ssh, S->ssh.p, nn);
-    add(f->M_sigma[0], S->sig0.p, ne);
-    add(f->M_sigma[1], S->sig1.p, ne);
-    add(f->M_sigma[2], S->sig2.p, ne);
-    add(f->M_damage, S->damage.p, ne);
-    add(f->M_conc, S->conc.p, ne);
-    add(f->M_thick, S->thick.p, ne);
-    add(f->M_snow_thick, S->snow.p, ne);
-    add(f->M_conc_young, S->conc_young.p, ne);
-    add(f->M_h_young, S->h_young.p, ne);
-    add(f->M_hs_young, S->hs_young.p, ne);
-    add(f->M_thick_myi, S->thick_myi.p, ne);
-    add(f->M_conc_myi, S->conc_myi.p, ne);
-    add(f->M_ridge_ratio, S->ridge_ratio.p, ne);
-    add(f->M_element_depth, S->depth.p, ne);
-    add(f->M_drag_ui, S->drag_ui.p, ne);
-    add(f->M_drag_ui_young, S->drag_ui_young.p, ne);
-    add(f->M_Cohesion, S->cohesion.p, ne);
-    add(f->M_time_relaxation_damage, S->t_heal.p, ne);
-    add(f->M_surface, S->surface.p, ne);
-    add(f->M_delta_x, S->delta_x.p, ne);
-    add(f->D_del_ci_ridge_myi, S->del_ci_ridge_myi.p, ne);
-    (void)upload;
+    auto add = [&](double* h, double* d, Kind k) { if (h) t.push_back({h, d, k}); };
+    add(f->M_VT, S->VT[S->cur], NODAL2);
+    add(f->M_UM, S->UM.p, NODAL2);
+    add(f->M_UT, S->UT.p, NODAL2);
+    add(f->M_wind, S->wind.p, NODAL2);
+    add(f->M_ocean, S->ocean.p, NODAL2);
+    add(f->M_tau_wi, S->tau_wi.p, NODAL2);
+    add(f->D_tau_a, S->tau_a.p, NODAL2);
+    add(f->D_tau_w, S->tau_w.p, NODAL2);
+    add(f->M_ssh, S->ssh.p, NODAL1);
+    add(f->M_sigma[0], S->sig[S->scur][0].p, ELEM);
+    add(f->M_sigma[1], S->sig[S->scur][1].p, ELEM);
+    add(f->M_sigma[2], S->sig[S->scur][2].p, ELEM);
+    add(f->M_damage, S->dmg[S->dcur].p, ELEM);
+    add(f->M_conc, S->conc.p, ELEM);
+    add(f->M_thick, S->thick.p, ELEM);
+    add(f->M_snow_thick, S->snow.p, ELEM);
+    add(f->M_conc_young, S->conc_young.p, ELEM);
+    add(f->M_h_young, S->h_young.p, ELEM);
+    add(f->M_hs_young, S->hs_young.p, ELEM);
+    add(f->M_thick_myi, S->thick_myi.p, ELEM);
+    add(f->M_conc_myi, S->conc_myi.p, ELEM);
+    add(f->M_ridge_ratio, S->ridge_ratio.p, ELEM);
+    add(f->M_element_depth, S->depth.p, ELEM);
+    add(f->M_drag_ui, S->drag_ui.p, ELEM);
+    add(f->M_drag_ui_young, S->drag_ui_young.p, ELEM);
+    add(f->M_Cohesion, S->cohesion.p, ELEM);
+    add(f->M_time_relaxation_damage, S->t_heal.p, ELEM);
+    add(f->M_surface, S->surface.p, ELEM);
+    add(f->M_delta_x, S->delta_x.p, ELEM);
+    add(f->D_del_ci_ridge_myi, S->del_ci_ridge_myi.p, ELEM);
 }
 
 extern "C" int nsx_upload(nsx_handle S, const NsxFields* f)
 {
     NSX_API_BEGIN(S)
     if (!f) throw std::invalid_argument("nsx_upload: NULL");
-    std::vector<FieldMap> t;
-    field_table(S, f, t, true);
-    for (auto& m : t)
-        NSX_CUDA(cudaMemcpyAsync(m.dev, m.host, m.n * sizeof(double), cudaMemcpyHostToDevice, S->stream));
-    if (f->M_tau_wi && !S->have_tau_wi) { S->have_tau_wi = true; S->graph_valid = false; }
     if (f->M_shape_coeff) throw std::invalid_argument("nsx_upload: M_shape_coeff is an output");
-    NSX_CUDA(cudaStreamSynchronize(S->stream));
+    std::vector<FieldMap> t;
+    field_table(S, f, t);
+    cudaStream_t st = S->stream;
+    for (auto& m : t) {
+        int const n = (m.kind == ELEM) ? S->ne : S->nn;
+        int const planes = (m.kind == NODAL2) ? 2 : 1;
+        NSX_CUDA(cudaMemcpyAsync(S->stage.p, m.host, (size_t)n * planes * sizeof(double), cudaMemcpyHostToDevice, st));
+        k_permute_in<<<nblk(n), TPB, 0, st>>>(n, planes, m.kind == ELEM ? S->elem_perm.p : S->node_perm.p, S->stage.p, m.dev);
+    }
+    NSX_CUDA(cudaGetLastError());
+    if (f->M_tau_wi && !S->have_tau_wi) { S->have_tau_wi = true; S->graph_valid = false; }
+    NSX_CUDA(cudaStreamSynchronize(st));
     NSX_API_END(S)
 }
 
@@ -361,23 +363,27 @@ extern "C" int nsx_download(nsx_handle S, NsxFields* f)
     NSX_API_BEGIN(S)
     if (!f) throw std::invalid_argument("nsx_download: NULL");
     std::vector<FieldMap> t;
-    field_table(S, f, t, false);
-    for (auto& m : t)
-        NSX_CUDA(cudaMemcpyAsync(m.host, m.dev, m.n * sizeof(double), cudaMemcpyDeviceToHost, S->stream));
-    if (f->M_shape_coeff) {
-        // device SoA planes -> M_shape_coeff[cpt][k]; contrib is free between solves and reused as scratch
-        k_shape_to_aos<<<nblk(6L * S->ne), TPB, 0, S->stream>>>(S->ne, S->shape.p, S->contrib.p);
-        NSX_CUDA(cudaGetLastError());
-        NSX_CUDA(cudaMemcpyAsync(f->M_shape_coeff, S->contrib.p, 6 * (size_t)S->ne * sizeof(double), cudaMemcpyDeviceToHost, S->stream));
+    field_table(S, f, t);
+    cudaStream_t st = S->stream;
+    for (auto& m : t) {
+        int const n = (m.kind == ELEM) ? S->ne : S->nn;
+        int const planes = (m.kind == NODAL2) ? 2 : 1;
+        k_permute_out<<<nblk(n), TPB, 0, st>>>(n, planes, m.kind == ELEM ? S->elem_perm.p : S->node_perm.p, m.dev, S->stage.p);
+        NSX_CUDA(cudaMemcpyAsync(m.host, S->stage.p, (size_t)n * planes * sizeof(double), cudaMemcpyDeviceToHost, st));
     }
-    NSX_CUDA(cudaStreamSynchronize(S->stream));
+    if (f->M_shape_coeff) {
+        k_shape_out<<<nblk(6L * S->ne), TPB, 0, st>>>(S->ne, S->elem_perm.p, S->shape.p, S->stage.p);
+        NSX_CUDA(cudaMemcpyAsync(f->M_shape_coeff, S->stage.p, 6 * (size_t)S->ne * sizeof(double), cudaMemcpyDeviceToHost, st));
+    }
+    NSX_CUDA(cudaGetLastError());
+    NSX_CUDA(cudaStreamSynchronize(st));
     int herr = 0;
     NSX_CUDA(cudaMemcpy(&herr, S->halo_err.p, sizeof(int), cudaMemcpyDeviceToHost));
     if (herr) throw std::runtime_error("halo exchange timed out waiting for rank " + std::to_string(herr - 1));
     NSX_API_END(S)
 }
 
-extern "C" int nsx_host_register(void* p, size_t bytes)
+extern "C" int nsx_host_register(void* p, unsigned long bytes)
 {
     return cudaHostRegister(p, bytes, cudaHostRegisterDefault) == cudaSuccess ? 0 : 2;
 }
@@ -404,6 +410,7 @@ static void finish_link(nsx_solver* S, PeerLink& p, double* base, int peer_nn, c
     p.peer_flags = (unsigned long long*)(base + 4 * (size_t)peer_nn);
     p.h_send_dst.assign(peer_recv_idx_for_me, peer_recv_idx_for_me + n);
     p.connected = true;
+    (void)S;
 }
 
 extern "C" int nsx_halo_connect_local(nsx_handle S, int peer_rank, nsx_handle Q)
@@ -477,14 +484,8 @@ extern "C" int nsx_halo_finalize(nsx_handle S)
         dst.insert(dst.end(), p.h_send_dst.begin(), p.h_send_dst.end());
     }
     S->n_send_total = (int)src.size();
-    S->d_send_src.alloc(src.size()); S->d_send_dst.alloc(dst.size());
-    if (!src.empty()) {
-        NSX_CUDA(cudaMemcpy(S->d_send_src.p, src.data(), src.size() * sizeof(int), cudaMemcpyHostToDevice));
-        NSX_CUDA(cudaMemcpy(S->d_send_dst.p, dst.data(), dst.size() * sizeof(int), cudaMemcpyHostToDevice));
-    }
-    S->d_epoch.alloc(1); S->d_done.alloc(1);
-    NSX_CUDA(cudaMemset(S->d_epoch.p, 0, sizeof(unsigned long long)));
-    NSX_CUDA(cudaMemset(S->d_done.p, 0, sizeof(unsigned int)));
+    S->d_send_src.upload(src, S->stream); S->d_send_dst.upload(dst, S->stream);
+    NSX_CUDA(cudaStreamSynchronize(S->stream));
     S->halo_ready = true;
     S->graph_valid = false;
     NSX_API_END(S)
@@ -534,10 +535,11 @@ static void phase_prep(nsx_solver* S)
     cudaStream_t st = S->stream;
     KParams const& K = S->K;
     S->ow_count.zero(st);
-    k_prep_elements<<<nblk(S->ne), TPB, 0, st>>>(K, S->en0.p, S->en1.p, S->en2.p, S->x.p, S->y.p, S->UM.p,
-        S->conc.p, S->thick.p, S->snow.p, S->conc_young.p, S->h_young.p, S->hs_young.p, S->depth.p, S->ssh.p,
-        S->cohesion.p, S->t_heal.p, S->surface.p, S->delta_x.p, S->shape.p, S->emass.p, S->ecbu.p, S->ec.p);
-    k_prep_nodes<<<nblk(S->nn), TPB, 0, st>>>(K, S->nflags.p, S->n2e.p, S->n2e_deg.p, S->nec.p, S->nec_w,
+    k_prep_elements<<<nblk(S->plan.nslots), TPB, 0, st>>>(K, S->plan.nslots, S->slot_elem.p, S->en0.p, S->en1.p, S->en2.p,
+        S->x.p, S->y.p, S->UM.p, S->conc.p, S->thick.p, S->snow.p, S->conc_young.p, S->h_young.p, S->hs_young.p,
+        S->depth.p, S->ssh.p, S->cohesion.p, S->t_heal.p, S->surface.p, S->delta_x.p, S->shape.p, S->emass.p, S->ecbu.p,
+        S->slot_shape.p, S->slot_ec.p);
+    k_prep_nodes<<<nblk(S->nn), TPB, 0, st>>>(K, S->nflags.p, S->n2e.p, S->n2e_deg.p, S->nec.p, S->plan.nec_w,
         S->en0.p, S->en1.p, S->en2.p, S->surface.p, S->emass.p, S->ecbu.p, S->shape.p, S->ssh.p,
         S->drag_ui.p, S->drag_ui_young.p, S->conc.p, S->conc_young.p, S->wind.p, S->lat.p,
         S->VT[S->cur], S->VTM.p, S->node_mass.p, S->rlmass.p, S->cbu.p, S->fcor.p, S->grad_ssh.p, S->tau_a.p,
@@ -546,25 +548,54 @@ static void phase_prep(nsx_solver* S)
     NSX_CUDA(cudaGetLastError());
 }
 
-// one sub-cycle up to (not including) the ghost exchange; flips S->cur
-static void phase_substep(nsx_solver* S, int s)
+static void launch_tiles(nsx_solver* S, SubArgs const& A, int tile_base, int ntiles, cudaStream_t st)
 {
-    cudaStream_t st = S->stream;
+    if (ntiles <= 0) return;
+    SubArgs a = A;
+    a.tile_base = tile_base;
+    if (S->K.dynamics_type == NSX_DYN_BBM) k_subcycle<1><<<ntiles, SUB_TPB, S->sub_smem, st>>>(S->K, a);
+    else k_subcycle<0><<<ntiles, SUB_TPB, S->sub_smem, st>>>(S->K, a);
+    S->n_launch++;
+}
+
+// one sub-cycle including its ghost exchange; flips the VT and sigma parities.
+// overlap: boundary tiles first, then the halo kernel on the main stream while the interior tiles run on stream2.
+static void phase_substep(nsx_solver* S, int s, bool exchange_sync, bool overlap)
+{
     KParams const& K = S->K;
-    const double* VTc = S->VT[S->cur];
-    double* VTn = S->VT[S->cur ^ 1];
-    if (K.dynamics_type == NSX_DYN_BBM)
-        k_element_bbm<<<nblk(S->ne), TPB, 0, st>>>(K, S->en0.p, S->en1.p, S->en2.p, VTc, S->shape.p, S->ec.p,
-                                                   S->sig0.p, S->sig1.p, S->sig2.p, S->damage.p, S->contrib.p);
-    else
-        k_element_vp<<<nblk(S->ne), TPB, 0, st>>>(K, S->en0.p, S->en1.p, S->en2.p, VTc, S->shape.p, S->ec.p,
-                                                  S->sig0.p, S->sig1.p, S->sig2.p, S->contrib.p);
-    int const move = (K.dynamics_type != NSX_DYN_MEVP);
-    k_node_solve<<<nblk(S->nn), TPB, 0, st>>>(K, move, move && s > 0, S->nflags.p, S->n2e.p, S->n2e_deg.p,
-        S->contrib.p, S->grad_ssh.p, S->node_mass.p, S->rlmass.p, S->cbu.p, S->fcor.p, S->tau_a.p,
-        S->have_tau_wi ? S->tau_wi.p : nullptr, S->ocean.p, S->VTM.p, VTc, VTn, S->UM.p, S->UT.p);
-    S->n_launch += 2;
-    S->cur ^= 1;
+    int const so = S->scur, sn = S->scur ^ 1;
+    bool const bbm = (K.dynamics_type == NSX_DYN_BBM);
+    SubArgs A{};
+    A.tiles = S->tiles.p; A.tile_order = S->tile_order.p; A.tile_base = 0;
+    A.halo_nodes = S->halo_nodes.p; A.halo_elems = S->halo_elems.p; A.slot_conn = S->slot_conn.p;
+    A.slot_shape = S->slot_shape.p; A.slot_ec = S->slot_ec.p; A.nslots = S->plan.nslots; A.inc = S->inc.p;
+    A.s0i = S->sig[so][0].p; A.s1i = S->sig[so][1].p; A.s2i = S->sig[so][2].p;
+    A.s0o = S->sig[sn][0].p; A.s1o = S->sig[sn][1].p; A.s2o = S->sig[sn][2].p;
+    A.di = bbm ? S->dmg[S->dcur].p : nullptr; A.dmo = bbm ? S->dmg[S->dcur ^ 1].p : nullptr;
+    A.nflags = S->nflags.p; A.grad_ssh = S->grad_ssh.p; A.node_mass = S->node_mass.p; A.rlmass = S->rlmass.p;
+    A.cbu = S->cbu.p; A.fcor = S->fcor.p; A.tau_a = S->tau_a.p; A.tau_wi = S->have_tau_wi ? S->tau_wi.p : nullptr;
+    A.ocean = S->ocean.p; A.VTM = S->VTM.p; A.VTc = S->VT[S->cur]; A.VTn = S->VT[S->cur ^ 1];
+    A.UM = S->UM.p; A.UT = S->UT.p;
+    A.max_local_nodes = S->plan.max_local_nodes; A.max_slots = S->plan.max_slots;
+    A.move_mesh = (K.dynamics_type != NSX_DYN_MEVP);
+    A.lag_ghost_move = (A.move_mesh && s > 0);
+    int const nt = S->plan.ntiles, nb = S->n_boundary_tiles;
+    if (overlap && nb > 0 && nb < nt) {
+        NSX_CUDA(cudaEventRecord(S->ev_fork, S->stream));
+        NSX_CUDA(cudaStreamWaitEvent(S->stream2, S->ev_fork, 0));
+        launch_tiles(S, A, 0, nb, S->stream);
+        launch_tiles(S, A, nb, nt - nb, S->stream2);
+        NSX_CUDA(cudaEventRecord(S->ev_join, S->stream2));
+        S->cur ^= 1;
+        halo_exchange(S, exchange_sync);
+        NSX_CUDA(cudaStreamWaitEvent(S->stream, S->ev_join, 0));
+    } else {
+        launch_tiles(S, A, 0, nt, S->stream);
+        S->cur ^= 1;
+        if (exchange_sync) halo_exchange(S, true);
+    }
+    S->scur = sn;
+    if (bbm) S->dcur ^= 1;              // EVP / mEVP never touch damage (FE.cpp:10649-10699)
     NSX_CUDA(cudaGetLastError());
 }
 
@@ -593,7 +624,7 @@ static void phase_ow_begin(nsx_solver* S)
 }
 static void phase_ow_sweep(nsx_solver* S)
 {
-    int const grid = std::min(nblk(S->ndof), 148 * 4);
+    int const grid = std::min(nblk(S->ndof), S->sm_count * 4);
     k_ow_sweep<<<grid, TPB, 0, S->stream>>>(S->nn, S->ow_list.p, S->ow_count.p, S->n2n.p, S->n2n_deg.p,
                                              S->VT[S->cur], S->VT[S->cur ^ 1]);
     S->n_launch++;
@@ -623,9 +654,9 @@ static void record(nsx_solver* S, int i)
 
 static void solve_group(int n, nsx_solver** W)
 {
-    // lock-step over ranks; for n == 1 this is the plain single-rank sequence.  Ranks in a group share a
-    // device and are serialised on their own streams through events only at exchange points; with one
-    // process per GPU (n == 1, peers remote) the exchange waits on NVLink flags instead.
+    // lock-step over ranks; for n == 1 this is the plain single-rank sequence.  Ranks in a group are
+    // serialised through events at exchange points; with one process per GPU (n == 1, peers remote) the
+    // exchange waits on NVLink flags instead.
     for (int r = 0; r < n; ++r) {
         nsx_solver* S = W[r];
         if (!S->have_params) throw std::runtime_error("nsx_explicit_solve before nsx_set_params");
@@ -636,9 +667,9 @@ static void solve_group(int n, nsx_solver** W)
         record(S, 1);
     }
     int const nrun = substeps_to_run(W[0]);
-    bool const remote = (n == 1) && !W[0]->halo_local;
-    auto exchange = [&]() {
-        if (n == 1) { halo_exchange(W[0], remote); return; }
+    bool const remote = (n == 1) && !W[0]->halo_local && !W[0]->peers.empty();
+    static const bool overlap_on = (env_int("NSX_OVERLAP", 1) != 0);
+    auto group_exchange = [&]() {
         // in-process group: all pushes, then a cross-stream join so nobody reads ghosts too early
         for (int r = 0; r < n; ++r) { NSX_CUDA(cudaSetDevice(W[r]->device)); halo_exchange(W[r], false); NSX_CUDA(cudaEventRecord(W[r]->ev[5], W[r]->stream)); }
         for (int r = 0; r < n; ++r)
@@ -646,8 +677,8 @@ static void solve_group(int n, nsx_solver** W)
                 if (q != r) NSX_CUDA(cudaStreamWaitEvent(W[r]->stream, W[q]->ev[5], 0));
     };
     for (int s = 0; s < nrun; ++s) {
-        for (int r = 0; r < n; ++r) { NSX_CUDA(cudaSetDevice(W[r]->device)); phase_substep(W[r], s); }
-        exchange();
+        for (int r = 0; r < n; ++r) { NSX_CUDA(cudaSetDevice(W[r]->device)); phase_substep(W[r], s, remote, remote && overlap_on); }
+        if (n > 1) group_exchange();
     }
     for (int r = 0; r < n; ++r) {
         NSX_CUDA(cudaSetDevice(W[r]->device));
@@ -658,7 +689,8 @@ static void solve_group(int n, nsx_solver** W)
         for (int r = 0; r < n; ++r) { NSX_CUDA(cudaSetDevice(W[r]->device)); phase_ow_begin(W[r]); }
         for (int nit = 0; nit < 50; ++nit) {       // hard-coded 50 sweeps, FE.cpp:10580
             for (int r = 0; r < n; ++r) { NSX_CUDA(cudaSetDevice(W[r]->device)); phase_ow_sweep(W[r]); }
-            exchange();
+            if (n > 1) group_exchange();
+            else if (remote) halo_exchange(W[0], true);
         }
     }
     for (int r = 0; r < n; ++r) {
@@ -672,10 +704,10 @@ static void solve_group(int n, nsx_solver** W)
     }
 }
 
-// explicitSolve() of one rank.  The whole launch sequence (2 prep kernels, `substeps` x {element, node[, halo]},
-// 50 smoother sweeps, tau_w) is captured once into a CUDA graph per entry parity of the VT ping-pong and
-// replayed afterwards: at 2e5 elements a sub-cycle is ~10 us of device work, less than the host cost of
-// launching its kernels one by one.  NSX_NO_GRAPH=1 disables this (debugging).
+// explicitSolve() of one rank.  The whole launch sequence (2 prep kernels, `substeps` x {tile kernel[, halo]},
+// 50 smoother sweeps, tau_w) is captured once into a CUDA graph per entry parity of the ping-pong buffers and
+// replayed afterwards: at 2e5 elements a sub-cycle is a few microseconds of device work, less than the host
+// cost of launching its kernels one by one.  NSX_NO_GRAPH=1 disables this (debugging).
 extern "C" int nsx_explicit_solve(nsx_handle S)
 {
     NSX_API_BEGIN(S)
@@ -688,7 +720,8 @@ extern "C" int nsx_explicit_solve(nsx_handle S)
             for (auto& g : S->graph_exec) if (g) { cudaGraphExecDestroy(g); g = nullptr; }
             S->graph_valid = true;
         }
-        int const slot = S->cur;
+        int const slot = S->cur + 2 * S->scur + 4 * S->dcur;
+        int const cur_in = S->cur, scur_in = S->scur, dcur_in = S->dcur;
         if (!S->graph_exec[slot]) {
             if (!S->have_params) throw std::runtime_error("nsx_explicit_solve before nsx_set_params");
             cudaGraph_t graph = nullptr;
@@ -700,7 +733,7 @@ extern "C" int nsx_explicit_solve(nsx_handle S)
                 S->capturing = false;
                 cudaStreamEndCapture(S->stream, &graph);
                 if (graph) cudaGraphDestroy(graph);
-                S->cur = slot;
+                S->cur = cur_in; S->scur = scur_in; S->dcur = dcur_in;
                 throw;
             }
             S->capturing = false;
@@ -709,12 +742,16 @@ extern "C" int nsx_explicit_solve(nsx_handle S)
             cudaGraphDestroy(graph);
             NSX_CUDA(e);
             S->graph_cur_out[slot] = S->cur;
+            S->graph_scur_out[slot] = S->scur;
+            S->graph_dcur_out[slot] = S->dcur;
             S->graph_launches[slot] = S->timing.n_launches;
             S->graph_nsub[slot] = S->timing.n_substeps;
-            S->cur = slot;
+            S->cur = cur_in; S->scur = scur_in; S->dcur = dcur_in;
         }
         NSX_CUDA(cudaGraphLaunch(S->graph_exec[slot], S->stream));
         S->cur = S->graph_cur_out[slot];
+        S->scur = S->graph_scur_out[slot];
+        S->dcur = S->graph_dcur_out[slot];
         S->timing.n_launches = S->graph_launches[slot];
         S->timing.n_substeps = S->graph_nsub[slot];
         S->timing_valid = true;
@@ -737,9 +774,10 @@ extern "C" int nsx_update(nsx_handle S)
     NSX_API_BEGIN(S)
     if (!S->have_params) throw std::runtime_error("nsx_update before nsx_set_params");
     NSX_CUDA(cudaEventRecord(S->ev[3], S->stream));
+    int const c = S->scur;
     k_update<<<nblk(S->ne), TPB, 0, S->stream>>>(S->K, S->nflags.p, S->en0.p, S->en1.p, S->en2.p, S->x.p, S->y.p, S->UM.p,
         S->surface.p, S->conc.p, S->thick.p, S->snow.p, S->thick_myi.p, S->conc_myi.p, S->ridge_ratio.p,
-        S->conc_young.p, S->h_young.p, S->hs_young.p, S->sig0.p, S->sig1.p, S->sig2.p, S->del_ci_ridge_myi.p);
+        S->conc_young.p, S->h_young.p, S->hs_young.p, S->sig[c][0].p, S->sig[c][1].p, S->sig[c][2].p, S->del_ci_ridge_myi.p);
     NSX_CUDA(cudaGetLastError());
     NSX_CUDA(cudaEventRecord(S->ev[4], S->stream));
     S->update_timed = true;
@@ -767,8 +805,9 @@ extern "C" int nsx_check(nsx_handle S, NsxCheck* out)
     if (!out) throw std::invalid_argument("nsx_check: NULL");
     S->check_i.zero(S->stream); S->check_d.zero(S->stream);
     int const n = std::max(S->nn, S->ne);
-    k_check<<<nblk(n), TPB, 0, S->stream>>>(S->nn, S->ndof, S->ne, S->VT[S->cur], S->sig0.p, S->sig1.p, S->sig2.p,
-                                            S->damage.p, S->conc.p, S->thick.p, S->check_i.p, (unsigned long long*)S->check_d.p);
+    int const c = S->scur;
+    k_check<<<nblk(n), TPB, 0, S->stream>>>(S->nn, S->ndof, S->ne, S->VT[S->cur], S->sig[c][0].p, S->sig[c][1].p, S->sig[c][2].p,
+                                            S->dmg[S->dcur].p, S->conc.p, S->thick.p, S->check_i.p, (unsigned long long*)S->check_d.p);
     NSX_CUDA(cudaGetLastError());
     int hi[4]; double hd;
     NSX_CUDA(cudaMemcpyAsync(hi, S->check_i.p, sizeof(hi), cudaMemcpyDeviceToHost, S->stream));
@@ -776,13 +815,4 @@ extern "C" int nsx_check(nsx_handle S, NsxCheck* out)
     NSX_CUDA(cudaStreamSynchronize(S->stream));
     out->n_nan = hi[0]; out->n_speed = hi[1]; out->n_range = hi[2]; out->pad_ = 0; out->max_speed = hd;
     NSX_API_END(S)
-}
-
-// sizeof() of every struct that crosses the ABI, so a binding can detect layout drift
-extern "C" int nsx_abi_sizes(int* out, int n)
-{
-    int const s[6] = {(int)sizeof(NsxDynParams), (int)sizeof(NsxMesh), (int)sizeof(NsxHalo),
-                      (int)sizeof(NsxFields), (int)sizeof(NsxCheck), (int)sizeof(NsxTiming)};
-    for (int i = 0; i < n && i < 6; ++i) out[i] = s[i];
-    return 6;
 }

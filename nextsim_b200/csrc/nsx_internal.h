@@ -3,12 +3,13 @@
 #include <cuda_runtime.h>
 #include <cstdint>
 #include <cstdio>
+#include <deque>
 #include <stdexcept>
 #include <string>
 #include <vector>
-#include <deque>
 
 #include "../../include/nsx.h"
+#include "nsx_mesh.h"
 
 namespace nsx {
 
@@ -27,7 +28,7 @@ constexpr double RHOI = 917., RHOW = 1025., RHOS = 330., GRAVITY = 9.80616, OMEG
 constexpr double PI_ = 3.14159265358979323846;
 constexpr double DAYS_IN_SEC = 86400.;
 
-// node flag bits
+// node flag bits (also written by nsx_mesh.cpp)
 enum : uint8_t { NF_DIRICHLET = 1, NF_NEUMANN = 2, NF_GHOST = 4, NF_LATNEG = 8 };
 
 template <class T>
@@ -40,6 +41,10 @@ struct DBuf {
         if (n) NSX_CUDA(cudaMalloc(&p, n * sizeof(T)));
     }
     void zero(cudaStream_t s) { if (n) NSX_CUDA(cudaMemsetAsync(p, 0, n * sizeof(T), s)); }
+    void upload(std::vector<T> const& h, cudaStream_t s) {
+        alloc(h.size());
+        if (n) NSX_CUDA(cudaMemcpyAsync(p, h.data(), n * sizeof(T), cudaMemcpyHostToDevice, s));
+    }
     void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
     ~DBuf() { release(); }
     DBuf() = default;
@@ -72,10 +77,9 @@ struct KParams {
 
 struct PeerLink {
     int rank = -1;
-    std::vector<int> h_send_idx;           // my local node ids to send (M_extract_local_index[peer])
-    std::vector<int> h_recv_idx;           // my ghost ids filled by that peer (M_local_ghosts_local_index[peer])
-    // device-side push tables
-    std::vector<int> h_send_dst;           // the peer's local ghost ids for my send list (same order)
+    std::vector<int> h_send_idx;           // my INTERNAL node ids to send (M_extract_local_index[peer], permuted)
+    std::vector<int> h_recv_idx;           // my INTERNAL ghost ids filled by that peer (M_local_ghosts_local_index[peer])
+    std::vector<int> h_send_dst;           // the peer's internal ghost ids for my send list (same order)
     double* peer_vt[2] = {nullptr, nullptr};   // peer's VT ping-pong buffers (mapped)
     unsigned long long* peer_flags = nullptr;  // peer's flag array (mapped); I write slot [my rank]
     int peer_nn = 0;
@@ -87,7 +91,10 @@ struct PeerLink {
 
 struct nsx_solver {
     int device = 0;
+    int sm_count = 148;
     cudaStream_t stream = nullptr;
+    cudaStream_t stream2 = nullptr;            // interior tiles while the halo of the boundary tiles is in flight
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     std::string err;
 
     int nn = 0, ndof = 0, ne = 0, ne_local = 0;
@@ -96,39 +103,43 @@ struct nsx_solver {
     bool have_params = false;
     nsx::KParams K{};
 
-    // ---- mesh (device) ----
+    // ---- mesh (device, internal numbering) ----
+    nsx::MeshPlan plan;                        // host copy (permutations are needed for the halo wiring)
+    nsx::DBuf<int> node_perm, elem_perm;       // reference id -> internal id
     nsx::DBuf<double> x, y, lat;
     nsx::DBuf<uint8_t> nflags;
-    nsx::DBuf<int> en0, en1, en2;              // element -> node, 0-based
-    int ell_w = 0;                             // node -> (element,local vertex) ascending element id
-    nsx::DBuf<int> n2e;                        // [ell_w * nn] column-major, value = 3*e + i
-    nsx::DBuf<int> n2e_deg;
-    int nc_w = 0;                              // node -> node, bamg order
-    nsx::DBuf<int> n2n;                        // [nc_w * nn] column-major
-    nsx::DBuf<int> n2n_deg;
-    int nec_w = 0;                             // bamg NodalElementConnectivity as int ELL (-1 padded), bamg order
-    nsx::DBuf<int> nec;
+    nsx::DBuf<int> en0, en1, en2;
+    nsx::DBuf<int> n2e, n2e_deg, nec, n2n, n2n_deg;
+    // tiles
+    nsx::DBuf<nsx::TileDesc> tiles;
+    nsx::DBuf<int> tile_order;                 // boundary tiles first
+    int n_boundary_tiles = 0;
+    nsx::DBuf<int> halo_nodes, halo_elems, slot_elem;
+    nsx::DBuf<unsigned long long> slot_conn;
+    nsx::DBuf<uint16_t> inc;
+    nsx::DBuf<double> slot_shape, slot_ec;     // [6*nslots] each (BBM) / ec uses 2 planes for EVP, mEVP
+    size_t sub_smem = 0;
 
     // ---- fields (device) ----
     // halo window: VT ping-pong buffers + flags live in ONE allocation so it can be IPC-exported
     void* window = nullptr;
     size_t window_bytes = 0;
     double* VT[2] = {nullptr, nullptr};        // [2*nn] each
-    unsigned long long* flags = nullptr;       // [nranks] arrival epochs written by peers
+    unsigned long long* flags = nullptr;       // [256] arrival epochs written by peers
     int cur = 0;                               // which VT buffer holds the current velocity
+    int scur = 0;                              // which sigma plane set is current
+    int dcur = 0;                              // which damage plane is current (flips only under BBM)
 
     nsx::DBuf<double> UM, UT, wind, ocean, tau_wi, tau_a, tau_w, ssh, VTM;
     bool have_tau_wi = false;
-    nsx::DBuf<double> sig0, sig1, sig2, damage;
+    nsx::DBuf<double> sig[2][3], dmg[2];       // ping-pong (tiles recompute neighbours' elements from the old state)
     nsx::DBuf<double> conc, thick, snow, conc_young, h_young, hs_young, thick_myi, conc_myi, ridge_ratio;
     nsx::DBuf<double> depth, drag_ui, drag_ui_young, cohesion, t_heal;
     nsx::DBuf<double> surface, delta_x, shape;   // shape: 6 SoA planes [6*ne]
     nsx::DBuf<double> del_ci_ridge_myi;
-    // prep products
     nsx::DBuf<double> emass, ecbu;               // element mass, element C_bu
     nsx::DBuf<double> node_mass, rlmass, cbu, fcor, grad_ssh;
-    nsx::DBuf<double> ec;                        // hoisted per-element constants [6*ne] (meaning depends on rheology)
-    nsx::DBuf<double> contrib;                   // element -> node stress contributions [6*ne]
+    nsx::DBuf<double> stage;                     // transfer staging (host numbering), max(2nn, 6ne)
     nsx::DBuf<int> ow_list;                      // open-water nodes to smooth
     nsx::DBuf<int> ow_count;
     nsx::DBuf<int> check_i; nsx::DBuf<double> check_d;
@@ -151,13 +162,10 @@ struct nsx_solver {
     bool update_timed = false;
     int n_launch = 0;
 
-    // CUDA graph of one explicitSolve (built lazily, invalidated by nsx_set_params / halo changes)
-    cudaGraphExec_t graph_exec[2] = {nullptr, nullptr};   // indexed by the VT parity at entry
-    int graph_cur_out[2] = {0, 0}, graph_launches[2] = {0, 0}, graph_nsub[2] = {0, 0};
+    // CUDA graphs of one explicitSolve, indexed by the ping-pong parities at entry (cur + 2*scur + 4*dcur)
+    cudaGraphExec_t graph_exec[8] = {};
+    int graph_cur_out[8] = {}, graph_scur_out[8] = {}, graph_dcur_out[8] = {};
+    int graph_launches[8] = {}, graph_nsub[8] = {};
     bool graph_valid = false;
     bool capturing = false;
-
-    // pinned staging for transfers
-    void* pinned = nullptr;
-    size_t pinned_bytes = 0;
 };

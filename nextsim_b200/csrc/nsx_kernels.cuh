@@ -10,6 +10,7 @@
 // plane, node kernels subtract them in the reference's order starting from grad_ssh.
 #pragma once
 #include "nsx_internal.h"
+#include "nsx_mesh.h"
 
 namespace nsx {
 
@@ -18,10 +19,13 @@ constexpr int TPB = 256;
 __device__ __forceinline__ double ld_nc(const double* p) { return __ldg(p); }
 
 // ---------------------------------------------------------------------------------------------------
-// prep elements  (FE.cpp:10235-10341 minus the nodal scatters, which k_prep_nodes gathers)
+// prep elements  (FE.cpp:10235-10341 minus the nodal scatters, which k_prep_nodes gathers).
+// One thread per SLOT of the tile decomposition (own slots + redundant halo slots): geometry and the
+// per-step constants of the rheology go to slot space (coalesced for the sub-cycle kernel); the writer
+// slot of an element also stores the per-element products the reference keeps as members.
 // ---------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(TPB)
-k_prep_elements(KParams K,
+k_prep_elements(KParams K, int nslots, const int* __restrict__ slot_elem,
                 const int* __restrict__ en0, const int* __restrict__ en1, const int* __restrict__ en2,
                 const double* __restrict__ x, const double* __restrict__ y, const double* __restrict__ UM,
                 const double* __restrict__ conc, const double* __restrict__ thick, const double* __restrict__ snow,
@@ -29,11 +33,15 @@ k_prep_elements(KParams K,
                 const double* __restrict__ depth, const double* __restrict__ ssh,
                 const double* __restrict__ cohesion, const double* __restrict__ t_heal,
                 double* __restrict__ surface, double* __restrict__ delta_x, double* __restrict__ shape,
-                double* __restrict__ emass, double* __restrict__ ecbu, double* __restrict__ ec)
+                double* __restrict__ emass, double* __restrict__ ecbu,
+                double* __restrict__ slot_shape, double* __restrict__ slot_ec)
 {
-    int const e = blockIdx.x * blockDim.x + threadIdx.x;
+    int const s = blockIdx.x * blockDim.x + threadIdx.x;
     int const ne = K.ne, nn = K.nn;
-    if (e >= ne) return;
+    if (s >= nslots) return;
+    int e = slot_elem[s];
+    bool const own = e >= 0;            // halo slots are stored as ~e
+    if (!own) e = ~e;
     int const a = en0[e], b = en1[e], c = en2[e];
     // GmshMesh::vertices(indices, um, 1.)  gmshmesh.cpp:1929-1939
     double const xa = x[a] + 1. * UM[a], ya = y[a] + 1. * UM[a + nn];
@@ -49,26 +57,44 @@ k_prep_elements(KParams K,
     acc = __double2int_rz((double)acc + s1);
     acc = __double2int_rz((double)acc + s2);
     double const dx = (double)(acc / 3);
-    delta_x[e] = dx;
 
     // jacobian / measure / shapeCoeff  FE.cpp:1613-1618, 1929-1933, 1951-1964
     double jac = (xb - xa) * (yc - ya);
     jac -= (xc - xa) * (yb - ya);
     double const A = 0.5 * fabs(jac);
+    double sc[6];
+    sc[0] = (yb - yc) / jac;  sc[1] = (yc - ya) / jac;  sc[2] = (ya - yb) / jac;
+    sc[3] = (xc - xb) / jac;  sc[4] = (xa - xc) / jac;  sc[5] = (xb - xa) / jac;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) slot_shape[(size_t)k * nslots + s] = sc[k];
+
+    double const cc = conc[e], hh = thick[e];
+    double const vol = hh * A;                                 // FE.cpp:10450
+    if (K.dynamics_type == NSX_DYN_BBM) {
+        bool const ice = !(cc <= 0.1);                         // quirk Q4 (FE.cpp:4146-4151)
+        double const expC = exp(K.compaction_param * (1. - cc));
+        slot_ec[0 * (size_t)nslots + s] = ice ? expC : 0.;     // 0 marks "no ice" (expC > 0 always)
+        slot_ec[1 * (size_t)nslots + s] = pow(hh, K.exp_compression) * K.compression_factor * expC;   // Pmax FE.cpp:4192
+        slot_ec[2 * (size_t)nslots + s] = cohesion[e];
+        slot_ec[3 * (size_t)nslots + s] = 1. / (dx * K.sqrt_nu_rhoi);   // FE.cpp:4232
+        slot_ec[4 * (size_t)nslots + s] = K.dte / t_heal[e] * expC;     // FE.cpp:4256-4257
+        slot_ec[5 * (size_t)nslots + s] = vol;
+    } else {
+        // P = Pstar*exp(-C(1-c)) FE.cpp:10684 ; negative marks thick==0 (quirk Q5, FE.cpp:10656)
+        slot_ec[0 * (size_t)nslots + s] = (hh == 0.) ? -1. : K.evp_Pstar * exp(-K.evp_C * (1. - cc));
+        slot_ec[1 * (size_t)nslots + s] = vol;
+    }
+    if (!own) return;
+
+    delta_x[e] = dx;
     surface[e] = A;
-    shape[0 * (size_t)ne + e] = (yb - yc) / jac;
-    shape[1 * (size_t)ne + e] = (yc - ya) / jac;
-    shape[2 * (size_t)ne + e] = (ya - yb) / jac;
-    shape[3 * (size_t)ne + e] = (xc - xb) / jac;
-    shape[4 * (size_t)ne + e] = (xa - xc) / jac;
-    shape[5 * (size_t)ne + e] = (xb - xa) / jac;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) shape[(size_t)k * ne + e] = sc[k];
 
     // slab mass FE.cpp:10255-10269
-    double const cc = conc[e], hh = thick[e];
     double tc = cc, tt = hh, ts = snow[e];
     if (K.young_ice) { tc += conc_y[e]; tt += h_y[e]; ts += hs_y[e]; }
-    double const m = (tc > 0.) ? (RHOI * tt + RHOS * ts) / tc : 0.;
-    emass[e] = m;
+    emass[e] = (tc > 0.) ? (RHOI * tt + RHOS * ts) / tc : 0.;
 
     // Lemieux basal stress numerator FE.cpp:10273-10308
     double element_ssh = 0.;
@@ -83,23 +109,6 @@ k_prep_elements(KParams K,
         critical_h_mod = mean_keel_depth / K.k1;
     }
     ecbu[e] = K.k2 * fmax(0., critical_h_mod - critical_h) * exp(-K.Cb * (1. - cc));
-
-    // per-step constants of the rheology, hoisted out of the sub-cycle loop
-    double const vol = hh * A;                                 // FE.cpp:10450
-    if (K.dynamics_type == NSX_DYN_BBM) {
-        bool const ice = !(cc <= 0.1);                         // quirk Q4 (FE.cpp:4146-4151)
-        double const expC = exp(K.compaction_param * (1. - cc));
-        ec[0 * (size_t)ne + e] = ice ? expC : 0.;              // 0 marks "no ice" (expC > 0 always)
-        ec[1 * (size_t)ne + e] = pow(hh, K.exp_compression) * K.compression_factor * expC;   // Pmax FE.cpp:4192
-        ec[2 * (size_t)ne + e] = cohesion[e];
-        ec[3 * (size_t)ne + e] = 1. / (dx * K.sqrt_nu_rhoi);   // FE.cpp:4232
-        ec[4 * (size_t)ne + e] = K.dte / t_heal[e] * expC;     // FE.cpp:4256-4257
-        ec[5 * (size_t)ne + e] = vol;
-    } else {
-        // P = Pstar*exp(-C(1-c)) FE.cpp:10684 ; negative marks thick==0 (quirk Q5, FE.cpp:10656)
-        ec[0 * (size_t)ne + e] = (hh == 0.) ? -1. : K.evp_Pstar * exp(-K.evp_C * (1. - cc));
-        ec[5 * (size_t)ne + e] = vol;
-    }
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -192,8 +201,21 @@ k_prep_nodes(KParams K, const uint8_t* __restrict__ nflags,
 }
 
 // ---------------------------------------------------------------------------------------------------
-// BBM element update  (FE.cpp:4137-4260) + element part of the stress-gradient assembly (10449-10465)
+// The sub-cycle kernel: ONE launch per sub-cycle, one CTA per tile.
+//   phase 0  stage the tile's nodal velocities (owned range + halo nodes) in shared memory
+//   phase 1  per slot: strain rate from the staged velocities, BBM (FE.cpp:4137-4260) or EVP/mEVP
+//            (FE.cpp:10649-10726) stress update, write sigma/damage (writer slots only; ping-pong planes, so
+//            tiles recomputing a neighbour's element read the old state), and leave the three nodal
+//            contributions V*(sigma.grad N_i) (FE.cpp:10464-10465) in shared memory
+//   phase 2  per owned node: subtract the contributions in ASCENDING reference element order starting from
+//            grad_ssh (no float atomics, FE.cpp:10445-10467), implicit drag/Coriolis/basal 2x2 solve
+//            (FE.cpp:10472-10529), write VT into the other ping-pong buffer, move the mesh (10539-10553);
+//            plus the lagged mesh move of this tile's share of the ghost nodes.
+// HBM traffic per element-sub-cycle ~ 104 B slot constants + 32 B sigma/d read (x ~1.1 redundancy) + 32 B
+// written + ~95 B of nodal planes = ~280 B (SURVEY 8(d) algorithmic floor: 264 B).
 // ---------------------------------------------------------------------------------------------------
+constexpr int SUB_TPB = 256;
+
 __device__ __forceinline__ double pow_relax(double q, KParams const& K)
 {
     switch (K.relax_int_pow) {
@@ -206,187 +228,188 @@ __device__ __forceinline__ double pow_relax(double q, KParams const& K)
     }
 }
 
-__global__ void __launch_bounds__(TPB)
-k_element_bbm(KParams K,
-              const int* __restrict__ en0, const int* __restrict__ en1, const int* __restrict__ en2,
-              const double* __restrict__ VT, const double* __restrict__ shape, const double* __restrict__ ec,
-              double* __restrict__ sig0, double* __restrict__ sig1, double* __restrict__ sig2,
-              double* __restrict__ damage, double* __restrict__ contrib)
+struct SubArgs {
+    const TileDesc* tiles; const int* tile_order; int tile_base;
+    const int* halo_nodes; const int* halo_elems; const unsigned long long* slot_conn;
+    const double* slot_shape; const double* slot_ec; int nslots; const uint16_t* inc;
+    const double* s0i; const double* s1i; const double* s2i; const double* di;
+    double* s0o; double* s1o; double* s2o; double* dmo;
+    const uint8_t* nflags; const double* grad_ssh; const double* node_mass; const double* rlmass;
+    const double* cbu; const double* fcor; const double* tau_a; const double* tau_wi; const double* ocean;
+    const double* VTM; const double* VTc; double* VTn; double* UM; double* UT;
+    int max_local_nodes, max_slots, move_mesh, lag_ghost_move;
+};
+
+template <int BBM>
+__global__ void __launch_bounds__(SUB_TPB, 3)
+k_subcycle(KParams K, SubArgs A)
 {
-    int const e = blockIdx.x * blockDim.x + threadIdx.x;
-    int const ne = K.ne, nn = K.nn;
-    if (e >= ne) return;
-    double const expC = ec[e];
-    double const vol = ec[5 * (size_t)ne + e];
-    double const dx0 = shape[e], dx1 = shape[(size_t)ne + e], dx2 = shape[2 * (size_t)ne + e];
-    double const dy0 = shape[3 * (size_t)ne + e], dy1 = shape[4 * (size_t)ne + e], dy2 = shape[5 * (size_t)ne + e];
-    double s0, s1, s2, d;
-    if (expC == 0.) {                   // conc <= 0.1 : no ice (FE.cpp:4151-4159)
-        s0 = s1 = s2 = 0.;
-        d = 0.;
-    } else {
-        int const a = en0[e], b = en1[e], c = en2[e];
-        double const ua = VT[a], va = VT[a + nn], ub = VT[b], vb = VT[b + nn], uc = VT[c], vc = VT[c + nn];
-        // epsilon_veloc = B0T * u  (FE.cpp:4167-4176; B0T rows: [dxN 0], [0 dyN], [dyN dxN])
-        double e0 = dx0 * ua; e0 += dx1 * ub; e0 += dx2 * uc;
-        double e1 = dy0 * va; e1 += dy1 * vb; e1 += dy2 * vc;
-        double e2 = dy0 * ua; e2 += dx0 * va; e2 += dy1 * ub; e2 += dx1 * vb; e2 += dy2 * uc; e2 += dx2 * vc;
+    extern __shared__ double sm[];
+    double* const su = sm;
+    double* const sv = sm + A.max_local_nodes;
+    double* const cs = sm + 2 * A.max_local_nodes;          // contributions: cs[i*max_slots + k], i = 0..5
+    int const MS = A.max_slots;
+    int const nn = K.nn;
+    int const tid = threadIdx.x;
+    TileDesc const td = A.tiles[A.tile_order ? A.tile_order[A.tile_base + blockIdx.x] : A.tile_base + blockIdx.x];
 
-        s0 = sig0[e]; s1 = sig1[e]; s2 = sig2[e]; d = damage[e];
-        double const dt = K.dte;
-        double sigma_n = (s0 + s1) * 0.5;
-        double const omd = 1. - d;
-        double const time_viscous = K.lambda0 * pow_relax(omd * expC, K);
-        double tildeP = 0.;
-        if (sigma_n < 0.) {
-            double const Pmax = ec[(size_t)ne + e];
-            tildeP = fmin(1., -Pmax / sigma_n);
-        }
-        double const mult = fmin(1. - 1e-12, time_viscous / (time_viscous + dt * (1. - tildeP)));
-        double const elasticity = K.young * omd * expC;
-        double const dtE = dt * elasticity;
-        s0 += dtE * K.D00 * e0;  s0 += dtE * K.D01 * e1;  s0 *= mult;
-        s1 += dtE * K.D01 * e0;  s1 += dtE * K.D00 * e1;  s1 *= mult;
-        s2 += dtE * K.D22 * e2;                           s2 *= mult;
+    // ---- phase 0 ----
+    for (int j = tid; j < td.n_own; j += SUB_TPB) {
+        su[j] = A.VTc[td.node_begin + j];
+        sv[j] = A.VTc[td.node_begin + j + nn];
+    }
+    for (int j = tid; j < td.n_halo; j += SUB_TPB) {
+        int const g = A.halo_nodes[td.halo_off + j];
+        su[td.n_own + j] = A.VTc[g];
+        sv[td.n_own + j] = A.VTc[g + nn];
+    }
+    __syncthreads();
 
-        double const sigma_s = hypot((s0 - s1) / 2., s2);
-        sigma_n = (s0 + s1) * 0.5;
-        double dcrit;
-        if (sigma_n < -K.compr_strength) dcrit = -K.compr_strength / sigma_n;
-        else dcrit = ec[2 * (size_t)ne + e] / (sigma_s + K.tan_phi * sigma_n);
-        if ((0. < dcrit) && (dcrit < 1.)) {
-            double const rtd = sqrt(elasticity) * ec[3 * (size_t)ne + e];
-            double const f = (1. - dcrit) * dt * rtd;
-            d += omd * f;
-            s0 -= s0 * f;  s1 -= s1 * f;  s2 -= s2 * f;
+    // ---- phase 1 ----
+    int const nsl = td.n_own_slots + td.n_halo_slots;
+    size_t const NS = (size_t)A.nslots;
+    for (int k = tid; k < nsl; k += SUB_TPB) {
+        size_t const s = (size_t)td.slot_begin + k;
+        bool const own = k < td.n_own_slots;
+        int const e = own ? td.elem_begin + k : A.halo_elems[td.halo_elem_off + k - td.n_own_slots];
+        unsigned long long const pc = A.slot_conn[s];
+        int const la = (int)(pc & 0xFFFF), lb = (int)((pc >> 16) & 0xFFFF), lc = (int)((pc >> 32) & 0xFFFF);
+        double const dx0 = A.slot_shape[s], dx1 = A.slot_shape[NS + s], dx2 = A.slot_shape[2 * NS + s];
+        double const dy0 = A.slot_shape[3 * NS + s], dy1 = A.slot_shape[4 * NS + s], dy2 = A.slot_shape[5 * NS + s];
+        double const c0 = A.slot_ec[s];
+        double s0, s1, s2, vol;
+        if (BBM) {
+            double const expC = c0;
+            vol = A.slot_ec[5 * NS + s];
+            double d;
+            if (expC == 0.) {                   // conc <= 0.1 : no ice (FE.cpp:4151-4159)
+                s0 = s1 = s2 = 0.;
+                d = 0.;
+            } else {
+                double const ua = su[la], va = sv[la], ub = su[lb], vb = sv[lb], uc = su[lc], vc = sv[lc];
+                // epsilon_veloc = B0T * u  (FE.cpp:4167-4176; B0T rows: [dxN 0], [0 dyN], [dyN dxN])
+                double e0 = dx0 * ua; e0 += dx1 * ub; e0 += dx2 * uc;
+                double e1 = dy0 * va; e1 += dy1 * vb; e1 += dy2 * vc;
+                double e2 = dy0 * ua; e2 += dx0 * va; e2 += dy1 * ub; e2 += dx1 * vb; e2 += dy2 * uc; e2 += dx2 * vc;
+                s0 = A.s0i[e]; s1 = A.s1i[e]; s2 = A.s2i[e]; d = A.di[e];
+                double const dt = K.dte;
+                double sigma_n = (s0 + s1) * 0.5;
+                double const omd = 1. - d;
+                double const time_viscous = K.lambda0 * pow_relax(omd * expC, K);
+                double tildeP = 0.;
+                if (sigma_n < 0.) {
+                    double const Pmax = A.slot_ec[NS + s];
+                    tildeP = fmin(1., -Pmax / sigma_n);
+                }
+                double const mult = fmin(1. - 1e-12, time_viscous / (time_viscous + dt * (1. - tildeP)));
+                double const elasticity = K.young * omd * expC;
+                double const dtE = dt * elasticity;
+                s0 += dtE * K.D00 * e0;  s0 += dtE * K.D01 * e1;  s0 *= mult;
+                s1 += dtE * K.D01 * e0;  s1 += dtE * K.D00 * e1;  s1 *= mult;
+                s2 += dtE * K.D22 * e2;                           s2 *= mult;
+                double const sigma_s = hypot((s0 - s1) / 2., s2);
+                sigma_n = (s0 + s1) * 0.5;
+                double dcrit;
+                if (sigma_n < -K.compr_strength) dcrit = -K.compr_strength / sigma_n;
+                else dcrit = A.slot_ec[2 * NS + s] / (sigma_s + K.tan_phi * sigma_n);
+                if ((0. < dcrit) && (dcrit < 1.)) {
+                    double const rtd = sqrt(elasticity) * A.slot_ec[3 * NS + s];
+                    double const f = (1. - dcrit) * dt * rtd;
+                    d += omd * f;
+                    s0 -= s0 * f;  s1 -= s1 * f;  s2 -= s2 * f;
+                }
+                d = fmax(0., d - A.slot_ec[4 * NS + s]);
+            }
+            if (own) A.dmo[e] = d;
+        } else {
+            double const Pp = c0;
+            vol = A.slot_ec[NS + s];
+            if (Pp < 0.) {                      // thick == 0 (FE.cpp:10656-10662)
+                s0 = s1 = s2 = 0.;
+            } else {
+                double const ua = su[la], va = sv[la], ub = su[lb], vb = sv[lb], uc = su[lc], vc = sv[lc];
+                double eps11 = dx0 * ua; eps11 += dx1 * ub; eps11 += dx2 * uc;
+                double eps22 = dy0 * va; eps22 += dy1 * vb; eps22 += dy2 * vc;
+                double eps12 = 0.5 * (dx0 * va + dy0 * ua); eps12 += 0.5 * (dx1 * vb + dy1 * ub); eps12 += 0.5 * (dx2 * vc + dy2 * uc);
+                double const eps1 = eps11 + eps22, eps2 = eps11 - eps22;
+                double const delta = sqrt(eps1 * eps1 + (eps2 * eps2 + 4 * eps12 * eps12) * K.re2);
+                double const zeta = Pp / (delta + K.evp_dmin);
+                s0 = A.s0i[e]; s1 = A.s1i[e]; s2 = A.s2i[e];
+                double sigma1 = s0 + s1, sigma2 = s0 - s1;
+                sigma1 += K.ralpha1 * (zeta * (eps1 - delta) - sigma1);
+                sigma2 += K.ralpha2 * (zeta * eps2 * K.re2 - sigma2);
+                s2 += K.ralpha2 * (zeta * eps12 * K.re2 - s2);
+                s0 = 0.5 * (sigma1 + sigma2);
+                s1 = 0.5 * (sigma1 - sigma2);
+            }
         }
-        d = fmax(0., d - ec[4 * (size_t)ne + e]);
+        if (own) { A.s0o[e] = s0; A.s1o[e] = s1; A.s2o[e] = s2; }
+        // nodal contributions V*(sigma . grad N_i)  (FE.cpp:10464-10465)
+        cs[0 * MS + k] = vol * (s0 * dx0 + s2 * dy0);
+        cs[1 * MS + k] = vol * (s0 * dx1 + s2 * dy1);
+        cs[2 * MS + k] = vol * (s0 * dx2 + s2 * dy2);
+        cs[3 * MS + k] = vol * (s2 * dx0 + s1 * dy0);
+        cs[4 * MS + k] = vol * (s2 * dx1 + s1 * dy1);
+        cs[5 * MS + k] = vol * (s2 * dx2 + s1 * dy2);
     }
-    sig0[e] = s0; sig1[e] = s1; sig2[e] = s2; damage[e] = d;
-    // nodal contributions V*(sigma . grad N_i)  (FE.cpp:10464-10465)
-    contrib[0 * (size_t)ne + e] = vol * (s0 * dx0 + s2 * dy0);
-    contrib[1 * (size_t)ne + e] = vol * (s0 * dx1 + s2 * dy1);
-    contrib[2 * (size_t)ne + e] = vol * (s0 * dx2 + s2 * dy2);
-    contrib[3 * (size_t)ne + e] = vol * (s2 * dx0 + s1 * dy0);
-    contrib[4 * (size_t)ne + e] = vol * (s2 * dx1 + s1 * dy1);
-    contrib[5 * (size_t)ne + e] = vol * (s2 * dx2 + s1 * dy2);
-}
+    __syncthreads();
 
-// ---------------------------------------------------------------------------------------------------
-// EVP / mEVP element update  (FE.cpp:10649-10726)
-// ---------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(TPB)
-k_element_vp(KParams K,
-             const int* __restrict__ en0, const int* __restrict__ en1, const int* __restrict__ en2,
-             const double* __restrict__ VT, const double* __restrict__ shape, const double* __restrict__ ec,
-             double* __restrict__ sig0, double* __restrict__ sig1, double* __restrict__ sig2,
-             double* __restrict__ contrib)
-{
-    int const e = blockIdx.x * blockDim.x + threadIdx.x;
-    int const ne = K.ne, nn = K.nn;
-    if (e >= ne) return;
-    double const Pp = ec[e];
-    double const vol = ec[5 * (size_t)ne + e];
-    double const dx0 = shape[e], dx1 = shape[(size_t)ne + e], dx2 = shape[2 * (size_t)ne + e];
-    double const dy0 = shape[3 * (size_t)ne + e], dy1 = shape[4 * (size_t)ne + e], dy2 = shape[5 * (size_t)ne + e];
-    double s0, s1, s2;
-    if (Pp < 0.) {
-        s0 = s1 = s2 = 0.;
-    } else {
-        int const a = en0[e], b = en1[e], c = en2[e];
-        double const ua = VT[a], va = VT[a + nn], ub = VT[b], vb = VT[b + nn], uc = VT[c], vc = VT[c + nn];
-        double eps11 = dx0 * ua; eps11 += dx1 * ub; eps11 += dx2 * uc;
-        double eps22 = dy0 * va; eps22 += dy1 * vb; eps22 += dy2 * vc;
-        double eps12 = 0.5 * (dx0 * va + dy0 * ua); eps12 += 0.5 * (dx1 * vb + dy1 * ub); eps12 += 0.5 * (dx2 * vc + dy2 * uc);
-        double const eps1 = eps11 + eps22, eps2 = eps11 - eps22;
-        double const delta = sqrt(eps1 * eps1 + (eps2 * eps2 + 4 * eps12 * eps12) * K.re2);
-        double const zeta = Pp / (delta + K.evp_dmin);
-        s0 = sig0[e]; s1 = sig1[e]; s2 = sig2[e];
-        double sigma1 = s0 + s1, sigma2 = s0 - s1;
-        sigma1 += K.ralpha1 * (zeta * (eps1 - delta) - sigma1);
-        sigma2 += K.ralpha2 * (zeta * eps2 * K.re2 - sigma2);
-        s2 += K.ralpha2 * (zeta * eps12 * K.re2 - s2);
-        s0 = 0.5 * (sigma1 + sigma2);
-        s1 = 0.5 * (sigma1 - sigma2);
-    }
-    sig0[e] = s0; sig1[e] = s1; sig2[e] = s2;
-    contrib[0 * (size_t)ne + e] = vol * (s0 * dx0 + s2 * dy0);
-    contrib[1 * (size_t)ne + e] = vol * (s0 * dx1 + s2 * dy1);
-    contrib[2 * (size_t)ne + e] = vol * (s0 * dx2 + s2 * dy2);
-    contrib[3 * (size_t)ne + e] = vol * (s2 * dx0 + s1 * dy0);
-    contrib[4 * (size_t)ne + e] = vol * (s2 * dx1 + s1 * dy1);
-    contrib[5 * (size_t)ne + e] = vol * (s2 * dx2 + s1 * dy2);
-}
-
-// ---------------------------------------------------------------------------------------------------
-// nodal solve: ordered gather of the stress gradient (10445-10467), implicit drag/Coriolis 2x2 solve
-// (10472-10529) and the Lagrangian mesh move (10539-10553).  Reads VTc, writes VTn (ping-pong).
-// Ghost nodes are written by their owner (halo push); their mesh move uses the received value and is
-// therefore applied one kernel later (`lag_ghost_move`), which is the same arithmetic sequence.
-// ---------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(TPB)
-k_node_solve(KParams K, int move_mesh, int lag_ghost_move,
-             const uint8_t* __restrict__ nflags, const int* __restrict__ n2e, const int* __restrict__ n2e_deg,
-             const double* __restrict__ contrib, const double* __restrict__ grad_ssh,
-             const double* __restrict__ node_mass, const double* __restrict__ rlmass,
-             const double* __restrict__ cbu, const double* __restrict__ fcor,
-             const double* __restrict__ tau_a, const double* __restrict__ tau_wi,
-             const double* __restrict__ ocean, const double* __restrict__ VTM,
-             const double* __restrict__ VTc, double* __restrict__ VTn,
-             double* __restrict__ UM, double* __restrict__ UT)
-{
-    int const n = blockIdx.x * blockDim.x + threadIdx.x;
-    int const nn = K.nn, ne = K.ne;
-    if (n >= nn) return;
-    uint8_t const fl = nflags[n];
-    double const uice = VTc[n], vice = VTc[n + nn];
-    if (fl & NF_GHOST) {
-        if (lag_ghost_move) {
-            UT[n] += K.dte * uice;  UT[n + nn] += K.dte * vice;
-            if (!(fl & NF_NEUMANN)) { UM[n] += K.dte * uice;  UM[n + nn] += K.dte * vice; }
+    // ---- phase 2 ----
+    for (int j = tid; j < td.n_own; j += SUB_TPB) {
+        int const n = td.node_begin + j;
+        uint8_t const fl = A.nflags[n];
+        double const uice = su[j], vice = sv[j];
+        double un = uice, vn = vice;
+        double const nm = A.node_mass[n];
+        if (!(fl & NF_DIRICHLET) && nm != 0.) {
+            double gu = A.grad_ssh[n], gv = A.grad_ssh[n + nn];
+            const uint16_t* ip = A.inc + td.inc_off + j;
+            for (int c = 0; c < td.inc_w; ++c) {
+                unsigned const code = ip[(size_t)c * td.n_own];
+                if (code == 0xFFFFu) break;
+                gu -= cs[code];
+                gv -= cs[code + 3 * MS];
+            }
+            double dtep = K.dte, delu = 0., delv = 0.;
+            if (K.dynamics_type == NSX_DYN_MEVP) {
+                delu = (A.VTM[n] - uice) / K.mevp_b;
+                delv = (A.VTM[n + nn] - vice) / K.mevp_b;
+                dtep = K.dte / K.mevp_b;
+            }
+            double const dte_over_mass = dtep / fmax(K.min_m, nm);
+            double const ou = A.ocean[n], ov = A.ocean[n + nn];
+            double const c_prime = K.rhow_cdw * hypot(ou - uice, ov - vice);
+            double const tau_b = A.cbu[n] / (hypot(uice, vice) + K.u0);
+            double const sin_s = (fl & NF_LATNEG) ? -K.sin_ota_abs : K.sin_ota_abs;   // std::copysign(sin, lat[i])
+            double const alpha = 1. + dte_over_mass * (c_prime * K.cos_ota + tau_b);
+            double const beta = dtep * A.fcor[n] + dte_over_mass * c_prime * sin_s;
+            double const rdenom = 1. / (alpha * alpha + beta * beta);
+            double tau_x = A.tau_a[n], tau_y = A.tau_a[n + nn];
+            if (A.tau_wi) { tau_x = tau_x + A.tau_wi[n]; tau_y = tau_y + A.tau_wi[n + nn]; }
+            tau_x = tau_x + c_prime * (ou * K.cos_ota - ov * sin_s);
+            tau_y = tau_y + c_prime * (ov * K.cos_ota + ou * sin_s);
+            double const rl = A.rlmass[n];
+            double const grad_x = gu * rl, grad_y = gv * rl;
+            un = alpha * uice + beta * vice + dte_over_mass * (alpha * (grad_x + tau_x) + beta * (grad_y + tau_y)) + alpha * delu + beta * delv;
+            un *= rdenom;
+            vn = alpha * vice - beta * uice + dte_over_mass * (alpha * (grad_y + tau_y) - beta * (grad_x + tau_x)) + alpha * delv - beta * delu;
+            vn *= rdenom;
         }
-        return;
-    }
-    double un = uice, vn = vice;
-    double const nm = node_mass[n];
-    if (!(fl & NF_DIRICHLET) && nm != 0.) {
-        double gu = grad_ssh[n], gv = grad_ssh[n + nn];
-        int const deg = n2e_deg[n];
-        for (int k = 0; k < deg; ++k) {
-            int const s = n2e[(size_t)k * nn + n];
-            gu -= contrib[s];
-            gv -= contrib[s + 3 * (size_t)ne];
+        A.VTn[n] = un;
+        A.VTn[n + nn] = vn;
+        if (A.move_mesh) {
+            A.UT[n] += K.dte * un;  A.UT[n + nn] += K.dte * vn;
+            if (!(fl & NF_NEUMANN)) { A.UM[n] += K.dte * un;  A.UM[n + nn] += K.dte * vn; }
         }
-        double dtep = K.dte, delu = 0., delv = 0.;
-        if (K.dynamics_type == NSX_DYN_MEVP) {
-            delu = (VTM[n] - uice) / K.mevp_b;
-            delv = (VTM[n + nn] - vice) / K.mevp_b;
-            dtep = K.dte / K.mevp_b;
-        }
-        double const dte_over_mass = dtep / fmax(K.min_m, nm);
-        double const ou = ocean[n], ov = ocean[n + nn];
-        double const c_prime = K.rhow_cdw * hypot(ou - uice, ov - vice);
-        double const tau_b = cbu[n] / (hypot(uice, vice) + K.u0);
-        double const sin_s = (fl & NF_LATNEG) ? -K.sin_ota_abs : K.sin_ota_abs;   // std::copysign(sin, lat[i])
-        double const alpha = 1. + dte_over_mass * (c_prime * K.cos_ota + tau_b);
-        double const beta = dtep * fcor[n] + dte_over_mass * c_prime * sin_s;
-        double const rdenom = 1. / (alpha * alpha + beta * beta);
-        double tau_x = tau_a[n], tau_y = tau_a[n + nn];
-        if (tau_wi) { tau_x = tau_x + tau_wi[n]; tau_y = tau_y + tau_wi[n + nn]; }
-        tau_x = tau_x + c_prime * (ou * K.cos_ota - ov * sin_s);
-        tau_y = tau_y + c_prime * (ov * K.cos_ota + ou * sin_s);
-        double const rl = rlmass[n];
-        double const grad_x = gu * rl, grad_y = gv * rl;
-        un = alpha * uice + beta * vice + dte_over_mass * (alpha * (grad_x + tau_x) + beta * (grad_y + tau_y)) + alpha * delu + beta * delv;
-        un *= rdenom;
-        vn = alpha * vice - beta * uice + dte_over_mass * (alpha * (grad_y + tau_y) - beta * (grad_x + tau_x)) + alpha * delv - beta * delu;
-        vn *= rdenom;
     }
-    VTn[n] = un;
-    VTn[n + nn] = vn;
-    if (move_mesh) {
-        UT[n] += K.dte * un;  UT[n + nn] += K.dte * vn;
-        if (!(fl & NF_NEUMANN)) { UM[n] += K.dte * un;  UM[n + nn] += K.dte * vn; }
+    // ghost nodes: moved with the velocity their owner pushed at the end of the previous sub-cycle
+    if (A.lag_ghost_move) {
+        for (int j = tid; j < td.n_ghost; j += SUB_TPB) {
+            int const n = td.ghost_begin + j;
+            double const u = A.VTc[n], v = A.VTc[n + nn];
+            A.UT[n] += K.dte * u;  A.UT[n + nn] += K.dte * v;
+            if (!(A.nflags[n] & NF_NEUMANN)) { A.UM[n] += K.dte * u;  A.UM[n + nn] += K.dte * v; }
+        }
     }
 }
 
@@ -591,13 +614,31 @@ k_check(int nn, int ndof, int ne, const double* __restrict__ VT,
     }
 }
 
-// element-major <-> SoA transposes for M_shape_coeff[cpt][k]
-__global__ void k_shape_to_aos(int ne, const double* __restrict__ soa, double* __restrict__ aos)
+// host numbering <-> internal numbering (nsx_upload / nsx_download); `planes` consecutive planes of n entries
+__global__ void __launch_bounds__(TPB)
+k_permute_in(int n, int planes, const int* __restrict__ perm, const double* __restrict__ src, double* __restrict__ dst)
+{
+    int const t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    int const q = perm[t];
+    for (int p = 0; p < planes; ++p) dst[(size_t)p * n + q] = src[(size_t)p * n + t];
+}
+__global__ void __launch_bounds__(TPB)
+k_permute_out(int n, int planes, const int* __restrict__ perm, const double* __restrict__ src, double* __restrict__ dst)
+{
+    int const t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    int const q = perm[t];
+    for (int p = 0; p < planes; ++p) dst[(size_t)p * n + t] = src[(size_t)p * n + q];
+}
+// M_shape_coeff[cpt][k] (element-major, reference numbering) from the internal SoA planes
+__global__ void __launch_bounds__(TPB)
+k_shape_out(int ne, const int* __restrict__ perm, const double* __restrict__ soa, double* __restrict__ aos)
 {
     int const t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= 6 * ne) return;
     int const e = t / 6, k = t - 6 * e;
-    aos[t] = soa[(size_t)k * ne + e];
+    aos[t] = soa[(size_t)k * ne + perm[e]];
 }
 
 // ---------------------------------------------------------------------------------------------------

@@ -1,0 +1,275 @@
+// nsx_mesh.cpp -- builds the MeshPlan (see nsx_mesh.h) from the reference-side mesh description.
+//
+// Internal numbering: owned nodes sorted along a Hilbert curve through their coordinates (ghost nodes after,
+// also Hilbert-sorted, so "id >= local_ndof <=> ghost" still holds); elements grouped by writer tile.  The
+// host never sees this numbering: nsx_upload / nsx_download permute on the device.  Summation orders that the
+// reference fixes (ascending element id for the stress gradient, bamg chain order for tau_a and the OW
+// smoother) are preserved by storing the incidence lists in REFERENCE order with internal ids as payload.
+#include "nsx_mesh.h"
+
+#include <algorithm>
+#include <cmath>
+#include <numeric>
+#include <stdexcept>
+
+namespace nsx {
+
+static uint64_t hilbert_xy2d(uint32_t x, uint32_t y)        // 16-bit coordinates -> 32-bit curve index
+{
+    uint32_t const n = 1u << 16;
+    uint64_t d = 0;
+    for (uint32_t s = n / 2; s > 0; s /= 2) {
+        uint32_t const rx = (x & s) > 0, ry = (y & s) > 0;
+        d += (uint64_t)s * s * ((3 * rx) ^ ry);
+        if (ry == 0) {
+            if (rx == 1) { x = n - 1 - x; y = n - 1 - y; }
+            std::swap(x, y);
+        }
+    }
+    return d;
+}
+
+void build_mesh_plan(const NsxMesh* M, MeshPlan& P, int target_tile_nodes, int sm_count)
+{
+    int const nn = M->num_nodes, ne = M->num_elements, ndof = M->local_ndof;
+    if (nn <= 0 || ne <= 0 || ndof <= 0 || ndof > nn || M->local_nelements > ne)
+        throw std::invalid_argument("nsx_create: inconsistent mesh sizes");
+    if (!M->coord_x || !M->coord_y || !M->indices || !M->lat || !M->nodal_element_connectivity || !M->nodal_connectivity)
+        throw std::invalid_argument("nsx_create: NULL mesh array");
+    if ((long)3 * ne >= (1L << 31)) throw std::invalid_argument("nsx_create: mesh too large for 32-bit slot ids");
+    P.nn = nn; P.ndof = ndof; P.ne = ne; P.ne_local = M->local_nelements;
+
+    // ---- reference connectivity, validated --------------------------------------------------------------
+    std::vector<int> r0(ne), r1(ne), r2(ne), rdeg(nn, 0);
+    for (int e = 0; e < ne; ++e) {
+        int const a = M->indices[3 * (size_t)e] - 1, b = M->indices[3 * (size_t)e + 1] - 1, c = M->indices[3 * (size_t)e + 2] - 1;
+        if (a < 0 || b < 0 || c < 0 || a >= nn || b >= nn || c >= nn)
+            throw std::invalid_argument("nsx_create: element index out of range");
+        if (M->ghost_nodes) {       // GMSHElement::ghostNodes == "local id >= local_ndof" (gmshmesh.cpp:1298-1301)
+            const unsigned char* g = M->ghost_nodes + 3 * (size_t)e;
+            if ((g[0] != 0) != (a >= ndof) || (g[1] != 0) != (b >= ndof) || (g[2] != 0) != (c >= ndof))
+                throw std::invalid_argument("nsx_create: ghost_nodes disagrees with the owned-first node numbering");
+        }
+        r0[e] = a; r1[e] = b; r2[e] = c;
+        rdeg[a]++; rdeg[b]++; rdeg[c]++;
+    }
+    int w = 0;
+    for (int n = 0; n < nn; ++n) {
+        if (rdeg[n] == 0) throw std::invalid_argument("nsx_create: orphan node");
+        w = std::max(w, rdeg[n]);
+    }
+    P.ell_w = w;
+
+    // ---- node permutation: Hilbert order, owned first ---------------------------------------------------
+    double xmin = M->coord_x[0], xmax = xmin, ymin = M->coord_y[0], ymax = ymin;
+    for (int n = 1; n < nn; ++n) {
+        xmin = std::min(xmin, M->coord_x[n]); xmax = std::max(xmax, M->coord_x[n]);
+        ymin = std::min(ymin, M->coord_y[n]); ymax = std::max(ymax, M->coord_y[n]);
+    }
+    double const span = std::max(std::max(xmax - xmin, ymax - ymin), 1e-300);
+    std::vector<uint64_t> key(nn);
+    for (int n = 0; n < nn; ++n) {
+        uint32_t const ix = (uint32_t)std::min(65535.0, (M->coord_x[n] - xmin) / span * 65535.0);
+        uint32_t const iy = (uint32_t)std::min(65535.0, (M->coord_y[n] - ymin) / span * 65535.0);
+        key[n] = hilbert_xy2d(ix, iy);
+    }
+    P.node_inv.resize(nn);
+    std::iota(P.node_inv.begin(), P.node_inv.end(), 0);
+    auto by_key = [&](int a, int b) { return key[a] != key[b] ? key[a] < key[b] : a < b; };
+    std::sort(P.node_inv.begin(), P.node_inv.begin() + ndof, by_key);
+    std::sort(P.node_inv.begin() + ndof, P.node_inv.end(), by_key);
+    P.node_perm.resize(nn);
+    for (int i = 0; i < nn; ++i) P.node_perm[P.node_inv[i]] = i;
+
+    P.x.resize(nn); P.y.resize(nn); P.lat.resize(nn); P.nflags.assign(nn, 0);
+    for (int i = 0; i < nn; ++i) {
+        int const r = P.node_inv[i];
+        P.x[i] = M->coord_x[r]; P.y[i] = M->coord_y[r]; P.lat[i] = M->lat[r];
+        if (M->mask_dirichlet && M->mask_dirichlet[r]) P.nflags[i] |= 1;      // NF_DIRICHLET
+        if (r >= ndof) P.nflags[i] |= 4;                                        // NF_GHOST
+        if (std::signbit(M->lat[r])) P.nflags[i] |= 8;                          // NF_LATNEG
+    }
+    for (int k = 0; k < M->n_neumann_flags; ++k) {
+        int const r = M->neumann_flags[k];
+        if (r < 0 || r >= nn) throw std::invalid_argument("nsx_create: neumann flag out of range");
+        P.nflags[P.node_perm[r]] |= 2;                                          // NF_NEUMANN
+    }
+
+    // ---- tiles over the owned nodes ------------------------------------------------------------------------
+    int T = std::max(32, target_tile_nodes);
+    int ntiles = (ndof + T - 1) / T;
+    // `sm_count` here is the number of CTAs of one full wave (SMs x resident CTAs per SM): small meshes get a
+    // whole number of waves so that no SM idles during a partial last wave
+    if (sm_count > 0 && ntiles < 8 * sm_count) {
+        int const nwaves = std::max(1, (ntiles + sm_count / 2) / sm_count);
+        ntiles = nwaves * sm_count;
+    }
+    ntiles = std::max(1, std::min(ntiles, ndof));
+    T = (ndof + ntiles - 1) / ntiles;
+    ntiles = (ndof + T - 1) / T;
+    P.ntiles = ntiles; P.tile_nodes = T;
+    auto tile_of_node = [&](int internal) { return internal / T; };
+
+    // ---- element permutation: by writer tile, then along the curve ------------------------------------------
+    std::vector<int> writer(ne);
+    std::vector<uint64_t> ekey(ne);
+    for (int e = 0; e < ne; ++e) {
+        int const v[3] = {P.node_perm[r0[e]], P.node_perm[r1[e]], P.node_perm[r2[e]]};
+        int lo = nn;
+        for (int i = 0; i < 3; ++i) if (v[i] < ndof) lo = std::min(lo, v[i]);
+        writer[e] = (lo < nn) ? tile_of_node(lo) : (e % ntiles);               // no owned node: any tile
+        ekey[e] = ((uint64_t)writer[e] << 32) | (uint32_t)std::min(std::min(v[0], v[1]), v[2]);
+    }
+    P.elem_inv.resize(ne);
+    std::iota(P.elem_inv.begin(), P.elem_inv.end(), 0);
+    std::sort(P.elem_inv.begin(), P.elem_inv.end(), [&](int a, int b) { return ekey[a] != ekey[b] ? ekey[a] < ekey[b] : a < b; });
+    P.elem_perm.resize(ne);
+    for (int i = 0; i < ne; ++i) P.elem_perm[P.elem_inv[i]] = i;
+    for (int i = 0; i < 3; ++i) P.en[i].resize(ne);
+    std::vector<int> iwriter(ne);
+    for (int i = 0; i < ne; ++i) {
+        int const r = P.elem_inv[i];
+        P.en[0][i] = P.node_perm[r0[r]]; P.en[1][i] = P.node_perm[r1[r]]; P.en[2][i] = P.node_perm[r2[r]];
+        iwriter[i] = writer[r];
+    }
+
+    // ---- node -> element ELL in ascending reference element order ---------------------------------------------
+    P.n2e.assign((size_t)w * nn, -1);
+    P.n2e_deg.assign(nn, 0);
+    for (int r = 0; r < ne; ++r) {
+        int const v[3] = {r0[r], r1[r], r2[r]};
+        int const ie = P.elem_perm[r];
+        for (int i = 0; i < 3; ++i) {
+            int const n = P.node_perm[v[i]];
+            P.n2e[(size_t)P.n2e_deg[n] * nn + n] = i * ne + ie;
+            P.n2e_deg[n]++;
+        }
+    }
+
+    // ---- bamg tables -> int ELL in the given order (quirks Q6, Q7) ---------------------------------------------
+    int const nw = M->nec_width;
+    P.nec_w = nw;
+    P.nec.assign((size_t)std::max(nw, 1) * nn, -1);
+    for (int r = 0; r < nn; ++r)
+        for (int j = 0; j < nw; ++j) {
+            double const raw = M->nodal_element_connectivity[(size_t)nw * r + j];
+            int e = -1;
+            if (!std::isnan(raw)) e = (int)raw - 1;
+            if (e >= ne) throw std::invalid_argument("nsx_create: NodalElementConnectivity entry out of range");
+            P.nec[(size_t)j * nn + P.node_perm[r]] = e < 0 ? -1 : P.elem_perm[e];
+        }
+    int const cw = M->nc_width;
+    if (cw < 1) throw std::invalid_argument("nsx_create: bad NodalConnectivity width");
+    P.nc_w = cw - 1;
+    P.n2n.assign((size_t)std::max(cw - 1, 1) * nn, 0);
+    P.n2n_deg.assign(nn, 0);
+    for (int r = 0; r < nn; ++r) {
+        int const cnt = (int)M->nodal_connectivity[(size_t)cw * (r + 1) - 1];
+        if (cnt < 0 || cnt > cw - 1) throw std::invalid_argument("nsx_create: bad NodalConnectivity count");
+        int const n = P.node_perm[r];
+        P.n2n_deg[n] = cnt;
+        for (int j = 0; j < cnt; ++j) {
+            int const q = (int)M->nodal_connectivity[(size_t)cw * r + j] - 1;
+            if (q < 0 || q >= nn) throw std::invalid_argument("nsx_create: NodalConnectivity entry out of range");
+            P.n2n[(size_t)j * nn + n] = P.node_perm[q];
+        }
+    }
+
+    // ---- per-tile structures ------------------------------------------------------------------------------------
+    std::vector<int> own_cnt(ntiles, 0), own_begin(ntiles + 1, 0);
+    for (int i = 0; i < ne; ++i) own_cnt[iwriter[i]]++;
+    for (int t = 0; t < ntiles; ++t) own_begin[t + 1] = own_begin[t] + own_cnt[t];
+    int const nghost = nn - ndof;
+    int const G = (nghost + ntiles - 1) / ntiles;
+
+    P.tiles.assign(ntiles, TileDesc{});
+    P.halo_nodes.clear(); P.halo_elems.clear(); P.slot_elem.clear(); P.slot_conn.clear(); P.inc.clear();
+    std::vector<int> stamp_e(ne, -1), slot_of(ne, 0), stamp_n(nn, -1), lidx(nn, 0);
+    P.max_local_nodes = 0; P.max_slots = 0;
+    for (int t = 0; t < ntiles; ++t) {
+        TileDesc& td = P.tiles[t];
+        td.node_begin = t * T;
+        td.n_own = std::min(T, ndof - td.node_begin);
+        td.elem_begin = own_begin[t];
+        td.n_own_slots = own_cnt[t];
+        td.slot_begin = (int)P.slot_elem.size();
+        td.halo_off = (int)P.halo_nodes.size();
+        td.halo_elem_off = (int)P.halo_elems.size();
+        td.ghost_begin = ndof + std::min(nghost, t * G);
+        td.n_ghost = std::min(nghost, (t + 1) * G) - std::min(nghost, t * G);
+        // own slots
+        for (int k = 0; k < td.n_own_slots; ++k) {
+            int const ie = td.elem_begin + k;
+            stamp_e[ie] = t; slot_of[ie] = k;
+            P.slot_elem.push_back(ie);
+        }
+        // halo slots: elements touching my owned nodes but written by another tile (reference order per node)
+        int nh = 0, dmax = 0;
+        for (int j = 0; j < td.n_own; ++j) {
+            int const n = td.node_begin + j;
+            dmax = std::max(dmax, P.n2e_deg[n]);
+            for (int c = 0; c < P.n2e_deg[n]; ++c) {
+                int const ie = P.n2e[(size_t)c * nn + n] % ne;
+                if (stamp_e[ie] != t) {
+                    stamp_e[ie] = t; slot_of[ie] = td.n_own_slots + nh; ++nh;
+                    P.halo_elems.push_back(ie);
+                    P.slot_elem.push_back(ie);
+                }
+            }
+        }
+        td.n_halo_slots = nh;
+        int const nslots = td.n_own_slots + nh;
+        // local nodes: owned range first, then every other node of the tile's elements
+        for (int j = 0; j < td.n_own; ++j) { stamp_n[td.node_begin + j] = t; lidx[td.node_begin + j] = j; }
+        int nhn = 0;
+        for (int k = 0; k < nslots; ++k) {
+            int const ie = P.slot_elem[td.slot_begin + k];
+            unsigned long long packed = 0;
+            for (int i = 0; i < 3; ++i) {
+                int const n = P.en[i][ie];
+                if (stamp_n[n] != t) {
+                    stamp_n[n] = t; lidx[n] = td.n_own + nhn; ++nhn;
+                    P.halo_nodes.push_back(n);
+                    if (n >= ndof) td.boundary = 1;          // reads a ghost slot
+                }
+                packed |= (unsigned long long)(lidx[n] & 0xFFFF) << (16 * i);
+            }
+            P.slot_conn.push_back(packed);
+        }
+        td.n_halo = nhn;
+        if (td.n_own + nhn > 65535 || 3 * nslots > 65534)
+            throw std::invalid_argument("nsx_create: tile too large for 16-bit local ids");
+        // incidence table of the owned nodes, reference-ascending element order, column-major
+        td.inc_off = (int)P.inc.size();
+        td.inc_w = dmax;
+        P.inc.resize(P.inc.size() + (size_t)dmax * td.n_own, (uint16_t)0xFFFF);
+        for (int j = 0; j < td.n_own; ++j) {
+            int const n = td.node_begin + j;
+            for (int c = 0; c < P.n2e_deg[n]; ++c) {
+                int const s = P.n2e[(size_t)c * nn + n];
+                int const i = s / ne, ie = s - i * ne;
+                P.inc[td.inc_off + (size_t)c * td.n_own + j] = (uint16_t)(slot_of[ie] * 3 + i);
+            }
+        }
+        P.max_local_nodes = std::max(P.max_local_nodes, td.n_own + nhn);
+        P.max_slots = std::max(P.max_slots, nslots);
+    }
+    P.nslots = (int)P.slot_elem.size();
+
+    // post-pass: incidence codes become shared-memory offsets (vertex * max_slots + slot); halo slots get ~e
+    int const MS = P.max_slots;
+    for (int t = 0; t < ntiles; ++t) {
+        TileDesc const& td = P.tiles[t];
+        for (size_t q = 0; q < (size_t)td.inc_w * td.n_own; ++q) {
+            uint16_t& code = P.inc[td.inc_off + q];
+            if (code == 0xFFFF) continue;
+            int const slot = code / 3, i = code % 3;
+            code = (uint16_t)(i * MS + slot);
+        }
+        for (int k = td.n_own_slots; k < td.n_own_slots + td.n_halo_slots; ++k)
+            P.slot_elem[td.slot_begin + k] = ~P.slot_elem[td.slot_begin + k];
+    }
+    if (3 * (long)MS > 65534) throw std::invalid_argument("nsx_create: tile too large for 16-bit incidence codes");
+}
+
+}  // namespace nsx

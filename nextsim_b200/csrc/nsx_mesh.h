@@ -1,0 +1,54 @@
+// nsx_mesh.h -- host-side mesh plan: internal (space-filling-curve) numbering and the tile decomposition the
+// fused sub-cycle kernel works on.  Pure host C++ (no CUDA types); built once per nsx_create, i.e. per remesh.
+#pragma once
+#include <cstdint>
+#include <vector>
+
+#include "../../include/nsx.h"
+
+namespace nsx {
+
+// One tile = one CTA of the sub-cycle kernel: a contiguous range of owned nodes (internal numbering) plus
+// every element touching them.  Elements whose writer is another tile are recomputed redundantly ("halo
+// slots", ~2/sqrt(T) of the tile) exactly like the reference recomputes ghost elements on the lower rank.
+struct TileDesc {
+    int node_begin, n_own;          // owned nodes [node_begin, node_begin + n_own)
+    int halo_off, n_halo;           // other nodes read by the tile: halo_nodes[halo_off ...]
+    int slot_begin;                 // first slot of the tile in slot space
+    int n_own_slots, n_halo_slots;  // own slots map to elements [elem_begin + k]; halo slots via halo_elems
+    int elem_begin;
+    int halo_elem_off;
+    int inc_off, inc_w;             // incidence table of the owned nodes: inc[inc_off + c*n_own + j]
+    int ghost_begin, n_ghost;       // ghost nodes whose (lagged) mesh move this tile performs
+    int boundary;                   // 1 if one of its owned nodes is sent to another rank
+    int pad_[2];
+};
+static_assert(sizeof(TileDesc) == 64, "TileDesc is 16 ints");
+
+struct MeshPlan {
+    int nn = 0, ndof = 0, ne = 0, ne_local = 0;
+    std::vector<int> node_perm, node_inv;      // reference local id -> internal id, and back
+    std::vector<int> elem_perm, elem_inv;
+    std::vector<double> x, y, lat;             // internal numbering
+    std::vector<uint8_t> nflags;
+    std::vector<int> en[3];                    // internal element -> internal node
+    // node -> (element, vertex) in ASCENDING REFERENCE element order (the order of FE.cpp:10445-10467),
+    // column-major ELL, value = vertex * ne + internal element id
+    int ell_w = 0;
+    std::vector<int> n2e, n2e_deg;
+    int nec_w = 0;                             // bamg NodalElementConnectivity order (FE.cpp:10376-10390)
+    std::vector<int> nec;
+    int nc_w = 0;                              // bamg NodalConnectivity order (FE.cpp:10597-10605)
+    std::vector<int> n2n, n2n_deg;
+    // tiles
+    int ntiles = 0, tile_nodes = 0, nslots = 0, max_local_nodes = 0, max_slots = 0;
+    std::vector<TileDesc> tiles;
+    std::vector<int> halo_nodes, halo_elems, slot_elem;
+    std::vector<unsigned long long> slot_conn; // 3 x 16-bit tile-local node ids
+    std::vector<uint16_t> inc;                 // slot*3 + vertex, 0xFFFF = padding
+};
+
+// throws std::invalid_argument on inconsistent input
+void build_mesh_plan(const NsxMesh* M, MeshPlan& P, int target_tile_nodes, int sm_count);
+
+}  // namespace nsx
