@@ -33,6 +33,35 @@ static int env_int(const char* name, int dflt)
 }
 
 // ---------------------------------------------------------------------------------------------------
+// shared-memory layout of the sub-cycle kernel for `n_node_planes` staged node planes
+// ---------------------------------------------------------------------------------------------------
+static SmemLayout sub_layout(MeshPlan const& P, int n_node_planes)
+{
+    auto al = [](size_t x) { return (x + 15) & ~size_t(15); };
+    SmemLayout L{};
+    size_t o = 0;
+    L.msp = P.msp;
+    L.mop = (P.max_own_slots + 3) & ~1;
+    L.mtp = (P.tile_nodes + 3) & ~1;
+    L.bar = (int)o;   o += 16;
+    L.conn = (int)o;  o += al((size_t)L.msp * 8);
+    L.shape = (int)o; o += (size_t)6 * L.msp * 8;
+    L.ec = (int)o;    o += (size_t)6 * L.msp * 8;
+    L.sig = (int)o;   o += (size_t)3 * L.mop * 8;
+    L.dmg = (int)o;   o += (size_t)L.mop * 8;
+    L.node = (int)o;  o += (size_t)n_node_planes * L.mtp * 8;
+    L.su = (int)o;    o += al(((size_t)P.max_local_nodes + 2) * 8);
+    L.sv = (int)o;    o += al(((size_t)P.max_local_nodes + 2) * 8);
+    L.hn = (int)o;    o += al((size_t)P.max_halo_nodes * 4 + 32);
+    L.he = (int)o;    o += al((size_t)P.max_halo_slots * 4 + 32);
+    L.inc = (int)o;   o += al((size_t)P.max_inc * 2 + 32);
+    L.fl = (int)o;    o += al((size_t)P.tile_nodes + 32);
+    L.total = (int)o;
+    return L;
+}
+constexpr int SUB_SMEM_CAP = 113 * 1024;      // two CTAs per SM: (228 KB - 2 x 1 KB reserved) / 2
+
+// ---------------------------------------------------------------------------------------------------
 // life cycle
 // ---------------------------------------------------------------------------------------------------
 static void upload_plan(nsx_solver* S)
@@ -51,8 +80,7 @@ static void upload_plan(nsx_solver* S)
     S->halo_nodes.upload(P.halo_nodes, st); S->halo_elems.upload(P.halo_elems, st);
     S->slot_elem.upload(P.slot_elem, st); S->slot_conn.upload(P.slot_conn, st);
     S->inc.upload(P.inc, st);
-    S->sub_smem = (2 * (size_t)P.max_local_nodes + 6 * (size_t)P.max_slots) * sizeof(double);
-    if (S->sub_smem > 200 * 1024) throw std::invalid_argument("nsx_create: tile does not fit in shared memory");
+    S->sub_smem = sub_layout(P, NP_COUNT).total;
     // the attribute is per function and device, shared by every handle: always ask for the cap
     NSX_CUDA(cudaFuncSetAttribute(k_subcycle<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     NSX_CUDA(cudaFuncSetAttribute(k_subcycle<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
@@ -176,8 +204,16 @@ extern "C" int nsx_create(const NsxMesh* mesh, const NsxHalo* halo, int device, 
         NSX_CUDA(cudaDeviceGetAttribute(&S->sm_count, cudaDevAttrMultiProcessorCount, device));
         NSX_CUDA(cudaStreamCreateWithFlags(&S->stream, cudaStreamNonBlocking));
         NSX_CUDA(cudaStreamCreateWithFlags(&S->stream2, cudaStreamNonBlocking));
-        // one wave of the sub-cycle kernel = SMs x resident CTAs (3 by its launch bounds)
-        build_mesh_plan(mesh, S->plan, env_int("NSX_TILE_NODES", 224), S->sm_count * env_int("NSX_SUB_OCC", 3));
+        // one wave of the sub-cycle kernel = SMs x resident CTAs (2: shared memory and launch bounds); shrink the
+        // tiles until the staged working set of the largest tile fits the per-CTA shared-memory budget
+        int target = env_int("NSX_TILE_NODES", 208);
+        for (int attempt = 0;; ++attempt) {
+            S->plan = MeshPlan();
+            build_mesh_plan(mesh, S->plan, target, S->sm_count * env_int("NSX_SUB_OCC", 2));
+            if (sub_layout(S->plan, 14).total <= SUB_SMEM_CAP) break;
+            if (attempt > 12 || target <= 32) throw std::invalid_argument("nsx_create: cannot fit a tile in shared memory");
+            target = std::max(32, (int)(target * 0.88));
+        }
         upload_plan(S);
         alloc_fields(S);
         build_halo(S, halo);
@@ -576,9 +612,19 @@ static void phase_substep(nsx_solver* S, int s, bool exchange_sync, bool overlap
     A.cbu = S->cbu.p; A.fcor = S->fcor.p; A.tau_a = S->tau_a.p; A.tau_wi = S->have_tau_wi ? S->tau_wi.p : nullptr;
     A.ocean = S->ocean.p; A.VTM = S->VTM.p; A.VTc = S->VT[S->cur]; A.VTn = S->VT[S->cur ^ 1];
     A.UM = S->UM.p; A.UT = S->UT.p;
-    A.max_local_nodes = S->plan.max_local_nodes; A.max_slots = S->plan.max_slots;
     A.move_mesh = (K.dynamics_type != NSX_DYN_MEVP);
     A.lag_ghost_move = (A.move_mesh && s > 0);
+    int npl = 0;
+    for (int p = 0; p < NP_COUNT; ++p) {
+        bool use = p < NP_UMU;
+        if (p >= NP_UMU && p <= NP_UTV) use = A.move_mesh;
+        if (p == NP_VMU || p == NP_VMV) use = (K.dynamics_type == NSX_DYN_MEVP);
+        if (p == NP_TWU || p == NP_TWV) use = S->have_tau_wi;
+        A.np[p] = use ? npl++ : 0;
+    }
+    A.L = sub_layout(S->plan, npl);
+    if (A.L.total > 200 * 1024) throw std::runtime_error("sub-cycle kernel: tile working set exceeds shared memory");
+    S->sub_smem = (size_t)A.L.total;
     int const nt = S->plan.ntiles, nb = S->n_boundary_tiles;
     if (overlap && nb > 0 && nb < nt) {
         NSX_CUDA(cudaEventRecord(S->ev_fork, S->stream));

@@ -38,7 +38,7 @@ struct DBuf {
     void alloc(size_t n_) {
         release();
         n = n_;
-        if (n) NSX_CUDA(cudaMalloc(&p, n * sizeof(T)));
+        if (n) NSX_CUDA(cudaMalloc(&p, n * sizeof(T) + 32));     // 32 B slack: TMA copies round up to 16 B granules
     }
     void zero(cudaStream_t s) { if (n) NSX_CUDA(cudaMemsetAsync(p, 0, n * sizeof(T), s)); }
     void upload(std::vector<T> const& h, cudaStream_t s) {

@@ -9,6 +9,7 @@
 // No float atomics anywhere: element kernels write their three nodal stress contributions to a staging
 // plane, node kernels subtract them in the reference's order starting from grad_ssh.
 #pragma once
+#include <climits>
 #include "nsx_internal.h"
 #include "nsx_mesh.h"
 
@@ -40,6 +41,7 @@ k_prep_elements(KParams K, int nslots, const int* __restrict__ slot_elem,
     int const ne = K.ne, nn = K.nn;
     if (s >= nslots) return;
     int e = slot_elem[s];
+    if (e == INT_MIN) return;           // pad slot of the even-sized slot space
     bool const own = e >= 0;            // halo slots are stored as ~e
     if (!own) e = ~e;
     int const a = en0[e], b = en1[e], c = en2[e];
@@ -201,12 +203,17 @@ k_prep_nodes(KParams K, const uint8_t* __restrict__ nflags,
 }
 
 // ---------------------------------------------------------------------------------------------------
-// The sub-cycle kernel: ONE launch per sub-cycle, one CTA per tile.
-//   phase 0  stage the tile's nodal velocities (owned range + halo nodes) in shared memory
+// The sub-cycle kernel: ONE launch per sub-cycle, one CTA per tile, tile data staged by TMA.
+//   stage    one thread issues cp.async.bulk (TMA, SASS UBLKCP) copies of every contiguous piece of the
+//            tile -- slot planes (connectivity, shape coefficients, rheology constants), the writer slots'
+//            sigma/damage, the owned nodes' planes, incidence table, halo lists -- into shared memory; all
+//            threads wait on one mbarrier.  Sources only need 8-byte alignment: each copy starts at the
+//            enclosing 16-byte boundary and the consumer applies the resulting element shift.
+//   phase 0  gather the velocities of the tile's halo nodes (the only irregular read besides halo sigma)
 //   phase 1  per slot: strain rate from the staged velocities, BBM (FE.cpp:4137-4260) or EVP/mEVP
 //            (FE.cpp:10649-10726) stress update, write sigma/damage (writer slots only; ping-pong planes, so
 //            tiles recomputing a neighbour's element read the old state), and leave the three nodal
-//            contributions V*(sigma.grad N_i) (FE.cpp:10464-10465) in shared memory
+//            contributions V*(sigma.grad N_i) (FE.cpp:10464-10465) in shared memory (over the shape planes)
 //   phase 2  per owned node: subtract the contributions in ASCENDING reference element order starting from
 //            grad_ssh (no float atomics, FE.cpp:10445-10467), implicit drag/Coriolis/basal 2x2 solve
 //            (FE.cpp:10472-10529), write VT into the other ping-pong buffer, move the mesh (10539-10553);
@@ -214,7 +221,7 @@ k_prep_nodes(KParams K, const uint8_t* __restrict__ nflags,
 // HBM traffic per element-sub-cycle ~ 104 B slot constants + 32 B sigma/d read (x ~1.1 redundancy) + 32 B
 // written + ~95 B of nodal planes = ~280 B (SURVEY 8(d) algorithmic floor: 264 B).
 // ---------------------------------------------------------------------------------------------------
-constexpr int SUB_TPB = 256;
+constexpr int SUB_TPB = 384;
 
 __device__ __forceinline__ double pow_relax(double q, KParams const& K)
 {
@@ -228,6 +235,55 @@ __device__ __forceinline__ double pow_relax(double q, KParams const& K)
     }
 }
 
+// ---- TMA / mbarrier primitives (PTX ISA 8.x, sm_90+) ----
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+// element shift of an 8-byte-or-less aligned source inside its enclosing 16-byte granule
+__device__ __forceinline__ int stage_shift(const void* src, int esz) { return (int)(((uintptr_t)src & 15) / esz); }
+// MODE 0: returns the bytes the copy will transfer; MODE 1: issues it
+template <int MODE>
+__device__ __forceinline__ uint32_t stage(void* dst16, const void* src, int n, int esz, uint64_t* bar)
+{
+    if (n <= 0) return 0;
+    uint32_t const lead = (uint32_t)((uintptr_t)src & 15);
+    uint32_t const bytes = (lead + (uint32_t)n * esz + 15u) & ~15u;
+    if (MODE) bulk_g2s(dst16, (const void*)((uintptr_t)src - lead), bytes, bar);
+    return bytes;
+}
+
+// byte offsets of the staging buffers inside dynamic shared memory (all multiples of 16) and plane strides
+struct SmemLayout {
+    int bar, conn, shape, ec, sig, dmg, node, su, sv, hn, he, inc, fl, total;
+    int msp, mop, mtp;          // slot / own-slot / node plane strides (elements)
+};
+enum { NP_GSU, NP_GSV, NP_MASS, NP_RL, NP_CBU, NP_FCOR, NP_TAU, NP_TAV, NP_OCU, NP_OCV, NP_UMU, NP_UMV, NP_UTU, NP_UTV,
+       NP_VMU, NP_VMV, NP_TWU, NP_TWV, NP_COUNT };
+
 struct SubArgs {
     const TileDesc* tiles; const int* tile_order; int tile_base;
     const int* halo_nodes; const int* halo_elems; const unsigned long long* slot_conn;
@@ -237,29 +293,97 @@ struct SubArgs {
     const uint8_t* nflags; const double* grad_ssh; const double* node_mass; const double* rlmass;
     const double* cbu; const double* fcor; const double* tau_a; const double* tau_wi; const double* ocean;
     const double* VTM; const double* VTc; double* VTn; double* UM; double* UT;
-    int max_local_nodes, max_slots, move_mesh, lag_ghost_move;
+    int move_mesh, lag_ghost_move;
+    int np[NP_COUNT];           // node plane -> staging slot (compacted: only the planes this configuration reads)
+    SmemLayout L;
 };
 
+template <int MODE, int BBM>
+__device__ __forceinline__ uint32_t stage_tile(KParams const& K, SubArgs const& A, TileDesc const& td, unsigned char* sm, uint64_t* bar)
+{
+    SmemLayout const& L = A.L;
+    int const nn = K.nn;
+    int const nsl = td.n_own_slots + td.n_halo_slots;
+    size_t const NS = (size_t)A.nslots;
+    size_t const s0 = (size_t)td.slot_begin;
+    uint32_t tx = 0;
+    tx += stage<MODE>(sm + L.conn, A.slot_conn + s0, nsl, 8, bar);
+#pragma unroll
+    for (int p = 0; p < 6; ++p)
+        tx += stage<MODE>(sm + L.shape + (size_t)p * L.msp * 8, A.slot_shape + p * NS + s0, nsl, 8, bar);
+#pragma unroll
+    for (int p = 0; p < (BBM ? 6 : 2); ++p)
+        tx += stage<MODE>(sm + L.ec + (size_t)p * L.msp * 8, A.slot_ec + p * NS + s0, nsl, 8, bar);
+    tx += stage<MODE>(sm + L.sig + (size_t)0 * L.mop * 8, A.s0i + td.elem_begin, td.n_own_slots, 8, bar);
+    tx += stage<MODE>(sm + L.sig + (size_t)1 * L.mop * 8, A.s1i + td.elem_begin, td.n_own_slots, 8, bar);
+    tx += stage<MODE>(sm + L.sig + (size_t)2 * L.mop * 8, A.s2i + td.elem_begin, td.n_own_slots, 8, bar);
+    if (BBM) tx += stage<MODE>(sm + L.dmg, A.di + td.elem_begin, td.n_own_slots, 8, bar);
+    // owned-node planes
+    int const nb = td.node_begin, no = td.n_own;
+    auto node_plane = [&](int p, const double* src) { return stage<MODE>(sm + L.node + (size_t)A.np[p] * L.mtp * 8, src + nb, no, 8, bar); };
+    tx += node_plane(NP_GSU, A.grad_ssh);   tx += node_plane(NP_GSV, A.grad_ssh + nn);
+    tx += node_plane(NP_MASS, A.node_mass); tx += node_plane(NP_RL, A.rlmass);
+    tx += node_plane(NP_CBU, A.cbu);        tx += node_plane(NP_FCOR, A.fcor);
+    tx += node_plane(NP_TAU, A.tau_a);      tx += node_plane(NP_TAV, A.tau_a + nn);
+    tx += node_plane(NP_OCU, A.ocean);      tx += node_plane(NP_OCV, A.ocean + nn);
+    if (A.move_mesh) {
+        tx += node_plane(NP_UMU, A.UM);     tx += node_plane(NP_UMV, A.UM + nn);
+        tx += node_plane(NP_UTU, A.UT);     tx += node_plane(NP_UTV, A.UT + nn);
+    }
+    if (K.dynamics_type == NSX_DYN_MEVP) { tx += node_plane(NP_VMU, A.VTM); tx += node_plane(NP_VMV, A.VTM + nn); }
+    if (A.tau_wi) { tx += node_plane(NP_TWU, A.tau_wi); tx += node_plane(NP_TWV, A.tau_wi + nn); }
+    tx += stage<MODE>(sm + L.su, A.VTc + nb, no, 8, bar);
+    tx += stage<MODE>(sm + L.sv, A.VTc + nn + nb, no, 8, bar);
+    tx += stage<MODE>(sm + L.hn, A.halo_nodes + td.halo_off, td.n_halo, 4, bar);
+    tx += stage<MODE>(sm + L.he, A.halo_elems + td.halo_elem_off, td.n_halo_slots, 4, bar);
+    tx += stage<MODE>(sm + L.inc, A.inc + td.inc_off, td.inc_w * td.n_own, 2, bar);
+    tx += stage<MODE>(sm + L.fl, A.nflags + nb, no, 1, bar);
+    return tx;
+}
+
 template <int BBM>
-__global__ void __launch_bounds__(SUB_TPB, 3)
+__global__ void __launch_bounds__(SUB_TPB, 2)
 k_subcycle(KParams K, SubArgs A)
 {
-    extern __shared__ double sm[];
-    double* const su = sm;
-    double* const sv = sm + A.max_local_nodes;
-    double* const cs = sm + 2 * A.max_local_nodes;          // contributions: cs[i*max_slots + k], i = 0..5
-    int const MS = A.max_slots;
+    extern __shared__ __align__(128) unsigned char sm[];
+    SmemLayout const& L = A.L;
     int const nn = K.nn;
     int const tid = threadIdx.x;
     TileDesc const td = A.tiles[A.tile_order ? A.tile_order[A.tile_base + blockIdx.x] : A.tile_base + blockIdx.x];
+    uint64_t* const bar = (uint64_t*)(sm + L.bar);
 
-    // ---- phase 0 ----
-    for (int j = tid; j < td.n_own; j += SUB_TPB) {
-        su[j] = A.VTc[td.node_begin + j];
-        sv[j] = A.VTc[td.node_begin + j + nn];
+    // ---- stage ----
+    if (tid == 0) {
+        mbar_init(bar, 1);
+        uint32_t const tx = stage_tile<0, BBM>(K, A, td, sm, bar);
+        mbar_expect_tx(bar, tx);
+        stage_tile<1, BBM>(K, A, td, sm, bar);
     }
+    __syncthreads();                     // barrier initialised before anybody polls it
+
+    // shifted views of the staged planes
+    int const nb = td.node_begin;
+    int const sh_slot = stage_shift(A.slot_conn + td.slot_begin, 8);      // nslots is even: same phase for every slot plane
+    int const sh_el = stage_shift(A.s0i + td.elem_begin, 8);
+    int const sh_nu = stage_shift(A.VTc + nb, 8), sh_nv = stage_shift(A.VTc + nn + nb, 8);
+    const unsigned long long* const conn = (const unsigned long long*)(sm + L.conn) + sh_slot;
+    double* const shp = (double*)(sm + L.shape) + sh_slot;                // also the contribution planes
+    const double* const ecp = (const double*)(sm + L.ec) + sh_slot;
+    const double* const sgp = (const double*)(sm + L.sig) + sh_el;
+    const double* const dgp = (const double*)(sm + L.dmg) + sh_el;
+    double* const su = (double*)(sm + L.su) + sh_nu;
+    double* const sv = (double*)(sm + L.sv) + sh_nv;
+    const int* const hn = (const int*)(sm + L.hn) + stage_shift(A.halo_nodes + td.halo_off, 4);
+    const int* const he = (const int*)(sm + L.he) + stage_shift(A.halo_elems + td.halo_elem_off, 4);
+    const uint16_t* const incp = (const uint16_t*)(sm + L.inc) + stage_shift(A.inc + td.inc_off, 2);
+    const uint8_t* const flp = (const uint8_t*)(sm + L.fl) + stage_shift(A.nflags + nb, 1);
+    int const MSP = L.msp, MOP = L.mop, MTP = L.mtp;
+
+    mbar_wait(bar, 0);
+
+    // ---- phase 0: halo node velocities ----
     for (int j = tid; j < td.n_halo; j += SUB_TPB) {
-        int const g = A.halo_nodes[td.halo_off + j];
+        int const g = hn[j];
         su[td.n_own + j] = A.VTc[g];
         sv[td.n_own + j] = A.VTc[g + nn];
     }
@@ -267,20 +391,18 @@ k_subcycle(KParams K, SubArgs A)
 
     // ---- phase 1 ----
     int const nsl = td.n_own_slots + td.n_halo_slots;
-    size_t const NS = (size_t)A.nslots;
     for (int k = tid; k < nsl; k += SUB_TPB) {
-        size_t const s = (size_t)td.slot_begin + k;
         bool const own = k < td.n_own_slots;
-        int const e = own ? td.elem_begin + k : A.halo_elems[td.halo_elem_off + k - td.n_own_slots];
-        unsigned long long const pc = A.slot_conn[s];
+        int const e = own ? td.elem_begin + k : he[k - td.n_own_slots];
+        unsigned long long const pc = conn[k];
         int const la = (int)(pc & 0xFFFF), lb = (int)((pc >> 16) & 0xFFFF), lc = (int)((pc >> 32) & 0xFFFF);
-        double const dx0 = A.slot_shape[s], dx1 = A.slot_shape[NS + s], dx2 = A.slot_shape[2 * NS + s];
-        double const dy0 = A.slot_shape[3 * NS + s], dy1 = A.slot_shape[4 * NS + s], dy2 = A.slot_shape[5 * NS + s];
-        double const c0 = A.slot_ec[s];
+        double const dx0 = shp[k], dx1 = shp[MSP + k], dx2 = shp[2 * MSP + k];
+        double const dy0 = shp[3 * MSP + k], dy1 = shp[4 * MSP + k], dy2 = shp[5 * MSP + k];
+        double const c0 = ecp[k];
         double s0, s1, s2, vol;
         if (BBM) {
             double const expC = c0;
-            vol = A.slot_ec[5 * NS + s];
+            vol = ecp[5 * MSP + k];
             double d;
             if (expC == 0.) {                   // conc <= 0.1 : no ice (FE.cpp:4151-4159)
                 s0 = s1 = s2 = 0.;
@@ -291,14 +413,15 @@ k_subcycle(KParams K, SubArgs A)
                 double e0 = dx0 * ua; e0 += dx1 * ub; e0 += dx2 * uc;
                 double e1 = dy0 * va; e1 += dy1 * vb; e1 += dy2 * vc;
                 double e2 = dy0 * ua; e2 += dx0 * va; e2 += dy1 * ub; e2 += dx1 * vb; e2 += dy2 * uc; e2 += dx2 * vc;
-                s0 = A.s0i[e]; s1 = A.s1i[e]; s2 = A.s2i[e]; d = A.di[e];
+                if (own) { s0 = sgp[k]; s1 = sgp[MOP + k]; s2 = sgp[2 * MOP + k]; d = dgp[k]; }
+                else     { s0 = A.s0i[e]; s1 = A.s1i[e]; s2 = A.s2i[e]; d = A.di[e]; }
                 double const dt = K.dte;
                 double sigma_n = (s0 + s1) * 0.5;
                 double const omd = 1. - d;
                 double const time_viscous = K.lambda0 * pow_relax(omd * expC, K);
                 double tildeP = 0.;
                 if (sigma_n < 0.) {
-                    double const Pmax = A.slot_ec[NS + s];
+                    double const Pmax = ecp[MSP + k];
                     tildeP = fmin(1., -Pmax / sigma_n);
                 }
                 double const mult = fmin(1. - 1e-12, time_viscous / (time_viscous + dt * (1. - tildeP)));
@@ -311,19 +434,19 @@ k_subcycle(KParams K, SubArgs A)
                 sigma_n = (s0 + s1) * 0.5;
                 double dcrit;
                 if (sigma_n < -K.compr_strength) dcrit = -K.compr_strength / sigma_n;
-                else dcrit = A.slot_ec[2 * NS + s] / (sigma_s + K.tan_phi * sigma_n);
+                else dcrit = ecp[2 * MSP + k] / (sigma_s + K.tan_phi * sigma_n);
                 if ((0. < dcrit) && (dcrit < 1.)) {
-                    double const rtd = sqrt(elasticity) * A.slot_ec[3 * NS + s];
+                    double const rtd = sqrt(elasticity) * ecp[3 * MSP + k];
                     double const f = (1. - dcrit) * dt * rtd;
                     d += omd * f;
                     s0 -= s0 * f;  s1 -= s1 * f;  s2 -= s2 * f;
                 }
-                d = fmax(0., d - A.slot_ec[4 * NS + s]);
+                d = fmax(0., d - ecp[4 * MSP + k]);
             }
             if (own) A.dmo[e] = d;
         } else {
             double const Pp = c0;
-            vol = A.slot_ec[NS + s];
+            vol = ecp[MSP + k];
             if (Pp < 0.) {                      // thick == 0 (FE.cpp:10656-10662)
                 s0 = s1 = s2 = 0.;
             } else {
@@ -334,7 +457,8 @@ k_subcycle(KParams K, SubArgs A)
                 double const eps1 = eps11 + eps22, eps2 = eps11 - eps22;
                 double const delta = sqrt(eps1 * eps1 + (eps2 * eps2 + 4 * eps12 * eps12) * K.re2);
                 double const zeta = Pp / (delta + K.evp_dmin);
-                s0 = A.s0i[e]; s1 = A.s1i[e]; s2 = A.s2i[e];
+                if (own) { s0 = sgp[k]; s1 = sgp[MOP + k]; s2 = sgp[2 * MOP + k]; }
+                else     { s0 = A.s0i[e]; s1 = A.s1i[e]; s2 = A.s2i[e]; }
                 double sigma1 = s0 + s1, sigma2 = s0 - s1;
                 sigma1 += K.ralpha1 * (zeta * (eps1 - delta) - sigma1);
                 sigma2 += K.ralpha2 * (zeta * eps2 * K.re2 - sigma2);
@@ -344,51 +468,53 @@ k_subcycle(KParams K, SubArgs A)
             }
         }
         if (own) { A.s0o[e] = s0; A.s1o[e] = s1; A.s2o[e] = s2; }
-        // nodal contributions V*(sigma . grad N_i)  (FE.cpp:10464-10465)
-        cs[0 * MS + k] = vol * (s0 * dx0 + s2 * dy0);
-        cs[1 * MS + k] = vol * (s0 * dx1 + s2 * dy1);
-        cs[2 * MS + k] = vol * (s0 * dx2 + s2 * dy2);
-        cs[3 * MS + k] = vol * (s2 * dx0 + s1 * dy0);
-        cs[4 * MS + k] = vol * (s2 * dx1 + s1 * dy1);
-        cs[5 * MS + k] = vol * (s2 * dx2 + s1 * dy2);
+        // nodal contributions V*(sigma . grad N_i) (FE.cpp:10464-10465) overwrite this slot's shape coefficients
+        shp[0 * MSP + k] = vol * (s0 * dx0 + s2 * dy0);
+        shp[1 * MSP + k] = vol * (s0 * dx1 + s2 * dy1);
+        shp[2 * MSP + k] = vol * (s0 * dx2 + s2 * dy2);
+        shp[3 * MSP + k] = vol * (s2 * dx0 + s1 * dy0);
+        shp[4 * MSP + k] = vol * (s2 * dx1 + s1 * dy1);
+        shp[5 * MSP + k] = vol * (s2 * dx2 + s1 * dy2);
     }
     __syncthreads();
 
     // ---- phase 2 ----
+    const double* const npl = (const double*)(sm + L.node);
+    int const shs = stage_shift(A.node_mass + nb, 8);       // scalar node planes and u halves: same phase as nb
     for (int j = tid; j < td.n_own; j += SUB_TPB) {
-        int const n = td.node_begin + j;
-        uint8_t const fl = A.nflags[n];
+        int const n = nb + j;
+        uint8_t const fl = flp[j];
         double const uice = su[j], vice = sv[j];
         double un = uice, vn = vice;
-        double const nm = A.node_mass[n];
+        double const nm = npl[A.np[NP_MASS] * MTP + shs + j];
         if (!(fl & NF_DIRICHLET) && nm != 0.) {
-            double gu = A.grad_ssh[n], gv = A.grad_ssh[n + nn];
-            const uint16_t* ip = A.inc + td.inc_off + j;
+            double gu = npl[A.np[NP_GSU] * MTP + shs + j], gv = npl[A.np[NP_GSV] * MTP + sh_nv + j];
+            const uint16_t* ip = incp + j;
             for (int c = 0; c < td.inc_w; ++c) {
-                unsigned const code = ip[(size_t)c * td.n_own];
+                unsigned const code = ip[c * td.n_own];
                 if (code == 0xFFFFu) break;
-                gu -= cs[code];
-                gv -= cs[code + 3 * MS];
+                gu -= shp[code];
+                gv -= shp[code + 3 * MSP];
             }
             double dtep = K.dte, delu = 0., delv = 0.;
             if (K.dynamics_type == NSX_DYN_MEVP) {
-                delu = (A.VTM[n] - uice) / K.mevp_b;
-                delv = (A.VTM[n + nn] - vice) / K.mevp_b;
+                delu = (npl[A.np[NP_VMU] * MTP + shs + j] - uice) / K.mevp_b;
+                delv = (npl[A.np[NP_VMV] * MTP + sh_nv + j] - vice) / K.mevp_b;
                 dtep = K.dte / K.mevp_b;
             }
             double const dte_over_mass = dtep / fmax(K.min_m, nm);
-            double const ou = A.ocean[n], ov = A.ocean[n + nn];
+            double const ou = npl[A.np[NP_OCU] * MTP + shs + j], ov = npl[A.np[NP_OCV] * MTP + sh_nv + j];
             double const c_prime = K.rhow_cdw * hypot(ou - uice, ov - vice);
-            double const tau_b = A.cbu[n] / (hypot(uice, vice) + K.u0);
+            double const tau_b = npl[A.np[NP_CBU] * MTP + shs + j] / (hypot(uice, vice) + K.u0);
             double const sin_s = (fl & NF_LATNEG) ? -K.sin_ota_abs : K.sin_ota_abs;   // std::copysign(sin, lat[i])
             double const alpha = 1. + dte_over_mass * (c_prime * K.cos_ota + tau_b);
-            double const beta = dtep * A.fcor[n] + dte_over_mass * c_prime * sin_s;
+            double const beta = dtep * npl[A.np[NP_FCOR] * MTP + shs + j] + dte_over_mass * c_prime * sin_s;
             double const rdenom = 1. / (alpha * alpha + beta * beta);
-            double tau_x = A.tau_a[n], tau_y = A.tau_a[n + nn];
-            if (A.tau_wi) { tau_x = tau_x + A.tau_wi[n]; tau_y = tau_y + A.tau_wi[n + nn]; }
+            double tau_x = npl[A.np[NP_TAU] * MTP + shs + j], tau_y = npl[A.np[NP_TAV] * MTP + sh_nv + j];
+            if (A.tau_wi) { tau_x = tau_x + npl[A.np[NP_TWU] * MTP + shs + j]; tau_y = tau_y + npl[A.np[NP_TWV] * MTP + sh_nv + j]; }
             tau_x = tau_x + c_prime * (ou * K.cos_ota - ov * sin_s);
             tau_y = tau_y + c_prime * (ov * K.cos_ota + ou * sin_s);
-            double const rl = A.rlmass[n];
+            double const rl = npl[A.np[NP_RL] * MTP + shs + j];
             double const grad_x = gu * rl, grad_y = gv * rl;
             un = alpha * uice + beta * vice + dte_over_mass * (alpha * (grad_x + tau_x) + beta * (grad_y + tau_y)) + alpha * delu + beta * delv;
             un *= rdenom;
@@ -398,8 +524,12 @@ k_subcycle(KParams K, SubArgs A)
         A.VTn[n] = un;
         A.VTn[n + nn] = vn;
         if (A.move_mesh) {
-            A.UT[n] += K.dte * un;  A.UT[n + nn] += K.dte * vn;
-            if (!(fl & NF_NEUMANN)) { A.UM[n] += K.dte * un;  A.UM[n + nn] += K.dte * vn; }
+            A.UT[n] = npl[A.np[NP_UTU] * MTP + shs + j] + K.dte * un;
+            A.UT[n + nn] = npl[A.np[NP_UTV] * MTP + sh_nv + j] + K.dte * vn;
+            if (!(fl & NF_NEUMANN)) {
+                A.UM[n] = npl[A.np[NP_UMU] * MTP + shs + j] + K.dte * un;
+                A.UM[n + nn] = npl[A.np[NP_UMV] * MTP + sh_nv + j] + K.dte * vn;
+            }
         }
     }
     // ghost nodes: moved with the velocity their owner pushed at the end of the previous sub-cycle

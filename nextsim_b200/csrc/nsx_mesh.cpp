@@ -8,6 +8,7 @@
 #include "nsx_mesh.h"
 
 #include <algorithm>
+#include <climits>
 #include <cmath>
 #include <numeric>
 #include <stdexcept>
@@ -185,7 +186,7 @@ void build_mesh_plan(const NsxMesh* M, MeshPlan& P, int target_tile_nodes, int s
     P.tiles.assign(ntiles, TileDesc{});
     P.halo_nodes.clear(); P.halo_elems.clear(); P.slot_elem.clear(); P.slot_conn.clear(); P.inc.clear();
     std::vector<int> stamp_e(ne, -1), slot_of(ne, 0), stamp_n(nn, -1), lidx(nn, 0);
-    P.max_local_nodes = 0; P.max_slots = 0;
+    P.max_local_nodes = 0; P.max_slots = 0; P.max_own_slots = 0; P.max_halo_slots = 0; P.max_halo_nodes = 0; P.max_inc = 0;
     for (int t = 0; t < ntiles; ++t) {
         TileDesc& td = P.tiles[t];
         td.node_begin = t * T;
@@ -253,11 +254,19 @@ void build_mesh_plan(const NsxMesh* M, MeshPlan& P, int target_tile_nodes, int s
         }
         P.max_local_nodes = std::max(P.max_local_nodes, td.n_own + nhn);
         P.max_slots = std::max(P.max_slots, nslots);
+        P.max_own_slots = std::max(P.max_own_slots, td.n_own_slots);
+        P.max_halo_slots = std::max(P.max_halo_slots, nh);
+        P.max_halo_nodes = std::max(P.max_halo_nodes, nhn);
+        P.max_inc = std::max(P.max_inc, dmax * td.n_own);
     }
+    // slot space is padded to an even count so that every slot plane (stride nslots) has the same 16-byte
+    // phase; the pad slot is never computed (marked INT_MIN)
+    if (P.slot_elem.size() & 1) { P.slot_elem.push_back(INT32_MIN); P.slot_conn.push_back(0ULL); }
     P.nslots = (int)P.slot_elem.size();
 
-    // post-pass: incidence codes become shared-memory offsets (vertex * max_slots + slot); halo slots get ~e
-    int const MS = P.max_slots;
+    // post-pass: incidence codes become shared-memory offsets (vertex * msp + slot); halo slots get ~e
+    P.msp = (P.max_slots + 3) & ~1;             // plane stride in shared memory: room for the alignment shift
+    int const MS = P.msp;
     for (int t = 0; t < ntiles; ++t) {
         TileDesc const& td = P.tiles[t];
         for (size_t q = 0; q < (size_t)td.inc_w * td.n_own; ++q) {
@@ -269,7 +278,7 @@ void build_mesh_plan(const NsxMesh* M, MeshPlan& P, int target_tile_nodes, int s
         for (int k = td.n_own_slots; k < td.n_own_slots + td.n_halo_slots; ++k)
             P.slot_elem[td.slot_begin + k] = ~P.slot_elem[td.slot_begin + k];
     }
-    if (3 * (long)MS > 65534) throw std::invalid_argument("nsx_create: tile too large for 16-bit incidence codes");
+    if (6 * (long)MS > 65534) throw std::invalid_argument("nsx_create: tile too large for 16-bit incidence codes");
 }
 
 }  // namespace nsx

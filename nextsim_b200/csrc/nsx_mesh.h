@@ -42,6 +42,7 @@ struct MeshPlan {
     std::vector<int> n2n, n2n_deg;
     // tiles
     int ntiles = 0, tile_nodes = 0, nslots = 0, max_local_nodes = 0, max_slots = 0;
+    int max_own_slots = 0, max_halo_slots = 0, max_halo_nodes = 0, max_inc = 0, msp = 0;
     std::vector<TileDesc> tiles;
     std::vector<int> halo_nodes, halo_elems, slot_elem;
     std::vector<unsigned long long> slot_conn; // 3 x 16-bit tile-local node ids
