@@ -33,7 +33,11 @@ def needs_build():
 def build(force=False, verbose=False):
     if not force and not needs_build():
         return LIB
-    cmd = [_nvcc()] + NVCC_FLAGS + [os.path.join(CSRC, s) for s in SOURCES] + ["-o", LIB]
+    extra = []
+    for k in ("NSX_SUB_TPB", "NSX_SUB_MINB"):           # kernel-shape experiments
+        if os.environ.get(k):
+            extra.append("-D%s=%s" % (k, os.environ[k]))
+    cmd = [_nvcc()] + NVCC_FLAGS + extra + [os.path.join(CSRC, s) for s in SOURCES] + ["-o", LIB]
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     log = os.path.join(HERE, "build.log")
     with open(log, "w") as f:

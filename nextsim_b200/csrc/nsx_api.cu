@@ -59,7 +59,7 @@ static SmemLayout sub_layout(MeshPlan const& P, int n_node_planes)
     L.total = (int)o;
     return L;
 }
-constexpr int SUB_SMEM_CAP = 113 * 1024;      // two CTAs per SM: (228 KB - 2 x 1 KB reserved) / 2
+constexpr int SUB_SMEM_CAP = 113 * 1024;      // per stage; two stages per persistent CTA, one CTA per SM (227 KB)
 
 // ---------------------------------------------------------------------------------------------------
 // life cycle
@@ -82,8 +82,8 @@ static void upload_plan(nsx_solver* S)
     S->inc.upload(P.inc, st);
     S->sub_smem = sub_layout(P, NP_COUNT).total;
     // the attribute is per function and device, shared by every handle: always ask for the cap
-    NSX_CUDA(cudaFuncSetAttribute(k_subcycle<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    NSX_CUDA(cudaFuncSetAttribute(k_subcycle<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    NSX_CUDA(cudaFuncSetAttribute(k_subcycle<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    NSX_CUDA(cudaFuncSetAttribute(k_subcycle<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     NSX_CUDA(cudaStreamSynchronize(st));
 }
 
@@ -209,7 +209,7 @@ extern "C" int nsx_create(const NsxMesh* mesh, const NsxHalo* halo, int device, 
         int target = env_int("NSX_TILE_NODES", 208);
         for (int attempt = 0;; ++attempt) {
             S->plan = MeshPlan();
-            build_mesh_plan(mesh, S->plan, target, S->sm_count * env_int("NSX_SUB_OCC", 2));
+            build_mesh_plan(mesh, S->plan, target, S->sm_count * env_int("NSX_SUB_OCC", 1));
             if (sub_layout(S->plan, 14).total <= SUB_SMEM_CAP) break;
             if (attempt > 12 || target <= 32) throw std::invalid_argument("nsx_create: cannot fit a tile in shared memory");
             target = std::max(32, (int)(target * 0.88));
@@ -589,8 +589,12 @@ static void launch_tiles(nsx_solver* S, SubArgs const& A, int tile_base, int nti
     if (ntiles <= 0) return;
     SubArgs a = A;
     a.tile_base = tile_base;
-    if (S->K.dynamics_type == NSX_DYN_BBM) k_subcycle<1><<<ntiles, SUB_TPB, S->sub_smem, st>>>(S->K, a);
-    else k_subcycle<0><<<ntiles, SUB_TPB, S->sub_smem, st>>>(S->K, a);
+    a.n_tiles = ntiles;
+    // persistent CTAs, one per SM (two shared-memory stages each); CTA b takes tiles b, b+grid, ...
+    int const grid = std::min(ntiles, S->sm_count);
+    size_t const smem = 64 + 2 * (size_t)A.L.total;
+    if (S->K.dynamics_type == NSX_DYN_BBM) k_subcycle<1><<<grid, SUB_TPB, smem, st>>>(S->K, a);
+    else k_subcycle<0><<<grid, SUB_TPB, smem, st>>>(S->K, a);
     S->n_launch++;
 }
 
@@ -623,7 +627,7 @@ static void phase_substep(nsx_solver* S, int s, bool exchange_sync, bool overlap
         A.np[p] = use ? npl++ : 0;
     }
     A.L = sub_layout(S->plan, npl);
-    if (A.L.total > 200 * 1024) throw std::runtime_error("sub-cycle kernel: tile working set exceeds shared memory");
+    if (64 + 2 * (size_t)A.L.total > 227 * 1024) throw std::runtime_error("sub-cycle kernel: tile working set exceeds shared memory");
     S->sub_smem = (size_t)A.L.total;
     int const nt = S->plan.ntiles, nb = S->n_boundary_tiles;
     if (overlap && nb > 0 && nb < nt) {

@@ -221,7 +221,13 @@ k_prep_nodes(KParams K, const uint8_t* __restrict__ nflags,
 // HBM traffic per element-sub-cycle ~ 104 B slot constants + 32 B sigma/d read (x ~1.1 redundancy) + 32 B
 // written + ~95 B of nodal planes = ~280 B (SURVEY 8(d) algorithmic floor: 264 B).
 // ---------------------------------------------------------------------------------------------------
-constexpr int SUB_TPB = 384;
+#ifndef NSX_SUB_TPB
+#define NSX_SUB_TPB 768
+#endif
+#ifndef NSX_SUB_MINB
+#define NSX_SUB_MINB 2
+#endif
+constexpr int SUB_TPB = NSX_SUB_TPB;
 
 __device__ __forceinline__ double pow_relax(double q, KParams const& K)
 {
@@ -267,12 +273,12 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
 __device__ __forceinline__ int stage_shift(const void* src, int esz) { return (int)(((uintptr_t)src & 15) / esz); }
 // MODE 0: returns the bytes the copy will transfer; MODE 1: issues it
 template <int MODE>
-__device__ __forceinline__ uint32_t stage(void* dst16, const void* src, int n, int esz, uint64_t* bar)
+__device__ __forceinline__ uint32_t stage(void* dst16, const void* src, int n, int esz, uint64_t* bar, int& ctr)
 {
     if (n <= 0) return 0;
     uint32_t const lead = (uint32_t)((uintptr_t)src & 15);
     uint32_t const bytes = (lead + (uint32_t)n * esz + 15u) & ~15u;
-    if (MODE) bulk_g2s(dst16, (const void*)((uintptr_t)src - lead), bytes, bar);
+    if (MODE) { bulk_g2s(dst16, (const void*)((uintptr_t)src - lead), bytes, bar); ++ctr; }
     return bytes;
 }
 
@@ -293,7 +299,7 @@ struct SubArgs {
     const uint8_t* nflags; const double* grad_ssh; const double* node_mass; const double* rlmass;
     const double* cbu; const double* fcor; const double* tau_a; const double* tau_wi; const double* ocean;
     const double* VTM; const double* VTc; double* VTn; double* UM; double* UT;
-    int move_mesh, lag_ghost_move;
+    int move_mesh, lag_ghost_move, n_tiles;
     int np[NP_COUNT];           // node plane -> staging slot (compacted: only the planes this configuration reads)
     SmemLayout L;
 };
@@ -307,20 +313,21 @@ __device__ __forceinline__ uint32_t stage_tile(KParams const& K, SubArgs const& 
     size_t const NS = (size_t)A.nslots;
     size_t const s0 = (size_t)td.slot_begin;
     uint32_t tx = 0;
-    tx += stage<MODE>(sm + L.conn, A.slot_conn + s0, nsl, 8, bar);
+    int ctr = 0;
+    tx += stage<MODE>(sm + L.conn, A.slot_conn + s0, nsl, 8, bar, ctr);
 #pragma unroll
     for (int p = 0; p < 6; ++p)
-        tx += stage<MODE>(sm + L.shape + (size_t)p * L.msp * 8, A.slot_shape + p * NS + s0, nsl, 8, bar);
+        tx += stage<MODE>(sm + L.shape + (size_t)p * L.msp * 8, A.slot_shape + p * NS + s0, nsl, 8, bar, ctr);
 #pragma unroll
     for (int p = 0; p < (BBM ? 6 : 2); ++p)
-        tx += stage<MODE>(sm + L.ec + (size_t)p * L.msp * 8, A.slot_ec + p * NS + s0, nsl, 8, bar);
-    tx += stage<MODE>(sm + L.sig + (size_t)0 * L.mop * 8, A.s0i + td.elem_begin, td.n_own_slots, 8, bar);
-    tx += stage<MODE>(sm + L.sig + (size_t)1 * L.mop * 8, A.s1i + td.elem_begin, td.n_own_slots, 8, bar);
-    tx += stage<MODE>(sm + L.sig + (size_t)2 * L.mop * 8, A.s2i + td.elem_begin, td.n_own_slots, 8, bar);
-    if (BBM) tx += stage<MODE>(sm + L.dmg, A.di + td.elem_begin, td.n_own_slots, 8, bar);
+        tx += stage<MODE>(sm + L.ec + (size_t)p * L.msp * 8, A.slot_ec + p * NS + s0, nsl, 8, bar, ctr);
+    tx += stage<MODE>(sm + L.sig + (size_t)0 * L.mop * 8, A.s0i + td.elem_begin, td.n_own_slots, 8, bar, ctr);
+    tx += stage<MODE>(sm + L.sig + (size_t)1 * L.mop * 8, A.s1i + td.elem_begin, td.n_own_slots, 8, bar, ctr);
+    tx += stage<MODE>(sm + L.sig + (size_t)2 * L.mop * 8, A.s2i + td.elem_begin, td.n_own_slots, 8, bar, ctr);
+    if (BBM) tx += stage<MODE>(sm + L.dmg, A.di + td.elem_begin, td.n_own_slots, 8, bar, ctr);
     // owned-node planes
     int const nb = td.node_begin, no = td.n_own;
-    auto node_plane = [&](int p, const double* src) { return stage<MODE>(sm + L.node + (size_t)A.np[p] * L.mtp * 8, src + nb, no, 8, bar); };
+    auto node_plane = [&](int p, const double* src) { return stage<MODE>(sm + L.node + (size_t)A.np[p] * L.mtp * 8, src + nb, no, 8, bar, ctr); };
     tx += node_plane(NP_GSU, A.grad_ssh);   tx += node_plane(NP_GSV, A.grad_ssh + nn);
     tx += node_plane(NP_MASS, A.node_mass); tx += node_plane(NP_RL, A.rlmass);
     tx += node_plane(NP_CBU, A.cbu);        tx += node_plane(NP_FCOR, A.fcor);
@@ -332,34 +339,65 @@ __device__ __forceinline__ uint32_t stage_tile(KParams const& K, SubArgs const& 
     }
     if (K.dynamics_type == NSX_DYN_MEVP) { tx += node_plane(NP_VMU, A.VTM); tx += node_plane(NP_VMV, A.VTM + nn); }
     if (A.tau_wi) { tx += node_plane(NP_TWU, A.tau_wi); tx += node_plane(NP_TWV, A.tau_wi + nn); }
-    tx += stage<MODE>(sm + L.su, A.VTc + nb, no, 8, bar);
-    tx += stage<MODE>(sm + L.sv, A.VTc + nn + nb, no, 8, bar);
-    tx += stage<MODE>(sm + L.hn, A.halo_nodes + td.halo_off, td.n_halo, 4, bar);
-    tx += stage<MODE>(sm + L.he, A.halo_elems + td.halo_elem_off, td.n_halo_slots, 4, bar);
-    tx += stage<MODE>(sm + L.inc, A.inc + td.inc_off, td.inc_w * td.n_own, 2, bar);
-    tx += stage<MODE>(sm + L.fl, A.nflags + nb, no, 1, bar);
+    tx += stage<MODE>(sm + L.su, A.VTc + nb, no, 8, bar, ctr);
+    tx += stage<MODE>(sm + L.sv, A.VTc + nn + nb, no, 8, bar, ctr);
+    tx += stage<MODE>(sm + L.hn, A.halo_nodes + td.halo_off, td.n_halo, 4, bar, ctr);
+    tx += stage<MODE>(sm + L.he, A.halo_elems + td.halo_elem_off, td.n_halo_slots, 4, bar, ctr);
+    tx += stage<MODE>(sm + L.inc, A.inc + td.inc_off, td.inc_w * td.n_own, 2, bar, ctr);
+    tx += stage<MODE>(sm + L.fl, A.nflags + nb, no, 1, bar, ctr);
     return tx;
 }
 
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+constexpr int SUB_CONS = SUB_TPB - 32;          // consumer threads; the last warp is the TMA producer
+__device__ __forceinline__ void cons_sync() { asm volatile("bar.sync 1, %0;" ::"n"(SUB_CONS) : "memory"); }
+
+// Persistent, warp-specialised, double-buffered: CTA b works on tiles b, b+grid, b+2*grid, ... of its launch
+// range.  The producer warp streams tile t+1 into the other stage while the consumer warps compute tile t
+// (full[s]: TMA transaction barrier, empty[s]: one arrival per consumer warp when the stage may be refilled).
 template <int BBM>
-__global__ void __launch_bounds__(SUB_TPB, 2)
+__global__ void __launch_bounds__(SUB_TPB, 1)
 k_subcycle(KParams K, SubArgs A)
 {
-    extern __shared__ __align__(128) unsigned char sm[];
+    extern __shared__ __align__(128) unsigned char sm_all[];
     SmemLayout const& L = A.L;
     int const nn = K.nn;
     int const tid = threadIdx.x;
-    TileDesc const td = A.tiles[A.tile_order ? A.tile_order[A.tile_base + blockIdx.x] : A.tile_base + blockIdx.x];
-    uint64_t* const bar = (uint64_t*)(sm + L.bar);
-
-    // ---- stage ----
+    uint64_t* const full = (uint64_t*)sm_all;
+    uint64_t* const empty = full + 2;
+    unsigned char* const stage0 = sm_all + 64;
     if (tid == 0) {
-        mbar_init(bar, 1);
-        uint32_t const tx = stage_tile<0, BBM>(K, A, td, sm, bar);
-        mbar_expect_tx(bar, tx);
-        stage_tile<1, BBM>(K, A, td, sm, bar);
+        mbar_init(full, 1); mbar_init(full + 1, 1);
+        mbar_init(empty, SUB_CONS / 32); mbar_init(empty + 1, SUB_CONS / 32);
     }
-    __syncthreads();                     // barrier initialised before anybody polls it
+    __syncthreads();
+    int const n_my = (A.n_tiles > (int)blockIdx.x) ? (A.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+
+    if (tid >= SUB_CONS) {
+        // ---- producer ----
+        if (tid == SUB_CONS) {
+            for (int it = 0; it < n_my; ++it) {
+                int const s = it & 1;
+                if (it >= 2) mbar_wait(empty + s, ((it >> 1) - 1) & 1);
+                int const tix = A.tile_base + (int)blockIdx.x + it * (int)gridDim.x;
+                TileDesc const td = A.tiles[A.tile_order ? A.tile_order[tix] : tix];
+                unsigned char* const sm = stage0 + (size_t)s * L.total;
+                mbar_expect_tx(full + s, stage_tile<0, BBM>(K, A, td, sm, full + s));
+                stage_tile<1, BBM>(K, A, td, sm, full + s);
+            }
+        }
+        return;
+    }
+
+    // ---- consumers ----
+    for (int it = 0; it < n_my; ++it) {
+    int const s = it & 1;
+    int const tix = A.tile_base + (int)blockIdx.x + it * (int)gridDim.x;
+    TileDesc const td = A.tiles[A.tile_order ? A.tile_order[tix] : tix];
+    unsigned char* const sm = stage0 + (size_t)s * L.total;
 
     // shifted views of the staged planes
     int const nb = td.node_begin;
@@ -379,19 +417,19 @@ k_subcycle(KParams K, SubArgs A)
     const uint8_t* const flp = (const uint8_t*)(sm + L.fl) + stage_shift(A.nflags + nb, 1);
     int const MSP = L.msp, MOP = L.mop, MTP = L.mtp;
 
-    mbar_wait(bar, 0);
+    mbar_wait(full + s, (it >> 1) & 1);
 
     // ---- phase 0: halo node velocities ----
-    for (int j = tid; j < td.n_halo; j += SUB_TPB) {
+    for (int j = tid; j < td.n_halo; j += SUB_CONS) {
         int const g = hn[j];
         su[td.n_own + j] = A.VTc[g];
         sv[td.n_own + j] = A.VTc[g + nn];
     }
-    __syncthreads();
+    cons_sync();
 
     // ---- phase 1 ----
     int const nsl = td.n_own_slots + td.n_halo_slots;
-    for (int k = tid; k < nsl; k += SUB_TPB) {
+    for (int k = tid; k < nsl; k += SUB_CONS) {
         bool const own = k < td.n_own_slots;
         int const e = own ? td.elem_begin + k : he[k - td.n_own_slots];
         unsigned long long const pc = conn[k];
@@ -476,12 +514,12 @@ k_subcycle(KParams K, SubArgs A)
         shp[4 * MSP + k] = vol * (s2 * dx1 + s1 * dy1);
         shp[5 * MSP + k] = vol * (s2 * dx2 + s1 * dy2);
     }
-    __syncthreads();
+    cons_sync();
 
     // ---- phase 2 ----
     const double* const npl = (const double*)(sm + L.node);
     int const shs = stage_shift(A.node_mass + nb, 8);       // scalar node planes and u halves: same phase as nb
-    for (int j = tid; j < td.n_own; j += SUB_TPB) {
+    for (int j = tid; j < td.n_own; j += SUB_CONS) {
         int const n = nb + j;
         uint8_t const fl = flp[j];
         double const uice = su[j], vice = sv[j];
@@ -534,13 +572,17 @@ k_subcycle(KParams K, SubArgs A)
     }
     // ghost nodes: moved with the velocity their owner pushed at the end of the previous sub-cycle
     if (A.lag_ghost_move) {
-        for (int j = tid; j < td.n_ghost; j += SUB_TPB) {
+        for (int j = tid; j < td.n_ghost; j += SUB_CONS) {
             int const n = td.ghost_begin + j;
             double const u = A.VTc[n], v = A.VTc[n + nn];
             A.UT[n] += K.dte * u;  A.UT[n + nn] += K.dte * v;
             if (!(A.nflags[n] & NF_NEUMANN)) { A.UM[n] += K.dte * u;  A.UM[n + nn] += K.dte * v; }
         }
     }
+    // every read of this stage is done: one arrival per consumer warp lets the producer refill it
+    __syncwarp();
+    if ((tid & 31) == 0) mbar_arrive(empty + s);
+    }   // tile loop
 }
 
 // mesh move over an explicit node range with an explicit time increment:
