@@ -52,8 +52,8 @@ static SmemLayout sub_layout(MeshPlan const& P, int n_node_planes)
     L.node = (int)o;  o += (size_t)n_node_planes * L.mtp * 8;
     L.su = (int)o;    o += al(((size_t)P.max_local_nodes + 2) * 8);
     L.sv = (int)o;    o += al(((size_t)P.max_local_nodes + 2) * 8);
-    L.hn = (int)o;    o += al((size_t)P.max_halo_nodes * 4 + 32);
-    L.he = (int)o;    o += al((size_t)P.max_halo_slots * 4 + 32);
+    L.mhs = (P.max_halo_slots + 3) & ~1;
+    L.hsig = (int)o;  o += (size_t)4 * L.mhs * 8;
     L.inc = (int)o;   o += al((size_t)P.max_inc * 2 + 32);
     L.fl = (int)o;    o += al((size_t)P.tile_nodes + 32);
     L.total = (int)o;

@@ -284,8 +284,8 @@ __device__ __forceinline__ uint32_t stage(void* dst16, const void* src, int n, i
 
 // byte offsets of the staging buffers inside dynamic shared memory (all multiples of 16) and plane strides
 struct SmemLayout {
-    int bar, conn, shape, ec, sig, dmg, node, su, sv, hn, he, inc, fl, total;
-    int msp, mop, mtp;          // slot / own-slot / node plane strides (elements)
+    int bar, conn, shape, ec, sig, dmg, node, su, sv, hsig, inc, fl, total;
+    int msp, mop, mtp, mhs;     // slot / own-slot / node / halo-slot plane strides (elements)
 };
 enum { NP_GSU, NP_GSV, NP_MASS, NP_RL, NP_CBU, NP_FCOR, NP_TAU, NP_TAV, NP_OCU, NP_OCV, NP_UMU, NP_UMV, NP_UTU, NP_UTV,
        NP_VMU, NP_VMV, NP_TWU, NP_TWV, NP_COUNT };
@@ -304,47 +304,52 @@ struct SubArgs {
     SmemLayout L;
 };
 
-template <int MODE, int BBM>
-__device__ __forceinline__ uint32_t stage_tile(KParams const& K, SubArgs const& A, TileDesc const& td, unsigned char* sm, uint64_t* bar)
+// Issues the TMA copies of copy-group `g` (0..3, one group per producer warp so that the four warps issue in
+// parallel) and returns the bytes they will deliver.  The caller posts arrive.expect_tx AFTERWARDS: the
+// transaction count of an mbarrier may go negative, and the phase cannot complete before that arrival.
+template <int BBM>
+__device__ __forceinline__ uint32_t stage_tile(int g, KParams const& K, SubArgs const& A, TileDesc const& td, unsigned char* sm, uint64_t* bar)
 {
     SmemLayout const& L = A.L;
     int const nn = K.nn;
     int const nsl = td.n_own_slots + td.n_halo_slots;
     size_t const NS = (size_t)A.nslots;
     size_t const s0 = (size_t)td.slot_begin;
+    int const nb = td.node_begin, no = td.n_own;
     uint32_t tx = 0;
     int ctr = 0;
-    tx += stage<MODE>(sm + L.conn, A.slot_conn + s0, nsl, 8, bar, ctr);
+    auto node_plane = [&](int p, const double* src) { return stage<1>(sm + L.node + (size_t)A.np[p] * L.mtp * 8, src + nb, no, 8, bar, ctr); };
+    if (g == 0) {
+        tx += stage<1>(sm + L.conn, A.slot_conn + s0, nsl, 8, bar, ctr);
 #pragma unroll
-    for (int p = 0; p < 6; ++p)
-        tx += stage<MODE>(sm + L.shape + (size_t)p * L.msp * 8, A.slot_shape + p * NS + s0, nsl, 8, bar, ctr);
+        for (int p = 0; p < 6; ++p)
+            tx += stage<1>(sm + L.shape + (size_t)p * L.msp * 8, A.slot_shape + p * NS + s0, nsl, 8, bar, ctr);
+        tx += stage<1>(sm + L.su, A.VTc + nb, no, 8, bar, ctr);
+        tx += stage<1>(sm + L.sv, A.VTc + nn + nb, no, 8, bar, ctr);
+    } else if (g == 1) {
 #pragma unroll
-    for (int p = 0; p < (BBM ? 6 : 2); ++p)
-        tx += stage<MODE>(sm + L.ec + (size_t)p * L.msp * 8, A.slot_ec + p * NS + s0, nsl, 8, bar, ctr);
-    tx += stage<MODE>(sm + L.sig + (size_t)0 * L.mop * 8, A.s0i + td.elem_begin, td.n_own_slots, 8, bar, ctr);
-    tx += stage<MODE>(sm + L.sig + (size_t)1 * L.mop * 8, A.s1i + td.elem_begin, td.n_own_slots, 8, bar, ctr);
-    tx += stage<MODE>(sm + L.sig + (size_t)2 * L.mop * 8, A.s2i + td.elem_begin, td.n_own_slots, 8, bar, ctr);
-    if (BBM) tx += stage<MODE>(sm + L.dmg, A.di + td.elem_begin, td.n_own_slots, 8, bar, ctr);
-    // owned-node planes
-    int const nb = td.node_begin, no = td.n_own;
-    auto node_plane = [&](int p, const double* src) { return stage<MODE>(sm + L.node + (size_t)A.np[p] * L.mtp * 8, src + nb, no, 8, bar, ctr); };
-    tx += node_plane(NP_GSU, A.grad_ssh);   tx += node_plane(NP_GSV, A.grad_ssh + nn);
-    tx += node_plane(NP_MASS, A.node_mass); tx += node_plane(NP_RL, A.rlmass);
-    tx += node_plane(NP_CBU, A.cbu);        tx += node_plane(NP_FCOR, A.fcor);
-    tx += node_plane(NP_TAU, A.tau_a);      tx += node_plane(NP_TAV, A.tau_a + nn);
-    tx += node_plane(NP_OCU, A.ocean);      tx += node_plane(NP_OCV, A.ocean + nn);
-    if (A.move_mesh) {
-        tx += node_plane(NP_UMU, A.UM);     tx += node_plane(NP_UMV, A.UM + nn);
-        tx += node_plane(NP_UTU, A.UT);     tx += node_plane(NP_UTV, A.UT + nn);
+        for (int p = 0; p < (BBM ? 6 : 2); ++p)
+            tx += stage<1>(sm + L.ec + (size_t)p * L.msp * 8, A.slot_ec + p * NS + s0, nsl, 8, bar, ctr);
+        tx += stage<1>(sm + L.sig + (size_t)0 * L.mop * 8, A.s0i + td.elem_begin, td.n_own_slots, 8, bar, ctr);
+        tx += stage<1>(sm + L.sig + (size_t)1 * L.mop * 8, A.s1i + td.elem_begin, td.n_own_slots, 8, bar, ctr);
+        tx += stage<1>(sm + L.sig + (size_t)2 * L.mop * 8, A.s2i + td.elem_begin, td.n_own_slots, 8, bar, ctr);
+        if (BBM) tx += stage<1>(sm + L.dmg, A.di + td.elem_begin, td.n_own_slots, 8, bar, ctr);
+    } else if (g == 2) {
+        tx += node_plane(NP_GSU, A.grad_ssh);   tx += node_plane(NP_GSV, A.grad_ssh + nn);
+        tx += node_plane(NP_MASS, A.node_mass); tx += node_plane(NP_RL, A.rlmass);
+        tx += node_plane(NP_CBU, A.cbu);        tx += node_plane(NP_FCOR, A.fcor);
+        tx += node_plane(NP_TAU, A.tau_a);      tx += node_plane(NP_TAV, A.tau_a + nn);
+        tx += node_plane(NP_OCU, A.ocean);      tx += node_plane(NP_OCV, A.ocean + nn);
+    } else {
+        if (A.move_mesh) {
+            tx += node_plane(NP_UMU, A.UM);     tx += node_plane(NP_UMV, A.UM + nn);
+            tx += node_plane(NP_UTU, A.UT);     tx += node_plane(NP_UTV, A.UT + nn);
+        }
+        if (K.dynamics_type == NSX_DYN_MEVP) { tx += node_plane(NP_VMU, A.VTM); tx += node_plane(NP_VMV, A.VTM + nn); }
+        if (A.tau_wi) { tx += node_plane(NP_TWU, A.tau_wi); tx += node_plane(NP_TWV, A.tau_wi + nn); }
+        tx += stage<1>(sm + L.inc, A.inc + td.inc_off, td.inc_w * td.n_own, 2, bar, ctr);
+        tx += stage<1>(sm + L.fl, A.nflags + nb, no, 1, bar, ctr);
     }
-    if (K.dynamics_type == NSX_DYN_MEVP) { tx += node_plane(NP_VMU, A.VTM); tx += node_plane(NP_VMV, A.VTM + nn); }
-    if (A.tau_wi) { tx += node_plane(NP_TWU, A.tau_wi); tx += node_plane(NP_TWV, A.tau_wi + nn); }
-    tx += stage<MODE>(sm + L.su, A.VTc + nb, no, 8, bar, ctr);
-    tx += stage<MODE>(sm + L.sv, A.VTc + nn + nb, no, 8, bar, ctr);
-    tx += stage<MODE>(sm + L.hn, A.halo_nodes + td.halo_off, td.n_halo, 4, bar, ctr);
-    tx += stage<MODE>(sm + L.he, A.halo_elems + td.halo_elem_off, td.n_halo_slots, 4, bar, ctr);
-    tx += stage<MODE>(sm + L.inc, A.inc + td.inc_off, td.inc_w * td.n_own, 2, bar, ctr);
-    tx += stage<MODE>(sm + L.fl, A.nflags + nb, no, 1, bar, ctr);
     return tx;
 }
 
@@ -352,7 +357,8 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar)
 {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-constexpr int SUB_CONS = SUB_TPB - 32;          // consumer threads; the last warp is the TMA producer
+constexpr int SUB_PROD = 128;                   // producer threads (4 warps): TMA issue + irregular gathers
+constexpr int SUB_CONS = SUB_TPB - SUB_PROD;    // consumer threads
 __device__ __forceinline__ void cons_sync() { asm volatile("bar.sync 1, %0;" ::"n"(SUB_CONS) : "memory"); }
 
 // Persistent, warp-specialised, double-buffered: CTA b works on tiles b, b+grid, b+2*grid, ... of its launch
@@ -370,24 +376,40 @@ k_subcycle(KParams K, SubArgs A)
     uint64_t* const empty = full + 2;
     unsigned char* const stage0 = sm_all + 64;
     if (tid == 0) {
-        mbar_init(full, 1); mbar_init(full + 1, 1);
+        mbar_init(full, SUB_PROD / 32); mbar_init(full + 1, SUB_PROD / 32);   // one arrival (with its TMA bytes) per producer warp
         mbar_init(empty, SUB_CONS / 32); mbar_init(empty + 1, SUB_CONS / 32);
     }
     __syncthreads();
     int const n_my = (A.n_tiles > (int)blockIdx.x) ? (A.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
 
     if (tid >= SUB_CONS) {
-        // ---- producer ----
-        if (tid == SUB_CONS) {
-            for (int it = 0; it < n_my; ++it) {
-                int const s = it & 1;
-                if (it >= 2) mbar_wait(empty + s, ((it >> 1) - 1) & 1);
-                int const tix = A.tile_base + (int)blockIdx.x + it * (int)gridDim.x;
-                TileDesc const td = A.tiles[A.tile_order ? A.tile_order[tix] : tix];
-                unsigned char* const sm = stage0 + (size_t)s * L.total;
-                mbar_expect_tx(full + s, stage_tile<0, BBM>(K, A, td, sm, full + s));
-                stage_tile<1, BBM>(K, A, td, sm, full + s);
+        // ---- producer warps: thread 0 streams the contiguous pieces with TMA; all producer threads gather the
+        // irregular ones (halo node velocities, halo slots' sigma/damage), one entry each, one tile ahead ----
+        int const p = tid - SUB_CONS;
+        for (int it = 0; it < n_my; ++it) {
+            int const s = it & 1;
+            int const tix = A.tile_base + (int)blockIdx.x + it * (int)gridDim.x;
+            TileDesc const td = A.tiles[A.tile_order ? A.tile_order[tix] : tix];
+            unsigned char* const sm = stage0 + (size_t)s * L.total;
+            if (it >= 2) mbar_wait(empty + s, ((it >> 1) - 1) & 1);
+            uint32_t tx = 0;
+            if ((p & 31) == 0) tx = stage_tile<BBM>(p >> 5, K, A, td, sm, full + s);
+            double* const su = (double*)(sm + L.su) + stage_shift(A.VTc + td.node_begin, 8);
+            double* const sv = (double*)(sm + L.sv) + stage_shift(A.VTc + nn + td.node_begin, 8);
+            double* const hsg = (double*)(sm + L.hsig);
+            int const nmax = max(td.n_halo, td.n_halo_slots);
+            for (int j = p; j < nmax; j += SUB_PROD) {
+                bool const hn_ok = j < td.n_halo, he_ok = j < td.n_halo_slots;
+                int const g = hn_ok ? A.halo_nodes[td.halo_off + j] : 0;
+                int const e = he_ok ? A.halo_elems[td.halo_elem_off + j] : 0;
+                double const u = A.VTc[g], v = A.VTc[g + nn];
+                double const a0 = A.s0i[e], a1 = A.s1i[e], a2 = A.s2i[e];
+                double const ad = BBM ? A.di[e] : 0.;
+                if (hn_ok) { su[td.n_own + j] = u; sv[td.n_own + j] = v; }
+                if (he_ok) { hsg[j] = a0; hsg[L.mhs + j] = a1; hsg[2 * L.mhs + j] = a2; if (BBM) hsg[3 * L.mhs + j] = ad; }
             }
+            __syncwarp();
+            if ((p & 31) == 0) mbar_expect_tx(full + s, tx);       // arrival of this warp: its gathers are done
         }
         return;
     }
@@ -411,27 +433,20 @@ k_subcycle(KParams K, SubArgs A)
     const double* const dgp = (const double*)(sm + L.dmg) + sh_el;
     double* const su = (double*)(sm + L.su) + sh_nu;
     double* const sv = (double*)(sm + L.sv) + sh_nv;
-    const int* const hn = (const int*)(sm + L.hn) + stage_shift(A.halo_nodes + td.halo_off, 4);
-    const int* const he = (const int*)(sm + L.he) + stage_shift(A.halo_elems + td.halo_elem_off, 4);
+    const double* const hsg = (const double*)(sm + L.hsig);       // halo slots' sigma/damage, gathered by the producer warp
+    int const MHS = L.mhs;
     const uint16_t* const incp = (const uint16_t*)(sm + L.inc) + stage_shift(A.inc + td.inc_off, 2);
     const uint8_t* const flp = (const uint8_t*)(sm + L.fl) + stage_shift(A.nflags + nb, 1);
     int const MSP = L.msp, MOP = L.mop, MTP = L.mtp;
 
     mbar_wait(full + s, (it >> 1) & 1);
 
-    // ---- phase 0: halo node velocities ----
-    for (int j = tid; j < td.n_halo; j += SUB_CONS) {
-        int const g = hn[j];
-        su[td.n_own + j] = A.VTc[g];
-        sv[td.n_own + j] = A.VTc[g + nn];
-    }
-    cons_sync();
-
     // ---- phase 1 ----
     int const nsl = td.n_own_slots + td.n_halo_slots;
     for (int k = tid; k < nsl; k += SUB_CONS) {
         bool const own = k < td.n_own_slots;
-        int const e = own ? td.elem_begin + k : he[k - td.n_own_slots];
+        int const e = td.elem_begin + k;            // meaningful for writer slots only
+        int const hk = k - td.n_own_slots;
         unsigned long long const pc = conn[k];
         int const la = (int)(pc & 0xFFFF), lb = (int)((pc >> 16) & 0xFFFF), lc = (int)((pc >> 32) & 0xFFFF);
         double const dx0 = shp[k], dx1 = shp[MSP + k], dx2 = shp[2 * MSP + k];
@@ -452,7 +467,7 @@ k_subcycle(KParams K, SubArgs A)
                 double e1 = dy0 * va; e1 += dy1 * vb; e1 += dy2 * vc;
                 double e2 = dy0 * ua; e2 += dx0 * va; e2 += dy1 * ub; e2 += dx1 * vb; e2 += dy2 * uc; e2 += dx2 * vc;
                 if (own) { s0 = sgp[k]; s1 = sgp[MOP + k]; s2 = sgp[2 * MOP + k]; d = dgp[k]; }
-                else     { s0 = A.s0i[e]; s1 = A.s1i[e]; s2 = A.s2i[e]; d = A.di[e]; }
+                else     { s0 = hsg[hk]; s1 = hsg[MHS + hk]; s2 = hsg[2 * MHS + hk]; d = hsg[3 * MHS + hk]; }
                 double const dt = K.dte;
                 double sigma_n = (s0 + s1) * 0.5;
                 double const omd = 1. - d;
@@ -496,7 +511,7 @@ k_subcycle(KParams K, SubArgs A)
                 double const delta = sqrt(eps1 * eps1 + (eps2 * eps2 + 4 * eps12 * eps12) * K.re2);
                 double const zeta = Pp / (delta + K.evp_dmin);
                 if (own) { s0 = sgp[k]; s1 = sgp[MOP + k]; s2 = sgp[2 * MOP + k]; }
-                else     { s0 = A.s0i[e]; s1 = A.s1i[e]; s2 = A.s2i[e]; }
+                else     { s0 = hsg[hk]; s1 = hsg[MHS + hk]; s2 = hsg[2 * MHS + hk]; }
                 double sigma1 = s0 + s1, sigma2 = s0 - s1;
                 sigma1 += K.ralpha1 * (zeta * (eps1 - delta) - sigma1);
                 sigma2 += K.ralpha2 * (zeta * eps2 * K.re2 - sigma2);
