@@ -43,7 +43,7 @@ static SmemLayout sub_layout(MeshPlan const& P, int n_node_planes)
     L.msp = P.msp;
     L.mop = (P.max_own_slots + 3) & ~1;
     L.mtp = (P.tile_nodes + 3) & ~1;
-    L.bar = (int)o;   o += 16;
+    L.bar = (int)o;   o += 64;              // the tile descriptor travels with the stage
     L.conn = (int)o;  o += al((size_t)L.msp * 8);
     L.shape = (int)o; o += (size_t)6 * L.msp * 8;
     L.ec = (int)o;    o += (size_t)6 * L.msp * 8;
@@ -59,7 +59,7 @@ static SmemLayout sub_layout(MeshPlan const& P, int n_node_planes)
     L.total = (int)o;
     return L;
 }
-constexpr int SUB_SMEM_CAP = 113 * 1024;      // per stage; two stages per persistent CTA, one CTA per SM (227 KB)
+constexpr int SUB_SMEM_CAP = (227 * 1024 - 64) / SUB_STAGES;     // per stage; one persistent CTA per SM (227 KB)
 
 // ---------------------------------------------------------------------------------------------------
 // life cycle
@@ -308,6 +308,8 @@ static KParams derive(nsx_solver const* S, NsxDynParams const& P)
         K.ralpha2 = 1. / P.mevp_alpha;
     }
     K.mevp_b = P.mevp_beta + 1.;
+    K.mevp_rb = 1. / K.mevp_b;
+    K.dte_mevp = K.dte / K.mevp_b;
     K.rhow_cdw = RHOW * P.quad_drag_coef_water;
     K.u0 = P.basal_u0;
     K.k1 = P.basal_k1; K.k2 = P.basal_k2; K.Cb = P.basal_Cb;
@@ -584,15 +586,15 @@ static void phase_prep(nsx_solver* S)
     NSX_CUDA(cudaGetLastError());
 }
 
-static void launch_tiles(nsx_solver* S, SubArgs const& A, int tile_base, int ntiles, cudaStream_t st)
+static void launch_tiles(nsx_solver* S, SubArgs const& A, int tile_base, int ntiles, cudaStream_t st, int max_ctas)
 {
     if (ntiles <= 0) return;
     SubArgs a = A;
     a.tile_base = tile_base;
     a.n_tiles = ntiles;
     // persistent CTAs, one per SM (two shared-memory stages each); CTA b takes tiles b, b+grid, ...
-    int const grid = std::min(ntiles, S->sm_count);
-    size_t const smem = 64 + 2 * (size_t)A.L.total;
+    int const grid = std::max(1, std::min(ntiles, max_ctas));
+    size_t const smem = 64 + (size_t)SUB_STAGES * A.L.total;
     if (S->K.dynamics_type == NSX_DYN_BBM) k_subcycle<1><<<grid, SUB_TPB, smem, st>>>(S->K, a);
     else k_subcycle<0><<<grid, SUB_TPB, smem, st>>>(S->K, a);
     S->n_launch++;
@@ -627,20 +629,47 @@ static void phase_substep(nsx_solver* S, int s, bool exchange_sync, bool overlap
         A.np[p] = use ? npl++ : 0;
     }
     A.L = sub_layout(S->plan, npl);
-    if (64 + 2 * (size_t)A.L.total > 227 * 1024) throw std::runtime_error("sub-cycle kernel: tile working set exceeds shared memory");
+    if (64 + (size_t)SUB_STAGES * A.L.total > 227 * 1024) throw std::runtime_error("sub-cycle kernel: tile working set exceeds shared memory");
     S->sub_smem = (size_t)A.L.total;
     int const nt = S->plan.ntiles, nb = S->n_boundary_tiles;
     if (overlap && nb > 0 && nb < nt) {
         NSX_CUDA(cudaEventRecord(S->ev_fork, S->stream));
         NSX_CUDA(cudaStreamWaitEvent(S->stream2, S->ev_fork, 0));
-        launch_tiles(S, A, 0, nb, S->stream);
-        launch_tiles(S, A, nb, nt - nb, S->stream2);
+        // The two persistent kernels must be co-resident (one CTA per SM each): give the boundary kernel B SMs and
+        // the interior kernel the rest, B balancing  boundary tiles / B + halo latency  against  interior / (SMs - B).
+        int B = 1;
+        double best = 1e300;
+        for (int b = 1; b <= std::min(nb, S->sm_count - 1); ++b) {
+            double const t_b = std::ceil((double)nb / b) * 4.0 + 8.0;
+            double const t_i = std::ceil((double)(nt - nb) / (S->sm_count - b)) * 4.0;
+            double const t = std::max(t_b, t_i);
+            if (t < best - 1e-9) { best = t; B = b; }
+        }
+        static const bool prof = (getenv("NSX_PROFILE_HALO") != nullptr);
+        cudaEvent_t pe[4] = {nullptr, nullptr, nullptr, nullptr};
+        if (prof && !S->capturing && s >= 8 && s < 40) {
+            for (auto& e : pe) NSX_CUDA(cudaEventCreate(&e));
+            NSX_CUDA(cudaEventRecord(pe[0], S->stream));
+        }
+        launch_tiles(S, A, 0, nb, S->stream, B);
+        if (pe[0]) NSX_CUDA(cudaEventRecord(pe[1], S->stream));
+        launch_tiles(S, A, nb, nt - nb, S->stream2, S->sm_count - B);
         NSX_CUDA(cudaEventRecord(S->ev_join, S->stream2));
+        if (pe[0]) NSX_CUDA(cudaEventRecord(pe[3], S->stream2));
         S->cur ^= 1;
         halo_exchange(S, exchange_sync);
+        if (pe[0]) NSX_CUDA(cudaEventRecord(pe[2], S->stream));
         NSX_CUDA(cudaStreamWaitEvent(S->stream, S->ev_join, 0));
+        if (pe[0]) {
+            NSX_CUDA(cudaStreamSynchronize(S->stream));
+            float tb = 0, th = 0, ti = 0;
+            cudaEventElapsedTime(&tb, pe[0], pe[1]); cudaEventElapsedTime(&th, pe[1], pe[2]); cudaEventElapsedTime(&ti, pe[0], pe[3]);
+            fprintf(stderr, "[nsx rank %d] sub-cycle %d: nb=%d nt=%d B=%d boundary %.1f us, halo %.1f us, interior(end) %.1f us\n",
+                    S->rank, s, nb, nt, B, tb * 1e3, th * 1e3, ti * 1e3);
+            for (auto& e : pe) cudaEventDestroy(e);
+        }
     } else {
-        launch_tiles(S, A, 0, nt, S->stream);
+        launch_tiles(S, A, 0, nt, S->stream, S->sm_count);
         S->cur ^= 1;
         if (exchange_sync) halo_exchange(S, true);
     }
@@ -865,4 +894,30 @@ extern "C" int nsx_check(nsx_handle S, NsxCheck* out)
     NSX_CUDA(cudaStreamSynchronize(S->stream));
     out->n_nan = hi[0]; out->n_speed = hi[1]; out->n_range = hi[2]; out->pad_ = 0; out->max_speed = hd;
     NSX_API_END(S)
+}
+
+// Host-only: builds the tile plan for a mesh exactly like nsx_create would (same shrink-to-fit loop) and returns
+// its statistics without touching the GPU.  out[0..9] = ntiles, nodes/tile, nslots, max_local_nodes, max_slots,
+// max_own_slots, max_halo_slots, max_halo_nodes, stage bytes (14 node planes), shrink attempts.
+extern "C" int nsx_plan_info(const NsxMesh* mesh, int target_tile_nodes, int wave_ctas, int* out, int n)
+{
+    try {
+        MeshPlan P;
+        int target = target_tile_nodes > 0 ? target_tile_nodes : 208;
+        int attempt = 0;
+        for (;; ++attempt) {
+            P = MeshPlan();
+            build_mesh_plan(mesh, P, target, wave_ctas);
+            if (sub_layout(P, 14).total <= SUB_SMEM_CAP) break;
+            if (attempt > 12 || target <= 32) break;
+            target = std::max(32, (int)(target * 0.88));
+        }
+        int const v[10] = {P.ntiles, P.tile_nodes, P.nslots, P.max_local_nodes, P.max_slots, P.max_own_slots,
+                           P.max_halo_slots, P.max_halo_nodes, sub_layout(P, 14).total, attempt};
+        for (int i = 0; i < n && i < 10; ++i) out[i] = v[i];
+        return 0;
+    } catch (std::exception const& e) {
+        g_create_err = e.what();
+        return 2;
+    }
 }

@@ -65,7 +65,7 @@ struct KParams {
     int    relax_int_pow;                  // exponent_relaxation_sigma-1 if a small integer, else -1
     // EVP / mEVP
     double evp_e, evp_Pstar, evp_C, evp_dmin, ralpha1, ralpha2, re2;
-    double mevp_b;                         // beta+1
+    double mevp_b, mevp_rb, dte_mevp;      // beta+1, 1/(beta+1), dte/(beta+1)
     // nodal solve
     double rhow_cdw, u0;
     // basal

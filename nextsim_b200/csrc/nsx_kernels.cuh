@@ -227,7 +227,51 @@ k_prep_nodes(KParams K, const uint8_t* __restrict__ nflags,
 #ifndef NSX_SUB_MINB
 #define NSX_SUB_MINB 2
 #endif
+#ifndef NSX_SUB_STAGES
+#define NSX_SUB_STAGES 2
+#endif
 constexpr int SUB_TPB = NSX_SUB_TPB;
+constexpr int SUB_STAGES = NSX_SUB_STAGES;     // shared-memory stages of the tile pipeline
+
+// ---- fast FP64 reciprocal / square root for the sub-cycle kernel ----
+// Hardware seed (MUFU.RCP64H / MUFU.RSQ64H, ~20 bits) + two Newton steps + one residual correction: <= 2 ulp,
+// a quarter of the instructions and of the dependent latency of the IEEE sequences.  Parity tolerance is 1e-9
+// relative L2, so the last-bit difference to the reference's libm/IEEE results is immaterial; arguments outside
+// a comfortable exponent range (zeros, denormals, infinities) take the exact slow path.
+__device__ __forceinline__ bool mid_range(double x)
+{
+    double const ax = fabs(x);
+    return ax > 1e-280 && ax < 1e280;
+}
+__device__ __forceinline__ double fast_div(double a, double b)
+{
+    if (!mid_range(b)) return a / b;
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(b));
+    double e = fma(-b, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-b, r, 1.0);
+    r = fma(r, e, r);
+    double const q = a * r;
+    return fma(r, fma(-b, q, a), q);
+}
+__device__ __forceinline__ double fast_sqrt(double x)
+{
+    if (!mid_range(x) || x < 0.) return sqrt(x);
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    double const h = 0.5 * x;
+    y = y * fma(-h * y, y, 1.5);
+    y = y * fma(-h * y, y, 1.5);
+    double const sq = x * y;
+    return fma(fma(-sq, sq, x), 0.5 * y, sq);
+}
+__device__ __forceinline__ double fast_hypot(double a, double b)
+{
+    double const q = fma(a, a, b * b);
+    if (!mid_range(q)) return hypot(a, b);
+    return fast_sqrt(q);
+}
 
 __device__ __forceinline__ double pow_relax(double q, KParams const& K)
 {
@@ -373,11 +417,13 @@ k_subcycle(KParams K, SubArgs A)
     int const nn = K.nn;
     int const tid = threadIdx.x;
     uint64_t* const full = (uint64_t*)sm_all;
-    uint64_t* const empty = full + 2;
+    uint64_t* const empty = full + SUB_STAGES;
     unsigned char* const stage0 = sm_all + 64;
     if (tid == 0) {
-        mbar_init(full, SUB_PROD / 32); mbar_init(full + 1, SUB_PROD / 32);   // one arrival (with its TMA bytes) per producer warp
-        mbar_init(empty, SUB_CONS / 32); mbar_init(empty + 1, SUB_CONS / 32);
+        for (int q = 0; q < SUB_STAGES; ++q) {
+            mbar_init(full + q, SUB_PROD / 32);       // one arrival (with its TMA bytes) per producer warp
+            mbar_init(empty + q, SUB_CONS / 32);      // one arrival per consumer warp
+        }
     }
     __syncthreads();
     int const n_my = (A.n_tiles > (int)blockIdx.x) ? (A.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
@@ -387,12 +433,13 @@ k_subcycle(KParams K, SubArgs A)
         // irregular ones (halo node velocities, halo slots' sigma/damage), one entry each, one tile ahead ----
         int const p = tid - SUB_CONS;
         for (int it = 0; it < n_my; ++it) {
-            int const s = it & 1;
+            int const s = it % SUB_STAGES;
             int const tix = A.tile_base + (int)blockIdx.x + it * (int)gridDim.x;
             TileDesc const td = A.tiles[A.tile_order ? A.tile_order[tix] : tix];
             unsigned char* const sm = stage0 + (size_t)s * L.total;
-            if (it >= 2) mbar_wait(empty + s, ((it >> 1) - 1) & 1);
+            if (it >= SUB_STAGES) mbar_wait(empty + s, ((it / SUB_STAGES) - 1) & 1);
             uint32_t tx = 0;
+            if (p == 0) *(TileDesc*)(sm + L.bar) = td;              // consumers read the descriptor from the stage
             if ((p & 31) == 0) tx = stage_tile<BBM>(p >> 5, K, A, td, sm, full + s);
             double* const su = (double*)(sm + L.su) + stage_shift(A.VTc + td.node_begin, 8);
             double* const sv = (double*)(sm + L.sv) + stage_shift(A.VTc + nn + td.node_begin, 8);
@@ -416,10 +463,10 @@ k_subcycle(KParams K, SubArgs A)
 
     // ---- consumers ----
     for (int it = 0; it < n_my; ++it) {
-    int const s = it & 1;
-    int const tix = A.tile_base + (int)blockIdx.x + it * (int)gridDim.x;
-    TileDesc const td = A.tiles[A.tile_order ? A.tile_order[tix] : tix];
+    int const s = it % SUB_STAGES;
     unsigned char* const sm = stage0 + (size_t)s * L.total;
+    mbar_wait(full + s, (it / SUB_STAGES) & 1);
+    TileDesc const td = *(const TileDesc*)(sm + L.bar);
 
     // shifted views of the staged planes
     int const nb = td.node_begin;
@@ -438,8 +485,6 @@ k_subcycle(KParams K, SubArgs A)
     const uint16_t* const incp = (const uint16_t*)(sm + L.inc) + stage_shift(A.inc + td.inc_off, 2);
     const uint8_t* const flp = (const uint8_t*)(sm + L.fl) + stage_shift(A.nflags + nb, 1);
     int const MSP = L.msp, MOP = L.mop, MTP = L.mtp;
-
-    mbar_wait(full + s, (it >> 1) & 1);
 
     // ---- phase 1 ----
     int const nsl = td.n_own_slots + td.n_halo_slots;
@@ -475,21 +520,21 @@ k_subcycle(KParams K, SubArgs A)
                 double tildeP = 0.;
                 if (sigma_n < 0.) {
                     double const Pmax = ecp[MSP + k];
-                    tildeP = fmin(1., -Pmax / sigma_n);
+                    tildeP = fmin(1., fast_div(-Pmax, sigma_n));
                 }
-                double const mult = fmin(1. - 1e-12, time_viscous / (time_viscous + dt * (1. - tildeP)));
+                double const mult = fmin(1. - 1e-12, fast_div(time_viscous, time_viscous + dt * (1. - tildeP)));
                 double const elasticity = K.young * omd * expC;
                 double const dtE = dt * elasticity;
                 s0 += dtE * K.D00 * e0;  s0 += dtE * K.D01 * e1;  s0 *= mult;
                 s1 += dtE * K.D01 * e0;  s1 += dtE * K.D00 * e1;  s1 *= mult;
                 s2 += dtE * K.D22 * e2;                           s2 *= mult;
-                double const sigma_s = hypot((s0 - s1) / 2., s2);
+                double const sigma_s = fast_hypot((s0 - s1) * 0.5, s2);
                 sigma_n = (s0 + s1) * 0.5;
                 double dcrit;
-                if (sigma_n < -K.compr_strength) dcrit = -K.compr_strength / sigma_n;
-                else dcrit = ecp[2 * MSP + k] / (sigma_s + K.tan_phi * sigma_n);
+                if (sigma_n < -K.compr_strength) dcrit = fast_div(-K.compr_strength, sigma_n);
+                else dcrit = fast_div(ecp[2 * MSP + k], sigma_s + K.tan_phi * sigma_n);
                 if ((0. < dcrit) && (dcrit < 1.)) {
-                    double const rtd = sqrt(elasticity) * ecp[3 * MSP + k];
+                    double const rtd = fast_sqrt(elasticity) * ecp[3 * MSP + k];
                     double const f = (1. - dcrit) * dt * rtd;
                     d += omd * f;
                     s0 -= s0 * f;  s1 -= s1 * f;  s2 -= s2 * f;
@@ -508,8 +553,8 @@ k_subcycle(KParams K, SubArgs A)
                 double eps22 = dy0 * va; eps22 += dy1 * vb; eps22 += dy2 * vc;
                 double eps12 = 0.5 * (dx0 * va + dy0 * ua); eps12 += 0.5 * (dx1 * vb + dy1 * ub); eps12 += 0.5 * (dx2 * vc + dy2 * uc);
                 double const eps1 = eps11 + eps22, eps2 = eps11 - eps22;
-                double const delta = sqrt(eps1 * eps1 + (eps2 * eps2 + 4 * eps12 * eps12) * K.re2);
-                double const zeta = Pp / (delta + K.evp_dmin);
+                double const delta = fast_sqrt(eps1 * eps1 + (eps2 * eps2 + 4 * eps12 * eps12) * K.re2);
+                double const zeta = fast_div(Pp, delta + K.evp_dmin);
                 if (own) { s0 = sgp[k]; s1 = sgp[MOP + k]; s2 = sgp[2 * MOP + k]; }
                 else     { s0 = hsg[hk]; s1 = hsg[MHS + hk]; s2 = hsg[2 * MHS + hk]; }
                 double sigma1 = s0 + s1, sigma2 = s0 - s1;
@@ -551,18 +596,18 @@ k_subcycle(KParams K, SubArgs A)
             }
             double dtep = K.dte, delu = 0., delv = 0.;
             if (K.dynamics_type == NSX_DYN_MEVP) {
-                delu = (npl[A.np[NP_VMU] * MTP + shs + j] - uice) / K.mevp_b;
-                delv = (npl[A.np[NP_VMV] * MTP + sh_nv + j] - vice) / K.mevp_b;
-                dtep = K.dte / K.mevp_b;
+                delu = (npl[A.np[NP_VMU] * MTP + shs + j] - uice) * K.mevp_rb;
+                delv = (npl[A.np[NP_VMV] * MTP + sh_nv + j] - vice) * K.mevp_rb;
+                dtep = K.dte_mevp;
             }
-            double const dte_over_mass = dtep / fmax(K.min_m, nm);
+            double const dte_over_mass = fast_div(dtep, fmax(K.min_m, nm));
             double const ou = npl[A.np[NP_OCU] * MTP + shs + j], ov = npl[A.np[NP_OCV] * MTP + sh_nv + j];
-            double const c_prime = K.rhow_cdw * hypot(ou - uice, ov - vice);
-            double const tau_b = npl[A.np[NP_CBU] * MTP + shs + j] / (hypot(uice, vice) + K.u0);
+            double const c_prime = K.rhow_cdw * fast_hypot(ou - uice, ov - vice);
+            double const tau_b = npl[A.np[NP_CBU] * MTP + shs + j] * fast_div(1., fast_hypot(uice, vice) + K.u0);
             double const sin_s = (fl & NF_LATNEG) ? -K.sin_ota_abs : K.sin_ota_abs;   // std::copysign(sin, lat[i])
             double const alpha = 1. + dte_over_mass * (c_prime * K.cos_ota + tau_b);
             double const beta = dtep * npl[A.np[NP_FCOR] * MTP + shs + j] + dte_over_mass * c_prime * sin_s;
-            double const rdenom = 1. / (alpha * alpha + beta * beta);
+            double const rdenom = fast_div(1., alpha * alpha + beta * beta);
             double tau_x = npl[A.np[NP_TAU] * MTP + shs + j], tau_y = npl[A.np[NP_TAV] * MTP + sh_nv + j];
             if (A.tau_wi) { tau_x = tau_x + npl[A.np[NP_TWU] * MTP + shs + j]; tau_y = tau_y + npl[A.np[NP_TWV] * MTP + sh_nv + j]; }
             tau_x = tau_x + c_prime * (ou * K.cos_ota - ov * sin_s);

@@ -9,6 +9,8 @@
 
 #include <algorithm>
 #include <climits>
+#include <cstdio>
+#include <cstdlib>
 #include <cmath>
 #include <numeric>
 #include <stdexcept>
@@ -62,17 +64,19 @@ void build_mesh_plan(const NsxMesh* M, MeshPlan& P, int target_tile_nodes, int s
     P.ell_w = w;
 
     // ---- node permutation: Hilbert order, owned first ---------------------------------------------------
+    // bounding box of the OWNED nodes, each axis stretched to the full curve square: a domain edge that pokes a
+    // little beyond a major quadrant line would otherwise be cut off as a one-node-wide sliver tile
     double xmin = M->coord_x[0], xmax = xmin, ymin = M->coord_y[0], ymax = ymin;
-    for (int n = 1; n < nn; ++n) {
+    for (int n = 1; n < ndof; ++n) {
         xmin = std::min(xmin, M->coord_x[n]); xmax = std::max(xmax, M->coord_x[n]);
         ymin = std::min(ymin, M->coord_y[n]); ymax = std::max(ymax, M->coord_y[n]);
     }
-    double const span = std::max(std::max(xmax - xmin, ymax - ymin), 1e-300);
+    double const spanx = std::max(xmax - xmin, 1e-300), spany = std::max(ymax - ymin, 1e-300);
     std::vector<uint64_t> key(nn);
     for (int n = 0; n < nn; ++n) {
-        uint32_t const ix = (uint32_t)std::min(65535.0, (M->coord_x[n] - xmin) / span * 65535.0);
-        uint32_t const iy = (uint32_t)std::min(65535.0, (M->coord_y[n] - ymin) / span * 65535.0);
-        key[n] = hilbert_xy2d(ix, iy);
+        double const fx = std::min(1.0, std::max(0.0, (M->coord_x[n] - xmin) / spanx));
+        double const fy = std::min(1.0, std::max(0.0, (M->coord_y[n] - ymin) / spany));
+        key[n] = hilbert_xy2d((uint32_t)(fx * 65535.0), (uint32_t)(fy * 65535.0));
     }
     P.node_inv.resize(nn);
     std::iota(P.node_inv.begin(), P.node_inv.end(), 0);
@@ -258,6 +262,8 @@ void build_mesh_plan(const NsxMesh* M, MeshPlan& P, int target_tile_nodes, int s
         P.max_halo_slots = std::max(P.max_halo_slots, nh);
         P.max_halo_nodes = std::max(P.max_halo_nodes, nhn);
         P.max_inc = std::max(P.max_inc, dmax * td.n_own);
+        if (getenv("NSX_PLAN_DEBUG") && (nh > 250 || nhn > 250))
+            fprintf(stderr, "tile %d/%d: node_begin %d n_own %d own_slots %d halo_slots %d halo_nodes %d x=%.0f y=%.0f\n", t, ntiles, td.node_begin, td.n_own, td.n_own_slots, nh, nhn, P.x[td.node_begin], P.y[td.node_begin]);
     }
     // slot space is padded to an even count so that every slot plane (stride nslots) has the same 16-byte
     // phase; the pad slot is never computed (marked INT_MIN)
