@@ -228,7 +228,7 @@ k_prep_nodes(KParams K, const uint8_t* __restrict__ nflags,
 #define NSX_SUB_MINB 2
 #endif
 #ifndef NSX_SUB_STAGES
-#define NSX_SUB_STAGES 2
+#define NSX_SUB_STAGES 3
 #endif
 constexpr int SUB_TPB = NSX_SUB_TPB;
 constexpr int SUB_STAGES = NSX_SUB_STAGES;     // shared-memory stages of the tile pipeline
@@ -403,7 +403,17 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar)
 }
 constexpr int SUB_PROD = 128;                   // producer threads (4 warps): TMA issue + irregular gathers
 constexpr int SUB_CONS = SUB_TPB - SUB_PROD;    // consumer threads
-__device__ __forceinline__ void cons_sync() { asm volatile("bar.sync 1, %0;" ::"n"(SUB_CONS) : "memory"); }
+#ifndef NSX_SUB_GROUPS
+#define NSX_SUB_GROUPS 2
+#endif
+constexpr int SUB_GROUPS = NSX_SUB_GROUPS;      // consumer groups, each working on its own tile (latency chains overlap)
+constexpr int SUB_GS = SUB_CONS / SUB_GROUPS;   // threads per consumer group
+static_assert(SUB_GS % 32 == 0 && SUB_GS * SUB_GROUPS == SUB_CONS, "consumer groups must be whole warps");
+static_assert(SUB_STAGES > SUB_GROUPS || SUB_GROUPS == 1, "need one more stage than tiles in compute");
+__device__ __forceinline__ void cons_sync(int group)
+{
+    asm volatile("bar.sync %0, %1;" ::"r"(1 + group), "n"(SUB_GS) : "memory");
+}
 
 // Persistent, warp-specialised, double-buffered: CTA b works on tiles b, b+grid, b+2*grid, ... of its launch
 // range.  The producer warp streams tile t+1 into the other stage while the consumer warps compute tile t
@@ -422,7 +432,7 @@ k_subcycle(KParams K, SubArgs A)
     if (tid == 0) {
         for (int q = 0; q < SUB_STAGES; ++q) {
             mbar_init(full + q, SUB_PROD / 32);       // one arrival (with its TMA bytes) per producer warp
-            mbar_init(empty + q, SUB_CONS / 32);      // one arrival per consumer warp
+            mbar_init(empty + q, SUB_GS / 32);        // one arrival per warp of the consuming group
         }
     }
     __syncthreads();
@@ -462,7 +472,9 @@ k_subcycle(KParams K, SubArgs A)
     }
 
     // ---- consumers ----
-    for (int it = 0; it < n_my; ++it) {
+    int const grp = tid / SUB_GS;               // consumer group; it takes tiles grp, grp + SUB_GROUPS, ...
+    int const gtid = tid - grp * SUB_GS;
+    for (int it = grp; it < n_my; it += SUB_GROUPS) {
     int const s = it % SUB_STAGES;
     unsigned char* const sm = stage0 + (size_t)s * L.total;
     mbar_wait(full + s, (it / SUB_STAGES) & 1);
@@ -488,7 +500,7 @@ k_subcycle(KParams K, SubArgs A)
 
     // ---- phase 1 ----
     int const nsl = td.n_own_slots + td.n_halo_slots;
-    for (int k = tid; k < nsl; k += SUB_CONS) {
+    for (int k = gtid; k < nsl; k += SUB_GS) {
         bool const own = k < td.n_own_slots;
         int const e = td.elem_begin + k;            // meaningful for writer slots only
         int const hk = k - td.n_own_slots;
@@ -574,12 +586,12 @@ k_subcycle(KParams K, SubArgs A)
         shp[4 * MSP + k] = vol * (s2 * dx1 + s1 * dy1);
         shp[5 * MSP + k] = vol * (s2 * dx2 + s1 * dy2);
     }
-    cons_sync();
+    cons_sync(grp);
 
     // ---- phase 2 ----
     const double* const npl = (const double*)(sm + L.node);
     int const shs = stage_shift(A.node_mass + nb, 8);       // scalar node planes and u halves: same phase as nb
-    for (int j = tid; j < td.n_own; j += SUB_CONS) {
+    for (int j = gtid; j < td.n_own; j += SUB_GS) {
         int const n = nb + j;
         uint8_t const fl = flp[j];
         double const uice = su[j], vice = sv[j];
@@ -632,7 +644,7 @@ k_subcycle(KParams K, SubArgs A)
     }
     // ghost nodes: moved with the velocity their owner pushed at the end of the previous sub-cycle
     if (A.lag_ghost_move) {
-        for (int j = tid; j < td.n_ghost; j += SUB_CONS) {
+        for (int j = gtid; j < td.n_ghost; j += SUB_GS) {
             int const n = td.ghost_begin + j;
             double const u = A.VTc[n], v = A.VTc[n + nn];
             A.UT[n] += K.dte * u;  A.UT[n + nn] += K.dte * v;
