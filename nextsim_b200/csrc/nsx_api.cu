@@ -115,6 +115,15 @@ static void alloc_fields(nsx_solver* S)
     S->slot_shape.alloc(6 * ns); S->slot_shape.zero(st);
     S->slot_ec.alloc(6 * ns); S->slot_ec.zero(st);
     S->stage.alloc(std::max(2 * nn, 6 * ne));
+    // Path selection: the sub-cycle working set (~300 B per element) either lives in the 126 MB L2 (direct path)
+    // or streams from HBM (TMA tile pipeline).  NSX_PATH=direct|tiles overrides.
+    {
+        const char* pth = getenv("NSX_PATH");
+        S->direct = (double)ne * 300.0 < 90e6;
+        if (pth && !strcmp(pth, "direct")) S->direct = true;
+        if (pth && !strcmp(pth, "tiles")) S->direct = false;
+        if (S->direct) { S->ec_e.alloc(6 * ne); S->ec_e.zero(st); S->contrib.alloc(6 * ne); S->contrib.zero(st); }
+    }
     S->ow_list.alloc(S->ndof); S->ow_count.alloc(1); S->ow_count.zero(st);
     S->check_i.alloc(4); S->check_d.alloc(1);
     S->halo_err.alloc(1); S->halo_err.zero(st);
@@ -576,7 +585,7 @@ static void phase_prep(nsx_solver* S)
     k_prep_elements<<<nblk(S->plan.nslots), TPB, 0, st>>>(K, S->plan.nslots, S->slot_elem.p, S->en0.p, S->en1.p, S->en2.p,
         S->x.p, S->y.p, S->UM.p, S->conc.p, S->thick.p, S->snow.p, S->conc_young.p, S->h_young.p, S->hs_young.p,
         S->depth.p, S->ssh.p, S->cohesion.p, S->t_heal.p, S->surface.p, S->delta_x.p, S->shape.p, S->emass.p, S->ecbu.p,
-        S->slot_shape.p, S->slot_ec.p);
+        S->slot_shape.p, S->slot_ec.p, S->direct ? S->ec_e.p : nullptr);
     k_prep_nodes<<<nblk(S->nn), TPB, 0, st>>>(K, S->nflags.p, S->n2e.p, S->n2e_deg.p, S->nec.p, S->plan.nec_w,
         S->en0.p, S->en1.p, S->en2.p, S->surface.p, S->emass.p, S->ecbu.p, S->shape.p, S->ssh.p,
         S->drag_ui.p, S->drag_ui_young.p, S->conc.p, S->conc_young.p, S->wind.p, S->lat.p,
@@ -632,7 +641,21 @@ static void phase_substep(nsx_solver* S, int s, bool exchange_sync, bool overlap
     if (64 + (size_t)SUB_STAGES * A.L.total > 227 * 1024) throw std::runtime_error("sub-cycle kernel: tile working set exceeds shared memory");
     S->sub_smem = (size_t)A.L.total;
     int const nt = S->plan.ntiles, nb = S->n_boundary_tiles;
-    if (overlap && nb > 0 && nb < nt) {
+    if (S->direct) {
+        cudaStream_t st = S->stream;
+        if (bbm)
+            k_element_direct<1><<<nblk(S->ne), TPB, 0, st>>>(K, S->en0.p, S->en1.p, S->en2.p, A.VTc, S->shape.p, S->ec_e.p,
+                A.s0i, A.s1i, A.s2i, A.di, A.s0o, A.s1o, A.s2o, A.dmo, S->contrib.p);
+        else
+            k_element_direct<0><<<nblk(S->ne), TPB, 0, st>>>(K, S->en0.p, S->en1.p, S->en2.p, A.VTc, S->shape.p, S->ec_e.p,
+                A.s0i, A.s1i, A.s2i, nullptr, A.s0o, A.s1o, A.s2o, nullptr, S->contrib.p);
+        k_node_direct<<<nblk(S->nn), TPB, 0, st>>>(K, A.move_mesh, A.lag_ghost_move, S->nflags.p, S->n2e.p, S->n2e_deg.p,
+            S->contrib.p, S->grad_ssh.p, S->node_mass.p, S->rlmass.p, S->cbu.p, S->fcor.p, S->tau_a.p, A.tau_wi,
+            S->ocean.p, S->VTM.p, A.VTc, A.VTn, S->UM.p, S->UT.p);
+        S->n_launch += 2;
+        S->cur ^= 1;
+        if (exchange_sync) halo_exchange(S, true);
+    } else if (overlap && nb > 0 && nb < nt) {
         NSX_CUDA(cudaEventRecord(S->ev_fork, S->stream));
         NSX_CUDA(cudaStreamWaitEvent(S->stream2, S->ev_fork, 0));
         // The two persistent kernels must be co-resident (one CTA per SM each): give the boundary kernel B SMs and

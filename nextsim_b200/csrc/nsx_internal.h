@@ -139,6 +139,8 @@ struct nsx_solver {
     nsx::DBuf<double> del_ci_ridge_myi;
     nsx::DBuf<double> emass, ecbu;               // element mass, element C_bu
     nsx::DBuf<double> node_mass, rlmass, cbu, fcor, grad_ssh;
+    nsx::DBuf<double> ec_e, contrib;             // direct path: element-space rheology constants, staged contributions
+    bool direct = false;                         // L2-resident mesh: element kernel + node kernel instead of the tile kernel
     nsx::DBuf<double> stage;                     // transfer staging (host numbering), max(2nn, 6ne)
     nsx::DBuf<int> ow_list;                      // open-water nodes to smooth
     nsx::DBuf<int> ow_count;

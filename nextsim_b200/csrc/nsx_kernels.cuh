@@ -35,7 +35,7 @@ k_prep_elements(KParams K, int nslots, const int* __restrict__ slot_elem,
                 const double* __restrict__ cohesion, const double* __restrict__ t_heal,
                 double* __restrict__ surface, double* __restrict__ delta_x, double* __restrict__ shape,
                 double* __restrict__ emass, double* __restrict__ ecbu,
-                double* __restrict__ slot_shape, double* __restrict__ slot_ec)
+                double* __restrict__ slot_shape, double* __restrict__ slot_ec, double* __restrict__ ec_e)
 {
     int const s = blockIdx.x * blockDim.x + threadIdx.x;
     int const ne = K.ne, nn = K.nn;
@@ -88,6 +88,10 @@ k_prep_elements(KParams K, int nslots, const int* __restrict__ slot_elem,
     }
     if (!own) return;
 
+    if (ec_e) {                 // element-space copy of the rheology constants for the direct (small-mesh) path
+        int const npl = (K.dynamics_type == NSX_DYN_BBM) ? 6 : 2;
+        for (int k = 0; k < npl; ++k) ec_e[(size_t)k * ne + e] = slot_ec[(size_t)k * nslots + s];
+    }
     delta_x[e] = dx;
     surface[e] = A;
 #pragma unroll
@@ -228,7 +232,7 @@ k_prep_nodes(KParams K, const uint8_t* __restrict__ nflags,
 #define NSX_SUB_MINB 2
 #endif
 #ifndef NSX_SUB_STAGES
-#define NSX_SUB_STAGES 3
+#define NSX_SUB_STAGES 2
 #endif
 constexpr int SUB_TPB = NSX_SUB_TPB;
 constexpr int SUB_STAGES = NSX_SUB_STAGES;     // shared-memory stages of the tile pipeline
@@ -404,7 +408,7 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar)
 constexpr int SUB_PROD = 128;                   // producer threads (4 warps): TMA issue + irregular gathers
 constexpr int SUB_CONS = SUB_TPB - SUB_PROD;    // consumer threads
 #ifndef NSX_SUB_GROUPS
-#define NSX_SUB_GROUPS 2
+#define NSX_SUB_GROUPS 1
 #endif
 constexpr int SUB_GROUPS = NSX_SUB_GROUPS;      // consumer groups, each working on its own tile (latency chains overlap)
 constexpr int SUB_GS = SUB_CONS / SUB_GROUPS;   // threads per consumer group
@@ -655,6 +659,166 @@ k_subcycle(KParams K, SubArgs A)
     __syncwarp();
     if ((tid & 31) == 0) mbar_arrive(empty + s);
     }   // tile loop
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Direct path for meshes whose working set is L2-resident (a few 1e5 elements per GPU): one thread per element,
+// then one thread per node.  The staging machinery of the tile kernel costs more latency per sub-cycle than it
+// saves in traffic when nothing comes from HBM anyway.  Same arithmetic, same summation order (the node kernel
+// walks the ascending-element ELL table and subtracts the staged contributions starting from grad_ssh).
+// ---------------------------------------------------------------------------------------------------
+template <int BBM>
+__global__ void __launch_bounds__(TPB)
+k_element_direct(KParams K, const int* __restrict__ en0, const int* __restrict__ en1, const int* __restrict__ en2,
+                 const double* __restrict__ VT, const double* __restrict__ shape, const double* __restrict__ ec,
+                 const double* __restrict__ s0i, const double* __restrict__ s1i, const double* __restrict__ s2i,
+                 const double* __restrict__ di, double* __restrict__ s0o, double* __restrict__ s1o,
+                 double* __restrict__ s2o, double* __restrict__ dmo, double* __restrict__ contrib)
+{
+    int const e = blockIdx.x * blockDim.x + threadIdx.x;
+    int const ne = K.ne, nn = K.nn;
+    if (e >= ne) return;
+    size_t const NE = (size_t)ne;
+    double const c0 = ec[e];
+    double const dx0 = shape[e], dx1 = shape[NE + e], dx2 = shape[2 * NE + e];
+    double const dy0 = shape[3 * NE + e], dy1 = shape[4 * NE + e], dy2 = shape[5 * NE + e];
+    double s0, s1, s2, vol;
+    if (BBM) {
+        double const expC = c0;
+        vol = ec[5 * NE + e];
+        double d;
+        if (expC == 0.) {
+            s0 = s1 = s2 = 0.;
+            d = 0.;
+        } else {
+            int const a = en0[e], b = en1[e], c = en2[e];
+            double const ua = VT[a], va = VT[a + nn], ub = VT[b], vb = VT[b + nn], uc = VT[c], vc = VT[c + nn];
+            double e0 = dx0 * ua; e0 += dx1 * ub; e0 += dx2 * uc;
+            double e1 = dy0 * va; e1 += dy1 * vb; e1 += dy2 * vc;
+            double e2 = dy0 * ua; e2 += dx0 * va; e2 += dy1 * ub; e2 += dx1 * vb; e2 += dy2 * uc; e2 += dx2 * vc;
+            s0 = s0i[e]; s1 = s1i[e]; s2 = s2i[e]; d = di[e];
+            double const dt = K.dte;
+            double sigma_n = (s0 + s1) * 0.5;
+            double const omd = 1. - d;
+            double const time_viscous = K.lambda0 * pow_relax(omd * expC, K);
+            double tildeP = 0.;
+            if (sigma_n < 0.) tildeP = fmin(1., fast_div(-ec[NE + e], sigma_n));
+            double const mult = fmin(1. - 1e-12, fast_div(time_viscous, time_viscous + dt * (1. - tildeP)));
+            double const elasticity = K.young * omd * expC;
+            double const dtE = dt * elasticity;
+            s0 += dtE * K.D00 * e0;  s0 += dtE * K.D01 * e1;  s0 *= mult;
+            s1 += dtE * K.D01 * e0;  s1 += dtE * K.D00 * e1;  s1 *= mult;
+            s2 += dtE * K.D22 * e2;                           s2 *= mult;
+            double const sigma_s = fast_hypot((s0 - s1) * 0.5, s2);
+            sigma_n = (s0 + s1) * 0.5;
+            double dcrit;
+            if (sigma_n < -K.compr_strength) dcrit = fast_div(-K.compr_strength, sigma_n);
+            else dcrit = fast_div(ec[2 * NE + e], sigma_s + K.tan_phi * sigma_n);
+            if ((0. < dcrit) && (dcrit < 1.)) {
+                double const rtd = fast_sqrt(elasticity) * ec[3 * NE + e];
+                double const f = (1. - dcrit) * dt * rtd;
+                d += omd * f;
+                s0 -= s0 * f;  s1 -= s1 * f;  s2 -= s2 * f;
+            }
+            d = fmax(0., d - ec[4 * NE + e]);
+        }
+        dmo[e] = d;
+    } else {
+        double const Pp = c0;
+        vol = ec[NE + e];
+        if (Pp < 0.) {
+            s0 = s1 = s2 = 0.;
+        } else {
+            int const a = en0[e], b = en1[e], c = en2[e];
+            double const ua = VT[a], va = VT[a + nn], ub = VT[b], vb = VT[b + nn], uc = VT[c], vc = VT[c + nn];
+            double eps11 = dx0 * ua; eps11 += dx1 * ub; eps11 += dx2 * uc;
+            double eps22 = dy0 * va; eps22 += dy1 * vb; eps22 += dy2 * vc;
+            double eps12 = 0.5 * (dx0 * va + dy0 * ua); eps12 += 0.5 * (dx1 * vb + dy1 * ub); eps12 += 0.5 * (dx2 * vc + dy2 * uc);
+            double const eps1 = eps11 + eps22, eps2 = eps11 - eps22;
+            double const delta = fast_sqrt(eps1 * eps1 + (eps2 * eps2 + 4 * eps12 * eps12) * K.re2);
+            double const zeta = fast_div(Pp, delta + K.evp_dmin);
+            s0 = s0i[e]; s1 = s1i[e]; s2 = s2i[e];
+            double sigma1 = s0 + s1, sigma2 = s0 - s1;
+            sigma1 += K.ralpha1 * (zeta * (eps1 - delta) - sigma1);
+            sigma2 += K.ralpha2 * (zeta * eps2 * K.re2 - sigma2);
+            s2 += K.ralpha2 * (zeta * eps12 * K.re2 - s2);
+            s0 = 0.5 * (sigma1 + sigma2);
+            s1 = 0.5 * (sigma1 - sigma2);
+        }
+    }
+    s0o[e] = s0; s1o[e] = s1; s2o[e] = s2;
+    contrib[0 * NE + e] = vol * (s0 * dx0 + s2 * dy0);
+    contrib[1 * NE + e] = vol * (s0 * dx1 + s2 * dy1);
+    contrib[2 * NE + e] = vol * (s0 * dx2 + s2 * dy2);
+    contrib[3 * NE + e] = vol * (s2 * dx0 + s1 * dy0);
+    contrib[4 * NE + e] = vol * (s2 * dx1 + s1 * dy1);
+    contrib[5 * NE + e] = vol * (s2 * dx2 + s1 * dy2);
+}
+
+__global__ void __launch_bounds__(TPB)
+k_node_direct(KParams K, int move_mesh, int lag_ghost_move,
+              const uint8_t* __restrict__ nflags, const int* __restrict__ n2e, const int* __restrict__ n2e_deg,
+              const double* __restrict__ contrib, const double* __restrict__ grad_ssh,
+              const double* __restrict__ node_mass, const double* __restrict__ rlmass,
+              const double* __restrict__ cbu, const double* __restrict__ fcor,
+              const double* __restrict__ tau_a, const double* __restrict__ tau_wi,
+              const double* __restrict__ ocean, const double* __restrict__ VTM,
+              const double* __restrict__ VTc, double* __restrict__ VTn,
+              double* __restrict__ UM, double* __restrict__ UT)
+{
+    int const n = blockIdx.x * blockDim.x + threadIdx.x;
+    int const nn = K.nn, ne = K.ne;
+    if (n >= nn) return;
+    uint8_t const fl = nflags[n];
+    double const uice = VTc[n], vice = VTc[n + nn];
+    if (fl & NF_GHOST) {
+        if (lag_ghost_move) {
+            UT[n] += K.dte * uice;  UT[n + nn] += K.dte * vice;
+            if (!(fl & NF_NEUMANN)) { UM[n] += K.dte * uice;  UM[n + nn] += K.dte * vice; }
+        }
+        return;
+    }
+    double un = uice, vn = vice;
+    double const nm = node_mass[n];
+    if (!(fl & NF_DIRICHLET) && nm != 0.) {
+        double gu = grad_ssh[n], gv = grad_ssh[n + nn];
+        int const deg = n2e_deg[n];
+        for (int k = 0; k < deg; ++k) {
+            int const s = n2e[(size_t)k * nn + n];
+            gu -= contrib[s];
+            gv -= contrib[s + 3 * (size_t)ne];
+        }
+        double dtep = K.dte, delu = 0., delv = 0.;
+        if (K.dynamics_type == NSX_DYN_MEVP) {
+            delu = (VTM[n] - uice) * K.mevp_rb;
+            delv = (VTM[n + nn] - vice) * K.mevp_rb;
+            dtep = K.dte_mevp;
+        }
+        double const dte_over_mass = fast_div(dtep, fmax(K.min_m, nm));
+        double const ou = ocean[n], ov = ocean[n + nn];
+        double const c_prime = K.rhow_cdw * fast_hypot(ou - uice, ov - vice);
+        double const tau_b = cbu[n] * fast_div(1., fast_hypot(uice, vice) + K.u0);
+        double const sin_s = (fl & NF_LATNEG) ? -K.sin_ota_abs : K.sin_ota_abs;
+        double const alpha = 1. + dte_over_mass * (c_prime * K.cos_ota + tau_b);
+        double const beta = dtep * fcor[n] + dte_over_mass * c_prime * sin_s;
+        double const rdenom = fast_div(1., alpha * alpha + beta * beta);
+        double tau_x = tau_a[n], tau_y = tau_a[n + nn];
+        if (tau_wi) { tau_x = tau_x + tau_wi[n]; tau_y = tau_y + tau_wi[n + nn]; }
+        tau_x = tau_x + c_prime * (ou * K.cos_ota - ov * sin_s);
+        tau_y = tau_y + c_prime * (ov * K.cos_ota + ou * sin_s);
+        double const rl = rlmass[n];
+        double const grad_x = gu * rl, grad_y = gv * rl;
+        un = alpha * uice + beta * vice + dte_over_mass * (alpha * (grad_x + tau_x) + beta * (grad_y + tau_y)) + alpha * delu + beta * delv;
+        un *= rdenom;
+        vn = alpha * vice - beta * uice + dte_over_mass * (alpha * (grad_y + tau_y) - beta * (grad_x + tau_x)) + alpha * delv - beta * delu;
+        vn *= rdenom;
+    }
+    VTn[n] = un;
+    VTn[n + nn] = vn;
+    if (move_mesh) {
+        UT[n] += K.dte * un;  UT[n + nn] += K.dte * vn;
+        if (!(fl & NF_NEUMANN)) { UM[n] += K.dte * un;  UM[n + nn] += K.dte * vn; }
+    }
 }
 
 // mesh move over an explicit node range with an explicit time increment:

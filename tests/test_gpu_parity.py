@@ -24,6 +24,14 @@ TOL = 1e-9
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(autouse=True, params=["tiles", "direct"])
+def solver_path(request, monkeypatch):
+    """Every parity test runs on both sub-cycle implementations: the TMA tile pipeline (HBM-bound meshes) and the
+    direct element/node kernels (L2-resident meshes).  NSX_PATH overrides the size heuristic of nsx_create."""
+    monkeypatch.setenv("NSX_PATH", request.param)
+    return request.param
+
+
 def solve_gpu(solvers):
     if len(solvers) == 1:
         solvers[0].explicit_solve()
