@@ -614,15 +614,17 @@ static void launch_tiles(nsx_solver* S, SubArgs const& A, int tile_base, int nti
 static void phase_substep(nsx_solver* S, int s, bool exchange_sync, bool overlap)
 {
     KParams const& K = S->K;
-    int const so = S->scur, sn = S->scur ^ 1;
+    // the direct path updates sigma/damage in place (no element is read by another thread): smaller L2 footprint
+    int const so = S->scur, sn = S->direct ? S->scur : (S->scur ^ 1);
     bool const bbm = (K.dynamics_type == NSX_DYN_BBM);
+    int const dn = S->direct ? S->dcur : (S->dcur ^ 1);
     SubArgs A{};
     A.tiles = S->tiles.p; A.tile_order = S->tile_order.p; A.tile_base = 0;
     A.halo_nodes = S->halo_nodes.p; A.halo_elems = S->halo_elems.p; A.slot_conn = S->slot_conn.p;
     A.slot_shape = S->slot_shape.p; A.slot_ec = S->slot_ec.p; A.nslots = S->plan.nslots; A.inc = S->inc.p;
     A.s0i = S->sig[so][0].p; A.s1i = S->sig[so][1].p; A.s2i = S->sig[so][2].p;
     A.s0o = S->sig[sn][0].p; A.s1o = S->sig[sn][1].p; A.s2o = S->sig[sn][2].p;
-    A.di = bbm ? S->dmg[S->dcur].p : nullptr; A.dmo = bbm ? S->dmg[S->dcur ^ 1].p : nullptr;
+    A.di = bbm ? S->dmg[S->dcur].p : nullptr; A.dmo = bbm ? S->dmg[dn].p : nullptr;
     A.nflags = S->nflags.p; A.grad_ssh = S->grad_ssh.p; A.node_mass = S->node_mass.p; A.rlmass = S->rlmass.p;
     A.cbu = S->cbu.p; A.fcor = S->fcor.p; A.tau_a = S->tau_a.p; A.tau_wi = S->have_tau_wi ? S->tau_wi.p : nullptr;
     A.ocean = S->ocean.p; A.VTM = S->VTM.p; A.VTc = S->VT[S->cur]; A.VTn = S->VT[S->cur ^ 1];
@@ -643,15 +645,28 @@ static void phase_substep(nsx_solver* S, int s, bool exchange_sync, bool overlap
     int const nt = S->plan.ntiles, nb = S->n_boundary_tiles;
     if (S->direct) {
         cudaStream_t st = S->stream;
+        // programmatic dependent launch (PDL): each kernel may start launching while its predecessor drains; the
+        // kernels themselves wait (griddepcontrol.wait) before reading anything the predecessor wrote
+        static const bool pdl = (env_int("NSX_PDL", 0) != 0);   // measured slower on B200 (waiting CTAs hold SM resources)
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cudaLaunchConfig_t cfg{};
+        cfg.blockDim = dim3(TPB); cfg.dynamicSmemBytes = 0; cfg.stream = st;
+        cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
+        cfg.gridDim = dim3(nblk(S->ne));
+        const double* dnull = nullptr; double* wnull = nullptr;
         if (bbm)
-            k_element_direct<1><<<nblk(S->ne), TPB, 0, st>>>(K, S->en0.p, S->en1.p, S->en2.p, A.VTc, S->shape.p, S->ec_e.p,
-                A.s0i, A.s1i, A.s2i, A.di, A.s0o, A.s1o, A.s2o, A.dmo, S->contrib.p);
+            NSX_CUDA(cudaLaunchKernelEx(&cfg, k_element_direct<1>, K, (const int*)S->en0.p, (const int*)S->en1.p, (const int*)S->en2.p,
+                A.VTc, (const double*)S->shape.p, (const double*)S->ec_e.p, A.s0i, A.s1i, A.s2i, A.di, A.s0o, A.s1o, A.s2o, A.dmo, S->contrib.p));
         else
-            k_element_direct<0><<<nblk(S->ne), TPB, 0, st>>>(K, S->en0.p, S->en1.p, S->en2.p, A.VTc, S->shape.p, S->ec_e.p,
-                A.s0i, A.s1i, A.s2i, nullptr, A.s0o, A.s1o, A.s2o, nullptr, S->contrib.p);
-        k_node_direct<<<nblk(S->nn), TPB, 0, st>>>(K, A.move_mesh, A.lag_ghost_move, S->nflags.p, S->n2e.p, S->n2e_deg.p,
-            S->contrib.p, S->grad_ssh.p, S->node_mass.p, S->rlmass.p, S->cbu.p, S->fcor.p, S->tau_a.p, A.tau_wi,
-            S->ocean.p, S->VTM.p, A.VTc, A.VTn, S->UM.p, S->UT.p);
+            NSX_CUDA(cudaLaunchKernelEx(&cfg, k_element_direct<0>, K, (const int*)S->en0.p, (const int*)S->en1.p, (const int*)S->en2.p,
+                A.VTc, (const double*)S->shape.p, (const double*)S->ec_e.p, A.s0i, A.s1i, A.s2i, dnull, A.s0o, A.s1o, A.s2o, wnull, S->contrib.p));
+        cfg.gridDim = dim3(nblk(S->nn));
+        NSX_CUDA(cudaLaunchKernelEx(&cfg, k_node_direct, K, A.move_mesh, A.lag_ghost_move, (const uint8_t*)S->nflags.p,
+            (const int*)S->n2e.p, (const int*)S->n2e_deg.p, (const double*)S->contrib.p, (const double*)S->grad_ssh.p,
+            (const double*)S->node_mass.p, (const double*)S->rlmass.p, (const double*)S->cbu.p, (const double*)S->fcor.p,
+            (const double*)S->tau_a.p, A.tau_wi, (const double*)S->ocean.p, (const double*)S->VTM.p, A.VTc, A.VTn, S->UM.p, S->UT.p));
         S->n_launch += 2;
         S->cur ^= 1;
         if (exchange_sync) halo_exchange(S, true);
@@ -697,7 +712,7 @@ static void phase_substep(nsx_solver* S, int s, bool exchange_sync, bool overlap
         if (exchange_sync) halo_exchange(S, true);
     }
     S->scur = sn;
-    if (bbm) S->dcur ^= 1;              // EVP / mEVP never touch damage (FE.cpp:10649-10699)
+    if (bbm) S->dcur = dn;              // EVP / mEVP never touch damage (FE.cpp:10649-10699)
     NSX_CUDA(cudaGetLastError());
 }
 

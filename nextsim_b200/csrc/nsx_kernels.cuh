@@ -671,12 +671,15 @@ template <int BBM>
 __global__ void __launch_bounds__(TPB)
 k_element_direct(KParams K, const int* __restrict__ en0, const int* __restrict__ en1, const int* __restrict__ en2,
                  const double* __restrict__ VT, const double* __restrict__ shape, const double* __restrict__ ec,
-                 const double* __restrict__ s0i, const double* __restrict__ s1i, const double* __restrict__ s2i,
-                 const double* __restrict__ di, double* __restrict__ s0o, double* __restrict__ s1o,
-                 double* __restrict__ s2o, double* __restrict__ dmo, double* __restrict__ contrib)
+                 const double* s0i, const double* s1i, const double* s2i, const double* di,
+                 double* s0o, double* s1o, double* s2o, double* dmo, double* __restrict__ contrib)
 {
     int const e = blockIdx.x * blockDim.x + threadIdx.x;
     int const ne = K.ne, nn = K.nn;
+    // programmatic dependent launch: let the node kernel's CTAs become resident while this grid drains, and do not
+    // read what the previous kernel wrote (VT) before it has completed
+    asm volatile("griddepcontrol.launch_dependents;");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     if (e >= ne) return;
     size_t const NE = (size_t)ne;
     double const c0 = ec[e];
@@ -768,6 +771,8 @@ k_node_direct(KParams K, int move_mesh, int lag_ghost_move,
 {
     int const n = blockIdx.x * blockDim.x + threadIdx.x;
     int const nn = K.nn, ne = K.ne;
+    asm volatile("griddepcontrol.launch_dependents;");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     if (n >= nn) return;
     uint8_t const fl = nflags[n];
     double const uice = VTc[n], vice = VTc[n + nn];
