@@ -150,6 +150,9 @@ int nsx_abi_sizes(int* out, int n);          /* sizeof NsxDynParams, NsxMesh, Ns
 /* tile decomposition of the sub-cycle kernel: ntiles, nodes/tile, slots, max local nodes, max slots,
  * boundary tiles, dynamic shared memory bytes */
 int nsx_tile_info(nsx_handle h, int* out, int n);
+/* host only (no GPU): the tile plan nsx_create would build for this mesh; out[0..9] = ntiles, nodes/tile, slots,
+ * max local nodes, max slots, max own slots, max halo slots, max halo nodes, stage bytes, shrink attempts */
+int nsx_plan_info(const NsxMesh* mesh, int target_tile_nodes, int wave_ctas, int* out, int n);
 const char* nsx_cfg_last_error(void);        /* message of the last failed nsx_params_from_cfg */
 
 /* ---- options ---- */
