@@ -804,10 +804,21 @@ static void solve_group(int n, nsx_solver** W)
     }
     if (!W[0]->P.skip_ow_smoother) {
         for (int r = 0; r < n; ++r) { NSX_CUDA(cudaSetDevice(W[r]->device)); phase_ow_begin(W[r]); }
-        for (int nit = 0; nit < 50; ++nit) {       // hard-coded 50 sweeps, FE.cpp:10580
-            for (int r = 0; r < n; ++r) { NSX_CUDA(cudaSetDevice(W[r]->device)); phase_ow_sweep(W[r]); }
-            if (n > 1) group_exchange();
-            else if (remote) halo_exchange(W[0], true);
+        if (n == 1 && W[0]->peers.empty()) {
+            // no neighbours: all 50 sweeps (hard-coded count, FE.cpp:10580) in one launch with a grid barrier
+            nsx_solver* S = W[0];
+            S->d_done.zero(S->stream);
+            int const grid = std::max(1, std::min(nblk(S->ndof), S->sm_count));
+            k_ow_smooth_all<<<grid, TPB, 0, S->stream>>>(S->nn, 50, S->ow_list.p, S->ow_count.p, S->n2n.p, S->n2n_deg.p,
+                                                         S->VT[S->cur], S->VT[S->cur ^ 1], S->d_done.p);
+            S->n_launch++;
+            NSX_CUDA(cudaGetLastError());
+        } else {
+            for (int nit = 0; nit < 50; ++nit) {       // hard-coded 50 sweeps, FE.cpp:10580
+                for (int r = 0; r < n; ++r) { NSX_CUDA(cudaSetDevice(W[r]->device)); phase_ow_sweep(W[r]); }
+                if (n > 1) group_exchange();
+                else if (remote) halo_exchange(W[0], true);
+            }
         }
     }
     for (int r = 0; r < n; ++r) {

@@ -862,6 +862,45 @@ k_ow_sweep(int nn, const int* __restrict__ ow_list, const int* __restrict__ ow_c
     }
 }
 
+// All 50 Jacobi sweeps in ONE launch for a rank without neighbours: a software grid barrier (the grid is at most one
+// CTA per SM, so every CTA is resident) separates the sweeps.  Exits at once when there is no open-water node.
+__global__ void __launch_bounds__(TPB)
+k_ow_smooth_all(int nn, int nsweeps, const int* __restrict__ ow_list, const int* __restrict__ ow_count,
+                const int* __restrict__ n2n, const int* __restrict__ n2n_deg,
+                double* VTa, double* VTb, unsigned int* bar)
+{
+    int const cnt = *ow_count;
+    if (cnt == 0) return;
+    // only as many CTAs as the list needs take part (a barrier over few CTAs is cheaper)
+    int const nact = min((int)gridDim.x, (cnt + (int)blockDim.x - 1) / (int)blockDim.x);
+    if ((int)blockIdx.x >= nact) return;
+    for (int it = 0; it < nsweeps; ++it) {
+        const double* VTin = (it & 1) ? VTb : VTa;
+        double* VTout = (it & 1) ? VTa : VTb;
+        for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < cnt; t += nact * blockDim.x) {
+            int const n = ow_list[t];
+            int const deg = n2n_deg[n];
+            double su = 0., sv = 0.;
+            for (int j = 0; j < deg; ++j) {
+                int const q = n2n[(size_t)j * nn + n];
+                su += __ldcg(VTin + q);              // L2: written by other SMs in the previous sweep
+                sv += __ldcg(VTin + q + nn);
+            }
+            VTout[n] = su / deg;
+            VTout[n + nn] = sv / deg;
+        }
+        // grid barrier
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            atomicAdd(bar, 1u);
+            unsigned int const target = (unsigned int)(it + 1) * (unsigned int)nact;
+            while (*((volatile unsigned int*)bar) < target) { }
+        }
+        __syncthreads();
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------
 // ice-ocean stress diagnostic + open-water mesh move  (FE.cpp:10615-10640)
 // ---------------------------------------------------------------------------------------------------
