@@ -59,7 +59,7 @@ static SmemLayout sub_layout(MeshPlan const& P, int n_node_planes)
     L.total = (int)o;
     return L;
 }
-constexpr int SUB_SMEM_CAP = (227 * 1024 - 64) / SUB_STAGES;     // per stage; one persistent CTA per SM (227 KB)
+constexpr int SUB_SMEM_CAP = (227 * 1024 - 128) / SUB_STAGES;     // per stage; one persistent CTA per SM (227 KB)
 
 // ---------------------------------------------------------------------------------------------------
 // life cycle
@@ -532,6 +532,36 @@ extern "C" int nsx_halo_finalize(nsx_handle S)
     }
     S->n_send_total = (int)src.size();
     S->d_send_src.upload(src, S->stream); S->d_send_dst.upload(dst, S->stream);
+    // per-node push lists for the fused boundary launch: owned node -> (send-peer slot, holder's ghost id)
+    {
+        std::vector<int> ptr(S->ndof + 1, 0);
+        int slot = 0;
+        for (auto& p : S->peers) {
+            if (p.h_send_idx.empty()) continue;
+            for (int n : p.h_send_idx) ptr[n + 1]++;
+            ++slot;
+        }
+        for (int n = 0; n < S->ndof; ++n) ptr[n + 1] += ptr[n];
+        std::vector<int2> ent(ptr[S->ndof]);
+        std::vector<int> fill(ptr.begin(), ptr.end() - 1);
+        slot = 0;
+        for (auto& p : S->peers) {
+            if (p.h_send_idx.empty()) continue;
+            for (size_t k = 0; k < p.h_send_idx.size(); ++k) ent[fill[p.h_send_idx[k]]++] = make_int2(slot, p.h_send_dst[k]);
+            ++slot;
+        }
+        S->push_ptr.upload(ptr, S->stream);
+        S->push_ent.upload(ent, S->stream);
+        // mixed direct/tile mode: elements written by boundary tiles, nodes owned by boundary tiles
+        std::vector<uint8_t> nowrite(S->ne, 0), fl = S->plan.nflags;
+        for (auto const& td : S->plan.tiles) {
+            if (!td.boundary) continue;
+            for (int k = 0; k < td.n_own_slots; ++k) nowrite[td.elem_begin + k] = 1;
+            for (int j = 0; j < td.n_own; ++j) fl[td.node_begin + j] |= NF_BTILE;
+        }
+        S->elem_nowrite.upload(nowrite, S->stream);
+        S->nflags.upload(fl, S->stream);
+    }
     NSX_CUDA(cudaStreamSynchronize(S->stream));
     S->halo_ready = true;
     S->graph_valid = false;
@@ -540,17 +570,15 @@ extern "C" int nsx_halo_finalize(nsx_handle S)
 
 // One ghost exchange of VT[cur] as a single kernel: push my owned values into every holder, publish the
 // epoch, wait for every owner of my ghosts.  `sync` is false for lock-step groups ordered by streams/events.
-static void halo_exchange(nsx_solver* S, bool sync)
+static HaloArgs halo_args(nsx_solver* S, int parity, bool sync)
 {
-    if (S->peers.empty()) return;
-    if (!S->halo_ready) throw std::runtime_error("halo exchange before nsx_halo_finalize");
     HaloArgs a{};
     a.sync = sync ? 1 : 0;
     int off = 0;
     for (auto& p : S->peers) {
         if (!p.h_send_idx.empty()) {
             a.peer_begin[a.n_peers] = off;
-            a.peer_vt[a.n_peers] = p.peer_vt[S->cur];
+            a.peer_vt[a.n_peers] = p.peer_vt[parity];
             a.peer_nn[a.n_peers] = p.peer_nn;
             a.peer_flag[a.n_peers] = p.peer_flags + S->rank;
             off += (int)p.h_send_idx.size();
@@ -560,6 +588,15 @@ static void halo_exchange(nsx_solver* S, bool sync)
     }
     a.peer_begin[a.n_peers] = off;
     a.n_total = off;
+    return a;
+}
+
+static void halo_exchange(nsx_solver* S, bool sync)
+{
+    if (S->peers.empty()) return;
+    if (!S->halo_ready) throw std::runtime_error("halo exchange before nsx_halo_finalize");
+    HaloArgs a = halo_args(S, S->cur, sync);
+    int const off = a.n_total;
     k_halo_exchange<<<std::max(1, nblk(off)), TPB, 0, S->stream>>>(a, S->nn, S->d_send_src.p, S->d_send_dst.p,
         S->VT[S->cur], S->flags, S->d_epoch.p, S->d_done.p, 40000000LL, S->halo_err.p);
     S->n_launch++;
@@ -603,7 +640,7 @@ static void launch_tiles(nsx_solver* S, SubArgs const& A, int tile_base, int nti
     a.n_tiles = ntiles;
     // persistent CTAs, one per SM (two shared-memory stages each); CTA b takes tiles b, b+grid, ...
     int const grid = std::max(1, std::min(ntiles, max_ctas));
-    size_t const smem = 64 + (size_t)SUB_STAGES * A.L.total;
+    size_t const smem = 128 + (size_t)SUB_STAGES * A.L.total;
     if (S->K.dynamics_type == NSX_DYN_BBM) k_subcycle<1><<<grid, SUB_TPB, smem, st>>>(S->K, a);
     else k_subcycle<0><<<grid, SUB_TPB, smem, st>>>(S->K, a);
     S->n_launch++;
@@ -615,9 +652,10 @@ static void phase_substep(nsx_solver* S, int s, bool exchange_sync, bool overlap
 {
     KParams const& K = S->K;
     // the direct path updates sigma/damage in place (no element is read by another thread): smaller L2 footprint
-    int const so = S->scur, sn = S->direct ? S->scur : (S->scur ^ 1);
+    bool const inplace = S->direct && S->peers.empty();
+    int const so = S->scur, sn = inplace ? S->scur : (S->scur ^ 1);
     bool const bbm = (K.dynamics_type == NSX_DYN_BBM);
-    int const dn = S->direct ? S->dcur : (S->dcur ^ 1);
+    int const dn = inplace ? S->dcur : (S->dcur ^ 1);
     SubArgs A{};
     A.tiles = S->tiles.p; A.tile_order = S->tile_order.p; A.tile_base = 0;
     A.halo_nodes = S->halo_nodes.p; A.halo_elems = S->halo_elems.p; A.slot_conn = S->slot_conn.p;
@@ -640,14 +678,15 @@ static void phase_substep(nsx_solver* S, int s, bool exchange_sync, bool overlap
         A.np[p] = use ? npl++ : 0;
     }
     A.L = sub_layout(S->plan, npl);
-    if (64 + (size_t)SUB_STAGES * A.L.total > 227 * 1024) throw std::runtime_error("sub-cycle kernel: tile working set exceeds shared memory");
+    if (128 + (size_t)SUB_STAGES * A.L.total > 227 * 1024) throw std::runtime_error("sub-cycle kernel: tile working set exceeds shared memory");
     S->sub_smem = (size_t)A.L.total;
     int const nt = S->plan.ntiles, nb = S->n_boundary_tiles;
-    if (S->direct) {
-        cudaStream_t st = S->stream;
-        // programmatic dependent launch (PDL): each kernel may start launching while its predecessor drains; the
-        // kernels themselves wait (griddepcontrol.wait) before reading anything the predecessor wrote
-        static const bool pdl = (env_int("NSX_PDL", 0) != 0);   // measured slower on B200 (waiting CTAs hold SM resources)
+    // direct path: one thread per element, then one per node.  `mixed`: the boundary tiles are handled by the tile
+    // kernel of the boundary launch; here their elements are evaluated but not written and their nodes are skipped.
+    auto launch_direct = [&](cudaStream_t st, bool mixed) {
+        // programmatic dependent launch (PDL) hooks exist in the kernels; measured slower on B200 (waiting CTAs hold
+        // SM resources), hence off unless NSX_PDL=1
+        static const bool pdl = (env_int("NSX_PDL", 0) != 0);
         cudaLaunchAttribute attr[1];
         attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
         attr[0].val.programmaticStreamSerializationAllowed = 1;
@@ -656,56 +695,57 @@ static void phase_substep(nsx_solver* S, int s, bool exchange_sync, bool overlap
         cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
         cfg.gridDim = dim3(nblk(S->ne));
         const double* dnull = nullptr; double* wnull = nullptr;
+        const uint8_t* nowrite = mixed ? S->elem_nowrite.p : nullptr;
         if (bbm)
             NSX_CUDA(cudaLaunchKernelEx(&cfg, k_element_direct<1>, K, (const int*)S->en0.p, (const int*)S->en1.p, (const int*)S->en2.p,
-                A.VTc, (const double*)S->shape.p, (const double*)S->ec_e.p, A.s0i, A.s1i, A.s2i, A.di, A.s0o, A.s1o, A.s2o, A.dmo, S->contrib.p));
+                A.VTc, (const double*)S->shape.p, (const double*)S->ec_e.p, A.s0i, A.s1i, A.s2i, A.di, A.s0o, A.s1o, A.s2o, A.dmo,
+                S->contrib.p, nowrite));
         else
             NSX_CUDA(cudaLaunchKernelEx(&cfg, k_element_direct<0>, K, (const int*)S->en0.p, (const int*)S->en1.p, (const int*)S->en2.p,
-                A.VTc, (const double*)S->shape.p, (const double*)S->ec_e.p, A.s0i, A.s1i, A.s2i, dnull, A.s0o, A.s1o, A.s2o, wnull, S->contrib.p));
+                A.VTc, (const double*)S->shape.p, (const double*)S->ec_e.p, A.s0i, A.s1i, A.s2i, dnull, A.s0o, A.s1o, A.s2o, wnull,
+                S->contrib.p, nowrite));
         cfg.gridDim = dim3(nblk(S->nn));
-        NSX_CUDA(cudaLaunchKernelEx(&cfg, k_node_direct, K, A.move_mesh, A.lag_ghost_move, (const uint8_t*)S->nflags.p,
+        int const skip = mixed ? (NF_BTILE | NF_GHOST) : 0;
+        NSX_CUDA(cudaLaunchKernelEx(&cfg, k_node_direct, K, A.move_mesh, mixed ? 0 : A.lag_ghost_move, skip, (const uint8_t*)S->nflags.p,
             (const int*)S->n2e.p, (const int*)S->n2e_deg.p, (const double*)S->contrib.p, (const double*)S->grad_ssh.p,
             (const double*)S->node_mass.p, (const double*)S->rlmass.p, (const double*)S->cbu.p, (const double*)S->fcor.p,
             (const double*)S->tau_a.p, A.tau_wi, (const double*)S->ocean.p, (const double*)S->VTM.p, A.VTc, A.VTn, S->UM.p, S->UT.p));
         S->n_launch += 2;
-        S->cur ^= 1;
-        if (exchange_sync) halo_exchange(S, true);
-    } else if (overlap && nb > 0 && nb < nt) {
+    };
+    bool const fused = overlap && exchange_sync && nb > 0 && nb < nt && S->halo_ready;
+    if (fused) {
+        // multi-GPU sub-cycle: [boundary tiles + NVLink push + epoch signal + wait] as ONE kernel on a few SMs of the
+        // main stream, the interior (tile kernel or direct kernels) concurrently on stream2 on the remaining SMs
         NSX_CUDA(cudaEventRecord(S->ev_fork, S->stream));
         NSX_CUDA(cudaStreamWaitEvent(S->stream2, S->ev_fork, 0));
-        // The two persistent kernels must be co-resident (one CTA per SM each): give the boundary kernel B SMs and
-        // the interior kernel the rest, B balancing  boundary tiles / B + halo latency  against  interior / (SMs - B).
-        int B = 1;
-        double best = 1e300;
-        for (int b = 1; b <= std::min(nb, S->sm_count - 1); ++b) {
-            double const t_b = std::ceil((double)nb / b) * 4.0 + 8.0;
-            double const t_i = std::ceil((double)(nt - nb) / (S->sm_count - b)) * 4.0;
-            double const t = std::max(t_b, t_i);
-            if (t < best - 1e-9) { best = t; B = b; }
+        int B;
+        if (S->direct) {
+            B = std::min(nb, 32);
+        } else {
+            B = 1;
+            double best = 1e300;
+            for (int b = 1; b <= std::min(nb, S->sm_count - 1); ++b) {
+                double const t_b = std::ceil((double)nb / b) * 4.0 + 6.0;
+                double const t_i = std::ceil((double)(nt - nb) / (S->sm_count - b)) * 4.0;
+                double const t = std::max(t_b, t_i);
+                if (t < best - 1e-9) { best = t; B = b; }
+            }
         }
-        static const bool prof = (getenv("NSX_PROFILE_HALO") != nullptr);
-        cudaEvent_t pe[4] = {nullptr, nullptr, nullptr, nullptr};
-        if (prof && !S->capturing && s >= 8 && s < 40) {
-            for (auto& e : pe) NSX_CUDA(cudaEventCreate(&e));
-            NSX_CUDA(cudaEventRecord(pe[0], S->stream));
-        }
-        launch_tiles(S, A, 0, nb, S->stream, B);
-        if (pe[0]) NSX_CUDA(cudaEventRecord(pe[1], S->stream));
-        launch_tiles(S, A, nb, nt - nb, S->stream2, S->sm_count - B);
+        SubArgs Ab = A;
+        Ab.fuse_halo = 1;
+        Ab.H = halo_args(S, S->cur ^ 1, true);
+        Ab.push_ptr = S->push_ptr.p; Ab.push_ent = S->push_ent.p;
+        Ab.my_flags = S->flags; Ab.epoch_ctr = S->d_epoch.p; Ab.done_ctr = S->d_done.p; Ab.halo_err = S->halo_err.p;
+        launch_tiles(S, Ab, 0, nb, S->stream, B);
+        if (S->direct) launch_direct(S->stream2, true);
+        else launch_tiles(S, A, nb, nt - nb, S->stream2, S->sm_count - B);
         NSX_CUDA(cudaEventRecord(S->ev_join, S->stream2));
-        if (pe[0]) NSX_CUDA(cudaEventRecord(pe[3], S->stream2));
         S->cur ^= 1;
-        halo_exchange(S, exchange_sync);
-        if (pe[0]) NSX_CUDA(cudaEventRecord(pe[2], S->stream));
         NSX_CUDA(cudaStreamWaitEvent(S->stream, S->ev_join, 0));
-        if (pe[0]) {
-            NSX_CUDA(cudaStreamSynchronize(S->stream));
-            float tb = 0, th = 0, ti = 0;
-            cudaEventElapsedTime(&tb, pe[0], pe[1]); cudaEventElapsedTime(&th, pe[1], pe[2]); cudaEventElapsedTime(&ti, pe[0], pe[3]);
-            fprintf(stderr, "[nsx rank %d] sub-cycle %d: nb=%d nt=%d B=%d boundary %.1f us, halo %.1f us, interior(end) %.1f us\n",
-                    S->rank, s, nb, nt, B, tb * 1e3, th * 1e3, ti * 1e3);
-            for (auto& e : pe) cudaEventDestroy(e);
-        }
+    } else if (S->direct) {
+        launch_direct(S->stream, false);
+        S->cur ^= 1;
+        if (exchange_sync) halo_exchange(S, true);
     } else {
         launch_tiles(S, A, 0, nt, S->stream, S->sm_count);
         S->cur ^= 1;

@@ -29,7 +29,7 @@ constexpr double PI_ = 3.14159265358979323846;
 constexpr double DAYS_IN_SEC = 86400.;
 
 // node flag bits (also written by nsx_mesh.cpp)
-enum : uint8_t { NF_DIRICHLET = 1, NF_NEUMANN = 2, NF_GHOST = 4, NF_LATNEG = 8 };
+enum : uint8_t { NF_DIRICHLET = 1, NF_NEUMANN = 2, NF_GHOST = 4, NF_LATNEG = 8, NF_BTILE = 16 };
 
 template <class T>
 struct DBuf {
@@ -152,6 +152,8 @@ struct nsx_solver {
     nsx::DBuf<unsigned long long> d_epoch;       // device-resident exchange counter (graph replay safe)
     nsx::DBuf<unsigned int> d_done;              // block completion counter of k_halo_exchange
     int n_send_total = 0;
+    nsx::DBuf<int> push_ptr; nsx::DBuf<int2> push_ent;   // owned node -> (send-peer slot, holder's ghost id)
+    nsx::DBuf<uint8_t> elem_nowrite;             // element written by a boundary tile (mixed direct/tile mode)
     nsx::DBuf<int> halo_err;                     // device error word (timeouts)
     bool halo_ready = false;
     bool halo_local = false;                     // all peers live in this process on this device

@@ -338,6 +338,18 @@ struct SmemLayout {
 enum { NP_GSU, NP_GSV, NP_MASS, NP_RL, NP_CBU, NP_FCOR, NP_TAU, NP_TAV, NP_OCU, NP_OCV, NP_UMU, NP_UMV, NP_UTU, NP_UTV,
        NP_VMU, NP_VMV, NP_TWU, NP_TWV, NP_COUNT };
 
+struct HaloArgs {
+    int n_total;                        // send entries over all peers
+    int n_peers;                        // peers I send to
+    int peer_begin[33];                 // entry ranges per send peer
+    double* peer_vt[32];                // holder's VT buffer (current parity)
+    int peer_nn[32];
+    unsigned long long* peer_flag[32];  // holder's flag slot for me
+    int n_wait;                         // owners I wait for
+    int wait_slot[32];
+    int sync;                           // 0: stream-ordered group on one device, no flags
+};
+
 struct SubArgs {
     const TileDesc* tiles; const int* tile_order; int tile_base;
     const int* halo_nodes; const int* halo_elems; const unsigned long long* slot_conn;
@@ -349,6 +361,12 @@ struct SubArgs {
     const double* VTM; const double* VTc; double* VTn; double* UM; double* UT;
     int move_mesh, lag_ghost_move, n_tiles;
     int np[NP_COUNT];           // node plane -> staging slot (compacted: only the planes this configuration reads)
+    // fused ghost exchange of the boundary launch (multi-GPU): phase 2 stores sent nodes straight into the holders'
+    // ghost slots over NVLink; the last CTA publishes the epoch and waits for the owners of this rank's ghosts
+    int fuse_halo;
+    const int* push_ptr; const int2* push_ent;
+    const unsigned long long* my_flags; unsigned long long* epoch_ctr; unsigned int* done_ctr; int* halo_err;
+    HaloArgs H;
     SmemLayout L;
 };
 
@@ -432,7 +450,7 @@ k_subcycle(KParams K, SubArgs A)
     int const tid = threadIdx.x;
     uint64_t* const full = (uint64_t*)sm_all;
     uint64_t* const empty = full + SUB_STAGES;
-    unsigned char* const stage0 = sm_all + 64;
+    unsigned char* const stage0 = sm_all + 128;     // header: barriers [0,96), fused-halo flag at 120
     if (tid == 0) {
         for (int q = 0; q < SUB_STAGES; ++q) {
             mbar_init(full + q, SUB_PROD / 32);       // one arrival (with its TMA bytes) per producer warp
@@ -637,6 +655,15 @@ k_subcycle(KParams K, SubArgs A)
         }
         A.VTn[n] = un;
         A.VTn[n + nn] = vn;
+        if (A.fuse_halo) {                      // updateGhosts: owner -> every holder's ghost slot (FE.cpp:13963-13996)
+            int const q1 = A.push_ptr[n + 1];
+            for (int q = A.push_ptr[n]; q < q1; ++q) {
+                int2 const pe = A.push_ent[q];
+                double* const dst = A.H.peer_vt[pe.x];
+                dst[pe.y] = un;
+                dst[pe.y + A.H.peer_nn[pe.x]] = vn;
+            }
+        }
         if (A.move_mesh) {
             A.UT[n] = npl[A.np[NP_UTU] * MTP + shs + j] + K.dte * un;
             A.UT[n + nn] = npl[A.np[NP_UTV] * MTP + sh_nv + j] + K.dte * vn;
@@ -659,6 +686,35 @@ k_subcycle(KParams K, SubArgs A)
     __syncwarp();
     if ((tid & 31) == 0) mbar_arrive(empty + s);
     }   // tile loop
+
+    if (A.fuse_halo) {
+        // every sent value of this CTA is on its way: count the CTA in; the last one publishes the epoch in every
+        // holder's flag slot (release, system scope) and waits for the owners of this rank's ghosts (bounded spin)
+        volatile int& s_last = *(volatile int*)(sm_all + 120);
+        __threadfence_system();
+        cons_sync(grp);
+        if (gtid == 0) s_last = (atomicAdd(A.done_ctr, 1u) == gridDim.x - 1);
+        cons_sync(grp);
+        if (s_last) {
+            __threadfence_system();
+            unsigned long long const epoch = *((volatile unsigned long long*)A.epoch_ctr) + 1ULL;
+            if (gtid < A.H.n_peers)
+                asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(A.H.peer_flag[gtid]), "l"(epoch) : "memory");
+            if (gtid < A.H.n_wait) {
+                const unsigned long long* f = A.my_flags + A.H.wait_slot[gtid];
+                long long spins = 0;
+                for (;;) {
+                    unsigned long long v;
+                    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(f) : "memory");
+                    if (v >= epoch) break;
+                    if (++spins > 40000000LL) { atomicExch(A.halo_err, 1 + A.H.wait_slot[gtid]); break; }
+                    __nanosleep(64);
+                }
+            }
+            cons_sync(grp);
+            if (gtid == 0) { *A.epoch_ctr = epoch; *A.done_ctr = 0u; }
+        }
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -672,7 +728,8 @@ __global__ void __launch_bounds__(TPB)
 k_element_direct(KParams K, const int* __restrict__ en0, const int* __restrict__ en1, const int* __restrict__ en2,
                  const double* __restrict__ VT, const double* __restrict__ shape, const double* __restrict__ ec,
                  const double* s0i, const double* s1i, const double* s2i, const double* di,
-                 double* s0o, double* s1o, double* s2o, double* dmo, double* __restrict__ contrib)
+                 double* s0o, double* s1o, double* s2o, double* dmo, double* __restrict__ contrib,
+                 const uint8_t* __restrict__ elem_nowrite)
 {
     int const e = blockIdx.x * blockDim.x + threadIdx.x;
     int const ne = K.ne, nn = K.nn;
@@ -682,6 +739,9 @@ k_element_direct(KParams K, const int* __restrict__ en0, const int* __restrict__
     asm volatile("griddepcontrol.wait;" ::: "memory");
     if (e >= ne) return;
     size_t const NE = (size_t)ne;
+    // elements whose writer tile is a boundary tile are written by the tile kernel of the boundary launch; they are
+    // still evaluated here because interior nodes next to them need their contributions
+    bool const nowrite = elem_nowrite && elem_nowrite[e];
     double const c0 = ec[e];
     double const dx0 = shape[e], dx1 = shape[NE + e], dx2 = shape[2 * NE + e];
     double const dy0 = shape[3 * NE + e], dy1 = shape[4 * NE + e], dy2 = shape[5 * NE + e];
@@ -725,7 +785,7 @@ k_element_direct(KParams K, const int* __restrict__ en0, const int* __restrict__
             }
             d = fmax(0., d - ec[4 * NE + e]);
         }
-        dmo[e] = d;
+        if (!nowrite) dmo[e] = d;
     } else {
         double const Pp = c0;
         vol = ec[NE + e];
@@ -749,7 +809,7 @@ k_element_direct(KParams K, const int* __restrict__ en0, const int* __restrict__
             s1 = 0.5 * (sigma1 - sigma2);
         }
     }
-    s0o[e] = s0; s1o[e] = s1; s2o[e] = s2;
+    if (!nowrite) { s0o[e] = s0; s1o[e] = s1; s2o[e] = s2; }
     contrib[0 * NE + e] = vol * (s0 * dx0 + s2 * dy0);
     contrib[1 * NE + e] = vol * (s0 * dx1 + s2 * dy1);
     contrib[2 * NE + e] = vol * (s0 * dx2 + s2 * dy2);
@@ -759,7 +819,7 @@ k_element_direct(KParams K, const int* __restrict__ en0, const int* __restrict__
 }
 
 __global__ void __launch_bounds__(TPB)
-k_node_direct(KParams K, int move_mesh, int lag_ghost_move,
+k_node_direct(KParams K, int move_mesh, int lag_ghost_move, int skip_flag_mask,
               const uint8_t* __restrict__ nflags, const int* __restrict__ n2e, const int* __restrict__ n2e_deg,
               const double* __restrict__ contrib, const double* __restrict__ grad_ssh,
               const double* __restrict__ node_mass, const double* __restrict__ rlmass,
@@ -775,6 +835,7 @@ k_node_direct(KParams K, int move_mesh, int lag_ghost_move,
     asm volatile("griddepcontrol.wait;" ::: "memory");
     if (n >= nn) return;
     uint8_t const fl = nflags[n];
+    if (fl & skip_flag_mask) return;            // nodes of boundary tiles (and ghosts) belong to the boundary launch
     double const uice = VTc[n], vice = VTc[n + nn];
     if (fl & NF_GHOST) {
         if (lag_ghost_move) {
@@ -1101,17 +1162,6 @@ k_shape_out(int ne, const int* __restrict__ perm, const double* __restrict__ soa
 //   3. and then waits (bounded spin) until every owner of MY ghosts has published the same epoch.
 // The epoch lives in device memory so a captured CUDA graph can be replayed.
 // ---------------------------------------------------------------------------------------------------
-struct HaloArgs {
-    int n_total;                        // send entries over all peers
-    int n_peers;                        // peers I send to
-    int peer_begin[33];                 // entry ranges per send peer
-    double* peer_vt[32];                // holder's VT buffer (current parity)
-    int peer_nn[32];
-    unsigned long long* peer_flag[32];  // holder's flag slot for me
-    int n_wait;                         // owners I wait for
-    int wait_slot[32];
-    int sync;                           // 0: stream-ordered group on one device, no flags
-};
 
 __global__ void __launch_bounds__(TPB)
 k_halo_exchange(HaloArgs a, int nn_src, const int* __restrict__ src_idx, const int* __restrict__ dst_idx,
