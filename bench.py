@@ -48,12 +48,15 @@ def parse():
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU time of the cpu_baseline sample")
+    ap.add_argument("--nx", type=int, default=0, help="override the mesh size (quads per side); experiments only")
     return ap.parse_args()
 
 
 def workload_nx(args):
     from nextsim_b200 import synthetic as syn
     nx, h = syn.SIZES[args.workload]
+    if args.nx:
+        return args.nx, h
     if args.scaling == "weak" and args.gpus > 1:
         nx = int(round(nx * np.sqrt(args.gpus)))
     return nx, h

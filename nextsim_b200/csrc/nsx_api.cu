@@ -718,19 +718,11 @@ static void phase_substep(nsx_solver* S, int s, bool exchange_sync, bool overlap
         // main stream, the interior (tile kernel or direct kernels) concurrently on stream2 on the remaining SMs
         NSX_CUDA(cudaEventRecord(S->ev_fork, S->stream));
         NSX_CUDA(cudaStreamWaitEvent(S->stream2, S->ev_fork, 0));
-        int B;
-        if (S->direct) {
-            B = std::min(nb, 32);
-        } else {
-            B = 1;
-            double best = 1e300;
-            for (int b = 1; b <= std::min(nb, S->sm_count - 1); ++b) {
-                double const t_b = std::ceil((double)nb / b) * 4.0 + 6.0;
-                double const t_i = std::ceil((double)(nt - nb) / (S->sm_count - b)) * 4.0;
-                double const t = std::max(t_b, t_i);
-                if (t < best - 1e-9) { best = t; B = b; }
-            }
-        }
+        // SM split between the two co-resident persistent kernels: the boundary chain (tiles + NVLink round trip) is
+        // latency-bound and sits on the critical path of BOTH ranks of a pair, so it gets enough SMs to take at most
+        // ~4 tiles per CTA (1 on the direct path); the interior keeps the rest.
+        int B = S->direct ? std::min(nb, 48) : std::max(1, std::min((nb + 5) / 6, S->sm_count / 4));
+        if (const char* e = getenv("NSX_BOUNDARY_SMS")) B = std::max(1, std::min(atoi(e), std::min(nb, S->sm_count - 1)));
         SubArgs Ab = A;
         Ab.fuse_halo = 1;
         Ab.H = halo_args(S, S->cur ^ 1, true);
@@ -855,9 +847,21 @@ static void solve_group(int n, nsx_solver** W)
             NSX_CUDA(cudaGetLastError());
         } else {
             for (int nit = 0; nit < 50; ++nit) {       // hard-coded 50 sweeps, FE.cpp:10580
+                if (n == 1 && remote) {
+                    // one process per GPU: sweep + ghost exchange in a single launch
+                    nsx_solver* S = W[0];
+                    HaloArgs a = halo_args(S, S->cur ^ 1, true);
+                    int const grid = std::max(1, std::min(nblk(S->ndof), S->sm_count));
+                    k_ow_sweep_exchange<<<grid, TPB, 0, S->stream>>>(a, S->nn, S->ow_list.p, S->ow_count.p, S->n2n.p, S->n2n_deg.p,
+                        S->VT[S->cur], S->VT[S->cur ^ 1], S->d_send_src.p, S->d_send_dst.p, S->flags, S->d_epoch.p,
+                        S->d_done.p, 40000000LL, S->halo_err.p);
+                    S->n_launch++;
+                    S->cur ^= 1;
+                    NSX_CUDA(cudaGetLastError());
+                    continue;
+                }
                 for (int r = 0; r < n; ++r) { NSX_CUDA(cudaSetDevice(W[r]->device)); phase_ow_sweep(W[r]); }
                 if (n > 1) group_exchange();
-                else if (remote) halo_exchange(W[0], true);
             }
         }
     }

@@ -707,6 +707,7 @@ k_subcycle(KParams K, SubArgs A)
                     unsigned long long v;
                     asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(f) : "memory");
                     if (v >= epoch) break;
+                    if (*((volatile int*)A.halo_err)) break;     // an earlier exchange already timed out
                     if (++spins > 40000000LL) { atomicExch(A.halo_err, 1 + A.H.wait_slot[gtid]); break; }
                     __nanosleep(64);
                 }
@@ -1195,6 +1196,67 @@ k_halo_exchange(HaloArgs a, int nn_src, const int* __restrict__ src_idx, const i
             unsigned long long v;
             asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(f) : "memory");
             if (v >= epoch) break;
+            if (*((volatile int*)err)) break;        // an earlier exchange already timed out: do not stall again
+            if (++spins > max_spins) { atomicExch(err, 1 + a.wait_slot[threadIdx.x]); break; }
+            __nanosleep(64);
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) { *epoch_ctr = epoch; *done_ctr = 0u; }
+}
+
+// Multi-rank smoother step: one Jacobi sweep over the open-water list AND the ghost exchange of the result in a
+// single launch.  All CTAs sweep; the last CTA to finish pushes this rank's sent nodes to their holders, publishes
+// the epoch and waits for the owners of this rank's ghosts (same protocol as k_halo_exchange).
+__global__ void __launch_bounds__(TPB)
+k_ow_sweep_exchange(HaloArgs a, int nn, const int* __restrict__ ow_list, const int* __restrict__ ow_count,
+                    const int* __restrict__ n2n, const int* __restrict__ n2n_deg,
+                    const double* VTin, double* VTout,
+                    const int* __restrict__ src_idx, const int* __restrict__ dst_idx, const unsigned long long* my_flags,
+                    unsigned long long* epoch_ctr, unsigned int* done_ctr, long long max_spins, int* err)
+{
+    int const cnt = *ow_count;
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < cnt; t += gridDim.x * blockDim.x) {
+        int const n = ow_list[t];
+        int const deg = n2n_deg[n];
+        double su = 0., sv = 0.;
+        for (int j = 0; j < deg; ++j) {
+            int const q = n2n[(size_t)j * nn + n];
+            su += VTin[q];
+            sv += VTin[q + nn];
+        }
+        VTout[n] = su / deg;
+        VTout[n + nn] = sv / deg;
+    }
+    __shared__ bool last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) last = (atomicAdd(done_ctr, 1u) == gridDim.x - 1);
+    __syncthreads();
+    if (!last) return;
+    __threadfence();
+    for (int t = threadIdx.x; t < a.n_total; t += blockDim.x) {
+        int p = 0;
+        while (t >= a.peer_begin[p + 1]) ++p;
+        int const s = src_idx[t], d = dst_idx[t];
+        double* dst = a.peer_vt[p];
+        dst[d] = __ldcg(VTout + s);
+        dst[d + a.peer_nn[p]] = __ldcg(VTout + s + nn);
+    }
+    if (!a.sync) { __syncthreads(); if (threadIdx.x == 0) *done_ctr = 0u; return; }
+    __threadfence_system();
+    __syncthreads();
+    unsigned long long const epoch = *((volatile unsigned long long*)epoch_ctr) + 1ULL;
+    if ((int)threadIdx.x < a.n_peers)
+        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(a.peer_flag[threadIdx.x]), "l"(epoch) : "memory");
+    if ((int)threadIdx.x < a.n_wait) {
+        const unsigned long long* f = my_flags + a.wait_slot[threadIdx.x];
+        long long spins = 0;
+        for (;;) {
+            unsigned long long v;
+            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(f) : "memory");
+            if (v >= epoch) break;
+            if (*((volatile int*)err)) break;        // an earlier exchange already timed out: do not stall again
             if (++spins > max_spins) { atomicExch(err, 1 + a.wait_slot[threadIdx.x]); break; }
             __nanosleep(64);
         }
