@@ -282,6 +282,18 @@ def run_ours(args):
         L.nsx_host_unregister(a.ctypes.data)
 
     chk = S.check()
+    import ctypes as _C
+    tinfo = (_C.c_int * 8)()
+    capi.lib().nsx_tile_info(S.h, tinfo, 8)
+    path = "direct" if tinfo[7] else "tiles"
+    traffic = None
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        key = "%s/%s/%s" % (args.workload, args.dyn, path)
+        if world == 1 and not args.nx and key in tj:
+            traffic = tj[key]["bytes"]
+    except Exception:
+        pass
     peak, peak_src = measured_peak()
     # roofline unit: one sub-cycle of THIS rank (its element kernel + node kernel [+ halo]); algorithmic bytes
     # = SURVEY 8(d) per-element figure x the elements this rank updates per sub-cycle
@@ -299,8 +311,11 @@ def run_ours(args):
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
         "gpu_launches": launches,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None, "peak_source": peak_src,
-                     "kernel": "one sub-cycle = element kernel + node kernel, %g B/element algorithmic" % ALGO_BYTES[args.dyn],
+                     "traffic": traffic, "peak_source": peak_src,
+                     "algorithmic_bytes_per_launch": ALGO_BYTES[args.dyn] * lm.num_elements,
+                     "kernel": ("one sub-cycle = k_element_direct + k_node_direct (L2-resident mesh)" if path == "direct"
+                                else "one sub-cycle = k_subcycle (TMA tile pipeline)") +
+                               ", %g B/element algorithmic" % ALGO_BYTES[args.dyn],
                      "us_per_subcycle": t_sub * 1e6},
         "subcycle_loop": {"value": sub_value, "unit": UNIT},
         "simulated_days_per_wallhour": (args.steps * c.params.dtime_step / 86400.0) / (total_ms * 1e-3 / 3600.0),

@@ -266,14 +266,15 @@ extern "C" int nsx_abi_sizes(int* out, int n)
     return 6;
 }
 
-// tile decomposition summary: ntiles, nodes per tile, slots, max local nodes, max slots, boundary tiles, smem bytes
+// tile decomposition summary: ntiles, nodes per tile, slots, max local nodes, max slots, boundary tiles, smem bytes,
+// and whether the direct (L2-resident) path is selected
 extern "C" int nsx_tile_info(nsx_handle S, int* out, int n)
 {
     if (!S) return 0;
-    int const v[7] = {S->plan.ntiles, S->plan.tile_nodes, S->plan.nslots, S->plan.max_local_nodes, S->plan.max_slots,
-                      S->n_boundary_tiles, (int)S->sub_smem};
-    for (int i = 0; i < n && i < 7; ++i) out[i] = v[i];
-    return 7;
+    int const v[8] = {S->plan.ntiles, S->plan.tile_nodes, S->plan.nslots, S->plan.max_local_nodes, S->plan.max_slots,
+                      S->n_boundary_tiles, (int)S->sub_smem, S->direct ? 1 : 0};
+    for (int i = 0; i < n && i < 8; ++i) out[i] = v[i];
+    return 8;
 }
 
 // ---------------------------------------------------------------------------------------------------

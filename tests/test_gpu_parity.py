@@ -186,3 +186,74 @@ def test_baseline_state_full_step_within_oracle_sensitivity():
     print("cuda vs oracle         :", err)
     for kk, e in err.items():
         assert e <= max(TOL, 100.0 * sens[kk]), (kk, e, sens[kk])
+
+
+# ---- boundary behaviour of the C ABI ----------------------------------------------------------------------
+def test_upload_download_roundtrip_is_bit_exact():
+    """The library renumbers internally (Hilbert order, tiles); the host must get back exactly what it sent."""
+    c = cases.make_case("10km_stable", nranks=1, nx=40, open_east=True)
+    s = cases.make_solvers(c)[0]
+    rng = np.random.default_rng(7)
+    nn, ne = c.lms[0].num_nodes, c.lms[0].num_elements
+    sent = {"M_VT": rng.standard_normal(2 * nn), "M_UM": rng.standard_normal(2 * nn), "M_ssh": rng.standard_normal(nn),
+            "M_damage": rng.random(ne), "M_conc": rng.random(ne), "M_sigma": [rng.standard_normal(ne) for _ in range(3)]}
+    s.upload(**sent)
+    got = s.download(*sent.keys())
+    for k, v in sent.items():
+        if k == "M_sigma":
+            for a, b in zip(got[k], v):
+                assert np.array_equal(a, b)
+        else:
+            assert np.array_equal(got[k], v), k
+    s.close()
+
+
+def test_wave_stress_slot():
+    """Optional OASIS wave stress tau_wi enters the nodal solve (FE.cpp:10408-10415, 10510-10517)."""
+    c = cases.make_case("10km_stable", nranks=1, dyn="bbm", nx=48)
+    rng = np.random.default_rng(3)
+    tau = 0.05 * rng.standard_normal(2 * c.lms[0].num_nodes)
+    R = ob.make_ranks(c)[0]
+    R.set("tau_wi", tau)
+    orc.explicit_solve([R], ob.orc_params(c.params))
+    s = cases.make_solvers(c)[0]
+    s.upload(M_tau_wi=tau)
+    s.explicit_solve()
+    got = s.download("M_VT", "M_damage")
+    assert ob.rel_l2(got["M_VT"], R.get("M_VT")) <= TOL
+    assert ob.rel_l2(got["M_damage"], R.get("M_damage")) <= TOL
+    # and it matters: without the stress the velocities differ
+    R2 = ob.make_ranks(c)[0]
+    orc.explicit_solve([R2], ob.orc_params(c.params))
+    assert ob.rel_l2(R2.get("M_VT"), R.get("M_VT")) > 1e-6
+    s.close()
+
+
+def test_check_reports_bad_fields():
+    """nsx_check is the device-side checkFieldsFast (FE.cpp:14536-14655)."""
+    c = cases.make_case("toy", nranks=1)
+    s = cases.make_solvers(c)[0]
+    assert s.check().n_nan == 0
+    vt = c.local[0]["M_VT"].copy()
+    vt[5] = np.nan
+    vt[7] = 9.0
+    s.upload(M_VT=vt)
+    chk = s.check()
+    assert chk.n_nan == 1 and chk.n_speed == 1 and chk.max_speed == 9.0
+    d = c.local[0]["M_damage"].copy()
+    d[3] = 1.5
+    s.upload(M_damage=d)
+    assert s.check().n_range == 1
+    s.close()
+
+
+def test_params_required_and_validated():
+    c = cases.make_case("toy", nranks=1)
+    s = capi.Solver(c.lms[0])
+    with pytest.raises(RuntimeError, match="before nsx_set_params"):
+        s.explicit_solve()
+    p = capi.default_params()
+    p.dynamics_type = 2                       # free_drift: outside the accelerated path
+    with pytest.raises(RuntimeError, match="dynamics_type"):
+        s.set_params(p)
+    s.close()
