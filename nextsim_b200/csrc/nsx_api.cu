@@ -692,9 +692,9 @@ static void phase_substep(nsx_solver* S, int s, bool exchange_sync, bool overlap
         attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
         attr[0].val.programmaticStreamSerializationAllowed = 1;
         cudaLaunchConfig_t cfg{};
-        cfg.blockDim = dim3(TPB); cfg.dynamicSmemBytes = 0; cfg.stream = st;
+        cfg.blockDim = dim3(DIRECT_TPB); cfg.dynamicSmemBytes = 0; cfg.stream = st;
         cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
-        cfg.gridDim = dim3(nblk(S->ne));
+        cfg.gridDim = dim3((S->ne + DIRECT_TPB - 1) / DIRECT_TPB);
         const double* dnull = nullptr; double* wnull = nullptr;
         const uint8_t* nowrite = mixed ? S->elem_nowrite.p : nullptr;
         if (bbm)
@@ -705,7 +705,7 @@ static void phase_substep(nsx_solver* S, int s, bool exchange_sync, bool overlap
             NSX_CUDA(cudaLaunchKernelEx(&cfg, k_element_direct<0>, K, (const int*)S->en0.p, (const int*)S->en1.p, (const int*)S->en2.p,
                 A.VTc, (const double*)S->shape.p, (const double*)S->ec_e.p, A.s0i, A.s1i, A.s2i, dnull, A.s0o, A.s1o, A.s2o, wnull,
                 S->contrib.p, nowrite));
-        cfg.gridDim = dim3(nblk(S->nn));
+        cfg.gridDim = dim3((S->nn + DIRECT_TPB - 1) / DIRECT_TPB);
         int const skip = mixed ? (NF_BTILE | NF_GHOST) : 0;
         NSX_CUDA(cudaLaunchKernelEx(&cfg, k_node_direct, K, A.move_mesh, mixed ? 0 : A.lag_ghost_move, skip, (const uint8_t*)S->nflags.p,
             (const int*)S->n2e.p, (const int*)S->n2e_deg.p, (const double*)S->contrib.p, (const double*)S->grad_ssh.p,

@@ -724,8 +724,16 @@ k_subcycle(KParams K, SubArgs A)
 // saves in traffic when nothing comes from HBM anyway.  Same arithmetic, same summation order (the node kernel
 // walks the ascending-element ELL table and subtracts the staged contributions starting from grad_ssh).
 // ---------------------------------------------------------------------------------------------------
+#ifndef NSX_DIRECT_TPB
+#define NSX_DIRECT_TPB 256
+#endif
+#ifndef NSX_DIRECT_MINB
+#define NSX_DIRECT_MINB 1
+#endif
+constexpr int DIRECT_TPB = NSX_DIRECT_TPB;
+
 template <int BBM>
-__global__ void __launch_bounds__(TPB)
+__global__ void __launch_bounds__(DIRECT_TPB, NSX_DIRECT_MINB)
 k_element_direct(KParams K, const int* __restrict__ en0, const int* __restrict__ en1, const int* __restrict__ en2,
                  const double* __restrict__ VT, const double* __restrict__ shape, const double* __restrict__ ec,
                  const double* s0i, const double* s1i, const double* s2i, const double* di,
@@ -819,7 +827,7 @@ k_element_direct(KParams K, const int* __restrict__ en0, const int* __restrict__
     contrib[5 * NE + e] = vol * (s2 * dx2 + s1 * dy2);
 }
 
-__global__ void __launch_bounds__(TPB)
+__global__ void __launch_bounds__(DIRECT_TPB, NSX_DIRECT_MINB)
 k_node_direct(KParams K, int move_mesh, int lag_ghost_move, int skip_flag_mask,
               const uint8_t* __restrict__ nflags, const int* __restrict__ n2e, const int* __restrict__ n2e_deg,
               const double* __restrict__ contrib, const double* __restrict__ grad_ssh,
