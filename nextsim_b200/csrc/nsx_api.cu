@@ -647,6 +647,21 @@ static void launch_tiles(nsx_solver* S, SubArgs const& A, int tile_base, int nti
     S->n_launch++;
 }
 
+static DirectArgs direct_args(nsx_solver* S, SubArgs const& A, bool mixed)
+{
+    DirectArgs D{};
+    D.en0 = S->en0.p; D.en1 = S->en1.p; D.en2 = S->en2.p;
+    D.shape = S->shape.p; D.ec = S->ec_e.p;
+    D.s0 = A.s0o; D.s1 = A.s1o; D.s2 = A.s2o; D.dm = A.dmo;
+    D.s0i = A.s0i; D.s1i = A.s1i; D.s2i = A.s2i; D.di = A.di;
+    D.contrib = S->contrib.p; D.elem_nowrite = mixed ? S->elem_nowrite.p : nullptr;
+    D.nflags = S->nflags.p; D.n2e = S->n2e.p; D.n2e_deg = S->n2e_deg.p;
+    D.grad_ssh = S->grad_ssh.p; D.node_mass = S->node_mass.p; D.rlmass = S->rlmass.p; D.cbu = S->cbu.p; D.fcor = S->fcor.p;
+    D.tau_a = S->tau_a.p; D.tau_wi = A.tau_wi; D.ocean = S->ocean.p; D.VTM = S->VTM.p;
+    D.UM = S->UM.p; D.UT = S->UT.p;
+    return D;
+}
+
 // one sub-cycle including its ghost exchange; flips the VT and sigma parities.
 // overlap: boundary tiles first, then the halo kernel on the main stream while the interior tiles run on stream2.
 static void phase_substep(nsx_solver* S, int s, bool exchange_sync, bool overlap)
@@ -685,32 +700,12 @@ static void phase_substep(nsx_solver* S, int s, bool exchange_sync, bool overlap
     // direct path: one thread per element, then one per node.  `mixed`: the boundary tiles are handled by the tile
     // kernel of the boundary launch; here their elements are evaluated but not written and their nodes are skipped.
     auto launch_direct = [&](cudaStream_t st, bool mixed) {
-        // programmatic dependent launch (PDL) hooks exist in the kernels; measured slower on B200 (waiting CTAs hold
-        // SM resources), hence off unless NSX_PDL=1
-        static const bool pdl = (env_int("NSX_PDL", 0) != 0);
-        cudaLaunchAttribute attr[1];
-        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-        attr[0].val.programmaticStreamSerializationAllowed = 1;
-        cudaLaunchConfig_t cfg{};
-        cfg.blockDim = dim3(DIRECT_TPB); cfg.dynamicSmemBytes = 0; cfg.stream = st;
-        cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
-        cfg.gridDim = dim3((S->ne + DIRECT_TPB - 1) / DIRECT_TPB);
-        const double* dnull = nullptr; double* wnull = nullptr;
-        const uint8_t* nowrite = mixed ? S->elem_nowrite.p : nullptr;
-        if (bbm)
-            NSX_CUDA(cudaLaunchKernelEx(&cfg, k_element_direct<1>, K, (const int*)S->en0.p, (const int*)S->en1.p, (const int*)S->en2.p,
-                A.VTc, (const double*)S->shape.p, (const double*)S->ec_e.p, A.s0i, A.s1i, A.s2i, A.di, A.s0o, A.s1o, A.s2o, A.dmo,
-                S->contrib.p, nowrite));
-        else
-            NSX_CUDA(cudaLaunchKernelEx(&cfg, k_element_direct<0>, K, (const int*)S->en0.p, (const int*)S->en1.p, (const int*)S->en2.p,
-                A.VTc, (const double*)S->shape.p, (const double*)S->ec_e.p, A.s0i, A.s1i, A.s2i, dnull, A.s0o, A.s1o, A.s2o, wnull,
-                S->contrib.p, nowrite));
-        cfg.gridDim = dim3((S->nn + DIRECT_TPB - 1) / DIRECT_TPB);
+        DirectArgs D = direct_args(S, A, mixed);
+        int const ge = (S->ne + DIRECT_TPB - 1) / DIRECT_TPB, gn = (S->nn + DIRECT_TPB - 1) / DIRECT_TPB;
+        if (bbm) k_element_direct<1><<<ge, DIRECT_TPB, 0, st>>>(K, D, A.VTc);
+        else k_element_direct<0><<<ge, DIRECT_TPB, 0, st>>>(K, D, A.VTc);
         int const skip = mixed ? (NF_BTILE | NF_GHOST) : 0;
-        NSX_CUDA(cudaLaunchKernelEx(&cfg, k_node_direct, K, A.move_mesh, mixed ? 0 : A.lag_ghost_move, skip, (const uint8_t*)S->nflags.p,
-            (const int*)S->n2e.p, (const int*)S->n2e_deg.p, (const double*)S->contrib.p, (const double*)S->grad_ssh.p,
-            (const double*)S->node_mass.p, (const double*)S->rlmass.p, (const double*)S->cbu.p, (const double*)S->fcor.p,
-            (const double*)S->tau_a.p, A.tau_wi, (const double*)S->ocean.p, (const double*)S->VTM.p, A.VTc, A.VTn, S->UM.p, S->UT.p));
+        k_node_direct<<<gn, DIRECT_TPB, 0, st>>>(K, D, A.move_mesh, mixed ? 0 : A.lag_ghost_move, skip, A.VTc, A.VTn);
         S->n_launch += 2;
     };
     bool const fused = overlap && exchange_sync && nb > 0 && nb < nt && S->halo_ready;
@@ -826,9 +821,31 @@ static void solve_group(int n, nsx_solver** W)
             for (int q = 0; q < n; ++q)
                 if (q != r) NSX_CUDA(cudaStreamWaitEvent(W[r]->stream, W[q]->ev[5], 0));
     };
-    for (int s = 0; s < nrun; ++s) {
-        for (int r = 0; r < n; ++r) { NSX_CUDA(cudaSetDevice(W[r]->device)); phase_substep(W[r], s, remote, remote && overlap_on); }
-        if (n > 1) group_exchange();
+    // measured on B200: 15.0-15.6 us per sub-cycle against 14.2 us for the graph of two launches per sub-cycle (the
+    // grid barriers cost what the launches cost, and one CTA per SM leaves half the threads idle in each phase): off
+    static const bool persist_on = (env_int("NSX_PERSIST", 0) != 0);
+    if (n == 1 && W[0]->direct && W[0]->peers.empty() && persist_on && nrun > 0) {
+        // a rank without neighbours on an L2-resident mesh: the whole sub-cycle loop is ONE persistent launch
+        nsx_solver* S = W[0];
+        KParams const& K = S->K;
+        bool const bbm = (K.dynamics_type == NSX_DYN_BBM);
+        SubArgs A{};
+        A.s0i = A.s0o = S->sig[S->scur][0].p; A.s1i = A.s1o = S->sig[S->scur][1].p; A.s2i = A.s2o = S->sig[S->scur][2].p;
+        A.di = A.dmo = bbm ? S->dmg[S->dcur].p : nullptr;
+        A.tau_wi = S->have_tau_wi ? S->tau_wi.p : nullptr;
+        DirectArgs D = direct_args(S, A, false);
+        S->d_done.zero(S->stream);
+        int const move = (K.dynamics_type != NSX_DYN_MEVP);
+        if (bbm) k_direct_persistent<1><<<S->sm_count, PERSIST_TPB, 0, S->stream>>>(K, D, nrun, move, S->VT[0], S->VT[1], S->cur, S->d_done.p);
+        else k_direct_persistent<0><<<S->sm_count, PERSIST_TPB, 0, S->stream>>>(K, D, nrun, move, S->VT[0], S->VT[1], S->cur, S->d_done.p);
+        NSX_CUDA(cudaGetLastError());
+        S->n_launch++;
+        S->cur = (S->cur + nrun) & 1;
+    } else {
+        for (int s = 0; s < nrun; ++s) {
+            for (int r = 0; r < n; ++r) { NSX_CUDA(cudaSetDevice(W[r]->device)); phase_substep(W[r], s, remote, remote && overlap_on); }
+            if (n > 1) group_exchange();
+        }
     }
     for (int r = 0; r < n; ++r) {
         NSX_CUDA(cudaSetDevice(W[r]->device));

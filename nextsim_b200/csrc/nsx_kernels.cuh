@@ -732,49 +732,54 @@ k_subcycle(KParams K, SubArgs A)
 #endif
 constexpr int DIRECT_TPB = NSX_DIRECT_TPB;
 
-template <int BBM>
-__global__ void __launch_bounds__(DIRECT_TPB, NSX_DIRECT_MINB)
-k_element_direct(KParams K, const int* __restrict__ en0, const int* __restrict__ en1, const int* __restrict__ en2,
-                 const double* __restrict__ VT, const double* __restrict__ shape, const double* __restrict__ ec,
-                 const double* s0i, const double* s1i, const double* s2i, const double* di,
-                 double* s0o, double* s1o, double* s2o, double* dmo, double* __restrict__ contrib,
-                 const uint8_t* __restrict__ elem_nowrite)
+// loads of data another SM may have written earlier in the SAME kernel (persistent variant) go to L2 (.cg)
+template <int CG> __device__ __forceinline__ double ldv(const double* p) { return CG ? __ldcg(p) : *p; }
+
+struct DirectArgs {
+    const int* en0; const int* en1; const int* en2;
+    const double* shape; const double* ec;
+    double* s0; double* s1; double* s2; double* dm;         // updated in place (persistent) or in -> out
+    const double* s0i; const double* s1i; const double* s2i; const double* di;
+    double* contrib; const uint8_t* elem_nowrite;
+    const uint8_t* nflags; const int* n2e; const int* n2e_deg;
+    const double* grad_ssh; const double* node_mass; const double* rlmass; const double* cbu; const double* fcor;
+    const double* tau_a; const double* tau_wi; const double* ocean; const double* VTM;
+    double* UM; double* UT;
+};
+
+template <int BBM, int CG>
+__device__ __forceinline__ void direct_element(KParams const& K, DirectArgs const& A, int e, const double* VT)
 {
-    int const e = blockIdx.x * blockDim.x + threadIdx.x;
     int const ne = K.ne, nn = K.nn;
-    // programmatic dependent launch: let the node kernel's CTAs become resident while this grid drains, and do not
-    // read what the previous kernel wrote (VT) before it has completed
-    asm volatile("griddepcontrol.launch_dependents;");
-    asm volatile("griddepcontrol.wait;" ::: "memory");
-    if (e >= ne) return;
     size_t const NE = (size_t)ne;
     // elements whose writer tile is a boundary tile are written by the tile kernel of the boundary launch; they are
     // still evaluated here because interior nodes next to them need their contributions
-    bool const nowrite = elem_nowrite && elem_nowrite[e];
-    double const c0 = ec[e];
-    double const dx0 = shape[e], dx1 = shape[NE + e], dx2 = shape[2 * NE + e];
-    double const dy0 = shape[3 * NE + e], dy1 = shape[4 * NE + e], dy2 = shape[5 * NE + e];
+    bool const nowrite = A.elem_nowrite && A.elem_nowrite[e];
+    double const c0 = A.ec[e];
+    double const dx0 = A.shape[e], dx1 = A.shape[NE + e], dx2 = A.shape[2 * NE + e];
+    double const dy0 = A.shape[3 * NE + e], dy1 = A.shape[4 * NE + e], dy2 = A.shape[5 * NE + e];
     double s0, s1, s2, vol;
     if (BBM) {
         double const expC = c0;
-        vol = ec[5 * NE + e];
+        vol = A.ec[5 * NE + e];
         double d;
-        if (expC == 0.) {
+        if (expC == 0.) {                   // conc <= 0.1 : no ice (FE.cpp:4151-4159)
             s0 = s1 = s2 = 0.;
             d = 0.;
         } else {
-            int const a = en0[e], b = en1[e], c = en2[e];
-            double const ua = VT[a], va = VT[a + nn], ub = VT[b], vb = VT[b + nn], uc = VT[c], vc = VT[c + nn];
+            int const a = A.en0[e], b = A.en1[e], c = A.en2[e];
+            double const ua = ldv<CG>(VT + a), va = ldv<CG>(VT + a + nn), ub = ldv<CG>(VT + b), vb = ldv<CG>(VT + b + nn),
+                         uc = ldv<CG>(VT + c), vc = ldv<CG>(VT + c + nn);
             double e0 = dx0 * ua; e0 += dx1 * ub; e0 += dx2 * uc;
             double e1 = dy0 * va; e1 += dy1 * vb; e1 += dy2 * vc;
             double e2 = dy0 * ua; e2 += dx0 * va; e2 += dy1 * ub; e2 += dx1 * vb; e2 += dy2 * uc; e2 += dx2 * vc;
-            s0 = s0i[e]; s1 = s1i[e]; s2 = s2i[e]; d = di[e];
+            s0 = A.s0i[e]; s1 = A.s1i[e]; s2 = A.s2i[e]; d = A.di[e];
             double const dt = K.dte;
             double sigma_n = (s0 + s1) * 0.5;
             double const omd = 1. - d;
             double const time_viscous = K.lambda0 * pow_relax(omd * expC, K);
             double tildeP = 0.;
-            if (sigma_n < 0.) tildeP = fmin(1., fast_div(-ec[NE + e], sigma_n));
+            if (sigma_n < 0.) tildeP = fmin(1., fast_div(-A.ec[NE + e], sigma_n));
             double const mult = fmin(1. - 1e-12, fast_div(time_viscous, time_viscous + dt * (1. - tildeP)));
             double const elasticity = K.young * omd * expC;
             double const dtE = dt * elasticity;
@@ -785,31 +790,32 @@ k_element_direct(KParams K, const int* __restrict__ en0, const int* __restrict__
             sigma_n = (s0 + s1) * 0.5;
             double dcrit;
             if (sigma_n < -K.compr_strength) dcrit = fast_div(-K.compr_strength, sigma_n);
-            else dcrit = fast_div(ec[2 * NE + e], sigma_s + K.tan_phi * sigma_n);
+            else dcrit = fast_div(A.ec[2 * NE + e], sigma_s + K.tan_phi * sigma_n);
             if ((0. < dcrit) && (dcrit < 1.)) {
-                double const rtd = fast_sqrt(elasticity) * ec[3 * NE + e];
+                double const rtd = fast_sqrt(elasticity) * A.ec[3 * NE + e];
                 double const f = (1. - dcrit) * dt * rtd;
                 d += omd * f;
                 s0 -= s0 * f;  s1 -= s1 * f;  s2 -= s2 * f;
             }
-            d = fmax(0., d - ec[4 * NE + e]);
+            d = fmax(0., d - A.ec[4 * NE + e]);
         }
-        if (!nowrite) dmo[e] = d;
+        if (!nowrite) A.dm[e] = d;
     } else {
         double const Pp = c0;
-        vol = ec[NE + e];
-        if (Pp < 0.) {
+        vol = A.ec[NE + e];
+        if (Pp < 0.) {                      // thick == 0 (FE.cpp:10656-10662)
             s0 = s1 = s2 = 0.;
         } else {
-            int const a = en0[e], b = en1[e], c = en2[e];
-            double const ua = VT[a], va = VT[a + nn], ub = VT[b], vb = VT[b + nn], uc = VT[c], vc = VT[c + nn];
+            int const a = A.en0[e], b = A.en1[e], c = A.en2[e];
+            double const ua = ldv<CG>(VT + a), va = ldv<CG>(VT + a + nn), ub = ldv<CG>(VT + b), vb = ldv<CG>(VT + b + nn),
+                         uc = ldv<CG>(VT + c), vc = ldv<CG>(VT + c + nn);
             double eps11 = dx0 * ua; eps11 += dx1 * ub; eps11 += dx2 * uc;
             double eps22 = dy0 * va; eps22 += dy1 * vb; eps22 += dy2 * vc;
             double eps12 = 0.5 * (dx0 * va + dy0 * ua); eps12 += 0.5 * (dx1 * vb + dy1 * ub); eps12 += 0.5 * (dx2 * vc + dy2 * uc);
             double const eps1 = eps11 + eps22, eps2 = eps11 - eps22;
             double const delta = fast_sqrt(eps1 * eps1 + (eps2 * eps2 + 4 * eps12 * eps12) * K.re2);
             double const zeta = fast_div(Pp, delta + K.evp_dmin);
-            s0 = s0i[e]; s1 = s1i[e]; s2 = s2i[e];
+            s0 = A.s0i[e]; s1 = A.s1i[e]; s2 = A.s2i[e];
             double sigma1 = s0 + s1, sigma2 = s0 - s1;
             sigma1 += K.ralpha1 * (zeta * (eps1 - delta) - sigma1);
             sigma2 += K.ralpha2 * (zeta * eps2 * K.re2 - sigma2);
@@ -818,70 +824,60 @@ k_element_direct(KParams K, const int* __restrict__ en0, const int* __restrict__
             s1 = 0.5 * (sigma1 - sigma2);
         }
     }
-    if (!nowrite) { s0o[e] = s0; s1o[e] = s1; s2o[e] = s2; }
-    contrib[0 * NE + e] = vol * (s0 * dx0 + s2 * dy0);
-    contrib[1 * NE + e] = vol * (s0 * dx1 + s2 * dy1);
-    contrib[2 * NE + e] = vol * (s0 * dx2 + s2 * dy2);
-    contrib[3 * NE + e] = vol * (s2 * dx0 + s1 * dy0);
-    contrib[4 * NE + e] = vol * (s2 * dx1 + s1 * dy1);
-    contrib[5 * NE + e] = vol * (s2 * dx2 + s1 * dy2);
+    if (!nowrite) { A.s0[e] = s0; A.s1[e] = s1; A.s2[e] = s2; }
+    // nodal contributions V*(sigma . grad N_i)  (FE.cpp:10464-10465)
+    A.contrib[0 * NE + e] = vol * (s0 * dx0 + s2 * dy0);
+    A.contrib[1 * NE + e] = vol * (s0 * dx1 + s2 * dy1);
+    A.contrib[2 * NE + e] = vol * (s0 * dx2 + s2 * dy2);
+    A.contrib[3 * NE + e] = vol * (s2 * dx0 + s1 * dy0);
+    A.contrib[4 * NE + e] = vol * (s2 * dx1 + s1 * dy1);
+    A.contrib[5 * NE + e] = vol * (s2 * dx2 + s1 * dy2);
 }
 
-__global__ void __launch_bounds__(DIRECT_TPB, NSX_DIRECT_MINB)
-k_node_direct(KParams K, int move_mesh, int lag_ghost_move, int skip_flag_mask,
-              const uint8_t* __restrict__ nflags, const int* __restrict__ n2e, const int* __restrict__ n2e_deg,
-              const double* __restrict__ contrib, const double* __restrict__ grad_ssh,
-              const double* __restrict__ node_mass, const double* __restrict__ rlmass,
-              const double* __restrict__ cbu, const double* __restrict__ fcor,
-              const double* __restrict__ tau_a, const double* __restrict__ tau_wi,
-              const double* __restrict__ ocean, const double* __restrict__ VTM,
-              const double* __restrict__ VTc, double* __restrict__ VTn,
-              double* __restrict__ UM, double* __restrict__ UT)
+template <int CG>
+__device__ __forceinline__ void direct_node(KParams const& K, DirectArgs const& A, int n, int move_mesh, int lag_ghost_move,
+                                            int skip_flag_mask, const double* VTc, double* VTn)
 {
-    int const n = blockIdx.x * blockDim.x + threadIdx.x;
     int const nn = K.nn, ne = K.ne;
-    asm volatile("griddepcontrol.launch_dependents;");
-    asm volatile("griddepcontrol.wait;" ::: "memory");
-    if (n >= nn) return;
-    uint8_t const fl = nflags[n];
+    uint8_t const fl = A.nflags[n];
     if (fl & skip_flag_mask) return;            // nodes of boundary tiles (and ghosts) belong to the boundary launch
-    double const uice = VTc[n], vice = VTc[n + nn];
+    double const uice = ldv<CG>(VTc + n), vice = ldv<CG>(VTc + n + nn);
     if (fl & NF_GHOST) {
         if (lag_ghost_move) {
-            UT[n] += K.dte * uice;  UT[n + nn] += K.dte * vice;
-            if (!(fl & NF_NEUMANN)) { UM[n] += K.dte * uice;  UM[n + nn] += K.dte * vice; }
+            A.UT[n] += K.dte * uice;  A.UT[n + nn] += K.dte * vice;
+            if (!(fl & NF_NEUMANN)) { A.UM[n] += K.dte * uice;  A.UM[n + nn] += K.dte * vice; }
         }
         return;
     }
     double un = uice, vn = vice;
-    double const nm = node_mass[n];
+    double const nm = A.node_mass[n];
     if (!(fl & NF_DIRICHLET) && nm != 0.) {
-        double gu = grad_ssh[n], gv = grad_ssh[n + nn];
-        int const deg = n2e_deg[n];
-        for (int k = 0; k < deg; ++k) {
-            int const s = n2e[(size_t)k * nn + n];
-            gu -= contrib[s];
-            gv -= contrib[s + 3 * (size_t)ne];
+        double gu = A.grad_ssh[n], gv = A.grad_ssh[n + nn];
+        int const deg = A.n2e_deg[n];
+        for (int k = 0; k < deg; ++k) {             // ascending reference element order (FE.cpp:10445-10467)
+            int const s = A.n2e[(size_t)k * nn + n];
+            gu -= ldv<CG>(A.contrib + s);
+            gv -= ldv<CG>(A.contrib + s + 3 * (size_t)ne);
         }
         double dtep = K.dte, delu = 0., delv = 0.;
         if (K.dynamics_type == NSX_DYN_MEVP) {
-            delu = (VTM[n] - uice) * K.mevp_rb;
-            delv = (VTM[n + nn] - vice) * K.mevp_rb;
+            delu = (A.VTM[n] - uice) * K.mevp_rb;
+            delv = (A.VTM[n + nn] - vice) * K.mevp_rb;
             dtep = K.dte_mevp;
         }
         double const dte_over_mass = fast_div(dtep, fmax(K.min_m, nm));
-        double const ou = ocean[n], ov = ocean[n + nn];
+        double const ou = A.ocean[n], ov = A.ocean[n + nn];
         double const c_prime = K.rhow_cdw * fast_hypot(ou - uice, ov - vice);
-        double const tau_b = cbu[n] * fast_div(1., fast_hypot(uice, vice) + K.u0);
-        double const sin_s = (fl & NF_LATNEG) ? -K.sin_ota_abs : K.sin_ota_abs;
+        double const tau_b = A.cbu[n] * fast_div(1., fast_hypot(uice, vice) + K.u0);
+        double const sin_s = (fl & NF_LATNEG) ? -K.sin_ota_abs : K.sin_ota_abs;   // std::copysign(sin, lat[i])
         double const alpha = 1. + dte_over_mass * (c_prime * K.cos_ota + tau_b);
-        double const beta = dtep * fcor[n] + dte_over_mass * c_prime * sin_s;
+        double const beta = dtep * A.fcor[n] + dte_over_mass * c_prime * sin_s;
         double const rdenom = fast_div(1., alpha * alpha + beta * beta);
-        double tau_x = tau_a[n], tau_y = tau_a[n + nn];
-        if (tau_wi) { tau_x = tau_x + tau_wi[n]; tau_y = tau_y + tau_wi[n + nn]; }
+        double tau_x = A.tau_a[n], tau_y = A.tau_a[n + nn];
+        if (A.tau_wi) { tau_x = tau_x + A.tau_wi[n]; tau_y = tau_y + A.tau_wi[n + nn]; }
         tau_x = tau_x + c_prime * (ou * K.cos_ota - ov * sin_s);
         tau_y = tau_y + c_prime * (ov * K.cos_ota + ou * sin_s);
-        double const rl = rlmass[n];
+        double const rl = A.rlmass[n];
         double const grad_x = gu * rl, grad_y = gv * rl;
         un = alpha * uice + beta * vice + dte_over_mass * (alpha * (grad_x + tau_x) + beta * (grad_y + tau_y)) + alpha * delu + beta * delv;
         un *= rdenom;
@@ -891,8 +887,63 @@ k_node_direct(KParams K, int move_mesh, int lag_ghost_move, int skip_flag_mask,
     VTn[n] = un;
     VTn[n + nn] = vn;
     if (move_mesh) {
-        UT[n] += K.dte * un;  UT[n + nn] += K.dte * vn;
-        if (!(fl & NF_NEUMANN)) { UM[n] += K.dte * un;  UM[n + nn] += K.dte * vn; }
+        A.UT[n] += K.dte * un;  A.UT[n + nn] += K.dte * vn;
+        if (!(fl & NF_NEUMANN)) { A.UM[n] += K.dte * un;  A.UM[n + nn] += K.dte * vn; }
+    }
+}
+
+template <int BBM>
+__global__ void __launch_bounds__(DIRECT_TPB, NSX_DIRECT_MINB)
+k_element_direct(KParams K, DirectArgs A, const double* __restrict__ VT)
+{
+    int const e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= K.ne) return;
+    direct_element<BBM, 0>(K, A, e, VT);
+}
+
+__global__ void __launch_bounds__(DIRECT_TPB, NSX_DIRECT_MINB)
+k_node_direct(KParams K, DirectArgs A, int move_mesh, int lag_ghost_move, int skip_flag_mask,
+              const double* __restrict__ VTc, double* __restrict__ VTn)
+{
+    int const n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= K.nn) return;
+    direct_node<0>(K, A, n, move_mesh, lag_ghost_move, skip_flag_mask, VTc, VTn);
+}
+
+// Whole sub-cycle loop of a rank WITHOUT neighbours in one launch: a persistent grid (one CTA per SM, all
+// resident) alternates the element phase and the node phase, separated by a software grid barrier.  No kernel
+// boundaries (a dependent launch costs ~3 us, a sub-cycle of the 2e5-element mesh ~8 us of work), sigma/damage
+// are updated in place, VT ping-pongs between the two buffers exactly like the launch-per-phase variant.
+constexpr int PERSIST_TPB = 768;
+
+__device__ __forceinline__ void grid_barrier(unsigned int* ctr, unsigned int& target)
+{
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        target += gridDim.x;
+        __threadfence();
+        atomicAdd(ctr, 1u);
+        unsigned int v;
+        long long spins = 0;                // bounded: a grid that is not fully resident must not hang the GPU
+        do { asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory"); } while (v < target && ++spins < (1LL << 31));
+        __threadfence();                    // also drops this SM's L1 lines: the next phase reads other SMs' results
+    }
+    __syncthreads();
+}
+
+template <int BBM>
+__global__ void __launch_bounds__(PERSIST_TPB, 1)
+k_direct_persistent(KParams K, DirectArgs A, int nsub, int move_mesh, double* VT0, double* VT1, int cur, unsigned int* bar)
+{
+    unsigned int target = 0;
+    int const gt = blockIdx.x * blockDim.x + threadIdx.x, gn = gridDim.x * blockDim.x;
+    for (int s = 0; s < nsub; ++s) {
+        const double* VTc = ((cur + s) & 1) ? VT1 : VT0;
+        double* VTn = ((cur + s) & 1) ? VT0 : VT1;
+        for (int e = gt; e < K.ne; e += gn) direct_element<BBM, 1>(K, A, e, VTc);
+        grid_barrier(bar, target);
+        for (int n = gt; n < K.nn; n += gn) direct_node<1>(K, A, n, move_mesh, 0, 0, VTc, VTn);
+        grid_barrier(bar, target);
     }
 }
 
