@@ -23,6 +23,7 @@ CONFIGS = {
     "10km": dict(mesh="10km", kind="large", dt=200.0, alea_factor=0.33),
     "10km_stable": dict(mesh="10km", kind="stable", dt=200.0, alea_factor=0.33),
     "3km": dict(mesh="3km", kind="large", dt=200.0, alea_factor=0.33),
+    "3km_stable": dict(mesh="3km", kind="stable", dt=200.0, alea_factor=0.33),
     "1km": dict(mesh="1km", kind="large", dt=200.0, alea_factor=0.33),
 }
 

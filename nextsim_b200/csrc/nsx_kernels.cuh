@@ -484,7 +484,7 @@ k_subcycle(KParams K, SubArgs A)
                 double const u = A.VTc[g], v = A.VTc[g + nn];
                 double const a0 = A.s0i[e], a1 = A.s1i[e], a2 = A.s2i[e];
                 double const ad = BBM ? A.di[e] : 0.;
-                if (hn_ok) { su[td.n_own + j] = u; sv[td.n_own + j] = v; }
+                if (hn_ok) { su[td.n_own + HALO_GAP + j] = u; sv[td.n_own + HALO_GAP + j] = v; }
                 if (he_ok) { hsg[j] = a0; hsg[L.mhs + j] = a1; hsg[2 * L.mhs + j] = a2; if (BBM) hsg[3 * L.mhs + j] = ad; }
             }
             __syncwarp();

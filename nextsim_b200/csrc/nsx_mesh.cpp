@@ -233,7 +233,7 @@ void build_mesh_plan(const NsxMesh* M, MeshPlan& P, int target_tile_nodes, int s
             for (int i = 0; i < 3; ++i) {
                 int const n = P.en[i][ie];
                 if (stamp_n[n] != t) {
-                    stamp_n[n] = t; lidx[n] = td.n_own + nhn; ++nhn;
+                    stamp_n[n] = t; lidx[n] = td.n_own + HALO_GAP + nhn; ++nhn;
                     P.halo_nodes.push_back(n);
                     if (n >= ndof) td.boundary = 1;          // reads a ghost slot
                 }
@@ -242,7 +242,7 @@ void build_mesh_plan(const NsxMesh* M, MeshPlan& P, int target_tile_nodes, int s
             P.slot_conn.push_back(packed);
         }
         td.n_halo = nhn;
-        if (td.n_own + nhn > 65535 || 3 * nslots > 65534)
+        if (td.n_own + HALO_GAP + nhn > 65535 || 3 * nslots > 65534)
             throw std::invalid_argument("nsx_create: tile too large for 16-bit local ids");
         // incidence table of the owned nodes, reference-ascending element order, column-major
         td.inc_off = (int)P.inc.size();
@@ -256,7 +256,7 @@ void build_mesh_plan(const NsxMesh* M, MeshPlan& P, int target_tile_nodes, int s
                 P.inc[td.inc_off + (size_t)c * td.n_own + j] = (uint16_t)(slot_of[ie] * 3 + i);
             }
         }
-        P.max_local_nodes = std::max(P.max_local_nodes, td.n_own + nhn);
+        P.max_local_nodes = std::max(P.max_local_nodes, td.n_own + HALO_GAP + nhn);
         P.max_slots = std::max(P.max_slots, nslots);
         P.max_own_slots = std::max(P.max_own_slots, td.n_own_slots);
         P.max_halo_slots = std::max(P.max_halo_slots, nh);

@@ -25,6 +25,10 @@ struct TileDesc {
 };
 static_assert(sizeof(TileDesc) == 64, "TileDesc is 16 ints");
 
+// The owned nodes' velocities are staged by a TMA copy that is rounded up to 16-byte granules, i.e. it may write up to
+// two doubles past the owned range; the halo nodes (written by plain stores) therefore start HALO_GAP entries later.
+constexpr int HALO_GAP = 2;
+
 struct MeshPlan {
     int nn = 0, ndof = 0, ne = 0, ne_local = 0;
     std::vector<int> node_perm, node_inv;      // reference local id -> internal id, and back

@@ -257,3 +257,39 @@ def test_params_required_and_validated():
     with pytest.raises(RuntimeError, match="dynamics_type"):
         s.set_params(p)
     s.close()
+
+
+# ---- full BASELINE sizes: size-independent properties -------------------------------------------------------
+@pytest.mark.parametrize("dyn", ["bbm", "mevp"])
+def test_3km_full_size_paths_agree_and_invariants(dyn, solver_path, monkeypatch):
+    """BASELINE config #4 mesh (2 000 000 elements; the oracle would need minutes): the two independent sub-cycle
+    implementations (TMA tile pipeline with Hilbert tiles and redundant halo slots vs. direct element/node
+    kernels) must agree to 1e-9 after a full model step + update(), the checkFieldsFast invariants must hold,
+    Dirichlet nodes must stay at rest and update() must conserve ice volume."""
+    if solver_path != "tiles":
+        pytest.skip("runs both paths itself")
+    c = cases.make_case("3km_stable", nranks=1, dyn=dyn, young=False)
+    keys = ("M_VT", "M_sigma", "M_damage", "M_UM", "M_thick", "M_conc", "M_surface")
+    res = {}
+    for path in ("tiles", "direct"):
+        monkeypatch.setenv("NSX_PATH", path)
+        s = cases.make_solvers(c)[0]
+        s.explicit_solve()
+        pre = s.download("M_thick", "M_surface")
+        s.update()
+        res[path] = s.download(*keys)
+        chk = s.check()
+        assert chk.n_nan == 0 and chk.n_range == 0 and chk.n_speed == 0
+        vol0 = pre["M_thick"] * pre["M_surface"]
+        vol1 = res[path]["M_thick"] * res[path]["M_surface"]
+        ice = pre["M_thick"] > 0
+        assert np.allclose(vol1[ice], vol0[ice], rtol=1e-12)
+        s.close()
+    for k in keys:
+        pairs = zip(res["tiles"][k], res["direct"][k]) if k == "M_sigma" else [(res["tiles"][k], res["direct"][k])]
+        for a, b in pairs:
+            assert ob.rel_l2(a, b) <= TOL, k
+    nn = c.gm.nn
+    d = c.gm.dirichlet_flags_root - 1
+    assert np.all(res["tiles"]["M_VT"][d] == 0.0) and np.all(res["tiles"]["M_VT"][d + nn] == 0.0)
+    assert np.abs(res["tiles"]["M_VT"]).max() < 5.0
