@@ -59,7 +59,7 @@ static SmemLayout sub_layout(MeshPlan const& P, int n_node_planes)
     L.total = (int)o;
     return L;
 }
-constexpr int SUB_SMEM_CAP = (227 * 1024 - 128) / SUB_STAGES;     // per stage; one persistent CTA per SM (227 KB)
+constexpr int SUB_SMEM_CAP = ((227 * 1024) / SUB_CTAS_PER_SM - 1024 * (SUB_CTAS_PER_SM - 1) - 128) / SUB_STAGES;     // per stage; one persistent CTA per SM (227 KB)
 
 // ---------------------------------------------------------------------------------------------------
 // life cycle
@@ -218,7 +218,7 @@ extern "C" int nsx_create(const NsxMesh* mesh, const NsxHalo* halo, int device, 
         int target = env_int("NSX_TILE_NODES", 208);
         for (int attempt = 0;; ++attempt) {
             S->plan = MeshPlan();
-            build_mesh_plan(mesh, S->plan, target, S->sm_count * env_int("NSX_SUB_OCC", 1));
+            build_mesh_plan(mesh, S->plan, target, S->sm_count * SUB_CTAS_PER_SM);
             if (sub_layout(S->plan, 14).total <= SUB_SMEM_CAP) break;
             if (attempt > 12 || target <= 32) throw std::invalid_argument("nsx_create: cannot fit a tile in shared memory");
             target = std::max(32, (int)(target * 0.88));
@@ -640,7 +640,7 @@ static void launch_tiles(nsx_solver* S, SubArgs const& A, int tile_base, int nti
     a.tile_base = tile_base;
     a.n_tiles = ntiles;
     // persistent CTAs, one per SM (two shared-memory stages each); CTA b takes tiles b, b+grid, ...
-    int const grid = std::max(1, std::min(ntiles, max_ctas));
+    int const grid = std::max(1, std::min(ntiles, max_ctas * SUB_CTAS_PER_SM));
     size_t const smem = 128 + (size_t)SUB_STAGES * A.L.total;
     if (S->K.dynamics_type == NSX_DYN_BBM) k_subcycle<1><<<grid, SUB_TPB, smem, st>>>(S->K, a);
     else k_subcycle<0><<<grid, SUB_TPB, smem, st>>>(S->K, a);

@@ -430,18 +430,39 @@ constexpr int SUB_CONS = SUB_TPB - SUB_PROD;    // consumer threads
 #endif
 constexpr int SUB_GROUPS = NSX_SUB_GROUPS;      // consumer groups, each working on its own tile (latency chains overlap)
 constexpr int SUB_GS = SUB_CONS / SUB_GROUPS;   // threads per consumer group
+#ifndef NSX_SUB_NODE_THREADS
+#define NSX_SUB_NODE_THREADS 0
+#endif
+// Role split of the consumers (0 = off): the last SUB_NODE_THREADS consumer threads only run phase 2 (nodes) and the
+// others only phase 1 (elements), so that phase 2 of tile t overlaps phase 1 of tile t+1; a third mbarrier ring
+// (p1done) hands the contributions from the element warps to the node warps.
+constexpr int SUB_NODE_THREADS = NSX_SUB_NODE_THREADS;
+constexpr int SUB_ELEM_THREADS = SUB_CONS - SUB_NODE_THREADS;
+static_assert(SUB_NODE_THREADS % 32 == 0 && (SUB_NODE_THREADS == 0 || SUB_GROUPS == 1), "role split needs whole warps, one group");
 static_assert(SUB_GS % 32 == 0 && SUB_GS * SUB_GROUPS == SUB_CONS, "consumer groups must be whole warps");
 static_assert(SUB_STAGES > SUB_GROUPS || SUB_GROUPS == 1, "need one more stage than tiles in compute");
+__device__ __forceinline__ void p2_sync();      // barrier over the threads that ran phase 2 (defined below)
 __device__ __forceinline__ void cons_sync(int group)
 {
     asm volatile("bar.sync %0, %1;" ::"r"(1 + group), "n"(SUB_GS) : "memory");
 }
 
+__device__ __forceinline__ void p2_sync()
+{
+    if (SUB_NODE_THREADS > 0) asm volatile("bar.sync 3, %0;" ::"n"(SUB_NODE_THREADS > 0 ? SUB_NODE_THREADS : 32) : "memory");
+    else asm volatile("bar.sync 1, %0;" ::"n"(SUB_GS) : "memory");
+}
+
 // Persistent, warp-specialised, double-buffered: CTA b works on tiles b, b+grid, b+2*grid, ... of its launch
 // range.  The producer warp streams tile t+1 into the other stage while the consumer warps compute tile t
 // (full[s]: TMA transaction barrier, empty[s]: one arrival per consumer warp when the stage may be refilled).
+#ifndef NSX_SUB_CTAS_PER_SM
+#define NSX_SUB_CTAS_PER_SM 1
+#endif
+constexpr int SUB_CTAS_PER_SM = NSX_SUB_CTAS_PER_SM;      // persistent CTAs per SM (each with its own stage ring)
+
 template <int BBM>
-__global__ void __launch_bounds__(SUB_TPB, 1)
+__global__ void __launch_bounds__(SUB_TPB, NSX_SUB_CTAS_PER_SM)
 k_subcycle(KParams K, SubArgs A)
 {
     extern __shared__ __align__(128) unsigned char sm_all[];
@@ -450,11 +471,14 @@ k_subcycle(KParams K, SubArgs A)
     int const tid = threadIdx.x;
     uint64_t* const full = (uint64_t*)sm_all;
     uint64_t* const empty = full + SUB_STAGES;
+    uint64_t* const p1done = empty + SUB_STAGES;
+    constexpr bool SPLIT = SUB_NODE_THREADS > 0;
     unsigned char* const stage0 = sm_all + 128;     // header: barriers [0,96), fused-halo flag at 120
     if (tid == 0) {
         for (int q = 0; q < SUB_STAGES; ++q) {
             mbar_init(full + q, SUB_PROD / 32);       // one arrival (with its TMA bytes) per producer warp
-            mbar_init(empty + q, SUB_GS / 32);        // one arrival per warp of the consuming group
+            mbar_init(empty + q, (SPLIT ? SUB_NODE_THREADS : SUB_GS) / 32);   // one arrival per warp that reads the stage last
+            mbar_init(p1done + q, SUB_ELEM_THREADS / 32);
         }
     }
     __syncthreads();
@@ -494,12 +518,16 @@ k_subcycle(KParams K, SubArgs A)
     }
 
     // ---- consumers ----
-    int const grp = tid / SUB_GS;               // consumer group; it takes tiles grp, grp + SUB_GROUPS, ...
-    int const gtid = tid - grp * SUB_GS;
+    bool const node_role = SPLIT && tid >= SUB_ELEM_THREADS;
+    bool const do_p1 = !SPLIT || !node_role, do_p2 = !SPLIT || node_role;
+    int const grp = SPLIT ? 0 : tid / SUB_GS;   // consumer group; it takes tiles grp, grp + SUB_GROUPS, ...
+    int const gtid = SPLIT ? (node_role ? tid - SUB_ELEM_THREADS : tid) : tid - grp * SUB_GS;
+    int const gstride = SPLIT ? (node_role ? SUB_NODE_THREADS : SUB_ELEM_THREADS) : SUB_GS;
     for (int it = grp; it < n_my; it += SUB_GROUPS) {
     int const s = it % SUB_STAGES;
     unsigned char* const sm = stage0 + (size_t)s * L.total;
-    mbar_wait(full + s, (it / SUB_STAGES) & 1);
+    if (node_role) mbar_wait(p1done + s, (it / SUB_STAGES) & 1);      // implies the stage is full
+    else mbar_wait(full + s, (it / SUB_STAGES) & 1);
     TileDesc const td = *(const TileDesc*)(sm + L.bar);
 
     // shifted views of the staged planes
@@ -522,7 +550,8 @@ k_subcycle(KParams K, SubArgs A)
 
     // ---- phase 1 ----
     int const nsl = td.n_own_slots + td.n_halo_slots;
-    for (int k = gtid; k < nsl; k += SUB_GS) {
+    if (do_p1)
+    for (int k = gtid; k < nsl; k += gstride) {
         bool const own = k < td.n_own_slots;
         int const e = td.elem_begin + k;            // meaningful for writer slots only
         int const hk = k - td.n_own_slots;
@@ -608,12 +637,16 @@ k_subcycle(KParams K, SubArgs A)
         shp[4 * MSP + k] = vol * (s2 * dx1 + s1 * dy1);
         shp[5 * MSP + k] = vol * (s2 * dx2 + s1 * dy2);
     }
-    cons_sync(grp);
+    if (SPLIT) {
+        if (!node_role) { __syncwarp(); if ((tid & 31) == 0) mbar_arrive(p1done + s); continue; }
+    } else {
+        cons_sync(grp);
+    }
 
     // ---- phase 2 ----
     const double* const npl = (const double*)(sm + L.node);
     int const shs = stage_shift(A.node_mass + nb, 8);       // scalar node planes and u halves: same phase as nb
-    for (int j = gtid; j < td.n_own; j += SUB_GS) {
+    for (int j = gtid; j < td.n_own; j += gstride) {
         int const n = nb + j;
         uint8_t const fl = flp[j];
         double const uice = su[j], vice = sv[j];
@@ -675,7 +708,7 @@ k_subcycle(KParams K, SubArgs A)
     }
     // ghost nodes: moved with the velocity their owner pushed at the end of the previous sub-cycle
     if (A.lag_ghost_move) {
-        for (int j = gtid; j < td.n_ghost; j += SUB_GS) {
+        for (int j = gtid; j < td.n_ghost; j += gstride) {
             int const n = td.ghost_begin + j;
             double const u = A.VTc[n], v = A.VTc[n + nn];
             A.UT[n] += K.dte * u;  A.UT[n + nn] += K.dte * v;
@@ -687,14 +720,14 @@ k_subcycle(KParams K, SubArgs A)
     if ((tid & 31) == 0) mbar_arrive(empty + s);
     }   // tile loop
 
-    if (A.fuse_halo) {
+    if (A.fuse_halo && do_p2) {
         // every sent value of this CTA is on its way: count the CTA in; the last one publishes the epoch in every
         // holder's flag slot (release, system scope) and waits for the owners of this rank's ghosts (bounded spin)
         volatile int& s_last = *(volatile int*)(sm_all + 120);
         __threadfence_system();
-        cons_sync(grp);
+        p2_sync();
         if (gtid == 0) s_last = (atomicAdd(A.done_ctr, 1u) == gridDim.x - 1);
-        cons_sync(grp);
+        p2_sync();
         if (s_last) {
             __threadfence_system();
             unsigned long long const epoch = *((volatile unsigned long long*)A.epoch_ctr) + 1ULL;
@@ -712,7 +745,7 @@ k_subcycle(KParams K, SubArgs A)
                     __nanosleep(64);
                 }
             }
-            cons_sync(grp);
+            p2_sync();
             if (gtid == 0) { *A.epoch_ctr = epoch; *A.done_ctr = 0u; }
         }
     }
