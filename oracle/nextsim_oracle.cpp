@@ -1055,22 +1055,22 @@ static void nodalGridAll(int const nranks, int const global_num_nodes, double co
     {
         for (int e=0; e<global_num_elements; ++e)
         {
+            // setPartition() (entities.hpp:105-134) decides from the tags alone; build the element only if it stays
+            bool on_proc = false, is_ghost = false;
+            if (nranks == 1) on_proc = true;
+            else if (r == gpart[e]) on_proc = true;
+            else
+                for (int q=ghost_ptr[e]; q<ghost_ptr[e+1]; ++q)
+                    if (ghost_val[q] % nranks == r) { on_proc = true; is_ghost = true; break; }
+            if (!on_proc) continue;
             GElt g;
             g.number = e+1;
             g.partition = gpart[e];
             for (int q=ghost_ptr[e]; q<ghost_ptr[e+1]; ++q)
                 g.ghosts.push_back(ghost_val[q] % nranks);
             for (int i=0;i<3;++i) { g.indices[i] = gtri[3*e+i]; g.ghostNodes[i]=0; }
-            bool on_proc = false;
-            g.is_ghost = false;
-            if (nranks == 1) on_proc = true;
-            else if (r == g.partition) on_proc = true;
-            else if (std::find(g.ghosts.begin(), g.ghosts.end(), r) != g.ghosts.end())
-            {
-                on_proc = true;
-                g.is_ghost = true;
-            }
-            if (on_proc) S[r].M_triangles.push_back(g);
+            g.is_ghost = is_ghost;
+            S[r].M_triangles.push_back(g);
         }
     }
 
