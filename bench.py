@@ -282,6 +282,34 @@ def run_ours(args):
         L.nsx_host_unregister(a.ctypes.data)
 
     chk = S.check()
+    # ---- SURVEY 8(f) rows 1-2 (device-side regrid check / diagnostics / forcing interpolation): explained numbers,
+    # not part of `value`.  GB/s against the algorithmic bytes of each map.
+    next_rows = None
+    if world == 1:
+        reps = 20
+        S.forcing_load("M_wind", 0, f["M_wind"]); S.forcing_load("M_wind", 1, f["M_wind"])
+
+        def timed(fn):
+            fn()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            with torch.cuda.stream(stream):
+                a.record(stream)
+                for _ in range(reps):
+                    fn()
+                b.record(stream)
+            torch.cuda.synchronize()
+            return a.elapsed_time(b) / reps * 1e3
+        us_diag = timed(S.update_ice_diagnostics)
+        us_forc = timed(lambda: S.forcing_apply("M_wind", True, 0.4, 0.0, 1.0))
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            rg = S.check_regridding(10.0)
+        us_regrid = (time.perf_counter() - t0) / reps * 1e6
+        nb = {"diag": 156.0 * lm.num_elements, "forcing": 48.0 * lm.num_nodes, "regrid": 28.0 * lm.num_elements}
+        next_rows = {"update_ice_diagnostics_us": us_diag, "update_ice_diagnostics_GBps": nb["diag"] / us_diag * 1e-3,
+                     "forcing_apply_wind_us": us_forc, "forcing_apply_wind_GBps": nb["forcing"] / us_forc * 1e-3,
+                     "check_regridding_us_incl_sync_and_readback": us_regrid, "min_angle_deg": rg.min_angle,
+                     "launches": 3 * reps + 3}
     import ctypes as _C
     tinfo = (_C.c_int * 8)()
     capi.lib().nsx_tile_info(S.h, tinfo, 8)
@@ -323,6 +351,8 @@ def run_ours(args):
                      "ow_smoother": float(np.mean(ow_ms)), "update": float(np.mean(upd_ms))},
         "check": {"n_nan": chk.n_nan, "n_speed": chk.n_speed, "max_speed": chk.max_speed},
     }
+    if next_rows is not None:
+        line["next_rows"] = next_rows
     S.close()
     if rank == 0:
         if not args.no_cpu_baseline and world == 1:

@@ -119,6 +119,10 @@ typedef struct NsxFields {
     double* M_surface; double* M_delta_x;       /* outputs of the prep loop (FE.cpp:10239-10240) */
     double* M_shape_coeff;                      /* output, [6*num_elements] element-major like M_shape_coeff[cpt][k] */
     double* D_del_ci_ridge_myi;                 /* output of update() */
+    /* outputs of nsx_update_ice_diagnostics (FE.cpp:7860-7900), download only */
+    double* D_conc; double* D_thick; double* D_snow_thick;
+    double* D_sigma[2];                         /* principal stresses */
+    double* D_divergence;
 } NsxFields;
 
 /* checkFieldsFast()-style summary computed on the device (FE.cpp:14536-14655). */
@@ -129,6 +133,19 @@ typedef struct NsxCheck {
     int pad_;
     double max_speed;
 } NsxCheck;
+
+/* Local part of FiniteElement::checkRegridding() (FE.cpp:8298-8309): the caller ORs `regrid` over the ranks
+ * (boost::mpi::all_reduce of one bool, FE.cpp:8306-8307). */
+typedef struct NsxRegrid {
+    double min_angle;       /* minAngle(M_mesh, M_UM, 1.) of this rank, degrees (FE.cpp:1795-1806) */
+    double min_jacobian;    /* min / max of jacobian(element, M_mesh, M_UM, 1.) over the local triangles */
+    double max_jacobian;    /*   (FE.cpp:1824-1839) */
+    int flip;               /* (min_jacobian <= 0) && (max_jacobian >= 0) */
+    int regrid;             /* (min_angle < regrid_angle) || flip */
+} NsxRegrid;
+
+/* ExternalData variables consumed by the path (FE.cpp:10842-10900: M_wind, M_ocean, M_ssh) */
+enum { NSX_FORCING_WIND = 0, NSX_FORCING_OCEAN = 1, NSX_FORCING_SSH = 2 };
 
 /* Device times (ms, CUDA events on the handle's stream) of the last nsx_explicit_solve / nsx_update,
  * named after the reference's Timer rows (FE.cpp:10217-10642, 8205-8212). */
@@ -146,7 +163,7 @@ int nsx_create(const NsxMesh* mesh, const NsxHalo* halo, int device, nsx_handle*
 int nsx_destroy(nsx_handle h);
 const char* nsx_last_error(nsx_handle h);      /* h may be NULL: error of the last failed nsx_create */
 int nsx_version(void);
-int nsx_abi_sizes(int* out, int n);          /* sizeof NsxDynParams, NsxMesh, NsxHalo, NsxFields, NsxCheck, NsxTiming */
+int nsx_abi_sizes(int* out, int n);          /* sizeof NsxDynParams, NsxMesh, NsxHalo, NsxFields, NsxCheck, NsxTiming, NsxRegrid */
 /* tile decomposition of the sub-cycle kernel: ntiles, nodes/tile, slots, max local nodes, max slots,
  * boundary tiles, dynamic shared memory bytes */
 int nsx_tile_info(nsx_handle h, int* out, int n);
@@ -169,6 +186,22 @@ int nsx_explicit_solve(nsx_handle h);   /* FiniteElement::explicitSolve()   FE.c
 int nsx_update(nsx_handle h);           /* FiniteElement::update(UM_P)      FE.cpp:3919  */
 int nsx_update_ghosts(nsx_handle h);    /* FiniteElement::updateGhosts(M_VT) FE.cpp:13963 */
 int nsx_check(nsx_handle h, NsxCheck* out);
+
+/* ---- the callers either side of the path, kept device-resident ----
+ * FiniteElement::checkRegridding() without the all_reduce (FE.cpp:8298-8309; minAngle 1795-1816, flip 1824-1839),
+ * on the device-resident M_UM: removes the per-step download of M_UM. */
+int nsx_check_regridding(nsx_handle h, double regrid_angle, NsxRegrid* out);
+/* FiniteElement::updateIceDiagnostics() (FE.cpp:7860-7900): D_conc, D_thick, D_snow_thick, D_sigma[2], D_divergence
+ * from the resident state; fetch them with nsx_download.  D_tsurf stays on the host (thermodynamics state). */
+int nsx_update_ice_diagnostics(nsx_handle h);
+/* ExternalData time interpolation on the device (externaldata.cpp:366-455).  nsx_forcing_load stores
+ * Dataset::variables[..].interpolated_data[slot] ([num_nodes] for ssh, [u | v] = [2*num_nodes] for wind / ocean,
+ * local numbering); nsx_forcing_apply evaluates ExternalData::getVector() into the resident M_wind / M_ocean / M_ssh:
+ *   interp_linear_time: M_factor*(fcoeff[0]*d0[i] + fcoeff[1]*d1[i]) + M_bias_correction, fcoeff from
+ *   |current_time - ftime_range[1 or 0]| / |ftime_range[1]-ftime_range[0]| (:368-370, 397-399); else M_factor*d0[i] + bias. */
+int nsx_forcing_load(nsx_handle h, int var, int slot, const double* interpolated_data);
+int nsx_forcing_apply(nsx_handle h, int var, int interp_linear_time, double current_time, double ftime0, double ftime1,
+                      double factor, double bias_correction);
 int nsx_synchronize(nsx_handle h);
 int nsx_get_timing(nsx_handle h, NsxTiming* out);
 void* nsx_get_stream(nsx_handle h);     /* cudaStream_t the handle launches on */

@@ -73,13 +73,23 @@ class NsxFields(C.Structure):
         + [(n, c_double_p) for n in ("M_conc", "M_thick", "M_snow_thick", "M_conc_young", "M_h_young", "M_hs_young",
                                      "M_thick_myi", "M_conc_myi", "M_ridge_ratio", "M_element_depth", "M_drag_ui",
                                      "M_drag_ui_young", "M_Cohesion", "M_time_relaxation_damage", "M_surface",
-                                     "M_delta_x", "M_shape_coeff", "D_del_ci_ridge_myi")]
+                                     "M_delta_x", "M_shape_coeff", "D_del_ci_ridge_myi",
+                                     "D_conc", "D_thick", "D_snow_thick")]
+        + [("D_sigma", c_double_p * 2), ("D_divergence", c_double_p)]
     )
 
 
 class NsxCheck(C.Structure):
     _fields_ = [("n_nan", C.c_int), ("n_speed", C.c_int), ("n_range", C.c_int), ("pad_", C.c_int),
                 ("max_speed", C.c_double)]
+
+
+class NsxRegrid(C.Structure):
+    _fields_ = [("min_angle", C.c_double), ("min_jacobian", C.c_double), ("max_jacobian", C.c_double),
+                ("flip", C.c_int), ("regrid", C.c_int)]
+
+
+FORCING = {"M_wind": 0, "M_ocean": 1, "M_ssh": 2}
 
 
 class NsxTiming(C.Structure):
@@ -92,7 +102,8 @@ EXPORTS = (
     "nsx_set_params", "nsx_upload", "nsx_download", "nsx_explicit_solve", "nsx_update", "nsx_update_ghosts",
     "nsx_check", "nsx_synchronize", "nsx_get_timing", "nsx_get_stream", "nsx_halo_blob_size", "nsx_halo_blob",
     "nsx_halo_connect_blob", "nsx_halo_connect_local", "nsx_halo_finalize", "nsx_group_explicit_solve",
-    "nsx_host_register", "nsx_host_unregister",
+    "nsx_host_register", "nsx_host_unregister", "nsx_abi_sizes", "nsx_tile_info", "nsx_plan_info", "nsx_cfg_last_error",
+    "nsx_check_regridding", "nsx_update_ice_diagnostics", "nsx_forcing_load", "nsx_forcing_apply",
 )
 
 _lib = None
@@ -116,6 +127,10 @@ def lib():
                   "nsx_update_ghosts", "nsx_check", "nsx_synchronize", "nsx_get_timing", "nsx_halo_finalize"):
             getattr(L, f).argtypes = [C.c_void_p] + ([C.c_void_p] if f in (
                 "nsx_set_params", "nsx_upload", "nsx_download", "nsx_check", "nsx_get_timing") else [])
+        L.nsx_check_regridding.argtypes = [C.c_void_p, C.c_double, C.c_void_p]
+        L.nsx_update_ice_diagnostics.argtypes = [C.c_void_p]
+        L.nsx_forcing_load.argtypes = [C.c_void_p, C.c_int, C.c_int, c_double_p]
+        L.nsx_forcing_apply.argtypes = [C.c_void_p, C.c_int, C.c_int] + [C.c_double] * 5
         L.nsx_halo_blob_size.argtypes = [C.c_void_p, C.c_int]
         L.nsx_halo_blob.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
         L.nsx_halo_connect_blob.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
@@ -221,11 +236,11 @@ class Solver:
         F = NsxFields()
         keep = []
         for k, v in d.items():
-            if k == "M_sigma":
-                for i in range(3):
+            if k in ("M_sigma", "D_sigma"):
+                for i in range(3 if k == "M_sigma" else 2):
                     a = v[i]
                     assert a.dtype == np.float64 and a.flags.c_contiguous and a.size == self.ne
-                    F.M_sigma[i] = a.ctypes.data_as(c_double_p)
+                    getattr(F, k)[i] = a.ctypes.data_as(c_double_p)
                     keep.append(a)
                 continue
             assert v.dtype == np.float64 and v.flags.c_contiguous, k
@@ -246,8 +261,8 @@ class Solver:
         for k in names:
             if k in out:
                 continue
-            if k == "M_sigma":
-                out[k] = [np.empty(self.ne) for _ in range(3)]
+            if k in ("M_sigma", "D_sigma"):
+                out[k] = [np.empty(self.ne) for _ in range(3 if k == "M_sigma" else 2)]
             else:
                 n = 2 * self.nn if k in NODAL2 else self.nn if k in NODAL1 else 6 * self.ne if k == "M_shape_coeff" else self.ne
                 out[k] = np.empty(n)
@@ -271,6 +286,26 @@ class Solver:
         c = NsxCheck()
         self._chk(self.L.nsx_check(self.h, C.byref(c)), "nsx_check")
         return c
+
+    def check_regridding(self, regrid_angle):
+        """Local part of FiniteElement::checkRegridding() on the resident M_UM (no download)."""
+        r = NsxRegrid()
+        self._chk(self.L.nsx_check_regridding(self.h, float(regrid_angle), C.byref(r)), "nsx_check_regridding")
+        return r
+
+    def update_ice_diagnostics(self):
+        self._chk(self.L.nsx_update_ice_diagnostics(self.h), "nsx_update_ice_diagnostics")
+
+    def forcing_load(self, name, slot, data):
+        """ExternalData time slice `slot` (0/1) of M_wind / M_ocean ([u | v]) or M_ssh, local numbering."""
+        a, p = _f64(data)
+        assert a.size == (self.nn if name == "M_ssh" else 2 * self.nn), (name, a.size)
+        self._chk(self.L.nsx_forcing_load(self.h, FORCING[name], int(slot), p), "nsx_forcing_load")
+
+    def forcing_apply(self, name, interp_linear_time, current_time, ftime0, ftime1, factor=1., bias_correction=0.):
+        self._chk(self.L.nsx_forcing_apply(self.h, FORCING[name], int(bool(interp_linear_time)), float(current_time),
+                                           float(ftime0), float(ftime1), float(factor), float(bias_correction)),
+                  "nsx_forcing_apply")
 
     def timing(self):
         t = NsxTiming()

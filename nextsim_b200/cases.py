@@ -71,6 +71,8 @@ def make_case(name="toy", nranks=1, dyn="bbm", open_east=False, substeps=120, nx
         c.ghost_val = np.zeros(0, np.int32)
         c.lms = pt.nodal_grid(1, gm.x, gm.y, gm.tri)
     for lm in c.lms:
+        if only_rank not in (None, lm.rank):
+            continue                                  # another process owns that rank: skip its tables
         pt.bc_marked_nodes(lm, gm.dirichlet_flags_root, gm.neumann_flags_root)
         lm.nodal_element_connectivity, lm.nodal_connectivity = pt.bamg_tables(lm.indices, lm.num_nodes)
         lm.lat = pt.scatter_nodal1(lm, gm.lat)

@@ -260,10 +260,10 @@ extern "C" void* nsx_get_stream(nsx_handle h) { return h ? (void*)h->stream : nu
 // sizeof() of every struct that crosses the ABI, so a binding can detect layout drift
 extern "C" int nsx_abi_sizes(int* out, int n)
 {
-    int const s[6] = {(int)sizeof(NsxDynParams), (int)sizeof(NsxMesh), (int)sizeof(NsxHalo),
-                      (int)sizeof(NsxFields), (int)sizeof(NsxCheck), (int)sizeof(NsxTiming)};
-    for (int i = 0; i < n && i < 6; ++i) out[i] = s[i];
-    return 6;
+    int const s[7] = {(int)sizeof(NsxDynParams), (int)sizeof(NsxMesh), (int)sizeof(NsxHalo),
+                      (int)sizeof(NsxFields), (int)sizeof(NsxCheck), (int)sizeof(NsxTiming), (int)sizeof(NsxRegrid)};
+    for (int i = 0; i < n && i < 7; ++i) out[i] = s[i];
+    return 7;
 }
 
 // tile decomposition summary: ntiles, nodes per tile, slots, max local nodes, max slots, boundary tiles, smem bytes,
@@ -384,6 +384,12 @@ static void field_table(nsx_solver* S, const NsxFields* f, std::vector<FieldMap>
     add(f->M_surface, S->surface.p, ELEM);
     add(f->M_delta_x, S->delta_x.p, ELEM);
     add(f->D_del_ci_ridge_myi, S->del_ci_ridge_myi.p, ELEM);
+    double* const dg[6] = {f->D_conc, f->D_thick, f->D_snow_thick, f->D_sigma[0], f->D_sigma[1], f->D_divergence};
+    for (int k = 0; k < 6; ++k) {
+        if (!dg[k]) continue;
+        if (!S->diag.p) throw std::runtime_error("diagnostics requested before nsx_update_ice_diagnostics");
+        add(dg[k], S->diag.p + (size_t)k * S->ne, ELEM);
+    }
 }
 
 extern "C" int nsx_upload(nsx_handle S, const NsxFields* f)
@@ -391,6 +397,8 @@ extern "C" int nsx_upload(nsx_handle S, const NsxFields* f)
     NSX_API_BEGIN(S)
     if (!f) throw std::invalid_argument("nsx_upload: NULL");
     if (f->M_shape_coeff) throw std::invalid_argument("nsx_upload: M_shape_coeff is an output");
+    if (f->D_conc || f->D_thick || f->D_snow_thick || f->D_sigma[0] || f->D_sigma[1] || f->D_divergence)
+        throw std::invalid_argument("nsx_upload: the D_* diagnostics are outputs");
     std::vector<FieldMap> t;
     field_table(S, f, t);
     cudaStream_t st = S->stream;
@@ -1004,6 +1012,91 @@ extern "C" int nsx_check(nsx_handle S, NsxCheck* out)
     NSX_CUDA(cudaMemcpyAsync(&hd, S->check_d.p, sizeof(hd), cudaMemcpyDeviceToHost, S->stream));
     NSX_CUDA(cudaStreamSynchronize(S->stream));
     out->n_nan = hi[0]; out->n_speed = hi[1]; out->n_range = hi[2]; out->pad_ = 0; out->max_speed = hd;
+    NSX_API_END(S)
+}
+
+// ---------------------------------------------------------------------------------------------------
+// regrid check, ice diagnostics and forcing interpolation on the resident state
+// ---------------------------------------------------------------------------------------------------
+static double key_to_double(unsigned long long k)
+{
+    unsigned long long const b = (k >> 63) ? (k & 0x7fffffffffffffffULL) : ~k;
+    double v;
+    std::memcpy(&v, &b, sizeof(v));
+    return v;
+}
+
+extern "C" int nsx_check_regridding(nsx_handle S, double regrid_angle, NsxRegrid* out)
+{
+    NSX_API_BEGIN(S)
+    if (!out) throw std::invalid_argument("nsx_check_regridding: NULL");
+    if (!S->regrid_keys.p) S->regrid_keys.alloc(4);
+    unsigned long long const init[4] = {~0ULL, ~0ULL, 0ULL, 0ULL};
+    NSX_CUDA(cudaMemcpyAsync(S->regrid_keys.p, init, sizeof(init), cudaMemcpyHostToDevice, S->stream));
+    int const grid = std::max(1, std::min(nblk(S->ne), 8 * S->sm_count));
+    k_regrid_check<<<grid, TPB, 0, S->stream>>>(S->ne, S->nn, S->en0.p, S->en1.p, S->en2.p, S->x.p, S->y.p, S->UM.p,
+                                                S->regrid_keys.p);
+    NSX_CUDA(cudaGetLastError());
+    unsigned long long k[4];
+    NSX_CUDA(cudaMemcpyAsync(k, S->regrid_keys.p, sizeof(k), cudaMemcpyDeviceToHost, S->stream));
+    NSX_CUDA(cudaStreamSynchronize(S->stream));
+    out->min_angle = key_to_double(k[0]);
+    out->min_jacobian = key_to_double(k[1]);
+    out->max_jacobian = key_to_double(k[2]);
+    out->flip = (out->min_jacobian <= 0.) && (out->max_jacobian >= 0.);
+    out->regrid = (out->min_angle < regrid_angle) || out->flip;
+    NSX_API_END(S)
+}
+
+extern "C" int nsx_update_ice_diagnostics(nsx_handle S)
+{
+    NSX_API_BEGIN(S)
+    if (!S->have_params) throw std::runtime_error("nsx_update_ice_diagnostics before nsx_set_params");
+    if (!S->diag.p) S->diag.alloc(6 * (size_t)S->ne);
+    int const c = S->scur;
+    k_ice_diagnostics<<<nblk(S->ne), TPB, 0, S->stream>>>(S->ne, S->nn, S->K.young_ice, S->en0.p, S->en1.p, S->en2.p,
+        S->x.p, S->y.p, S->UM.p, S->VT[S->cur], S->conc.p, S->thick.p, S->snow.p, S->conc_young.p, S->h_young.p,
+        S->hs_young.p, S->sig[c][0].p, S->sig[c][1].p, S->sig[c][2].p, S->diag.p);
+    NSX_CUDA(cudaGetLastError());
+    NSX_API_END(S)
+}
+
+static int forcing_planes(int var) { return var == NSX_FORCING_SSH ? 1 : 2; }
+
+extern "C" int nsx_forcing_load(nsx_handle S, int var, int slot, const double* data)
+{
+    NSX_API_BEGIN(S)
+    if (var < 0 || var > 2 || slot < 0 || slot > 1 || !data) throw std::invalid_argument("nsx_forcing_load: bad argument");
+    int const planes = forcing_planes(var);
+    auto& buf = S->forcing[var][slot];
+    if (!buf.p) buf.alloc((size_t)planes * S->nn);
+    NSX_CUDA(cudaMemcpyAsync(S->stage.p, data, (size_t)planes * S->nn * sizeof(double), cudaMemcpyHostToDevice, S->stream));
+    k_permute_in<<<nblk(S->nn), TPB, 0, S->stream>>>(S->nn, planes, S->node_perm.p, S->stage.p, buf.p);
+    NSX_CUDA(cudaGetLastError());
+    NSX_CUDA(cudaStreamSynchronize(S->stream));             // the caller may reuse `data` right away
+    S->forcing_loaded[var][slot] = true;
+    NSX_API_END(S)
+}
+
+extern "C" int nsx_forcing_apply(nsx_handle S, int var, int interp_linear_time, double current_time, double ftime0,
+                                 double ftime1, double factor, double bias_correction)
+{
+    NSX_API_BEGIN(S)
+    if (var < 0 || var > 2) throw std::invalid_argument("nsx_forcing_apply: unknown variable");
+    if (!S->forcing_loaded[var][0] || (interp_linear_time && !S->forcing_loaded[var][1]))
+        throw std::runtime_error("nsx_forcing_apply: time slice not loaded (nsx_forcing_load)");
+    double c0 = 1., c1 = 0.;
+    if (interp_linear_time) {                               // externaldata.cpp:368-370
+        double const fdt = std::fabs(ftime1 - ftime0);
+        c0 = std::fabs(current_time - ftime1) / fdt;
+        c1 = std::fabs(current_time - ftime0) / fdt;
+    }
+    long const n = (long)forcing_planes(var) * S->nn;
+    double* const dst = var == NSX_FORCING_WIND ? S->wind.p : var == NSX_FORCING_OCEAN ? S->ocean.p : S->ssh.p;
+    double const* const d0 = S->forcing[var][0].p;
+    double const* const d1 = interp_linear_time ? S->forcing[var][1].p : d0;
+    k_forcing_apply<<<nblk(n), TPB, 0, S->stream>>>(n, interp_linear_time, c0, c1, factor, bias_correction, d0, d1, dst);
+    NSX_CUDA(cudaGetLastError());
     NSX_API_END(S)
 }
 

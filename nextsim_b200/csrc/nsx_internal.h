@@ -145,6 +145,11 @@ struct nsx_solver {
     nsx::DBuf<int> ow_list;                      // open-water nodes to smooth
     nsx::DBuf<int> ow_count;
     nsx::DBuf<int> check_i; nsx::DBuf<double> check_d;
+    // device-side diagnostics / regrid check / forcing time interpolation (allocated on first use)
+    nsx::DBuf<double> diag;                      // D_conc, D_thick, D_snow_thick, D_sigma[0], D_sigma[1], D_divergence  [6*ne]
+    nsx::DBuf<unsigned long long> regrid_keys;   // min-angle bits, ordered keys of min / max jacobian
+    nsx::DBuf<double> forcing[3][2];             // interpolated_data[0..1] of wind, ocean (2 planes) and ssh (1 plane)
+    bool forcing_loaded[3][2] = {};
 
     // ---- halo ----
     std::deque<nsx::PeerLink> peers;             // union of send/recv peers

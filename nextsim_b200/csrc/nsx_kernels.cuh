@@ -1357,4 +1357,121 @@ k_ow_sweep_exchange(HaloArgs a, int nn, const int* __restrict__ ow_list, const i
     if (threadIdx.x == 0) { *epoch_ctr = epoch; *done_ctr = 0u; }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// checkRegridding (FE.cpp:8298-8309) and updateIceDiagnostics (FE.cpp:7860-7900) on the
+// resident state.  Products and sums are written with explicit round-to-nearest intrinsics (no FMA contraction)
+// so the jacobians, the flip test, the divergence and the forcing values are bit-identical to the host code.
+// ---------------------------------------------------------------------------------------------------
+// order-preserving map double -> u64: integer atomicMin / atomicMax on the keys order like the doubles
+__device__ __forceinline__ unsigned long long ordered_key(double v)
+{
+    unsigned long long const b = (unsigned long long)__double_as_longlong(v);
+    return (b >> 63) ? ~b : (b | 0x8000000000000000ULL);
+}
+
+struct MovedTri { double xa, ya, xb, yb, xc, yc; };
+// GmshMesh::vertices(indices, M_UM, 1.)  (gmshmesh.cpp:1929-1939)
+__device__ __forceinline__ MovedTri moved_triangle(int a, int b, int c, int nn, const double* __restrict__ x,
+                                                   const double* __restrict__ y, const double* __restrict__ UM)
+{
+    MovedTri t;
+    t.xa = x[a] + 1. * UM[a];  t.ya = y[a] + 1. * UM[a + nn];
+    t.xb = x[b] + 1. * UM[b];  t.yb = y[b] + 1. * UM[b + nn];
+    t.xc = x[c] + 1. * UM[c];  t.yc = y[c] + 1. * UM[c + nn];
+    return t;
+}
+// FiniteElement::jacobian (FE.cpp:1613-1618)
+__device__ __forceinline__ double tri_jacobian(MovedTri const& t)
+{
+    return __dsub_rn(__dmul_rn(t.xb - t.xa, t.yc - t.ya), __dmul_rn(t.xc - t.xa, t.yb - t.ya));
+}
+
+// keys[0] = min over elements of minAngles() (FE.cpp:1758-1768), keys[1] / keys[2] = min / max jacobian
+__global__ void __launch_bounds__(TPB)
+k_regrid_check(int ne, int nn, const int* __restrict__ en0, const int* __restrict__ en1, const int* __restrict__ en2,
+               const double* __restrict__ x, const double* __restrict__ y, const double* __restrict__ UM,
+               unsigned long long* __restrict__ keys)
+{
+    unsigned long long kang = ~0ULL, kmin = ~0ULL, kmax = 0ULL;
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < ne; e += gridDim.x * blockDim.x) {
+        MovedTri const t = moved_triangle(en0[e], en1[e], en2[e], nn, x, y, UM);
+        double s0 = hypot(t.xb - t.xa, t.yb - t.ya);
+        double s1 = hypot(t.xc - t.xb, t.yc - t.yb);
+        double s2 = hypot(t.xc - t.xa, t.yc - t.ya);
+        double w;                                         // std::sort of three
+        if (s0 > s1) { w = s0; s0 = s1; s1 = w; }
+        if (s1 > s2) { w = s1; s1 = s2; s2 = w; }
+        if (s0 > s1) { w = s0; s0 = s1; s1 = w; }
+        double const num = __dsub_rn(__dadd_rn(__dmul_rn(s1, s1), __dmul_rn(s2, s2)), __dmul_rn(s0, s0));
+        double const den = __dmul_rn(__dmul_rn(2., s1), s2);
+        double ang = acos(__ddiv_rn(num, den));
+        ang = __ddiv_rn(__dmul_rn(ang, 45.0), 0.78539816339744828);       // *45/atan(1)
+        if (ang == ang) kang = min(kang, ordered_key(ang));               // std::min_element never selects a NaN
+        double const jac = tri_jacobian(t);
+        kmin = min(kmin, ordered_key(jac));
+        kmax = max(kmax, ordered_key(jac));
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        kang = min(kang, __shfl_down_sync(0xffffffffu, kang, o));
+        kmin = min(kmin, __shfl_down_sync(0xffffffffu, kmin, o));
+        kmax = max(kmax, __shfl_down_sync(0xffffffffu, kmax, o));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicMin(keys + 0, kang);
+        atomicMin(keys + 1, kmin);
+        atomicMax(keys + 2, kmax);
+    }
+}
+
+// diag planes: D_conc, D_thick, D_snow_thick, D_sigma[0], D_sigma[1], D_divergence
+__global__ void __launch_bounds__(TPB)
+k_ice_diagnostics(int ne, int nn, int young_ice,
+                  const int* __restrict__ en0, const int* __restrict__ en1, const int* __restrict__ en2,
+                  const double* __restrict__ x, const double* __restrict__ y, const double* __restrict__ UM,
+                  const double* __restrict__ VT,
+                  const double* __restrict__ conc, const double* __restrict__ thick, const double* __restrict__ snow,
+                  const double* __restrict__ conc_y, const double* __restrict__ h_y, const double* __restrict__ hs_y,
+                  const double* __restrict__ sig0, const double* __restrict__ sig1, const double* __restrict__ sig2,
+                  double* __restrict__ diag)
+{
+    int const e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= ne) return;
+    double dc = conc[e], dh = thick[e], dhs = snow[e];
+    if (young_ice) { dc += conc_y[e];  dh += h_y[e];  dhs += hs_y[e]; }
+    double const a0 = sig0[e], a1 = sig1[e], a2 = sig2[e];
+    int const n[3] = {en0[e], en1[e], en2[e]};
+    MovedTri const t = moved_triangle(n[0], n[1], n[2], nn, x, y, UM);
+    double const jac = tri_jacobian(t);
+    double const vx[3] = {t.xa, t.xb, t.xc}, vy[3] = {t.ya, t.yb, t.yc};
+    double div = 0.;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        int const kp1 = (k + 1) % 3, kp2 = (k + 2) % 3;
+        double const dxN = __ddiv_rn(vy[kp1] - vy[kp2], jac);              // shapeCoeff (FE.cpp:1951-1964)
+        double const dyN = __ddiv_rn(vx[kp2] - vx[kp1], jac);
+        double const u = VT[n[k]], v = VT[n[k] + nn];
+        div = __dadd_rn(div, __dadd_rn(__dmul_rn(dxN, u), __dmul_rn(dyN, v)));
+    }
+    size_t const E = (size_t)ne;
+    diag[e] = dc;
+    diag[E + e] = dh;
+    diag[2 * E + e] = dhs;
+    diag[3 * E + e] = (a0 + a1) / 2.;
+    diag[4 * E + e] = hypot((a0 - a1) / 2., a2);
+    diag[5 * E + e] = div;
+}
+
+// ExternalData::get() for every node (externaldata.cpp:366-436)
+__global__ void __launch_bounds__(TPB)
+k_forcing_apply(long n, int linear, double c0, double c1, double factor, double bias,
+                const double* __restrict__ d0, const double* __restrict__ d1, double* __restrict__ out)
+{
+    long const i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double value;
+    if (linear) value = __dmul_rn(factor, __dadd_rn(__dmul_rn(c0, d0[i]), __dmul_rn(c1, d1[i])));
+    else value = __dmul_rn(factor, d0[i]);
+    out[i] = __dadd_rn(value, bias);
+}
+
 } // namespace nsx

@@ -87,6 +87,37 @@ public:
                                      " elements out of range");
     }
 
+    // ---- the callers either side of the path, on the resident state ----
+    //! FiniteElement::checkRegridding() (FE.cpp:8298-8309).  `any_rank` stands for the reference's
+    //! boost::mpi::all_reduce(M_comm, regrid_local, regrid, std::plus<bool>()) and stays with the host.
+    template <class AllReduceOr>
+    bool checkRegridding(double regrid_angle, AllReduceOr any_rank)
+    {
+        NsxRegrid r;
+        check(nsx_check_regridding(M_handle, regrid_angle, &r), "checkRegridding");
+        M_min_angle = r.min_angle;
+        return any_rank(r.regrid != 0);
+    }
+    bool checkRegridding(double regrid_angle)
+    {
+        return this->checkRegridding(regrid_angle, [](bool b) { return b; });
+    }
+    //! FiniteElement::updateIceDiagnostics() (FE.cpp:7860-7900); results through download(D_conc, D_sigma, ...)
+    void updateIceDiagnostics() { check(nsx_update_ice_diagnostics(M_handle), "updateIceDiagnostics"); }
+    //! Dataset::variables[..].interpolated_data[slot] of M_wind / M_ocean / M_ssh after the spatial interpolation
+    void loadForcing(int var, int slot, std::vector<double> const& interpolated_data)
+    {
+        check(nsx_forcing_load(M_handle, var, slot, interpolated_data.data()), "loadForcing");
+    }
+    //! ExternalData::getVector() (externaldata.cpp:366-455) evaluated into the resident M_wind / M_ocean / M_ssh
+    void applyForcing(int var, bool interp_linear_time, double M_current_time, double ftime_range0, double ftime_range1,
+                      double M_factor = 1., double M_bias_correction = 0.)
+    {
+        check(nsx_forcing_apply(M_handle, var, interp_linear_time ? 1 : 0, M_current_time, ftime_range0, ftime_range1,
+                                M_factor, M_bias_correction), "applyForcing");
+    }
+    double M_min_angle = 0.;    //!< "REGRID ANGLE" of the last checkRegridding (FE.cpp:8302)
+
     nsx_handle handle() const { return M_handle; }
     double scale_coef = 1., C_fix = 0., C_alea = 0.;
 

@@ -32,6 +32,12 @@
 //   contrib/bamg/src/Mesh.cpp 514-543, 583-629, 798-865 (connectivity tables)
 //                                        -> orc_bamg_tables
 //   model/constants.hpp 56-86            -> namespace physical
+//   SURVEY.md section 8(f) rows 1-2 (the callers either side of the path):
+//     model/finiteelement.cpp 1758-1768 minAngles(um), 1795-1816 minAngle(um), 1824-1839 flip,
+//       8298-8309 checkRegridding (local part)   -> orc_check_regridding
+//     model/finiteelement.cpp 7860-7900 updateIceDiagnostics -> orc_update_ice_diagnostics
+//     model/externaldata.cpp 366-436 ExternalData::get / 437-455 getVector
+//                                        -> orc_external_data_get_vector
 // =====================================================================================
 #include <algorithm>
 #include <cmath>
@@ -1428,6 +1434,111 @@ static void bcMarkedNodes(Rank& R, int const* flags_root, int dir_size, int nmn_
     R.I("M_neumann_flags") = M_neumann_flags;
 }
 
+// ---- section 8(f) row 1: checkRegridding / updateIceDiagnostics --------------------------------------
+// FE.cpp:1758-1768  minAngles(element, mesh, um, factor=1)
+static double minAngles(Rank& R, int cpt)
+{
+    double side[3];
+    sides(R, cpt, side);
+    std::sort(side, side+3);
+    double minang = std::acos( (std::pow(side[1],2.) + std::pow(side[2],2.) - std::pow(side[0],2.) )/(2*side[1]*side[2]) );
+    minang = minang*45.0/std::atan(1.0);
+    return minang;
+}
+
+// FE.cpp:8298-8309 without the final all_reduce (one bool; the caller ORs the ranks)
+//   out[0] = minAngle(M_mesh, M_UM, 1.) of THIS rank (FE.cpp:1795-1806, before the all_reduce at 1812)
+//   out[1], out[2] = min / max jacobian of flip() (FE.cpp:1824-1839)
+//   flags[0] = flip(), flags[1] = regrid_local
+static void checkRegriddingLocal(Rank& R, double const regrid_angle, double* out, int* flags)
+{
+    int const ne = R.M_num_elements;       // M_mesh.triangles(): owned + ghost elements
+    std::vector<double> all_min_angle(ne), area(ne);
+    for (int cpt=0; cpt<ne; ++cpt)
+    {
+        all_min_angle[cpt] = minAngles(R, cpt);
+        double v[3][2];
+        vertices(R, cpt, v);
+        area[cpt] = jacobian(v);
+    }
+    double const minang = *std::min_element(all_min_angle.begin(), all_min_angle.end());
+    double const minarea = *std::min_element(area.begin(), area.end());
+    double const maxarea = *std::max_element(area.begin(), area.end());
+    bool const flipped = ((minarea <= 0.) && (maxarea >= 0.));
+    out[0] = minang; out[1] = minarea; out[2] = maxarea;
+    flags[0] = flipped;
+    flags[1] = (minang < regrid_angle) || flipped;
+}
+
+// FE.cpp:7860-7900.  D_tsurf needs M_tice / M_sst / M_tsurf_young (thermodynamics state that never
+// enters the path) and is left to the host; D_dmean / D_dmax are constants.
+static void updateIceDiagnostics(Rank& R, OrcParams const& P)
+{
+    int const ne = R.M_num_elements, nn = R.M_num_nodes;
+    auto& D_conc = R.D("D_conc"); D_conc.resize(ne);
+    auto& D_thick = R.D("D_thick"); D_thick.resize(ne);
+    auto& D_snow_thick = R.D("D_snow_thick"); D_snow_thick.resize(ne);
+    auto& D_sigma0 = R.D("D_sigma0"); D_sigma0.resize(ne);
+    auto& D_sigma1 = R.D("D_sigma1"); D_sigma1.resize(ne);
+    auto& D_divergence = R.D("D_divergence"); D_divergence.resize(ne);
+    auto const& M_conc = R.D("M_conc"); auto const& M_thick = R.D("M_thick"); auto const& M_snow_thick = R.D("M_snow_thick");
+    auto const& M_conc_young = R.D("M_conc_young"); auto const& M_h_young = R.D("M_h_young"); auto const& M_hs_young = R.D("M_hs_young");
+    auto const& s0 = R.D("M_sigma0"); auto const& s1 = R.D("M_sigma1"); auto const& s2 = R.D("M_sigma2");
+    auto const& M_VT = R.D("M_VT");
+    auto const& idx = R.I("indices");
+    for (int i=0; i<ne; ++i)
+    {
+        D_conc[i] = M_conc[i];
+        D_thick[i] = M_thick[i];
+        D_snow_thick[i] = M_snow_thick[i];
+        if (P.ice_cat_type == 1)
+        {
+            D_conc[i] += M_conc_young[i];
+            D_thick[i] += M_h_young[i];
+            D_snow_thick[i] += M_hs_young[i];
+        }
+        D_sigma0[i] =            (s0[i]+s1[i])/2.;
+        D_sigma1[i] = std::hypot((s0[i]-s1[i])/2., s2[i]);
+
+        D_divergence[i] = 0.;
+        double shape_coeff[6];
+        shapeCoeff(R, i, shape_coeff);
+        for (int j=0; j<3; ++j)
+        {
+            double const u = M_VT[idx[3*i+j]-1];
+            double const v = M_VT[idx[3*i+j]-1 + nn];
+            double const dxN = shape_coeff[j];
+            double const dyN = shape_coeff[j+3];
+            D_divergence[i] += dxN*u + dyN*v;
+        }
+    }
+}
+
+// ---- section 8(f) row 2: ExternalData::getVector()  externaldata.cpp:366-455 ----------------------------
+// d0 / d1 = Dataset::variables[...].interpolated_data[0/1] of the variable (scalars) or of its two
+// components concatenated [u | v] (vectors: get(i) picks component i>=M_target_size, :386-395).
+static void externalDataGetVector(long n, double const* d0, double const* d1, int interp_linear_time,
+                                  double M_current_time, double const ftime_range[2], double M_factor,
+                                  double M_bias_correction, double* out)
+{
+    double fcoeff[2] = {1., 0.};
+    if (interp_linear_time)
+    {
+        double const fdt = std::abs(ftime_range[1]-ftime_range[0]);
+        fcoeff[0] = std::abs(M_current_time-ftime_range[1])/fdt;
+        fcoeff[1] = std::abs(M_current_time-ftime_range[0])/fdt;
+    }
+    for (long i=0; i<n; ++i)
+    {
+        double value;
+        if (interp_linear_time)
+            value = M_factor*(fcoeff[0]*d0[i] + fcoeff[1]*d1[i]);
+        else
+            value = M_factor*d0[i];
+        out[i] = value + M_bias_correction;
+    }
+}
+
 } // namespace
 
 // =====================================================================================
@@ -1543,6 +1654,20 @@ int orc_explicit_solve(int nranks, void** handles, const OrcParams* P)
 }
 
 int orc_update(void* h, const OrcParams* P) { ORC_TRY update(*(Rank*)h, *P); ORC_CATCH }
+
+int orc_check_regridding(void* h, double regrid_angle, double* out3, int* flags2)
+{ ORC_TRY checkRegriddingLocal(*(Rank*)h, regrid_angle, out3, flags2); ORC_CATCH }
+
+int orc_update_ice_diagnostics(void* h, const OrcParams* P) { ORC_TRY updateIceDiagnostics(*(Rank*)h, *P); ORC_CATCH }
+
+int orc_external_data_get_vector(long n, const double* d0, const double* d1, int interp_linear_time, double current_time,
+                                 double ftime0, double ftime1, double factor, double bias_correction, double* out)
+{
+    ORC_TRY
+    double const ftime_range[2] = {ftime0, ftime1};
+    externalDataGetVector(n, d0, d1, interp_linear_time, current_time, ftime_range, factor, bias_correction, out);
+    ORC_CATCH
+}
 
 int orc_update_ghosts(int nranks, void** handles, const char* name)
 {

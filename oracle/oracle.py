@@ -142,6 +142,16 @@ class Rank:
     def update(self, params):
         self._chk(self.L.orc_update(self.h, C.byref(params)))
 
+    def check_regridding(self, regrid_angle):
+        """Local part of FiniteElement::checkRegridding(): (min_angle, min_jac, max_jac, flip, regrid_local)."""
+        out = (C.c_double * 3)()
+        flags = (C.c_int * 2)()
+        self._chk(self.L.orc_check_regridding(self.h, C.c_double(regrid_angle), out, flags))
+        return out[0], out[1], out[2], bool(flags[0]), bool(flags[1])
+
+    def update_ice_diagnostics(self, params):
+        self._chk(self.L.orc_update_ice_diagnostics(self.h, C.byref(params)))
+
 
 def single_rank_mesh(x, y, tri1, fast=False):
     R = Rank(fast)
@@ -188,3 +198,18 @@ def time_subcycles(ranks, params, nsub, threads=False):
     if t < 0:
         raise RuntimeError("oracle: " + ranks[0].L.orc_last_error().decode())
     return t
+
+
+def external_data_get_vector(d0, d1, interp_linear_time, current_time, ftime0, ftime1, factor, bias_correction,
+                             fast=False):
+    """ExternalData::getVector() for one variable: d0/d1 are its two time slices on the mesh nodes."""
+    d0 = np.ascontiguousarray(d0, np.float64)
+    d1 = np.ascontiguousarray(d1, np.float64)
+    out = np.empty_like(d0)
+    L = lib(fast)
+    rc = L.orc_external_data_get_vector(C.c_long(d0.size), _dp(d0), _dp(d1), int(interp_linear_time),
+                                        C.c_double(current_time), C.c_double(ftime0), C.c_double(ftime1),
+                                        C.c_double(factor), C.c_double(bias_correction), _dp(out))
+    if rc != 0:
+        raise RuntimeError("oracle: " + L.orc_last_error().decode())
+    return out

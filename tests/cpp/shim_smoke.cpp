@@ -21,6 +21,12 @@ int main(int argc, char** argv)
         Nextsim::FiniteElementGPU fe(m, 0);
         fe.initOptAndParam(p, 7071.);
         std::printf("handle created (GPU present), scale_coef=%g\n", fe.scale_coef);
+        // section 8(f) rows: instantiate the templates (reached only with a GPU)
+        std::vector<double> w(6, 1.);
+        fe.loadForcing(NSX_FORCING_WIND, 0, w);
+        fe.applyForcing(NSX_FORCING_WIND, false, 0., 0., 1.);
+        bool const regrid = fe.checkRegridding(10., [](bool b) { return b; }) || fe.checkRegridding(10.);
+        std::printf("regrid=%d min angle=%g\n", (int)regrid, fe.M_min_angle);
     } catch (std::runtime_error const& e) {
         std::printf("threw: %s\n", e.what());
         return std::strstr(e.what(), "nsx_create") ? 0 : 1;

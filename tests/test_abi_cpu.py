@@ -25,16 +25,16 @@ def test_header_symbols_exported():
     assert len(names) >= 20
     for n in names:
         assert hasattr(L, n), "libnsx.so does not export %s" % n
-    assert set(capi.EXPORTS) <= set(names)
+    assert set(capi.EXPORTS) == set(names)
     assert L.nsx_version() == 1
 
 
 def test_struct_layouts_match_ctypes():
     L = capi.lib()
-    out = (C.c_int * 6)()
-    assert L.nsx_abi_sizes(out, 6) == 6
+    out = (C.c_int * 7)()
+    assert L.nsx_abi_sizes(out, 7) == 7
     expect = [C.sizeof(capi.NsxDynParams), C.sizeof(capi.NsxMesh), C.sizeof(capi.NsxHalo),
-              C.sizeof(capi.NsxFields), C.sizeof(capi.NsxCheck), C.sizeof(capi.NsxTiming)]
+              C.sizeof(capi.NsxFields), C.sizeof(capi.NsxCheck), C.sizeof(capi.NsxTiming), C.sizeof(capi.NsxRegrid)]
     assert list(out) == expect
 
 
