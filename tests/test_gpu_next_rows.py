@@ -6,7 +6,7 @@
 They are element- or node-wise maps of the resident state, so the bar is tighter than for the sub-cycled solve:
 on identical inputs jacobians, flip flags, concentrations, divergence and forcing values are BIT-EXACT (the kernels
 spell every product / sum with round-to-nearest intrinsics, the oracle is built with -ffp-contract=off); hypot()
-and acos() differ from glibc by <= 2 ulp, held to 1e-14 relative.
+and acos() differ from glibc by <= 2 ulp: 1e-14 relative, plus the conditioning of acos for the minimum angle.
 """
 import numpy as np
 import pytest
@@ -45,7 +45,10 @@ def regrid_both(c, angle):
         got = s.check_regridding(angle)
         out.append((ref, got))
         assert got.min_jacobian == ref[1] and got.max_jacobian == ref[2], "jacobian extrema are bit-exact"
-        assert abs(got.min_angle - ref[0]) <= 1e-14 * abs(ref[0]) + 1e-13
+        # acos is ill-conditioned for small angles: 1 ulp of its argument (hypot differs from glibc by <= 1 ulp per
+        # side) moves the angle by eps/sin(angle); allow 16 ulp of the argument
+        cond = 16 * np.finfo(float).eps / max(np.sin(np.deg2rad(ref[0])), 1e-300) * 180.0 / np.pi
+        assert abs(got.min_angle - ref[0]) <= 1e-14 * abs(ref[0]) + cond
         assert bool(got.flip) == ref[3]
         assert bool(got.regrid) == ref[4]
     for s in solvers:
