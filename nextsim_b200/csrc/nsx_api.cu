@@ -129,6 +129,7 @@ static void alloc_fields(nsx_solver* S)
     S->halo_err.alloc(1); S->halo_err.zero(st);
     S->d_epoch.alloc(1); S->d_done.alloc(1);
     S->d_epoch.zero(st); S->d_done.zero(st);
+    S->ow_pair.alloc(64); S->ow_pair.zero(st);
     for (auto& e : S->ev) NSX_CUDA(cudaEventCreate(&e));
     NSX_CUDA(cudaEventCreateWithFlags(&S->ev_fork, cudaEventDisableTiming));
     NSX_CUDA(cudaEventCreateWithFlags(&S->ev_join, cudaEventDisableTiming));
@@ -589,11 +590,13 @@ static HaloArgs halo_args(nsx_solver* S, int parity, bool sync)
             a.peer_begin[a.n_peers] = off;
             a.peer_vt[a.n_peers] = p.peer_vt[parity];
             a.peer_nn[a.n_peers] = p.peer_nn;
-            a.peer_flag[a.n_peers] = p.peer_flags + S->rank;
+            a.peer_link[a.n_peers] = a.n_link;
             off += (int)p.h_send_idx.size();
             a.n_peers++;
         }
-        if (!p.h_recv_idx.empty()) a.wait_slot[a.n_wait++] = p.rank;
+        a.link_flag[a.n_link] = p.peer_flags + S->rank;
+        a.link_rank[a.n_link] = p.rank;
+        a.n_link++;
     }
     a.peer_begin[a.n_peers] = off;
     a.n_total = off;
@@ -653,6 +656,27 @@ static void launch_tiles(nsx_solver* S, SubArgs const& A, int tile_base, int nti
     if (S->K.dynamics_type == NSX_DYN_BBM) k_subcycle<1><<<grid, SUB_TPB, smem, st>>>(S->K, a);
     else k_subcycle<0><<<grid, SUB_TPB, smem, st>>>(S->K, a);
     S->n_launch++;
+}
+
+// SMs for the boundary launch when the interior runs the tile kernel next to it.  Both are persistent kernels that
+// take tiles round-robin: with B SMs the boundary chain lasts ceil(nb/B) boundary tile-times plus the NVLink round
+// trip (push, flag, wait), the interior ceil((nt-nb)/(SMs-B)) tile-times.  Measured on B200 (3 km mesh on 2 GPUs,
+// nb ~ 50 of 2412 tiles, sweep of B in profiles/r1_boundary_sm_sweep.txt): a boundary tile costs ~1.65 interior
+// tile-times (6.2 us against 3.8 us: remote stores, larger halos, no neighbours sharing L2 lines) and the round trip
+// ~4; the model below keeps a margin on the boundary side, whose penalty is the steeper one (B=4: 90 us, B=6..8:
+// 70 us, B=24: 76 us per sub-cycle).  Pick the B minimising the longer of the two.
+static int balanced_boundary_sms(int nb, int nt, int sms)
+{
+    double const boundary_tile = 1.8, latency_tiles = 5.0;
+    int best = 1;
+    double best_t = 1e300;
+    for (int B = 1; B < sms && B <= nb; ++B) {
+        double const tb = boundary_tile * std::ceil((double)nb / B) + latency_tiles;
+        double const ti = std::ceil((double)(nt - nb) / (sms - B));
+        double const t = std::max(tb, ti);
+        if (t < best_t - 1e-9) { best_t = t; best = B; }
+    }
+    return best;
 }
 
 static DirectArgs direct_args(nsx_solver* S, SubArgs const& A, bool mixed)
@@ -722,10 +746,10 @@ static void phase_substep(nsx_solver* S, int s, bool exchange_sync, bool overlap
         // main stream, the interior (tile kernel or direct kernels) concurrently on stream2 on the remaining SMs
         NSX_CUDA(cudaEventRecord(S->ev_fork, S->stream));
         NSX_CUDA(cudaStreamWaitEvent(S->stream2, S->ev_fork, 0));
-        // SM split between the two co-resident persistent kernels: the boundary chain (tiles + NVLink round trip) is
-        // latency-bound and sits on the critical path of BOTH ranks of a pair, so it gets enough SMs to take at most
-        // ~4 tiles per CTA (1 on the direct path); the interior keeps the rest.
-        int B = S->direct ? std::min(nb, 48) : std::max(1, std::min((nb + 5) / 6, S->sm_count / 4));
+        // SM split between the two co-resident persistent kernels.  Direct path (small meshes): the boundary chain
+        // (tiles + NVLink round trip) is latency-bound and on the critical path of both ranks of a pair: one tile per
+        // CTA.  Tile path: the split that lets both kernels finish together (balanced_boundary_sms).
+        int B = S->direct ? std::min(nb, 48) : balanced_boundary_sms(nb, nt, S->sm_count);
         if (const char* e = getenv("NSX_BOUNDARY_SMS")) B = std::max(1, std::min(atoi(e), std::min(nb, S->sm_count - 1)));
         SubArgs Ab = A;
         Ab.fuse_halo = 1;
@@ -878,9 +902,11 @@ static void solve_group(int n, nsx_solver** W)
                     nsx_solver* S = W[0];
                     HaloArgs a = halo_args(S, S->cur ^ 1, true);
                     int const grid = std::max(1, std::min(nblk(S->ndof), S->sm_count));
-                    k_ow_sweep_exchange<<<grid, TPB, 0, S->stream>>>(a, S->nn, S->ow_list.p, S->ow_count.p, S->n2n.p, S->n2n_deg.p,
-                        S->VT[S->cur], S->VT[S->cur ^ 1], S->d_send_src.p, S->d_send_dst.p, S->flags, S->d_epoch.p,
-                        S->d_done.p, 40000000LL, S->halo_err.p);
+                    static const bool ow_skip = (env_int("NSX_OW_SKIP", 1) != 0);
+                    int const mode = !ow_skip ? 2 : (nit == 0) ? 0 : (nit == 49) ? 2 : 1;
+                    k_ow_sweep_exchange<<<grid, TPB, 0, S->stream>>>(a, mode, S->nn, S->ow_list.p, S->ow_count.p, S->n2n.p, S->n2n_deg.p,
+                        S->VT[S->cur], S->VT[S->cur ^ 1], S->d_send_src.p, S->d_send_dst.p, S->push_ptr.p, S->push_ent.p,
+                        S->ow_pair.p, S->ow_pair.p + 32, S->flags, S->d_epoch.p, S->d_done.p, 40000000LL, S->halo_err.p);
                     S->n_launch++;
                     S->cur ^= 1;
                     NSX_CUDA(cudaGetLastError());
@@ -1102,7 +1128,7 @@ extern "C" int nsx_forcing_apply(nsx_handle S, int var, int interp_linear_time, 
 
 // Host-only: builds the tile plan for a mesh exactly like nsx_create would (same shrink-to-fit loop) and returns
 // its statistics without touching the GPU.  out[0..9] = ntiles, nodes/tile, nslots, max_local_nodes, max_slots,
-// max_own_slots, max_halo_slots, max_halo_nodes, stage bytes (14 node planes), shrink attempts.
+// max_own_slots, max_halo_slots, max_halo_nodes, stage bytes (14 node planes), shrink attempts, tiles reading ghosts.
 extern "C" int nsx_plan_info(const NsxMesh* mesh, int target_tile_nodes, int wave_ctas, int* out, int n)
 {
     try {
@@ -1116,9 +1142,11 @@ extern "C" int nsx_plan_info(const NsxMesh* mesh, int target_tile_nodes, int wav
             if (attempt > 12 || target <= 32) break;
             target = std::max(32, (int)(target * 0.88));
         }
-        int const v[10] = {P.ntiles, P.tile_nodes, P.nslots, P.max_local_nodes, P.max_slots, P.max_own_slots,
-                           P.max_halo_slots, P.max_halo_nodes, sub_layout(P, 14).total, attempt};
-        for (int i = 0; i < n && i < 10; ++i) out[i] = v[i];
+        int nbt = 0;
+        for (auto const& td : P.tiles) nbt += td.boundary;      // tiles that read ghost nodes
+        int const v[11] = {P.ntiles, P.tile_nodes, P.nslots, P.max_local_nodes, P.max_slots, P.max_own_slots,
+                           P.max_halo_slots, P.max_halo_nodes, sub_layout(P, 14).total, attempt, nbt};
+        for (int i = 0; i < n && i < 11; ++i) out[i] = v[i];
         return 0;
     } catch (std::exception const& e) {
         g_create_err = e.what();

@@ -344,11 +344,40 @@ struct HaloArgs {
     int peer_begin[33];                 // entry ranges per send peer
     double* peer_vt[32];                // holder's VT buffer (current parity)
     int peer_nn[32];
-    unsigned long long* peer_flag[32];  // holder's flag slot for me
-    int n_wait;                         // owners I wait for
-    int wait_slot[32];
+    int peer_link[32];                  // send peer -> its index in the link lists below
+    // every neighbour (send or receive relation) is signalled AND waited for, so the two ranks of a pair never drift
+    // by more than one exchange: a push can only land in a buffer its holder has finished reading
+    int n_link;
+    unsigned long long* link_flag[32];  // the neighbour's flag slot for me
+    int link_rank[32];                  // my flag slot that neighbour writes
     int sync;                           // 0: stream-ordered group on one device, no flags
 };
+// Flag word = exchange epoch; bit 63 is the "my send list to you contains open-water nodes" marker of the smoother
+// (k_ow_sweep_exchange).  Every waiter compares the masked value.
+constexpr unsigned long long FLAG_OW = 0x8000000000000000ULL;
+
+// Publishes `word` in the flag slot of every neighbour selected by `mask` and waits until each of them has
+// published an epoch >= `epoch` (bounded spin).  Called by ONE block after its pushes; thread i serves link i.
+// Returns (to thread i) the last flag word read from neighbour i, 0 if not selected.
+__device__ __forceinline__ unsigned long long flag_signal_wait(HaloArgs const& a, int i, bool selected, unsigned long long word,
+                                                               unsigned long long epoch, const unsigned long long* my_flags,
+                                                               long long max_spins, int* err)
+{
+    unsigned long long v = 0ULL;
+    if (i < a.n_link && selected) {
+        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(a.link_flag[i]), "l"(word) : "memory");
+        const unsigned long long* f = my_flags + a.link_rank[i];
+        long long spins = 0;
+        for (;;) {
+            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(f) : "memory");
+            if ((v & ~FLAG_OW) >= epoch) break;
+            if (*((volatile int*)err)) break;        // an earlier exchange already timed out: do not stall again
+            if (++spins > max_spins) { atomicExch(err, 1 + a.link_rank[i]); break; }
+            __nanosleep(64);
+        }
+    }
+    return v;
+}
 
 struct SubArgs {
     const TileDesc* tiles; const int* tile_order; int tile_base;
@@ -731,20 +760,7 @@ k_subcycle(KParams K, SubArgs A)
         if (s_last) {
             __threadfence_system();
             unsigned long long const epoch = *((volatile unsigned long long*)A.epoch_ctr) + 1ULL;
-            if (gtid < A.H.n_peers)
-                asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(A.H.peer_flag[gtid]), "l"(epoch) : "memory");
-            if (gtid < A.H.n_wait) {
-                const unsigned long long* f = A.my_flags + A.H.wait_slot[gtid];
-                long long spins = 0;
-                for (;;) {
-                    unsigned long long v;
-                    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(f) : "memory");
-                    if (v >= epoch) break;
-                    if (*((volatile int*)A.halo_err)) break;     // an earlier exchange already timed out
-                    if (++spins > 40000000LL) { atomicExch(A.halo_err, 1 + A.H.wait_slot[gtid]); break; }
-                    __nanosleep(64);
-                }
-            }
+            flag_signal_wait(A.H, gtid, true, epoch, epoch, A.my_flags, 40000000LL, A.halo_err);
             p2_sync();
             if (gtid == 0) { *A.epoch_ctr = epoch; *A.done_ctr = 0u; }
         }
@@ -1279,32 +1295,28 @@ k_halo_exchange(HaloArgs a, int nn_src, const int* __restrict__ src_idx, const i
     if (!last) return;
     __threadfence_system();
     unsigned long long const epoch = *((volatile unsigned long long*)epoch_ctr) + 1ULL;
-    if ((int)threadIdx.x < a.n_peers)
-        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(a.peer_flag[threadIdx.x]), "l"(epoch) : "memory");
-    if ((int)threadIdx.x < a.n_wait) {
-        const unsigned long long* f = my_flags + a.wait_slot[threadIdx.x];
-        long long spins = 0;
-        for (;;) {
-            unsigned long long v;
-            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(f) : "memory");
-            if (v >= epoch) break;
-            if (*((volatile int*)err)) break;        // an earlier exchange already timed out: do not stall again
-            if (++spins > max_spins) { atomicExch(err, 1 + a.wait_slot[threadIdx.x]); break; }
-            __nanosleep(64);
-        }
-    }
+    flag_signal_wait(a, (int)threadIdx.x, true, epoch, epoch, my_flags, max_spins, err);
     __syncthreads();
     if (threadIdx.x == 0) { *epoch_ctr = epoch; *done_ctr = 0u; }
 }
 
 // Multi-rank smoother step: one Jacobi sweep over the open-water list AND the ghost exchange of the result in a
 // single launch.  All CTAs sweep; the last CTA to finish pushes this rank's sent nodes to their holders, publishes
-// the epoch and waits for the owners of this rank's ghosts (same protocol as k_halo_exchange).
+// the epoch and waits for its neighbours (same protocol as k_halo_exchange).
+//
+// A sweep only rewrites open-water nodes, so a pair of ranks whose send lists contain none has nothing to exchange
+// for the whole smoother.  mode 0 (first sweep): full exchange; every rank marks, per neighbour, whether its send
+// list holds open-water nodes, publishes that bit with the epoch and records the neighbour's bit.  mode 1 (middle
+// sweeps): only pairs with a bit set on either side push, signal and wait.  mode 2 (last sweep): full exchange again
+// (values of skipped pairs are unchanged, so re-storing them is idempotent), which re-establishes the one-exchange
+// drift bound of the protocol before the next phase.
 __global__ void __launch_bounds__(TPB)
-k_ow_sweep_exchange(HaloArgs a, int nn, const int* __restrict__ ow_list, const int* __restrict__ ow_count,
+k_ow_sweep_exchange(HaloArgs a, int mode, int nn, const int* __restrict__ ow_list, const int* __restrict__ ow_count,
                     const int* __restrict__ n2n, const int* __restrict__ n2n_deg,
                     const double* VTin, double* VTout,
-                    const int* __restrict__ src_idx, const int* __restrict__ dst_idx, const unsigned long long* my_flags,
+                    const int* __restrict__ src_idx, const int* __restrict__ dst_idx,
+                    const int* __restrict__ push_ptr, const int2* __restrict__ push_ent,
+                    int* send_ow, int* pair_active, const unsigned long long* my_flags,
                     unsigned long long* epoch_ctr, unsigned int* done_ctr, long long max_spins, int* err)
 {
     int const cnt = *ow_count;
@@ -1319,17 +1331,25 @@ k_ow_sweep_exchange(HaloArgs a, int nn, const int* __restrict__ ow_list, const i
         }
         VTout[n] = su / deg;
         VTout[n + nn] = sv / deg;
+        if (mode == 0)                                       // open-water node in a send list: that pair stays active
+            for (int q = push_ptr[n]; q < push_ptr[n + 1]; ++q) atomicOr(send_ow + push_ent[q].x, 1);
     }
     __shared__ bool last;
+    __shared__ int s_act[32];
     __threadfence();
     __syncthreads();
     if (threadIdx.x == 0) last = (atomicAdd(done_ctr, 1u) == gridDim.x - 1);
     __syncthreads();
     if (!last) return;
     __threadfence();
+    int const i = (int)threadIdx.x;
+    // per link: do I exchange with this neighbour in this sweep, and my own open-water bit for it
+    if (i < 32) s_act[i] = (mode != 1) ? 1 : (i < a.n_link ? __ldcg(pair_active + i) : 0);
+    __syncthreads();
     for (int t = threadIdx.x; t < a.n_total; t += blockDim.x) {
         int p = 0;
         while (t >= a.peer_begin[p + 1]) ++p;
+        if (!s_act[a.peer_link[p]]) continue;
         int const s = src_idx[t], d = dst_idx[t];
         double* dst = a.peer_vt[p];
         dst[d] = __ldcg(VTout + s);
@@ -1339,22 +1359,16 @@ k_ow_sweep_exchange(HaloArgs a, int nn, const int* __restrict__ ow_list, const i
     __threadfence_system();
     __syncthreads();
     unsigned long long const epoch = *((volatile unsigned long long*)epoch_ctr) + 1ULL;
-    if ((int)threadIdx.x < a.n_peers)
-        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(a.peer_flag[threadIdx.x]), "l"(epoch) : "memory");
-    if ((int)threadIdx.x < a.n_wait) {
-        const unsigned long long* f = my_flags + a.wait_slot[threadIdx.x];
-        long long spins = 0;
-        for (;;) {
-            unsigned long long v;
-            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(f) : "memory");
-            if (v >= epoch) break;
-            if (*((volatile int*)err)) break;        // an earlier exchange already timed out: do not stall again
-            if (++spins > max_spins) { atomicExch(err, 1 + a.wait_slot[threadIdx.x]); break; }
-            __nanosleep(64);
-        }
-    }
+    int my_bit = 0;
+    if (i < a.n_link && mode != 2)
+        for (int p = 0; p < a.n_peers; ++p)
+            if (a.peer_link[p] == i) my_bit = __ldcg(send_ow + p);
+    bool const sel = (i < a.n_link) && s_act[i];
+    unsigned long long const v = flag_signal_wait(a, i, sel, epoch | (my_bit ? FLAG_OW : 0ULL), epoch, my_flags, max_spins, err);
+    if (mode == 0 && i < a.n_link) pair_active[i] = (my_bit || (v & FLAG_OW)) ? 1 : 0;
     __syncthreads();
     if (threadIdx.x == 0) { *epoch_ctr = epoch; *done_ctr = 0u; }
+    if (mode == 2 && i < 32) send_ow[i] = 0;                 // ready for the next model step
 }
 
 // ---------------------------------------------------------------------------------------------------
