@@ -221,6 +221,32 @@ int nsx_halo_finalize(nsx_handle h);
 /* lock-step explicitSolve of several ranks that live in this process (one stream-ordered device) */
 int nsx_group_explicit_solve(int n, nsx_handle* handles);
 
+/* ---- remesh-time host library (no GPU) ----
+ * One rank's view of the partitioned mesh, built without std::map / bimap: the msh-2.2 reader
+ * (GmshMesh::readFromFileASCII / readFromFileBinary, core/src/gmshmesh.cpp:133-409, 411-712), GmshMesh::nodalGrid()
+ * (core/src/gmshmesh.cpp:856-1498), the lists of FiniteElement::initUpdateGhosts() (FE.cpp:14003-14088, derived from
+ * the file instead of MPI exchanges), bcMarkedNodes() (FE.cpp:150-271) and bamg's NodalElementConnectivity /
+ * NodalConnectivity (contrib/bamg/src/Mesh.cpp:526-537, 583-629, 798-865).  Numbering is bit-exact with the
+ * reference's; nsx_partmesh_views() fills the structs nsx_create() takes. */
+typedef struct nsx_partmesh* nsx_partmesh_handle;
+/* `path` = <exporter_path>/par<N><mesh.filename> (FE.cpp:1430-1434); format "ascii"|"binary" (mesh.fileformat),
+ * ordering "gmsh"|"bamg" (mesh.ordering, swaps vertices 2 and 3) */
+int nsx_partmesh_read(const char* path, const char* format, const char* ordering, int rank, int nranks,
+                      nsx_partmesh_handle* out);
+/* same from memory: root mesh (1-based triangles) + per-element partition (0-based) + ghost partitions (CSR) */
+int nsx_partmesh_build(int nn, const double* x, const double* y, int ne, const int* tri, const int* partition,
+                       const int* ghost_ptr, const int* ghost_val, int rank, int nranks, nsx_partmesh_handle* out);
+/* M_dirichlet_flags_root / M_neumann_flags_root: 1-based root node ids */
+int nsx_partmesh_bc_marked_nodes(nsx_partmesh_handle h, const int* dirichlet_flags_root, int n_dirichlet,
+                                 const int* neumann_flags_root, int n_neumann);
+int nsx_partmesh_set_lat(nsx_partmesh_handle h, const double* lat_local);     /* M_mesh.lat(), local numbering */
+int nsx_partmesh_views(nsx_partmesh_handle h, NsxMesh* mesh, NsxHalo* halo);  /* pointers valid until destroy */
+/* ids[0..3]: local node -> root node id (1-based), local node -> reordered global id, local element -> file element
+ * number, local element -> partition; sizes[0..3]: global nodes, global triangles, ghost nodes, dirichlet flags */
+int nsx_partmesh_ids(nsx_partmesh_handle h, const int** ids, int* sizes);
+int nsx_partmesh_destroy(nsx_partmesh_handle h);
+const char* nsx_partmesh_last_error(void);
+
 /* ---- pinned host memory for the per-step transfers (cudaHostRegister on the caller's vectors) ---- */
 int nsx_host_register(void* p, unsigned long bytes);
 int nsx_host_unregister(void* p);

@@ -104,6 +104,8 @@ EXPORTS = (
     "nsx_halo_connect_blob", "nsx_halo_connect_local", "nsx_halo_finalize", "nsx_group_explicit_solve",
     "nsx_host_register", "nsx_host_unregister", "nsx_abi_sizes", "nsx_tile_info", "nsx_plan_info", "nsx_cfg_last_error",
     "nsx_check_regridding", "nsx_update_ice_diagnostics", "nsx_forcing_load", "nsx_forcing_apply",
+    "nsx_partmesh_read", "nsx_partmesh_build", "nsx_partmesh_bc_marked_nodes", "nsx_partmesh_set_lat",
+    "nsx_partmesh_views", "nsx_partmesh_ids", "nsx_partmesh_destroy", "nsx_partmesh_last_error",
 )
 
 _lib = None
@@ -131,6 +133,15 @@ def lib():
         L.nsx_update_ice_diagnostics.argtypes = [C.c_void_p]
         L.nsx_forcing_load.argtypes = [C.c_void_p, C.c_int, C.c_int, c_double_p]
         L.nsx_forcing_apply.argtypes = [C.c_void_p, C.c_int, C.c_int] + [C.c_double] * 5
+        L.nsx_partmesh_last_error.restype = C.c_char_p
+        L.nsx_partmesh_read.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, C.c_int, C.c_int, C.c_void_p]
+        L.nsx_partmesh_build.argtypes = [C.c_int, c_double_p, c_double_p, C.c_int, c_int_p, c_int_p, c_int_p, c_int_p,
+                                         C.c_int, C.c_int, C.c_void_p]
+        L.nsx_partmesh_bc_marked_nodes.argtypes = [C.c_void_p, c_int_p, C.c_int, c_int_p, C.c_int]
+        L.nsx_partmesh_set_lat.argtypes = [C.c_void_p, c_double_p]
+        L.nsx_partmesh_views.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.nsx_partmesh_ids.argtypes = [C.c_void_p, C.c_void_p, c_int_p]
+        L.nsx_partmesh_destroy.argtypes = [C.c_void_p]
         L.nsx_halo_blob_size.argtypes = [C.c_void_p, C.c_int]
         L.nsx_halo_blob.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
         L.nsx_halo_connect_blob.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
@@ -346,3 +357,98 @@ def connect_local_group(solvers):
             s.halo_connect_local(p, by_rank[p])
     for s in solvers:
         s.halo_finalize()
+
+
+class PartMesh:
+    """One rank's partitioned mesh from the host library: msh-2.2 reader or in-memory tags ->
+    nodalGrid numbering, halo lists, boundary masks, bamg tables.  No GPU needed."""
+
+    def __init__(self, handle):
+        self.L = lib()
+        self.h = handle
+
+    @staticmethod
+    def _chk(rc, what):
+        if rc != 0:
+            raise RuntimeError("%s: %s" % (what, lib().nsx_partmesh_last_error().decode()))
+
+    @classmethod
+    def read(cls, path, rank, nranks, fmt="binary", ordering="gmsh"):
+        h = C.c_void_p()
+        cls._chk(lib().nsx_partmesh_read(str(path).encode(), fmt.encode(), ordering.encode(), int(rank), int(nranks),
+                                         C.byref(h)), "nsx_partmesh_read")
+        return cls(h)
+
+    @classmethod
+    def build(cls, x, y, tri1, rank=0, nranks=1, elem_part=None, ghost_ptr=None, ghost_val=None):
+        xa, xp = _f64(x)
+        ya, yp = _f64(y)
+        ta, tp = _i32(np.asarray(tri1).reshape(-1))
+        if nranks > 1:
+            pa, pp = _i32(elem_part)
+            ga, gp = _i32(ghost_ptr)
+            va, vp = _i32(ghost_val if len(ghost_val) else np.zeros(1, np.int32))
+        else:
+            pp = gp = vp = None
+        h = C.c_void_p()
+        cls._chk(lib().nsx_partmesh_build(xa.size, xp, yp, ta.size // 3, tp, pp, gp, vp, int(rank), int(nranks),
+                                          C.byref(h)), "nsx_partmesh_build")
+        return cls(h)
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.nsx_partmesh_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def bc_marked_nodes(self, dirichlet_flags_root, neumann_flags_root):
+        da, dp = _i32(dirichlet_flags_root)
+        na, npp = _i32(neumann_flags_root)
+        self._chk(self.L.nsx_partmesh_bc_marked_nodes(self.h, dp, da.size, npp, na.size), "nsx_partmesh_bc_marked_nodes")
+
+    def set_lat(self, lat):
+        a, p = _f64(lat)
+        self._chk(self.L.nsx_partmesh_set_lat(self.h, p), "nsx_partmesh_set_lat")
+
+    def views(self):
+        M, H = NsxMesh(), NsxHalo()
+        self._chk(self.L.nsx_partmesh_views(self.h, C.byref(M), C.byref(H)), "nsx_partmesh_views")
+        return M, H
+
+    def to_local_mesh(self):
+        """Copy into a partition.LocalMesh (what Solver() and the tests consume)."""
+        from . import partition as pt
+        M, H = self.views()
+        ids = (c_int_p * 4)()
+        sizes = (C.c_int * 4)()
+        self._chk(self.L.nsx_partmesh_ids(self.h, ids, sizes), "nsx_partmesh_ids")
+        nn, ne = M.num_nodes, M.num_elements
+
+        def arr(p, n, dt):
+            return np.ctypeslib.as_array(p, shape=(n,)).astype(dt, copy=True) if n else np.zeros(0, dt)
+        lm = pt.LocalMesh(rank=H.rank, nranks=max(H.nranks, 1), num_nodes=nn, local_ndof=M.local_ndof, num_elements=ne,
+                          local_nelements=M.local_nelements, x=arr(M.coord_x, nn, np.float64),
+                          y=arr(M.coord_y, nn, np.float64), indices=arr(M.indices, 3 * ne, np.int32).reshape(ne, 3),
+                          ghostNodes=arr(M.ghost_nodes, 3 * ne, np.uint8).reshape(ne, 3),
+                          node_gid=arr(ids[0], nn, np.int32), node_rid=arr(ids[1], nn, np.int32),
+                          elem_gid=arr(ids[2], ne, np.int32), elem_part=arr(ids[3], ne, np.int32),
+                          local_ghost=np.zeros(0, np.int32))
+        lm.local_ghost = np.sort(lm.node_rid[M.local_ndof:])
+        for k in range(H.n_send_peers):
+            a, b = H.send_ptr[k], H.send_ptr[k + 1]
+            lm.send_to[int(H.send_peer[k])] = arr(C.cast(C.addressof(H.send_idx.contents) + 4 * a, c_int_p), b - a, np.int32)
+        for k in range(H.n_recv_peers):
+            a, b = H.recv_ptr[k], H.recv_ptr[k + 1]
+            lm.recv_from[int(H.recv_peer[k])] = arr(C.cast(C.addressof(H.recv_idx.contents) + 4 * a, c_int_p), b - a, np.int32)
+        lm.mask_dirichlet = arr(M.mask_dirichlet, nn, np.uint8)
+        lm.neumann_flags = arr(M.neumann_flags, M.n_neumann_flags, np.int32)
+        lm.dirichlet_flags = np.nonzero(lm.mask_dirichlet)[0].astype(np.int32)
+        lm.lat = arr(M.lat, nn, np.float64)
+        lm.nodal_element_connectivity = arr(M.nodal_element_connectivity, nn * M.nec_width, np.float64).reshape(nn, M.nec_width)
+        lm.nodal_connectivity = arr(M.nodal_connectivity, nn * M.nc_width, np.float64).reshape(nn, M.nc_width)
+        return lm

@@ -64,7 +64,19 @@ def make_case(name="toy", nranks=1, dyn="bbm", open_east=False, substeps=120, nx
     if nranks > 1:
         c.elem_part = pt.partition_elements(gm.x, gm.y, gm.tri, nranks)
         c.ghost_ptr, c.ghost_val = pt.ghost_tags(gm.tri, c.elem_part, nranks)
-        c.lms = pt.nodal_grid(nranks, gm.x, gm.y, gm.tri, c.elem_part, c.ghost_ptr, c.ghost_val)
+        if only_rank is None:
+            c.lms = pt.nodal_grid(nranks, gm.x, gm.y, gm.tri, c.elem_part, c.ghost_ptr, c.ghost_val)
+        else:
+            # one process per GPU: this rank's mesh, halo lists, masks and bamg tables from the host library
+            # (nsx_partmesh_*); the other ranks' entries stay None
+            pm = capi.PartMesh.build(gm.x, gm.y, gm.tri, only_rank, nranks, c.elem_part, c.ghost_ptr, c.ghost_val)
+            pm.bc_marked_nodes(gm.dirichlet_flags_root, gm.neumann_flags_root)
+            lm = pm.to_local_mesh()
+            pm.close()
+            lm.lat = pt.scatter_nodal1(lm, gm.lat)
+            c.lms = [lm if r == only_rank else None for r in range(nranks)]
+            c.local = [local_fields(c, l) if l is not None else None for l in c.lms]
+            return c
     else:
         c.elem_part = np.zeros(gm.ne, np.int32)
         c.ghost_ptr = np.zeros(gm.ne + 1, np.int32)
