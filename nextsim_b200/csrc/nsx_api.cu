@@ -115,6 +115,7 @@ static void alloc_fields(nsx_solver* S)
     S->slot_shape.alloc(6 * ns); S->slot_shape.zero(st);
     S->slot_ec.alloc(6 * ns); S->slot_ec.zero(st);
     S->stage.alloc(std::max(2 * nn, 6 * ne));
+    S->stage2.alloc(std::max(2 * nn, ne));
     // Path selection: the sub-cycle working set (~300 B per element) either lives in the 126 MB L2 (direct path)
     // or streams from HBM (TMA tile pipeline).  NSX_PATH=direct|tiles overrides.
     {
@@ -214,6 +215,11 @@ extern "C" int nsx_create(const NsxMesh* mesh, const NsxHalo* halo, int device, 
         NSX_CUDA(cudaDeviceGetAttribute(&S->sm_count, cudaDevAttrMultiProcessorCount, device));
         NSX_CUDA(cudaStreamCreateWithFlags(&S->stream, cudaStreamNonBlocking));
         NSX_CUDA(cudaStreamCreateWithFlags(&S->stream2, cudaStreamNonBlocking));
+        NSX_CUDA(cudaStreamCreateWithFlags(&S->stream_copy, cudaStreamNonBlocking));
+        for (int b = 0; b < 2; ++b) {
+            NSX_CUDA(cudaEventCreateWithFlags(&S->ev_stage_copy[b], cudaEventDisableTiming));
+            NSX_CUDA(cudaEventCreateWithFlags(&S->ev_stage_perm[b], cudaEventDisableTiming));
+        }
         // one wave of the sub-cycle kernel = SMs x resident CTAs (2: shared memory and launch bounds); shrink the
         // tiles until the staged working set of the largest tile fits the per-CTA shared-memory budget
         int target = env_int("NSX_TILE_NODES", 208);
@@ -249,6 +255,11 @@ extern "C" int nsx_destroy(nsx_handle S)
     if (S->ev_fork) cudaEventDestroy(S->ev_fork);
     if (S->ev_join) cudaEventDestroy(S->ev_join);
     if (S->window) cudaFree(S->window);
+    if (S->stream_copy) { cudaStreamSynchronize(S->stream_copy); cudaStreamDestroy(S->stream_copy); }
+    for (int b = 0; b < 2; ++b) {
+        if (S->ev_stage_copy[b]) cudaEventDestroy(S->ev_stage_copy[b]);
+        if (S->ev_stage_perm[b]) cudaEventDestroy(S->ev_stage_perm[b]);
+    }
     if (S->stream2) cudaStreamDestroy(S->stream2);
     if (S->stream) cudaStreamDestroy(S->stream);
     delete S;
@@ -393,6 +404,8 @@ static void field_table(nsx_solver* S, const NsxFields* f, std::vector<FieldMap>
     }
 }
 
+// Field k is staged in buffer k&1: its PCIe copy (copy stream) overlaps the permutation kernel of field k-1 (main
+// stream), so the copy engine never waits for a kernel.  Every call drains both streams before returning.
 extern "C" int nsx_upload(nsx_handle S, const NsxFields* f)
 {
     NSX_API_BEGIN(S)
@@ -402,15 +415,23 @@ extern "C" int nsx_upload(nsx_handle S, const NsxFields* f)
         throw std::invalid_argument("nsx_upload: the D_* diagnostics are outputs");
     std::vector<FieldMap> t;
     field_table(S, f, t);
-    cudaStream_t st = S->stream;
-    for (auto& m : t) {
+    cudaStream_t st = S->stream, sc = S->stream_copy;
+    double* const stg[2] = {S->stage.p, S->stage2.p};
+    for (size_t k = 0; k < t.size(); ++k) {
+        auto& m = t[k];
+        int const b = (int)(k & 1);
         int const n = (m.kind == ELEM) ? S->ne : S->nn;
         int const planes = (m.kind == NODAL2) ? 2 : 1;
-        NSX_CUDA(cudaMemcpyAsync(S->stage.p, m.host, (size_t)n * planes * sizeof(double), cudaMemcpyHostToDevice, st));
-        k_permute_in<<<nblk(n), TPB, 0, st>>>(n, planes, m.kind == ELEM ? S->elem_perm.p : S->node_perm.p, S->stage.p, m.dev);
+        if (k >= 2) NSX_CUDA(cudaStreamWaitEvent(sc, S->ev_stage_perm[b], 0));      // buffer b was read by field k-2
+        NSX_CUDA(cudaMemcpyAsync(stg[b], m.host, (size_t)n * planes * sizeof(double), cudaMemcpyHostToDevice, sc));
+        NSX_CUDA(cudaEventRecord(S->ev_stage_copy[b], sc));
+        NSX_CUDA(cudaStreamWaitEvent(st, S->ev_stage_copy[b], 0));
+        k_permute_in<<<nblk(n), TPB, 0, st>>>(n, planes, m.kind == ELEM ? S->elem_perm.p : S->node_perm.p, stg[b], m.dev);
+        NSX_CUDA(cudaEventRecord(S->ev_stage_perm[b], st));
     }
     NSX_CUDA(cudaGetLastError());
     if (f->M_tau_wi && !S->have_tau_wi) { S->have_tau_wi = true; S->graph_valid = false; }
+    NSX_CUDA(cudaStreamSynchronize(sc));
     NSX_CUDA(cudaStreamSynchronize(st));
     NSX_API_END(S)
 }
@@ -421,18 +442,27 @@ extern "C" int nsx_download(nsx_handle S, NsxFields* f)
     if (!f) throw std::invalid_argument("nsx_download: NULL");
     std::vector<FieldMap> t;
     field_table(S, f, t);
-    cudaStream_t st = S->stream;
-    for (auto& m : t) {
+    cudaStream_t st = S->stream, sc = S->stream_copy;
+    double* const stg[2] = {S->stage.p, S->stage2.p};
+    for (size_t k = 0; k < t.size(); ++k) {
+        auto& m = t[k];
+        int const b = (int)(k & 1);
         int const n = (m.kind == ELEM) ? S->ne : S->nn;
         int const planes = (m.kind == NODAL2) ? 2 : 1;
-        k_permute_out<<<nblk(n), TPB, 0, st>>>(n, planes, m.kind == ELEM ? S->elem_perm.p : S->node_perm.p, m.dev, S->stage.p);
-        NSX_CUDA(cudaMemcpyAsync(m.host, S->stage.p, (size_t)n * planes * sizeof(double), cudaMemcpyDeviceToHost, st));
-    }
-    if (f->M_shape_coeff) {
-        k_shape_out<<<nblk(6L * S->ne), TPB, 0, st>>>(S->ne, S->elem_perm.p, S->shape.p, S->stage.p);
-        NSX_CUDA(cudaMemcpyAsync(f->M_shape_coeff, S->stage.p, 6 * (size_t)S->ne * sizeof(double), cudaMemcpyDeviceToHost, st));
+        if (k >= 2) NSX_CUDA(cudaStreamWaitEvent(st, S->ev_stage_copy[b], 0));      // buffer b was copied out for field k-2
+        k_permute_out<<<nblk(n), TPB, 0, st>>>(n, planes, m.kind == ELEM ? S->elem_perm.p : S->node_perm.p, m.dev, stg[b]);
+        NSX_CUDA(cudaEventRecord(S->ev_stage_perm[b], st));
+        NSX_CUDA(cudaStreamWaitEvent(sc, S->ev_stage_perm[b], 0));
+        NSX_CUDA(cudaMemcpyAsync(m.host, stg[b], (size_t)n * planes * sizeof(double), cudaMemcpyDeviceToHost, sc));
+        NSX_CUDA(cudaEventRecord(S->ev_stage_copy[b], sc));
     }
     NSX_CUDA(cudaGetLastError());
+    NSX_CUDA(cudaStreamSynchronize(sc));
+    if (f->M_shape_coeff) {                       // 6 planes: needs the large staging buffer, after the pipeline drained
+        k_shape_out<<<nblk(6L * S->ne), TPB, 0, st>>>(S->ne, S->elem_perm.p, S->shape.p, S->stage.p);
+        NSX_CUDA(cudaMemcpyAsync(f->M_shape_coeff, S->stage.p, 6 * (size_t)S->ne * sizeof(double), cudaMemcpyDeviceToHost, st));
+        NSX_CUDA(cudaGetLastError());
+    }
     NSX_CUDA(cudaStreamSynchronize(st));
     int herr = 0;
     NSX_CUDA(cudaMemcpy(&herr, S->halo_err.p, sizeof(int), cudaMemcpyDeviceToHost));

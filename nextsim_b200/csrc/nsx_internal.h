@@ -142,6 +142,9 @@ struct nsx_solver {
     nsx::DBuf<double> ec_e, contrib;             // direct path: element-space rheology constants, staged contributions
     bool direct = false;                         // L2-resident mesh: element kernel + node kernel instead of the tile kernel
     nsx::DBuf<double> stage;                     // transfer staging (host numbering), max(2nn, 6ne)
+    nsx::DBuf<double> stage2;                    // second staging buffer, max(2nn, ne): copies and permutations overlap
+    cudaStream_t stream_copy = nullptr;          // host<->device copies of nsx_upload / nsx_download
+    cudaEvent_t ev_stage_copy[2] = {nullptr, nullptr}, ev_stage_perm[2] = {nullptr, nullptr};
     nsx::DBuf<int> ow_list;                      // open-water nodes to smooth
     nsx::DBuf<int> ow_count;
     nsx::DBuf<int> check_i; nsx::DBuf<double> check_d;
