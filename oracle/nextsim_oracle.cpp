@@ -6,11 +6,16 @@
 // cpu_baseline / --impl reference legs of bench.py may load this library; the product
 // path (libnsx.so) never links, imports or calls it.
 //
-// PARITY UNPINNED: the reference ships no test, fixture or stored output for this path
-//  and its executable cannot be built in this image (needs
-// Boost, MPI, Gmsh, NetCDF).  The restatement below follows the reference's loop nests
-// and operation order line by line and is built with -O2 -ffp-contract=off; the golden
-// vectors under tests/golden/ are generated from it (tests/golden/make_golden.py).
+// PARITY UNPINNED for the physics: the reference ships no test, fixture or stored output
+// for this path and its executable cannot be built in this
+// image (needs Boost, MPI, Gmsh, NetCDF).  The restatement below follows the reference's
+// loop nests and operation order line by line and is built with -O2 -ffp-contract=off;
+// the golden vectors under tests/golden/ are generated from it (tests/golden/make_golden.py).
+// PINNED against the reference's own code: bamgTables() -- contrib/bamg compiles standalone
+// and is built UNMODIFIED from /root/reference into oracle/_ref/libref_bamg.so
+// (oracle/ref_bamg/Makefile); tests/test_ref_bamg_cpu.py checks NodalElementConnectivity and
+// NodalConnectivity of BamgConvertMeshx (the call of FE.cpp:77-80) against bamgTables()
+// bit for bit on root and partition-local meshes.
 //
 // Reference files followed (paths relative to /root/reference):
 //   model/finiteelement.cpp

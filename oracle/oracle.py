@@ -2,7 +2,8 @@
 
 TEST INFRASTRUCTURE ONLY.  Importers allowed: tests/, __graft_entry__.smoke(), and the
 cpu_baseline / ``--impl reference`` legs of bench.py.  The product package ``nextsim_b200``
-never imports this module.  PARITY UNPINNED: see the header of nextsim_oracle.cpp.
+never imports this module.  PARITY UNPINNED for the physics, bamg tables pinned against the
+reference's own bamg library (oracle/ref_bamg): see the header of nextsim_oracle.cpp.
 """
 import ctypes as C
 import os
