@@ -131,6 +131,7 @@ static void alloc_fields(nsx_solver* S)
     S->d_epoch.alloc(1); S->d_done.alloc(1);
     S->d_epoch.zero(st); S->d_done.zero(st);
     S->ow_pair.alloc(64); S->ow_pair.zero(st);
+    S->ow_bar.alloc(1); S->ow_bar.zero(st);
     for (auto& e : S->ev) NSX_CUDA(cudaEventCreate(&e));
     NSX_CUDA(cudaEventCreateWithFlags(&S->ev_fork, cudaEventDisableTiming));
     NSX_CUDA(cudaEventCreateWithFlags(&S->ev_join, cudaEventDisableTiming));
@@ -925,6 +926,20 @@ static void solve_group(int n, nsx_solver** W)
                                                          S->VT[S->cur], S->VT[S->cur ^ 1], S->d_done.p);
             S->n_launch++;
             NSX_CUDA(cudaGetLastError());
+        } else if (n == 1 && remote && env_int("NSX_OW_PERSIST", 0) != 0) {
+            // one process per GPU: the 50 sweeps AND their ghost exchanges in a single launch.  Measured on 2 B200s
+            // (weak bench): 0.73 ms per step against 0.68 ms for 50 launches of k_ow_sweep_exchange -- a sweep + exchange
+            // is bound by the NVLink fence / flag round trip (~13 us), not by launches; off by default.
+            nsx_solver* S = W[0];
+            static const bool ow_skip = (env_int("NSX_OW_SKIP", 1) != 0);
+            S->ow_bar.zero(S->stream);
+            HaloArgs aA = halo_args(S, S->cur, true), aB = halo_args(S, S->cur ^ 1, true);
+            int const grid = std::max(1, std::min(nblk(S->ndof), S->sm_count));
+            k_ow_smooth_exchange_all<<<grid, TPB, 0, S->stream>>>(aA, aB, 50, ow_skip ? 1 : 0, S->nn, S->ow_list.p, S->ow_count.p,
+                S->n2n.p, S->n2n_deg.p, S->VT[S->cur], S->VT[S->cur ^ 1], S->d_send_src.p, S->d_send_dst.p, S->push_ptr.p,
+                S->push_ent.p, S->ow_pair.p, S->ow_pair.p + 32, S->flags, S->d_epoch.p, S->ow_bar.p, 40000000LL, S->halo_err.p);
+            S->n_launch++;
+            NSX_CUDA(cudaGetLastError());            // 50 sweeps: the result is back in VT[cur]
         } else {
             for (int nit = 0; nit < 50; ++nit) {       // hard-coded 50 sweeps, FE.cpp:10580
                 if (n == 1 && remote) {

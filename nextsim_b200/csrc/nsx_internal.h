@@ -161,6 +161,7 @@ struct nsx_solver {
     nsx::DBuf<unsigned int> d_done;              // block completion counter of k_halo_exchange
     int n_send_total = 0;
     nsx::DBuf<int> push_ptr; nsx::DBuf<int2> push_ent;   // owned node -> (send-peer slot, holder's ghost id)
+    nsx::DBuf<unsigned int> ow_bar;              // grid-barrier counter of the single-launch multi-rank smoother
     nsx::DBuf<int> ow_pair;                      // smoother: [0..32) my open-water bit per send peer, [32..64) active links
     nsx::DBuf<uint8_t> elem_nowrite;             // element written by a boundary tile (mixed direct/tile mode)
     nsx::DBuf<int> halo_err;                     // device error word (timeouts)

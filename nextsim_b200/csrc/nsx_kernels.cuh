@@ -1371,6 +1371,92 @@ k_ow_sweep_exchange(HaloArgs a, int mode, int nn, const int* __restrict__ ow_lis
     if (mode == 2 && i < 32) send_ow[i] = 0;                 // ready for the next model step
 }
 
+// All 50 sweeps of the multi-rank smoother in ONE launch: per sweep every CTA relaxes its share of the open-water
+// list, a software grid barrier makes the result visible, CTA 0 runs the ghost exchange (same pushes, flags and
+// open-water pair skipping as k_ow_sweep_exchange: mode 0 for the first sweep, 2 for the last, 1 in between) and a
+// second barrier releases the other CTAs into the next sweep.  Saves the launch and the last-CTA detection of 50
+// kernels (about half of the ~16 us a sweep + exchange costs as separate launches).  The grid is at most one CTA
+// per SM and nothing else runs on the stream, so every CTA is resident; all spins are bounded.
+// aA / aB: halo arguments whose peer buffers have the parity of VTa / VTb.
+__global__ void __launch_bounds__(TPB)
+k_ow_smooth_exchange_all(HaloArgs aA, HaloArgs aB, int nsweeps, int ow_skip, int nn,
+                         const int* __restrict__ ow_list, const int* __restrict__ ow_count,
+                         const int* __restrict__ n2n, const int* __restrict__ n2n_deg,
+                         double* VTa, double* VTb,
+                         const int* __restrict__ src_idx, const int* __restrict__ dst_idx,
+                         const int* __restrict__ push_ptr, const int2* __restrict__ push_ent,
+                         int* send_ow, int* pair_active, const unsigned long long* my_flags,
+                         unsigned long long* epoch_ctr, unsigned int* bar, long long max_spins, int* err)
+{
+    int const cnt = *ow_count;
+    int const nact = max(1, min((int)gridDim.x, (cnt + (int)blockDim.x - 1) / (int)blockDim.x));
+    if ((int)blockIdx.x >= nact) return;
+    __shared__ int s_act[32];
+    unsigned int target = 0;
+    auto barrier = [&]() {
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            target += (unsigned int)nact;
+            __threadfence();
+            atomicAdd(bar, 1u);
+            unsigned int v;
+            long long spins = 0;
+            do { asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(bar) : "memory"); } while (v < target && ++spins < (1LL << 26));
+            __threadfence();
+        }
+        __syncthreads();
+    };
+    int const i = (int)threadIdx.x;
+    for (int it = 0; it < nsweeps; ++it) {
+        int const mode = !ow_skip ? 2 : (it == 0) ? 0 : (it == nsweeps - 1) ? 2 : 1;
+        const double* VTin = (it & 1) ? VTb : VTa;
+        double* VTout = (it & 1) ? VTa : VTb;
+        HaloArgs const& a = (it & 1) ? aA : aB;
+        for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < cnt; t += nact * blockDim.x) {
+            int const n = ow_list[t];
+            int const deg = n2n_deg[n];
+            double su = 0., sv = 0.;
+            for (int j = 0; j < deg; ++j) {
+                int const q = n2n[(size_t)j * nn + n];
+                su += __ldcg(VTin + q);
+                sv += __ldcg(VTin + q + nn);
+            }
+            VTout[n] = su / deg;
+            VTout[n + nn] = sv / deg;
+            if (mode == 0 && ow_skip)
+                for (int q = push_ptr[n]; q < push_ptr[n + 1]; ++q) atomicOr(send_ow + push_ent[q].x, 1);
+        }
+        barrier();
+        if (blockIdx.x == 0) {
+            if (i < 32) s_act[i] = (mode != 1) ? 1 : (i < a.n_link ? __ldcg(pair_active + i) : 0);
+            __syncthreads();
+            for (int t = threadIdx.x; t < a.n_total; t += blockDim.x) {
+                int p = 0;
+                while (t >= a.peer_begin[p + 1]) ++p;
+                if (!s_act[a.peer_link[p]]) continue;
+                int const s = src_idx[t], d = dst_idx[t];
+                double* dst = a.peer_vt[p];
+                dst[d] = __ldcg(VTout + s);
+                dst[d + a.peer_nn[p]] = __ldcg(VTout + s + nn);
+            }
+            __threadfence_system();
+            __syncthreads();
+            unsigned long long const epoch = *((volatile unsigned long long*)epoch_ctr) + 1ULL;
+            int my_bit = 0;
+            if (i < a.n_link && mode != 2)
+                for (int p = 0; p < a.n_peers; ++p)
+                    if (a.peer_link[p] == i) my_bit = __ldcg(send_ow + p);
+            bool const sel = (i < a.n_link) && s_act[i];
+            unsigned long long const v = flag_signal_wait(a, i, sel, epoch | (my_bit ? FLAG_OW : 0ULL), epoch, my_flags, max_spins, err);
+            if (mode == 0 && i < a.n_link) pair_active[i] = (my_bit || (v & FLAG_OW)) ? 1 : 0;
+            __syncthreads();
+            if (i == 0) *epoch_ctr = epoch;
+            if (it == nsweeps - 1 && i < 32) send_ow[i] = 0;        // ready for the next model step
+        }
+        barrier();
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------
 // checkRegridding (FE.cpp:8298-8309) and updateIceDiagnostics (FE.cpp:7860-7900) on the
 // resident state.  Products and sums are written with explicit round-to-nearest intrinsics (no FMA contraction)
