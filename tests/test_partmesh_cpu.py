@@ -52,6 +52,19 @@ def test_library_bit_exact_against_oracle(nx, P, method, open_east):
         pm.close()
 
 
+@pytest.mark.parametrize("nx,P,seed", [(12, 3, 0), (20, 6, 1), (16, 11, 2)])
+def test_library_bit_exact_on_random_partitions(nx, P, seed):
+    """Salt-and-pepper tags (every element on a random rank): many neighbours per rank, most nodes on interfaces."""
+    m = syn.make_mesh(nx, 10e3, open_east=True)
+    ep = np.random.default_rng(seed).integers(0, P, m.ne).astype(np.int32)
+    gp, gv = pt.ghost_tags(m.tri, ep, P)
+    ors = orc.nodal_grid(P, m.x, m.y, m.tri, ep, gp, gv)
+    for r in range(P):
+        pm = capi.PartMesh.build(m.x, m.y, m.tri, r, P, ep, gp, gv)
+        pm.bc_marked_nodes(m.dirichlet_flags_root, m.neumann_flags_root)
+        assert_matches_oracle(pm.to_local_mesh(), ors[r], m, P)
+
+
 def test_single_rank_library():
     m = syn.make_mesh(12, 1.0)
     pm = capi.PartMesh.build(m.x, m.y, m.tri)
