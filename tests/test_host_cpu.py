@@ -71,3 +71,24 @@ def test_tile_plan_is_compact(name, nx, nranks):
         assert info["shrinks"] <= 2
         if lm.num_elements > 50000:
             assert info["max_halo_slots"] < 0.6 * info["max_slots"]
+
+
+def test_cpp_host_step_program_runs_up_to_the_device(tmp_path):
+    """tests/cpp/host_step.cpp (a C++ host process: cfg -> options, host mesh library, shim) parses its inputs,
+    builds the mesh and tables, and stops at nsx_create when there is no GPU (exit 3): no CPU fallback."""
+    import host_step_common as hs
+    try:
+        import torch
+        if torch.cuda.is_available():
+            pytest.skip("a GPU is present: covered by tests/test_gpu_host_step.py")
+    except ImportError:
+        pass
+    exe = hs.build_exe(tmp_path)
+    c = cases.make_case("toy")
+    hs.write_case(tmp_path / "case.bin", c)
+    hs.write_cfg(tmp_path / "nextsim.cfg", c, "bbm")
+    r = subprocess.run([str(exe), str(tmp_path / "case.bin"), str(tmp_path / "nextsim.cfg"), str(tmp_path / "out.bin"), "1"],
+                       stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert r.returncode == 3, r.stdout
+    assert "case: 1089 nodes, 2048 elements" in r.stdout and "threw: nsx_create" in r.stdout
+    assert not (tmp_path / "out.bin").exists()
