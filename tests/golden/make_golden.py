@@ -61,7 +61,46 @@ def run(spec):
     return out
 
 
+# SURVEY 8(f) rows 1-2 (regrid check, ice diagnostics, forcing interpolation) on a displaced mesh, one rank
+NEXT_CASES = {
+    # name: (case name, nx, displacement amplitude in mesh sizes, seed)
+    "nextrows_stable24": ("10km_stable", 24, 0.2, 7),
+}
+FORCING_T = (23741.25, 23741.5, 23741.25 + 0.25 * 0.3771)      # ftime_range[0], [1], current time
+
+
+def next_inputs(spec):
+    """Seeded inputs shared by the oracle run here and the CUDA run of tests/test_gpu_golden.py."""
+    name, nx, amp, seed = spec
+    c = cases.make_case(name, nranks=1, dyn="bbm", nx=nx, open_east=True)
+    rng = np.random.default_rng(seed)
+    c.state["M_UM"] = amp * c.gm.resolution * rng.uniform(-1.0, 1.0, 2 * c.gm.nn)
+    c.local = [cases.local_fields(c, lm) for lm in c.lms]
+    nn = c.gm.nn
+    slices = {k: (rng.normal(0.0, 7.0, n), rng.normal(0.0, 7.0, n)) for k, n in
+              (("M_wind", 2 * nn), ("M_ocean", 2 * nn), ("M_ssh", nn))}
+    return c, slices
+
+
+def run_next(spec):
+    c, slices = next_inputs(spec)
+    (R,) = ob.make_ranks(c)
+    ang, jmin, jmax, flip, regrid = R.check_regridding(10.0)
+    R.update_ice_diagnostics(ob.orc_params(c.params))
+    out = {"regrid": np.array([ang, jmin, jmax, float(flip), float(regrid)])}
+    for k in ("D_conc", "D_thick", "D_snow_thick", "D_sigma0", "D_sigma1", "D_divergence"):
+        out[k] = R.get(k)
+    t0, t1, t = FORCING_T
+    for k, (d0, d1) in slices.items():
+        out["forcing_" + k] = orc.external_data_get_vector(d0, d1, True, t, t0, t1, 0.97, -0.013)
+    return out
+
+
 def main():
+    for key, spec in NEXT_CASES.items():
+        out = run_next(spec)
+        np.savez_compressed(os.path.join(HERE, key + ".npz"), **out)
+        print(key, out["regrid"])
     for key, spec in CASES.items():
         out = run(spec)
         np.savez_compressed(os.path.join(HERE, key + ".npz"), **out)

@@ -29,7 +29,7 @@ def _golden_cases():
 @pytest.mark.parametrize("key", sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLD, "*.npz"))))
 def test_oracle_reproduces_golden(key):
     mg = _golden_cases()
-    out = mg.run(mg.CASES[key])
+    out = mg.run_next(mg.NEXT_CASES[key]) if key in mg.NEXT_CASES else mg.run(mg.CASES[key])
     ref = np.load(os.path.join(GOLD, key + ".npz"))
     assert set(out) == set(ref.files)
     for k in ref.files:
