@@ -161,6 +161,8 @@ typedef struct NsxTiming {
 /* ---- life cycle (replaces the member allocation in distributedMeshProcessing / initVariables) ---- */
 int nsx_create(const NsxMesh* mesh, const NsxHalo* halo, int device, nsx_handle* out);
 int nsx_destroy(nsx_handle h);
+/* host-only input checks of nsx_create (sizes, index ranges, list ordering); message in nsx_last_error(NULL) */
+int nsx_validate_mesh(const NsxMesh* mesh, const NsxHalo* halo);
 const char* nsx_last_error(nsx_handle h);      /* h may be NULL: error of the last failed nsx_create */
 int nsx_version(void);
 int nsx_abi_sizes(int* out, int n);          /* sizeof NsxDynParams, NsxMesh, NsxHalo, NsxFields, NsxCheck, NsxTiming, NsxRegrid */

@@ -104,7 +104,7 @@ EXPORTS = (
     "nsx_halo_connect_blob", "nsx_halo_connect_local", "nsx_halo_finalize", "nsx_group_explicit_solve",
     "nsx_host_register", "nsx_host_unregister", "nsx_abi_sizes", "nsx_tile_info", "nsx_plan_info", "nsx_cfg_last_error",
     "nsx_check_regridding", "nsx_update_ice_diagnostics", "nsx_forcing_load", "nsx_forcing_apply",
-    "nsx_partmesh_read", "nsx_partmesh_build", "nsx_partmesh_bc_marked_nodes", "nsx_partmesh_set_lat",
+    "nsx_validate_mesh", "nsx_partmesh_read", "nsx_partmesh_build", "nsx_partmesh_bc_marked_nodes", "nsx_partmesh_set_lat",
     "nsx_partmesh_views", "nsx_partmesh_ids", "nsx_partmesh_destroy", "nsx_partmesh_last_error",
 )
 
@@ -179,6 +179,50 @@ def _u8(a):
     return a, a.ctypes.data_as(c_ubyte_p)
 
 
+def mesh_structs(lm):
+    """NsxMesh / NsxHalo views of a partition.LocalMesh (plus the arrays that must stay alive)."""
+    keep = []
+    M = NsxMesh()
+    M.num_nodes, M.local_ndof = lm.num_nodes, lm.local_ndof
+    M.num_elements, M.local_nelements = lm.num_elements, lm.local_nelements
+    a, M.coord_x = _f64(lm.x); keep.append(a)
+    a, M.coord_y = _f64(lm.y); keep.append(a)
+    a, M.indices = _i32(lm.indices.reshape(-1)); keep.append(a)
+    a, M.ghost_nodes = _u8(lm.ghostNodes.reshape(-1)); keep.append(a)
+    a, M.mask_dirichlet = _u8(lm.mask_dirichlet); keep.append(a)
+    a, M.neumann_flags = _i32(lm.neumann_flags); keep.append(a)
+    M.n_neumann_flags = int(lm.neumann_flags.size)
+    a, M.nodal_element_connectivity = _f64(lm.nodal_element_connectivity.reshape(-1)); keep.append(a)
+    M.nec_width = int(lm.nodal_element_connectivity.shape[1])
+    a, M.nodal_connectivity = _f64(lm.nodal_connectivity.reshape(-1)); keep.append(a)
+    M.nc_width = int(lm.nodal_connectivity.shape[1])
+    a, M.lat = _f64(lm.lat); keep.append(a)
+    H = None
+    if lm.nranks > 1:
+        H = NsxHalo()
+        H.rank, H.nranks = lm.rank, lm.nranks
+        sp = sorted(lm.send_to)
+        rp = sorted(lm.recv_from)
+        H.n_send_peers, H.n_recv_peers = len(sp), len(rp)
+        a, H.send_peer = _i32(np.array(sp, np.int32)); keep.append(a)
+        a, H.recv_peer = _i32(np.array(rp, np.int32)); keep.append(a)
+        sptr = np.cumsum([0] + [lm.send_to[p].size for p in sp])
+        rptr = np.cumsum([0] + [lm.recv_from[p].size for p in rp])
+        a, H.send_ptr = _i32(sptr); keep.append(a)
+        a, H.recv_ptr = _i32(rptr); keep.append(a)
+        a, H.send_idx = _i32(np.concatenate([lm.send_to[p] for p in sp]) if sp else np.zeros(0)); keep.append(a)
+        a, H.recv_idx = _i32(np.concatenate([lm.recv_from[p] for p in rp]) if rp else np.zeros(0)); keep.append(a)
+    return M, H, keep
+
+
+def validate_mesh(lm):
+    """Host-only input checks of nsx_create (no GPU): raises RuntimeError with nsx_create's message."""
+    M, H, keep = mesh_structs(lm)
+    L = lib()
+    if L.nsx_validate_mesh(C.byref(M), C.byref(H) if H is not None else None) != 0:
+        raise RuntimeError(L.nsx_last_error(None).decode())
+
+
 class Solver:
     """Thin owner of one nsx_handle.  Methods map 1:1 on the C ABI."""
 
@@ -187,37 +231,7 @@ class Solver:
         self.L = lib()
         self.lm = lm
         self.nn, self.ne = lm.num_nodes, lm.num_elements
-        keep = []
-        M = NsxMesh()
-        M.num_nodes, M.local_ndof = lm.num_nodes, lm.local_ndof
-        M.num_elements, M.local_nelements = lm.num_elements, lm.local_nelements
-        a, M.coord_x = _f64(lm.x); keep.append(a)
-        a, M.coord_y = _f64(lm.y); keep.append(a)
-        a, M.indices = _i32(lm.indices.reshape(-1)); keep.append(a)
-        a, M.ghost_nodes = _u8(lm.ghostNodes.reshape(-1)); keep.append(a)
-        a, M.mask_dirichlet = _u8(lm.mask_dirichlet); keep.append(a)
-        a, M.neumann_flags = _i32(lm.neumann_flags); keep.append(a)
-        M.n_neumann_flags = int(lm.neumann_flags.size)
-        a, M.nodal_element_connectivity = _f64(lm.nodal_element_connectivity.reshape(-1)); keep.append(a)
-        M.nec_width = int(lm.nodal_element_connectivity.shape[1])
-        a, M.nodal_connectivity = _f64(lm.nodal_connectivity.reshape(-1)); keep.append(a)
-        M.nc_width = int(lm.nodal_connectivity.shape[1])
-        a, M.lat = _f64(lm.lat); keep.append(a)
-        H = None
-        if lm.nranks > 1:
-            H = NsxHalo()
-            H.rank, H.nranks = lm.rank, lm.nranks
-            sp = sorted(lm.send_to)
-            rp = sorted(lm.recv_from)
-            H.n_send_peers, H.n_recv_peers = len(sp), len(rp)
-            a, H.send_peer = _i32(np.array(sp, np.int32)); keep.append(a)
-            a, H.recv_peer = _i32(np.array(rp, np.int32)); keep.append(a)
-            sptr = np.cumsum([0] + [lm.send_to[p].size for p in sp])
-            rptr = np.cumsum([0] + [lm.recv_from[p].size for p in rp])
-            a, H.send_ptr = _i32(sptr); keep.append(a)
-            a, H.recv_ptr = _i32(rptr); keep.append(a)
-            a, H.send_idx = _i32(np.concatenate([lm.send_to[p] for p in sp]) if sp else np.zeros(0)); keep.append(a)
-            a, H.recv_idx = _i32(np.concatenate([lm.recv_from[p] for p in rp]) if rp else np.zeros(0)); keep.append(a)
+        M, H, keep = mesh_structs(lm)
         h = C.c_void_p()
         rc = self.L.nsx_create(C.byref(M), C.byref(H) if H is not None else None, int(device), C.byref(h))
         if rc != 0:

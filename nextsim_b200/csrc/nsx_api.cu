@@ -202,12 +202,67 @@ static void build_halo(nsx_solver* S, const NsxHalo* H)
 
 extern "C" int nsx_version(void) { return NSX_VERSION; }
 
+// Host-only checks of what the caller hands to nsx_create (no CUDA call): sizes, index ranges, list ordering.  The
+// reference would fail later and less clearly (out-of-range vector access); here the handle is never created.
+static void validate_inputs(const NsxMesh* M, const NsxHalo* H)
+{
+    auto fail = [](std::string const& m) { throw std::invalid_argument("nsx_create: " + m); };
+    if (M->num_nodes <= 0 || M->num_elements <= 0) fail("the rank holds no nodes or no elements");
+    if (M->local_ndof < 0 || M->local_ndof > M->num_nodes) fail("local_ndof outside [0, num_nodes]");
+    if (M->local_nelements < 0 || M->local_nelements > M->num_elements) fail("local_nelements outside [0, num_elements]");
+    if (!M->coord_x || !M->coord_y || !M->indices || !M->mask_dirichlet || !M->nodal_element_connectivity ||
+        !M->nodal_connectivity || !M->lat)
+        fail("NULL mesh array");
+    if (M->n_neumann_flags < 0 || (M->n_neumann_flags > 0 && !M->neumann_flags)) fail("bad neumann_flags");
+    if (M->nec_width < 1 || M->nc_width < 2) fail("connectivity table widths must be >= 1 (elements) and >= 2 (nodes)");
+    for (long k = 0; k < 3L * M->num_elements; ++k)
+        if (M->indices[k] < 1 || M->indices[k] > M->num_nodes)
+            fail("indices[" + std::to_string(k) + "] = " + std::to_string(M->indices[k]) + " is not a 1-based local node id");
+    for (int k = 0; k < M->n_neumann_flags; ++k) {
+        if (M->neumann_flags[k] < 0 || M->neumann_flags[k] >= M->num_nodes) fail("neumann flag outside the local nodes");
+        if (k && M->neumann_flags[k] <= M->neumann_flags[k - 1]) fail("neumann_flags must be sorted and unique (std::binary_search, FE.cpp:3957)");
+    }
+    for (int n = 0; n < M->num_nodes; ++n) {
+        double const cnt = M->nodal_connectivity[(size_t)n * M->nc_width + M->nc_width - 1];
+        if (!(cnt >= 0 && cnt <= M->nc_width - 1)) fail("NodalConnectivity count column out of range at node " + std::to_string(n));
+    }
+    if (M->local_ndof < M->num_nodes && !H) fail("ghost nodes without halo lists");
+    if (!H) return;
+    if (H->nranks < 1 || H->rank < 0 || H->rank >= H->nranks) fail("rank outside [0, nranks)");
+    if (H->n_send_peers < 0 || H->n_recv_peers < 0) fail("negative peer count");
+    if ((H->n_send_peers && (!H->send_peer || !H->send_ptr || !H->send_idx)) ||
+        (H->n_recv_peers && (!H->recv_peer || !H->recv_ptr || !H->recv_idx)))
+        fail("NULL halo list");
+    for (int k = 0; k < H->n_send_peers; ++k) {
+        if (H->send_peer[k] < 0 || H->send_peer[k] >= H->nranks || H->send_peer[k] == H->rank) fail("bad send peer");
+        if (H->send_ptr[k + 1] < H->send_ptr[k]) fail("send_ptr not monotone");
+    }
+    for (int k = 0; k < H->n_recv_peers; ++k) {
+        if (H->recv_peer[k] < 0 || H->recv_peer[k] >= H->nranks || H->recv_peer[k] == H->rank) fail("bad receive peer");
+        if (H->recv_ptr[k + 1] < H->recv_ptr[k]) fail("recv_ptr not monotone");
+    }
+    int nrecv = H->n_recv_peers ? H->recv_ptr[H->n_recv_peers] : 0;
+    if (nrecv != M->num_nodes - M->local_ndof) fail("the receive lists must cover every ghost node exactly once (" +
+        std::to_string(nrecv) + " entries for " + std::to_string(M->num_nodes - M->local_ndof) + " ghosts)");
+}
+
+// exported so that hosts (and the CPU test-suite) can check a mesh without a device; same messages as nsx_create
+extern "C" int nsx_validate_mesh(const NsxMesh* mesh, const NsxHalo* halo)
+{
+    try {
+        if (!mesh) throw std::invalid_argument("nsx_create: NULL argument");
+        validate_inputs(mesh, halo);
+    } catch (std::exception const& e) { g_create_err = e.what(); return 2; }
+    return 0;
+}
+
 extern "C" int nsx_create(const NsxMesh* mesh, const NsxHalo* halo, int device, nsx_handle* out)
 {
     if (!mesh || !out) { g_create_err = "nsx_create: NULL argument"; return 1; }
     *out = nullptr;
     nsx_solver* S = new nsx_solver();
     try {
+        validate_inputs(mesh, halo);
         int ndev = 0;
         NSX_CUDA(cudaGetDeviceCount(&ndev));
         if (device < 0 || device >= ndev) throw std::invalid_argument("nsx_create: no such CUDA device");
