@@ -91,6 +91,40 @@ def test_cfg_reader(tmp_path):
         capi.params_from_cfg(tmp_path / "missing.cfg")
 
 
+REF_CFG = "/root/reference/config-files"
+
+
+@pytest.mark.skipif(not os.path.isdir(REF_CFG), reason="the reference tree is not present on this box")
+def test_reference_config_files_parse():
+    """The three nextsim.cfg files the reference ships (config-files/) go through nsx_params_from_cfg unchanged: every
+    [dynamics] key they use is known, keys outside the path are ignored, and the values land in NsxDynParams."""
+    p = capi.params_from_cfg(os.path.join(REF_CFG, "nextsim.toy.cfg"))
+    assert (p.dtime_step, p.C_lab, p.alea_factor, p.use_coriolis, p.ocean_turning_angle_rad) == (300.0, 1.5e6, 0.33, 0, 0.0)
+    assert p.dynamics_type == 0 and p.ice_cat_type == 1 and p.substeps == 120
+    p = capi.params_from_cfg(os.path.join(REF_CFG, "nextsim.cfg"))
+    assert p.dtime_step == 200.0 and p.use_coriolis == 1 and p.substeps == 120
+    p = capi.params_from_cfg(os.path.join(REF_CFG, "cpl_run_opa4.cfg"))
+    assert (p.compression_factor, p.C_lab, p.substeps, p.time_relaxation_damage_days) == (3e3, 2e6, 75, 15.0)
+    assert (p.quad_drag_coef_water, p.basal_k1, p.min_h) == (0.0067, 5.0, 0.1)
+
+
+def test_every_reference_dynamics_option_is_known(tmp_path):
+    """All 37 options of the [dynamics] section (model/options.cpp:309-376) are either consumed or explicitly ignored."""
+    keys = ["alea_factor", "young", "C_lab", "nu0", "tan_phi", "compr_strength", "compaction_param", "min_h", "min_c",
+            "time_relaxation_damage", "use_temperature_dependent_healing", "deltaT_relaxation_damage",
+            "undamaged_time_relaxation_sigma", "exponent_relaxation_sigma", "ERA5_quad_drag_coef_air",
+            "ECMWF_quad_drag_coef_air", "ASR_quad_drag_coef_air", "CFSR_quad_drag_coef_air", "lin_drag_coef_air",
+            "quad_drag_coef_water", "lin_drag_coef_water", "use_coriolis", "oceanic_turning_angle", "Lemieux_basal_k1",
+            "Lemieux_basal_k2", "Lemieux_basal_Cb", "Lemieux_basal_u_0", "Lemieux_basal_u_crit",
+            "exponent_compression_factor", "compression_factor", "substeps", "evp.e", "evp.Pstar", "evp.C", "evp.dmin",
+            "mevp.alpha", "mevp.beta"]
+    assert len(keys) == 37
+    f = tmp_path / "all.cfg"
+    f.write_text("[dynamics]\n" + "".join("%s=%s\n" % (k, "true" if k.startswith("use_") else "1") for k in keys))
+    p = capi.params_from_cfg(f)
+    assert p.substeps == 1 and p.evp_dmin == 1.0 and p.basal_u0 == 1.0
+
+
 def test_create_fails_loudly_without_gpu():
     try:
         import torch
