@@ -242,6 +242,12 @@ int nsx_partmesh_build(int nn, const double* x, const double* y, int ne, const i
 int nsx_partmesh_bc_marked_nodes(nsx_partmesh_handle h, const int* dirichlet_flags_root, int n_dirichlet,
                                  const int* neumann_flags_root, int n_neumann);
 int nsx_partmesh_set_lat(nsx_partmesh_handle h, const double* lat_local);     /* M_mesh.lat(), local numbering */
+/* GmshMesh::lat() / lon() (core/src/gmshmesh.cpp:1800-1824, called by explicitSolve at FE.cpp:10351): inverse polar
+ * stereographic map of n points in map units with the projection of `mppfile` (mesh.mppfile: NpsNextsim.mpp /
+ * NpsASR.mpp, mapx positional format).  lat or lon may be NULL.  nsx_partmesh_lat_from_mpp fills the handle's lat. */
+int nsx_mapx_latlon(const char* mppfile, int n, const double* x, const double* y, double* lat, double* lon);
+int nsx_partmesh_lat_from_mpp(nsx_partmesh_handle h, const char* mppfile);
+const char* nsx_mapx_last_error(void);
 int nsx_partmesh_views(nsx_partmesh_handle h, NsxMesh* mesh, NsxHalo* halo);  /* pointers valid until destroy */
 /* ids[0..3]: local node -> root node id (1-based), local node -> reordered global id, local element -> file element
  * number, local element -> partition; sizes[0..3]: global nodes, global triangles, ghost nodes, dirichlet flags */

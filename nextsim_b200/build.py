@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libnsx.so")
-SOURCES = ["nsx_api.cu", "nsx_mesh.cpp", "nsx_cfg.cpp", "nsx_partmesh.cpp"]
+SOURCES = ["nsx_api.cu", "nsx_mesh.cpp", "nsx_cfg.cpp", "nsx_partmesh.cpp", "nsx_mapx.cpp"]
 HEADERS = ["nsx_kernels.cuh", "nsx_internal.h", "nsx_mesh.h", os.path.join("..", "..", "include", "nsx.h")]
 
 NVCC_FLAGS = [

@@ -104,7 +104,7 @@ EXPORTS = (
     "nsx_halo_connect_blob", "nsx_halo_connect_local", "nsx_halo_finalize", "nsx_group_explicit_solve",
     "nsx_host_register", "nsx_host_unregister", "nsx_abi_sizes", "nsx_tile_info", "nsx_plan_info", "nsx_cfg_last_error",
     "nsx_check_regridding", "nsx_update_ice_diagnostics", "nsx_forcing_load", "nsx_forcing_apply",
-    "nsx_validate_mesh", "nsx_partmesh_read", "nsx_partmesh_build", "nsx_partmesh_bc_marked_nodes", "nsx_partmesh_set_lat",
+    "nsx_validate_mesh", "nsx_mapx_latlon", "nsx_partmesh_lat_from_mpp", "nsx_mapx_last_error", "nsx_partmesh_read", "nsx_partmesh_build", "nsx_partmesh_bc_marked_nodes", "nsx_partmesh_set_lat",
     "nsx_partmesh_views", "nsx_partmesh_ids", "nsx_partmesh_destroy", "nsx_partmesh_last_error",
 )
 
@@ -142,6 +142,9 @@ def lib():
         L.nsx_partmesh_views.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.nsx_partmesh_ids.argtypes = [C.c_void_p, C.c_void_p, c_int_p]
         L.nsx_partmesh_destroy.argtypes = [C.c_void_p]
+        L.nsx_mapx_last_error.restype = C.c_char_p
+        L.nsx_mapx_latlon.argtypes = [C.c_char_p, C.c_int, c_double_p, c_double_p, c_double_p, c_double_p]
+        L.nsx_partmesh_lat_from_mpp.argtypes = [C.c_void_p, C.c_char_p]
         L.nsx_halo_blob_size.argtypes = [C.c_void_p, C.c_int]
         L.nsx_halo_blob.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
         L.nsx_halo_connect_blob.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
@@ -429,6 +432,10 @@ class PartMesh:
         a, p = _f64(lat)
         self._chk(self.L.nsx_partmesh_set_lat(self.h, p), "nsx_partmesh_set_lat")
 
+    def lat_from_mpp(self, mppfile):
+        """GmshMesh::lat(): node latitudes from the projection file (mesh.mppfile)."""
+        self._chk(self.L.nsx_partmesh_lat_from_mpp(self.h, str(mppfile).encode()), "nsx_partmesh_lat_from_mpp")
+
     def views(self):
         M, H = NsxMesh(), NsxHalo()
         self._chk(self.L.nsx_partmesh_views(self.h, C.byref(M), C.byref(H)), "nsx_partmesh_views")
@@ -466,3 +473,15 @@ class PartMesh:
         lm.nodal_element_connectivity = arr(M.nodal_element_connectivity, nn * M.nec_width, np.float64).reshape(nn, M.nec_width)
         lm.nodal_connectivity = arr(M.nodal_connectivity, nn * M.nc_width, np.float64).reshape(nn, M.nc_width)
         return lm
+
+
+def mapx_latlon(mppfile, x, y):
+    """Inverse polar stereographic map of mesh coordinates (GmshMesh::lat() / lon())."""
+    xa, xp = _f64(x)
+    ya, yp = _f64(y)
+    lat, lon = np.empty(xa.size), np.empty(xa.size)
+    L = lib()
+    if L.nsx_mapx_latlon(str(mppfile).encode(), xa.size, xp, yp, lat.ctypes.data_as(c_double_p),
+                         lon.ctypes.data_as(c_double_p)) != 0:
+        raise RuntimeError(L.nsx_mapx_last_error().decode())
+    return lat, lon

@@ -583,6 +583,16 @@ extern "C" int nsx_partmesh_set_lat(nsx_partmesh_handle M, const double* lat_loc
     PM_CATCH
 }
 
+extern "C" int nsx_partmesh_lat_from_mpp(nsx_partmesh_handle M, const char* mppfile)
+{
+    PM_TRY
+    if (!M || !mppfile) throw std::invalid_argument("NULL argument");
+    M->lat.assign(M->num_nodes, 0.);
+    if (nsx_mapx_latlon(mppfile, M->num_nodes, M->x.data(), M->y.data(), M->lat.data(), nullptr) != 0)
+        throw std::runtime_error(nsx_mapx_last_error());
+    PM_CATCH
+}
+
 // Fills the structs nsx_create() takes; the pointers stay valid until nsx_partmesh_destroy.
 extern "C" int nsx_partmesh_views(nsx_partmesh_handle M, NsxMesh* mesh, NsxHalo* halo)
 {

@@ -16,6 +16,8 @@
 // (oracle/ref_bamg/Makefile); tests/test_ref_bamg_cpu.py checks NodalElementConnectivity and
 // NodalConnectivity of BamgConvertMeshx (the call of FE.cpp:77-80) against bamgTables()
 // bit for bit on root and partition-local meshes.
+// Also built unmodified: contrib/mapx (oracle/ref_mapx) for GmshMesh::lat(), which pins the product's
+// nsx_mapx_latlon (tests/test_ref_mapx_cpu.py); the oracle itself takes lat as an input.
 //
 // Reference files followed (paths relative to /root/reference):
 //   model/finiteelement.cpp
