@@ -84,6 +84,8 @@ static void upload_plan(nsx_solver* S)
     // the attribute is per function and device, shared by every handle: always ask for the cap
     NSX_CUDA(cudaFuncSetAttribute(k_subcycle<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     NSX_CUDA(cudaFuncSetAttribute(k_subcycle<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    NSX_CUDA(cudaFuncSetAttribute(k_resident<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    NSX_CUDA(cudaFuncSetAttribute(k_resident<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     NSX_CUDA(cudaStreamSynchronize(st));
 }
 
@@ -123,6 +125,7 @@ static void alloc_fields(nsx_solver* S)
         S->direct = (double)ne * 300.0 < 90e6;
         if (pth && !strcmp(pth, "direct")) S->direct = true;
         if (pth && !strcmp(pth, "tiles")) S->direct = false;
+        if (S->resident) S->direct = false;
         if (S->direct) { S->ec_e.alloc(6 * ne); S->ec_e.zero(st); S->contrib.alloc(6 * ne); S->contrib.zero(st); }
     }
     S->ow_list.alloc(S->ndof); S->ow_count.alloc(1); S->ow_count.zero(st);
@@ -279,6 +282,21 @@ extern "C" int nsx_create(const NsxMesh* mesh, const NsxHalo* halo, int device, 
         // one wave of the sub-cycle kernel = SMs x resident CTAs (2: shared memory and launch bounds); shrink the
         // tiles until the staged working set of the largest tile fits the per-CTA shared-memory budget
         int target = env_int("NSX_TILE_NODES", 208);
+        const char* pth0 = getenv("NSX_PATH");
+        S->resident = (pth0 && !strcmp(pth0, "resident"));
+        if (S->resident) {
+            // EXPERIMENTAL: one large tile per SM, resident for the whole sub-cycle loop (k_resident); one rank only
+            if (halo) throw std::invalid_argument("nsx_create: NSX_PATH=resident supports a single rank only");
+            int const T = (mesh->local_ndof + S->sm_count - 1) / S->sm_count;
+            S->plan = MeshPlan();
+            build_mesh_plan(mesh, S->plan, std::max(32, T), 1);
+            MeshPlan const& P = S->plan;
+            size_t const smem = (size_t)(15 * P.msp + 2 * (P.max_local_nodes + 2)) * sizeof(double);
+            if (P.ntiles > S->sm_count || P.tile_nodes > RES_TPB || P.max_slots > RES_SPT * RES_TPB || smem > 227 * 1024)
+                throw std::invalid_argument("nsx_create: NSX_PATH=resident does not fit this mesh (tiles " + std::to_string(P.ntiles) +
+                    ", nodes per tile " + std::to_string(P.tile_nodes) + ", max slots " + std::to_string(P.max_slots) +
+                    ", shared memory " + std::to_string(smem) + " B)");
+        } else
         for (int attempt = 0;; ++attempt) {
             S->plan = MeshPlan();
             build_mesh_plan(mesh, S->plan, target, S->sm_count * SUB_CTAS_PER_SM);
@@ -942,7 +960,31 @@ static void solve_group(int n, nsx_solver** W)
     // measured on B200: 15.0-15.6 us per sub-cycle against 14.2 us for the graph of two launches per sub-cycle (the
     // grid barriers cost what the launches cost, and one CTA per SM leaves half the threads idle in each phase): off
     static const bool persist_on = (env_int("NSX_PERSIST", 0) != 0);
-    if (n == 1 && W[0]->direct && W[0]->peers.empty() && persist_on && nrun > 0) {
+    if (n == 1 && W[0]->resident && W[0]->peers.empty() && nrun > 0) {
+        // EXPERIMENTAL: the whole sub-cycle loop in one launch with the state resident in shared memory / registers
+        nsx_solver* S = W[0];
+        KParams const& K = S->K;
+        bool const bbm = (K.dynamics_type == NSX_DYN_BBM);
+        ResidentArgs A{};
+        A.tiles = S->tiles.p; A.halo_nodes = S->halo_nodes.p; A.halo_elems = S->halo_elems.p; A.slot_conn = S->slot_conn.p;
+        A.slot_shape = S->slot_shape.p; A.slot_ec = S->slot_ec.p; A.nslots = S->plan.nslots; A.inc = S->inc.p;
+        A.s0 = S->sig[S->scur][0].p; A.s1 = S->sig[S->scur][1].p; A.s2 = S->sig[S->scur][2].p;
+        A.dm = bbm ? S->dmg[S->dcur].p : nullptr;
+        A.nflags = S->nflags.p; A.grad_ssh = S->grad_ssh.p; A.node_mass = S->node_mass.p; A.rlmass = S->rlmass.p;
+        A.cbu = S->cbu.p; A.fcor = S->fcor.p; A.tau_a = S->tau_a.p; A.tau_wi = S->have_tau_wi ? S->tau_wi.p : nullptr;
+        A.ocean = S->ocean.p; A.VTM = S->VTM.p;
+        A.VT0 = S->VT[0]; A.VT1 = S->VT[1]; A.cur = S->cur; A.UM = S->UM.p; A.UT = S->UT.p;
+        A.move_mesh = (K.dynamics_type != NSX_DYN_MEVP); A.nsub = nrun;
+        A.bar = S->ow_bar.p;
+        A.MS = S->plan.msp; A.MLN = S->plan.max_local_nodes + 2;
+        size_t const smem = (size_t)((bbm ? 15 : 11) * A.MS + 2 * A.MLN) * sizeof(double);
+        S->ow_bar.zero(S->stream);
+        if (bbm) k_resident<1><<<S->plan.ntiles, RES_TPB, smem, S->stream>>>(K, A);
+        else k_resident<0><<<S->plan.ntiles, RES_TPB, smem, S->stream>>>(K, A);
+        NSX_CUDA(cudaGetLastError());
+        S->n_launch++;
+        S->cur = (S->cur + nrun) & 1;
+    } else if (n == 1 && W[0]->direct && W[0]->peers.empty() && persist_on && nrun > 0) {
         // a rank without neighbours on an L2-resident mesh: the whole sub-cycle loop is ONE persistent launch
         nsx_solver* S = W[0];
         KParams const& K = S->K;
@@ -1233,12 +1275,13 @@ extern "C" int nsx_plan_info(const NsxMesh* mesh, int target_tile_nodes, int wav
 {
     try {
         MeshPlan P;
-        int target = target_tile_nodes > 0 ? target_tile_nodes : 208;
+        bool const no_shrink = target_tile_nodes < 0;          // resident path: exactly the requested tile size
+        int target = target_tile_nodes > 0 ? target_tile_nodes : (no_shrink ? -target_tile_nodes : 208);
         int attempt = 0;
         for (;; ++attempt) {
             P = MeshPlan();
             build_mesh_plan(mesh, P, target, wave_ctas);
-            if (sub_layout(P, 14).total <= SUB_SMEM_CAP) break;
+            if (no_shrink || sub_layout(P, 14).total <= SUB_SMEM_CAP) break;
             if (attempt > 12 || target <= 32) break;
             target = std::max(32, (int)(target * 0.88));
         }

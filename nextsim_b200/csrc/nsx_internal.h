@@ -140,6 +140,7 @@ struct nsx_solver {
     nsx::DBuf<double> emass, ecbu;               // element mass, element C_bu
     nsx::DBuf<double> node_mass, rlmass, cbu, fcor, grad_ssh;
     nsx::DBuf<double> ec_e, contrib;             // direct path: element-space rheology constants, staged contributions
+    bool resident = false;                       // EXPERIMENTAL state-resident persistent solver (NSX_PATH=resident)
     bool direct = false;                         // L2-resident mesh: element kernel + node kernel instead of the tile kernel
     nsx::DBuf<double> stage;                     // transfer staging (host numbering), max(2nn, 6ne)
     nsx::DBuf<double> stage2;                    // second staging buffer, max(2nn, ne): copies and permutations overlap

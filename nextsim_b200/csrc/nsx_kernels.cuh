@@ -996,6 +996,236 @@ k_direct_persistent(KParams K, DirectArgs A, int nsub, int move_mesh, double* VT
     }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// EXPERIMENTAL (NSX_PATH=resident, off by default, written at the end of round 1 and NOT yet validated on a GPU):
+// state-resident persistent solver for meshes of the headline class (<= ~2.2e5 elements on one GPU).
+//
+// One CTA per SM owns ONE large tile (ndof / #SMs owned nodes, ~1350 elements + ~10 % redundant halo slots) for the
+// whole sub-cycle loop of a model step.  Shape coefficients, rheology constants and the stress of every slot stay in
+// shared memory (120 B per slot), damage and the slot connectivity in registers of the thread that owns the slot,
+// the velocity of the tile's local nodes in shared memory, UM / UT of the owned nodes in registers.  Per sub-cycle the
+// only global traffic is: node constants re-read from L2 (88 B per node), the owned velocities written to the
+// ping-pong VT buffer, one grid barrier, and the halo-node velocities read back (~15 % of the nodes).  HBM is not
+// touched inside the loop.  Same arithmetic and the same summation order as k_subcycle; contributions are recomputed
+// in phase 2 from the resident stress instead of being staged, so results may differ from the other paths in the
+// last bit (FMA contraction), well inside the 1e-9 tolerance.
+// ---------------------------------------------------------------------------------------------------
+#ifndef NSX_RES_TPB
+#define NSX_RES_TPB 768
+#endif
+constexpr int RES_TPB = NSX_RES_TPB;
+constexpr int RES_SPT = 3;                      // slots per thread (static unroll): tiles of up to 3 * RES_TPB slots
+
+struct ResidentArgs {
+    const TileDesc* tiles; const int* halo_nodes; const int* halo_elems; const unsigned long long* slot_conn;
+    const double* slot_shape; const double* slot_ec; int nslots; const uint16_t* inc;
+    double* s0; double* s1; double* s2; double* dm;               // updated in place at the end of the loop
+    const uint8_t* nflags; const double* grad_ssh; const double* node_mass; const double* rlmass; const double* cbu;
+    const double* fcor; const double* tau_a; const double* tau_wi; const double* ocean; const double* VTM;
+    double* VT0; double* VT1; int cur; double* UM; double* UT;
+    int move_mesh, nsub;
+    unsigned int* bar;
+    int MS, MLN;                                                  // shared-memory strides: slots per plane, local nodes
+};
+
+template <int BBM>
+__global__ void __launch_bounds__(RES_TPB, 1)
+k_resident(KParams K, ResidentArgs A)
+{
+    extern __shared__ __align__(16) unsigned char sm_res[];
+    int const nn = K.nn, tid = threadIdx.x, MS = A.MS, MLN = A.MLN;
+    constexpr int NEC = BBM ? 6 : 2;
+    double* const shp = (double*)sm_res;                          // [6][MS]
+    double* const ecp = shp + 6 * (size_t)MS;                     // [NEC][MS]
+    double* const sgp = ecp + NEC * (size_t)MS;                   // [3][MS]
+    double* const su = sgp + 3 * (size_t)MS;                      // [MLN]
+    double* const sv = su + MLN;                                  // [MLN]
+    TileDesc const td = A.tiles[blockIdx.x];
+    int const nsl = td.n_own_slots + td.n_halo_slots;
+    size_t const NS = (size_t)A.nslots;
+
+    // ---- load the tile once ----
+    unsigned long long conn[RES_SPT];
+    double dmg[RES_SPT];
+#pragma unroll
+    for (int q = 0; q < RES_SPT; ++q) {
+        int const k = tid + q * RES_TPB;
+        conn[q] = 0ULL; dmg[q] = 0.;
+        if (k < nsl) {
+            size_t const g = (size_t)td.slot_begin + k;
+            conn[q] = A.slot_conn[g];
+#pragma unroll
+            for (int c = 0; c < 6; ++c) shp[c * MS + k] = A.slot_shape[c * NS + g];
+#pragma unroll
+            for (int c = 0; c < NEC; ++c) ecp[c * MS + k] = A.slot_ec[c * NS + g];
+            int const e = (k < td.n_own_slots) ? td.elem_begin + k : A.halo_elems[td.halo_elem_off + (k - td.n_own_slots)];
+            sgp[k] = A.s0[e]; sgp[MS + k] = A.s1[e]; sgp[2 * MS + k] = A.s2[e];
+            if (BBM) dmg[q] = A.dm[e];
+        }
+    }
+    double* VTr = A.cur ? A.VT1 : A.VT0;                          // buffer holding the current velocity
+    double* VTw = A.cur ? A.VT0 : A.VT1;
+    for (int j = tid; j < td.n_own; j += RES_TPB) { su[j] = VTr[td.node_begin + j]; sv[j] = VTr[td.node_begin + j + nn]; }
+    for (int h = tid; h < td.n_halo; h += RES_TPB) {
+        int const g = A.halo_nodes[td.halo_off + h];
+        su[td.n_own + HALO_GAP + h] = VTr[g]; sv[td.n_own + HALO_GAP + h] = VTr[g + nn];
+    }
+    bool const has_node = tid < td.n_own;                         // one owned node per thread (checked by the host)
+    int const n = td.node_begin + tid;
+    uint8_t const fl = has_node ? A.nflags[n] : (uint8_t)NF_DIRICHLET;
+    double umu = 0., umv = 0., utu = 0., utv = 0.;
+    if (has_node && A.move_mesh) { umu = A.UM[n]; umv = A.UM[n + nn]; utu = A.UT[n]; utv = A.UT[n + nn]; }
+    unsigned int bar_target = 0;
+    __syncthreads();
+
+    for (int s = 0; s < A.nsub; ++s) {
+        // ---- phase 1: stress (and damage) of every slot of the tile ----
+#pragma unroll
+        for (int q = 0; q < RES_SPT; ++q) {
+            int const k = tid + q * RES_TPB;
+            if (k >= nsl) continue;
+            unsigned long long const pc = conn[q];
+            int const la = (int)(pc & 0xFFFF), lb = (int)((pc >> 16) & 0xFFFF), lc = (int)((pc >> 32) & 0xFFFF);
+            double const dx0 = shp[k], dx1 = shp[MS + k], dx2 = shp[2 * MS + k];
+            double const dy0 = shp[3 * MS + k], dy1 = shp[4 * MS + k], dy2 = shp[5 * MS + k];
+            double const c0 = ecp[k];
+            double s0, s1, s2;
+            if (BBM) {
+                double const expC = c0;
+                double d = dmg[q];
+                if (expC == 0.) {                   // conc <= 0.1 : no ice (FE.cpp:4151-4159)
+                    s0 = s1 = s2 = 0.;
+                    d = 0.;
+                } else {
+                    double const ua = su[la], va = sv[la], ub = su[lb], vb = sv[lb], uc = su[lc], vc = sv[lc];
+                    double e0 = dx0 * ua; e0 += dx1 * ub; e0 += dx2 * uc;
+                    double e1 = dy0 * va; e1 += dy1 * vb; e1 += dy2 * vc;
+                    double e2 = dy0 * ua; e2 += dx0 * va; e2 += dy1 * ub; e2 += dx1 * vb; e2 += dy2 * uc; e2 += dx2 * vc;
+                    s0 = sgp[k]; s1 = sgp[MS + k]; s2 = sgp[2 * MS + k];
+                    double const dt = K.dte;
+                    double sigma_n = (s0 + s1) * 0.5;
+                    double const omd = 1. - d;
+                    double const time_viscous = K.lambda0 * pow_relax(omd * expC, K);
+                    double tildeP = 0.;
+                    if (sigma_n < 0.) tildeP = fmin(1., fast_div(-ecp[MS + k], sigma_n));
+                    double const mult = fmin(1. - 1e-12, fast_div(time_viscous, time_viscous + dt * (1. - tildeP)));
+                    double const elasticity = K.young * omd * expC;
+                    double const dtE = dt * elasticity;
+                    s0 += dtE * K.D00 * e0;  s0 += dtE * K.D01 * e1;  s0 *= mult;
+                    s1 += dtE * K.D01 * e0;  s1 += dtE * K.D00 * e1;  s1 *= mult;
+                    s2 += dtE * K.D22 * e2;                           s2 *= mult;
+                    double const sigma_s = fast_hypot((s0 - s1) * 0.5, s2);
+                    sigma_n = (s0 + s1) * 0.5;
+                    double dcrit;
+                    if (sigma_n < -K.compr_strength) dcrit = fast_div(-K.compr_strength, sigma_n);
+                    else dcrit = fast_div(ecp[2 * MS + k], sigma_s + K.tan_phi * sigma_n);
+                    if ((0. < dcrit) && (dcrit < 1.)) {
+                        double const rtd = fast_sqrt(elasticity) * ecp[3 * MS + k];
+                        double const f = (1. - dcrit) * dt * rtd;
+                        d += omd * f;
+                        s0 -= s0 * f;  s1 -= s1 * f;  s2 -= s2 * f;
+                    }
+                    d = fmax(0., d - ecp[4 * MS + k]);
+                }
+                dmg[q] = d;
+            } else {
+                double const Pp = c0;
+                if (Pp < 0.) {                      // thick == 0 (FE.cpp:10656-10662)
+                    s0 = s1 = s2 = 0.;
+                } else {
+                    double const ua = su[la], va = sv[la], ub = su[lb], vb = sv[lb], uc = su[lc], vc = sv[lc];
+                    double eps11 = dx0 * ua; eps11 += dx1 * ub; eps11 += dx2 * uc;
+                    double eps22 = dy0 * va; eps22 += dy1 * vb; eps22 += dy2 * vc;
+                    double eps12 = 0.5 * (dx0 * va + dy0 * ua); eps12 += 0.5 * (dx1 * vb + dy1 * ub); eps12 += 0.5 * (dx2 * vc + dy2 * uc);
+                    double const eps1 = eps11 + eps22, eps2 = eps11 - eps22;
+                    double const delta = fast_sqrt(eps1 * eps1 + (eps2 * eps2 + 4 * eps12 * eps12) * K.re2);
+                    double const zeta = fast_div(Pp, delta + K.evp_dmin);
+                    s0 = sgp[k]; s1 = sgp[MS + k]; s2 = sgp[2 * MS + k];
+                    double sigma1 = s0 + s1, sigma2 = s0 - s1;
+                    sigma1 += K.ralpha1 * (zeta * (eps1 - delta) - sigma1);
+                    sigma2 += K.ralpha2 * (zeta * eps2 * K.re2 - sigma2);
+                    s2 += K.ralpha2 * (zeta * eps12 * K.re2 - s2);
+                    s0 = 0.5 * (sigma1 + sigma2);
+                    s1 = 0.5 * (sigma1 - sigma2);
+                }
+            }
+            sgp[k] = s0; sgp[MS + k] = s1; sgp[2 * MS + k] = s2;
+        }
+        __syncthreads();
+
+        // ---- phase 2: one owned node per thread ----
+        if (has_node) {
+            double const uice = su[tid], vice = sv[tid];
+            double un = uice, vn = vice;
+            double const nm = __ldg(A.node_mass + n);
+            if (!(fl & NF_DIRICHLET) && nm != 0.) {
+                double gu = __ldg(A.grad_ssh + n), gv = __ldg(A.grad_ssh + n + nn);
+                double const rl = __ldg(A.rlmass + n), cb = __ldg(A.cbu + n), fc = __ldg(A.fcor + n);
+                double tau_x = __ldg(A.tau_a + n), tau_y = __ldg(A.tau_a + n + nn);
+                double const ou = __ldg(A.ocean + n), ov = __ldg(A.ocean + n + nn);
+                if (A.tau_wi) { tau_x = tau_x + __ldg(A.tau_wi + n); tau_y = tau_y + __ldg(A.tau_wi + n + nn); }
+                const uint16_t* ip = A.inc + td.inc_off + tid;
+                for (int c = 0; c < td.inc_w; ++c) {
+                    unsigned const code = __ldg(ip + (size_t)c * td.n_own);
+                    if (code == 0xFFFFu) break;
+                    int const i = (int)(code / (unsigned)MS), k = (int)(code - (unsigned)i * (unsigned)MS);
+                    double const a0 = sgp[k], a1 = sgp[MS + k], a2 = sgp[2 * MS + k];
+                    double const vol = ecp[(BBM ? 5 : 1) * MS + k];
+                    double const dxi = shp[i * MS + k], dyi = shp[(3 + i) * MS + k];
+                    gu -= vol * (a0 * dxi + a2 * dyi);           // V*(sigma . grad N_i), FE.cpp:10464-10465
+                    gv -= vol * (a2 * dxi + a1 * dyi);
+                }
+                double dtep = K.dte, delu = 0., delv = 0.;
+                if (K.dynamics_type == NSX_DYN_MEVP) {
+                    delu = (__ldg(A.VTM + n) - uice) * K.mevp_rb;
+                    delv = (__ldg(A.VTM + n + nn) - vice) * K.mevp_rb;
+                    dtep = K.dte_mevp;
+                }
+                double const dte_over_mass = fast_div(dtep, fmax(K.min_m, nm));
+                double const c_prime = K.rhow_cdw * fast_hypot(ou - uice, ov - vice);
+                double const tau_b = cb * fast_div(1., fast_hypot(uice, vice) + K.u0);
+                double const sin_s = (fl & NF_LATNEG) ? -K.sin_ota_abs : K.sin_ota_abs;
+                double const alpha = 1. + dte_over_mass * (c_prime * K.cos_ota + tau_b);
+                double const beta = dtep * fc + dte_over_mass * c_prime * sin_s;
+                double const rdenom = fast_div(1., alpha * alpha + beta * beta);
+                tau_x = tau_x + c_prime * (ou * K.cos_ota - ov * sin_s);
+                tau_y = tau_y + c_prime * (ov * K.cos_ota + ou * sin_s);
+                double const grad_x = gu * rl, grad_y = gv * rl;
+                un = alpha * uice + beta * vice + dte_over_mass * (alpha * (grad_x + tau_x) + beta * (grad_y + tau_y)) + alpha * delu + beta * delv;
+                un *= rdenom;
+                vn = alpha * vice - beta * uice + dte_over_mass * (alpha * (grad_y + tau_y) - beta * (grad_x + tau_x)) + alpha * delv - beta * delu;
+                vn *= rdenom;
+            }
+            su[tid] = un; sv[tid] = vn;                          // phase 1 is over: nobody reads the old value any more
+            VTw[n] = un; VTw[n + nn] = vn;
+            if (A.move_mesh) {
+                utu = utu + K.dte * un;  utv = utv + K.dte * vn;
+                if (!(fl & NF_NEUMANN)) { umu = umu + K.dte * un;  umv = umv + K.dte * vn; }
+            }
+        }
+        // ---- every tile has published its velocities: read the halo nodes back ----
+        grid_barrier(A.bar, bar_target);
+        for (int h = tid; h < td.n_halo; h += RES_TPB) {
+            int const g = A.halo_nodes[td.halo_off + h];
+            su[td.n_own + HALO_GAP + h] = __ldcg(VTw + g); sv[td.n_own + HALO_GAP + h] = __ldcg(VTw + g + nn);
+        }
+        __syncthreads();
+        double* const t = VTr; VTr = VTw; VTw = t;
+    }
+
+    // ---- write the resident state back ----
+#pragma unroll
+    for (int q = 0; q < RES_SPT; ++q) {
+        int const k = tid + q * RES_TPB;
+        if (k < td.n_own_slots) {
+            int const e = td.elem_begin + k;
+            A.s0[e] = sgp[k]; A.s1[e] = sgp[MS + k]; A.s2[e] = sgp[2 * MS + k];
+            if (BBM) A.dm[e] = dmg[q];
+        }
+    }
+    if (has_node && A.move_mesh) { A.UM[n] = umu; A.UM[n + nn] = umv; A.UT[n] = utu; A.UT[n + nn] = utv; }
+}
+
 // mesh move over an explicit node range with an explicit time increment:
 //   mEVP: once after the loop with dtime_step (FE.cpp:10559-10573); ghosts: final lagged move.
 __global__ void __launch_bounds__(TPB)

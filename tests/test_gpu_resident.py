@@ -1,0 +1,60 @@
+"""EXPERIMENTAL state-resident persistent solver (NSX_PATH=resident, k_resident): written at the end of round 1 without
+GPU budget left to run it, so these tests are opt-in (NSX_TEST_RESIDENT=1) until the path has been validated once:
+
+    NSX_TEST_RESIDENT=1 python -m pytest tests/test_gpu_resident.py -q
+
+Same bar as the other paths: rel-L2 <= 1e-9 against the oracle after a full model step + update(); it also has to agree
+with the direct path to rounding."""
+import os
+
+import numpy as np
+import pytest
+
+from nextsim_b200 import cases
+import oracle_bridge as ob
+from oracle import oracle as orc
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(os.environ.get("NSX_TEST_RESIDENT") != "1",
+                                 reason="experimental path, not yet validated on a GPU (set NSX_TEST_RESIDENT=1)")]
+KEYS = cases.STATE_OUT
+
+
+def run_path(c, path, monkeypatch, update=True):
+    monkeypatch.setenv("NSX_PATH", path)
+    (s,) = cases.make_solvers(c)
+    s.explicit_solve()
+    out = s.download(*KEYS)
+    if update:
+        s.update()
+        out.update(s.download(*cases.UPDATE_OUT))
+    s.close()
+    return out
+
+
+@pytest.mark.parametrize("name,nx,dyn,nsub", [("toy", None, "bbm", 1), ("toy", None, "bbm", 0), ("toy", None, "mevp", 0),
+                                              ("10km_stable", 64, "bbm", 0), ("10km_stable", 64, "evp", 0),
+                                              ("10km_stable", None, "bbm", 0)])
+def test_resident_path(monkeypatch, name, nx, dyn, nsub):
+    c = cases.make_case(name, nranks=1, dyn=dyn, nx=nx, open_east=True)
+    if nsub:
+        c.params.stop_after_substeps = nsub
+        c.params.skip_ow_smoother = 1
+    got = run_path(c, "resident", monkeypatch, update=not nsub)
+    ref_gpu = run_path(c, "direct", monkeypatch, update=not nsub)
+    (R,) = ob.make_ranks(c)
+    q = ob.orc_params(c.params)
+    orc.explicit_solve([R], q)
+    ref = ob.get_state(R, KEYS)
+    for k in KEYS:
+        pairs = zip(got[k], ref[k], ref_gpu[k]) if k == "M_sigma" else [(got[k], ref[k], ref_gpu[k])]
+        for g, o, d in pairs:
+            assert ob.rel_l2(g, o) <= 1e-9, (k, "vs oracle", ob.rel_l2(g, o))
+            assert ob.rel_l2(g, d) <= 1e-11, (k, "vs direct path", ob.rel_l2(g, d))
+    if not nsub:
+        R.update(q)
+        for k in cases.UPDATE_OUT:
+            o = ob.get_state(R, (k,))[k]
+            pairs = zip(got[k], o) if k == "M_sigma" else [(got[k], o)]
+            for g, r in pairs:
+                assert ob.rel_l2(g, r) <= 1e-9, ("update", k)
