@@ -84,8 +84,10 @@ static void upload_plan(nsx_solver* S)
     // the attribute is per function and device, shared by every handle: always ask for the cap
     NSX_CUDA(cudaFuncSetAttribute(k_subcycle<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     NSX_CUDA(cudaFuncSetAttribute(k_subcycle<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    NSX_CUDA(cudaFuncSetAttribute(k_resident<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    NSX_CUDA(cudaFuncSetAttribute(k_resident<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    if (S->resident) {      // experimental path only: the default paths never touch k_resident
+        NSX_CUDA(cudaFuncSetAttribute(k_resident<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        NSX_CUDA(cudaFuncSetAttribute(k_resident<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    }
     NSX_CUDA(cudaStreamSynchronize(st));
 }
 
