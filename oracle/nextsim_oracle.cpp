@@ -6,11 +6,19 @@
 // cpu_baseline / --impl reference legs of bench.py may load this library; the product
 // path (libnsx.so) never links, imports or calls it.
 //
-// PARITY UNPINNED for the physics: the reference ships no test, fixture or stored output
-// for this path and its executable cannot be built in this
-// image (needs Boost, MPI, Gmsh, NetCDF).  The restatement below follows the reference's
-// loop nests and operation order line by line and is built with -O2 -ffp-contract=off;
-// the golden vectors under tests/golden/ are generated from it (tests/golden/make_golden.py).
+// PARITY PINNED against the reference's own text (round 2): oracle/ref_fe cuts the definitions of
+// explicitSolve, update, updateSigmaDamage, updateSigmaVP/EVP/MEVP, updateGhosts, sides, measure, shapeCoeff,
+// jacobian, minAngle, flip, checkRegridding, updateIceDiagnostics, calcCohesion and initFETensors out of
+// /root/reference/model/finiteelement.cpp at build time, compiles that text against a stub class
+// (oracle/ref_fe/stub_fe.hpp; the real header needs Boost / MPI / Gmsh / NetCDF, absent here) into
+// oracle/_ref/libref_fe.so, and tests/test_ref_fe_cpu.py requires this restatement to reproduce those
+// bodies BIT FOR BIT (np.array_equal on every output) for BBM / EVP / mEVP, 1-4 ranks, young ice, open
+// boundaries, Lemieux basal stress.  The reference ships no test, fixture or stored output for this path
+//  and its executable cannot be built in this image, so that comparison is the pin.
+// NOT pinned (no reference code can run it here): nodalGrid() -- it needs Gmsh-written partition tags and
+// boost::mpi; the restatement follows gmshmesh.cpp:856-1498 line by line.
+// The restatement is built with -O2 -ffp-contract=off, like libref_fe.so; the golden vectors under tests/golden/
+// are generated from it (tests/golden/make_golden.py).
 // PINNED against the reference's own code: bamgTables() -- contrib/bamg compiles standalone
 // and is built UNMODIFIED from /root/reference into oracle/_ref/libref_bamg.so
 // (oracle/ref_bamg/Makefile); tests/test_ref_bamg_cpu.py checks NodalElementConnectivity and

@@ -2,8 +2,9 @@
 
 TEST INFRASTRUCTURE ONLY.  Importers allowed: tests/, __graft_entry__.smoke(), and the
 cpu_baseline / ``--impl reference`` legs of bench.py.  The product package ``nextsim_b200``
-never imports this module.  PARITY UNPINNED for the physics, bamg tables pinned against the
-reference's own bamg library (oracle/ref_bamg): see the header of nextsim_oracle.cpp.
+never imports this module.  Physics PINNED bit for bit against the reference's own function bodies
+(oracle/ref_fe, tests/test_ref_fe_cpu.py), bamg tables against the reference's own bamg library (oracle/ref_bamg);
+nodalGrid() is restated from gmshmesh.cpp and unpinned: see the header of nextsim_oracle.cpp.
 """
 import ctypes as C
 import os
