@@ -310,10 +310,7 @@ def run_ours(args):
                      "forcing_apply_wind_us": us_forc, "forcing_apply_wind_GBps": nb["forcing"] / us_forc * 1e-3,
                      "check_regridding_us_incl_sync_and_readback": us_regrid, "min_angle_deg": rg.min_angle,
                      "launches": 3 * reps + 3}
-    import ctypes as _C
-    tinfo = (_C.c_int * 8)()
-    capi.lib().nsx_tile_info(S.h, tinfo, 8)
-    path = "direct" if tinfo[7] else "tiles"
+    path = S.path
     traffic = None
     try:
         tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
@@ -341,9 +338,12 @@ def run_ours(args):
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": ALGO_BYTES[args.dyn] * lm.num_elements,
-                     "kernel": ("one sub-cycle = k_element_direct + k_node_direct (L2-resident mesh)" if path == "direct"
-                                else "one sub-cycle = k_subcycle (TMA tile pipeline)") +
+                     "kernel": {"direct": "one sub-cycle = k_element_direct + k_node_direct (L2-resident mesh)",
+                                "tiles": "one sub-cycle = k_subcycle (TMA tile pipeline)",
+                                "resident": "k_resident: ONE launch = all sub-cycles + the 50 smoother sweeps, state resident in "
+                                            "shared memory / registers; duration / sub-cycles (smoother time included)"}[path] +
                                ", %g B/element algorithmic" % ALGO_BYTES[args.dyn],
+                     "path": path,
                      "us_per_subcycle": t_sub * 1e6},
         "subcycle_loop": {"value": sub_value, "unit": UNIT},
         "simulated_days_per_wallhour": (args.steps * c.params.dtime_step / 86400.0) / (total_ms * 1e-3 / 3600.0),

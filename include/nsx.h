@@ -158,8 +158,30 @@ typedef struct NsxTiming {
     int   n_substeps;       /* sub-cycles executed */
 } NsxTiming;
 
+/* How the sub-cycle loop (FE.cpp:10423-10554) is mapped on the device.  AUTO picks by size:
+ *   RESIDENT  one persistent launch per model step, state resident in shared memory / registers (<= ~2.2e5 elements
+ *             per GPU), tile-to-tile and GPU-to-GPU synchronisation by release/acquire flags;
+ *   DIRECT    element kernel + node kernel per sub-cycle for meshes whose working set fits L2;
+ *   TILES     persistent TMA tile pipeline streaming from HBM (large meshes). */
+enum { NSX_PATH_AUTO = 0, NSX_PATH_TILES = 1, NSX_PATH_DIRECT = 2, NSX_PATH_RESIDENT = 3 };
+
+/* Creation options (nsx_create uses the defaults).  Nothing in libnsx.so reads environment variables. */
+typedef struct NsxCreateOptions {
+    int path;           /* NSX_PATH_*                                                     (AUTO) */
+    int tile_nodes;     /* owned nodes per tile of the TILES path                         (0 = 208) */
+    int max_sms;        /* SMs this handle may occupy; ranks sharing one GPU pass SMs/nranks (0 = all) */
+    int use_graph;      /* capture explicitSolve() once into a CUDA graph and replay it   (1) */
+    int overlap;        /* multi-GPU TILES / DIRECT: fused boundary launch overlapped with the interior (1) */
+    int boundary_sms;   /* SMs of that boundary launch                                    (0 = automatic) */
+    int ow_skip;        /* multi-GPU TILES / DIRECT smoother: skip exchanges between ranks without open water (1) */
+    int pad_;
+} NsxCreateOptions;
+void nsx_create_options_defaults(NsxCreateOptions* o);
+
 /* ---- life cycle (replaces the member allocation in distributedMeshProcessing / initVariables) ---- */
 int nsx_create(const NsxMesh* mesh, const NsxHalo* halo, int device, nsx_handle* out);
+int nsx_create_ex(const NsxMesh* mesh, const NsxHalo* halo, int device, const NsxCreateOptions* opt, nsx_handle* out);
+int nsx_device_sm_count(int device);        /* multiprocessors of a CUDA device (-1: no such device) */
 int nsx_destroy(nsx_handle h);
 /* host-only input checks of nsx_create (sizes, index ranges, list ordering); message in nsx_last_error(NULL) */
 int nsx_validate_mesh(const NsxMesh* mesh, const NsxHalo* halo);
@@ -167,7 +189,7 @@ const char* nsx_last_error(nsx_handle h);      /* h may be NULL: error of the la
 int nsx_version(void);
 int nsx_abi_sizes(int* out, int n);          /* sizeof NsxDynParams, NsxMesh, NsxHalo, NsxFields, NsxCheck, NsxTiming, NsxRegrid */
 /* tile decomposition of the sub-cycle kernel: ntiles, nodes/tile, slots, max local nodes, max slots,
- * boundary tiles, dynamic shared memory bytes */
+ * boundary tiles, dynamic shared memory bytes, selected path (NSX_PATH_TILES / DIRECT / RESIDENT) */
 int nsx_tile_info(nsx_handle h, int* out, int n);
 /* host only (no GPU): the tile plan nsx_create would build for this mesh; out[0..9] = ntiles, nodes/tile, slots,
  * max local nodes, max slots, max own slots, max halo slots, max halo nodes, stage bytes, shrink attempts */

@@ -79,6 +79,41 @@ class NsxFields(C.Structure):
     )
 
 
+PATHS = {"auto": 0, "tiles": 1, "direct": 2, "resident": 3}
+PATH_NAMES = {v: k for k, v in PATHS.items()}
+
+
+class NsxCreateOptions(C.Structure):
+    _fields_ = [("path", C.c_int), ("tile_nodes", C.c_int), ("max_sms", C.c_int), ("use_graph", C.c_int),
+                ("overlap", C.c_int), ("boundary_sms", C.c_int), ("ow_skip", C.c_int), ("pad_", C.c_int)]
+
+
+def create_options(**over):
+    """NsxCreateOptions with the library defaults.  libnsx.so itself reads no environment variable; this HARNESS maps the
+    variables the tests and profiling scripts use (NSX_PATH, NSX_TILE_NODES, NSX_NO_GRAPH, NSX_OVERLAP, NSX_BOUNDARY_SMS,
+    NSX_OW_SKIP) onto the struct, explicit keyword arguments win."""
+    o = NsxCreateOptions()
+    lib().nsx_create_options_defaults(C.byref(o))
+    env = os.environ
+    if env.get("NSX_PATH"):
+        o.path = PATHS[env["NSX_PATH"]]
+    if env.get("NSX_TILE_NODES"):
+        o.tile_nodes = int(env["NSX_TILE_NODES"])
+    if env.get("NSX_NO_GRAPH"):
+        o.use_graph = 0
+    if env.get("NSX_OVERLAP"):
+        o.overlap = int(env["NSX_OVERLAP"])
+    if env.get("NSX_BOUNDARY_SMS"):
+        o.boundary_sms = int(env["NSX_BOUNDARY_SMS"])
+    if env.get("NSX_OW_SKIP"):
+        o.ow_skip = int(env["NSX_OW_SKIP"])
+    for k, v in over.items():
+        if v is None:
+            continue
+        setattr(o, k, PATHS[v] if k == "path" and isinstance(v, str) else int(v))
+    return o
+
+
 class NsxCheck(C.Structure):
     _fields_ = [("n_nan", C.c_int), ("n_speed", C.c_int), ("n_range", C.c_int), ("pad_", C.c_int),
                 ("max_speed", C.c_double)]
@@ -98,7 +133,7 @@ class NsxTiming(C.Structure):
 
 
 EXPORTS = (
-    "nsx_create", "nsx_destroy", "nsx_last_error", "nsx_version", "nsx_params_defaults", "nsx_params_from_cfg",
+    "nsx_create", "nsx_create_ex", "nsx_create_options_defaults", "nsx_device_sm_count", "nsx_destroy", "nsx_last_error", "nsx_version", "nsx_params_defaults", "nsx_params_from_cfg",
     "nsx_set_params", "nsx_upload", "nsx_download", "nsx_explicit_solve", "nsx_update", "nsx_update_ghosts",
     "nsx_check", "nsx_synchronize", "nsx_get_timing", "nsx_get_stream", "nsx_halo_blob_size", "nsx_halo_blob",
     "nsx_halo_connect_blob", "nsx_halo_connect_local", "nsx_halo_finalize", "nsx_group_explicit_solve",
@@ -229,18 +264,31 @@ def validate_mesh(lm):
 class Solver:
     """Thin owner of one nsx_handle.  Methods map 1:1 on the C ABI."""
 
-    def __init__(self, lm, device=0):
-        """lm: partition.LocalMesh with bamg tables, BC masks and lat filled in."""
+    def __init__(self, lm, device=0, **options):
+        """lm: partition.LocalMesh with bamg tables, BC masks and lat filled in.  options: NsxCreateOptions fields
+        (path="auto"|"tiles"|"direct"|"resident", tile_nodes, max_sms, use_graph, ...)."""
         self.L = lib()
         self.lm = lm
         self.nn, self.ne = lm.num_nodes, lm.num_elements
         M, H, keep = mesh_structs(lm)
         h = C.c_void_p()
-        rc = self.L.nsx_create(C.byref(M), C.byref(H) if H is not None else None, int(device), C.byref(h))
+        self.options = create_options(**options)
+        rc = self.L.nsx_create_ex(C.byref(M), C.byref(H) if H is not None else None, int(device), C.byref(self.options),
+                                  C.byref(h))
         if rc != 0:
             raise RuntimeError("nsx_create: " + self.L.nsx_last_error(None).decode())
         self.h = h
         self.peers = sorted(set(lm.send_to) | set(lm.recv_from)) if lm.nranks > 1 else []
+
+    def tile_info(self):
+        """ntiles, nodes/tile, slots, max local nodes, max slots, boundary tiles, smem bytes, path name."""
+        t = (C.c_int * 8)()
+        self.L.nsx_tile_info(self.h, t, 8)
+        return list(t[:7]) + [PATH_NAMES.get(t[7], "?")]
+
+    @property
+    def path(self):
+        return self.tile_info()[7]
 
     def close(self):
         if getattr(self, "h", None):

@@ -25,6 +25,7 @@ CONFIGS = {
     "3km": dict(mesh="3km", kind="large", dt=200.0, alea_factor=0.33),
     "3km_stable": dict(mesh="3km", kind="stable", dt=200.0, alea_factor=0.33),
     "1km": dict(mesh="1km", kind="large", dt=200.0, alea_factor=0.33),
+    "1km_stable": dict(mesh="1km", kind="stable", dt=200.0, alea_factor=0.33),
 }
 
 
@@ -117,9 +118,14 @@ UPDATE_OUT = ("M_conc", "M_thick", "M_snow_thick", "M_thick_myi", "M_conc_myi", 
               "M_h_young", "M_hs_young", "M_sigma", "M_surface", "D_del_ci_ridge_myi")
 
 
-def make_solvers(c, device=0):
-    """One nsx handle per rank, all on `device`, halos wired in-process."""
-    solvers = [capi.Solver(lm, device) for lm in c.lms]
+def make_solvers(c, device=0, **options):
+    """One nsx handle per rank, all on `device`, halos wired in-process.  Ranks sharing the GPU split its SMs: the
+    resident path runs one persistent launch per rank and they synchronise through flags, so they must be co-resident."""
+    if c.nranks > 1 and "max_sms" not in options:
+        sms = capi.lib().nsx_device_sm_count(int(device))
+        if sms > 0:
+            options["max_sms"] = max(1, sms // c.nranks)
+    solvers = [capi.Solver(lm, device, **options) for lm in c.lms]
     for s, f in zip(solvers, c.local):
         s.set_params(c.params)
         s.upload(**{k: f[k] for k in UPLOAD_KEYS})

@@ -26,10 +26,11 @@ static std::string g_create_err;
 
 static inline int nblk(long n) { return (int)((n + TPB - 1) / TPB); }
 
-static int env_int(const char* name, int dflt)
+extern "C" void nsx_create_options_defaults(NsxCreateOptions* o)
 {
-    const char* v = getenv(name);
-    return (v && *v) ? atoi(v) : dflt;
+    if (!o) return;
+    *o = NsxCreateOptions{};
+    o->path = NSX_PATH_AUTO; o->tile_nodes = 0; o->max_sms = 0; o->use_graph = 1; o->overlap = 1; o->boundary_sms = 0; o->ow_skip = 1;
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -59,6 +60,7 @@ static SmemLayout sub_layout(MeshPlan const& P, int n_node_planes)
     L.total = (int)o;
     return L;
 }
+constexpr int RES_SMEM_MAX = 227 * 1024 - 256;        // dynamic shared memory of k_resident (its static part holds the tile descriptors)
 constexpr int SUB_SMEM_CAP = ((227 * 1024) / SUB_CTAS_PER_SM - 1024 * (SUB_CTAS_PER_SM - 1) - 128) / SUB_STAGES;     // per stage; one persistent CTA per SM (227 KB)
 
 // ---------------------------------------------------------------------------------------------------
@@ -84,9 +86,11 @@ static void upload_plan(nsx_solver* S)
     // the attribute is per function and device, shared by every handle: always ask for the cap
     NSX_CUDA(cudaFuncSetAttribute(k_subcycle<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     NSX_CUDA(cudaFuncSetAttribute(k_subcycle<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    if (S->resident) {      // experimental path only: the default paths never touch k_resident
-        NSX_CUDA(cudaFuncSetAttribute(k_resident<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        NSX_CUDA(cudaFuncSetAttribute(k_resident<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    if (S->resident) {
+        S->res_tiles.upload(P.res_tiles, st); S->res_nbr.upload(P.res_nbr, st);
+        S->res_n2n.upload(P.res_n2n, st); S->res_n2n_deg.upload(P.res_n2n_deg, st); S->halo_move.upload(P.halo_move, st);
+        NSX_CUDA(cudaFuncSetAttribute(k_resident<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, RES_SMEM_MAX));
+        NSX_CUDA(cudaFuncSetAttribute(k_resident<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, RES_SMEM_MAX));
     }
     NSX_CUDA(cudaStreamSynchronize(st));
 }
@@ -118,15 +122,15 @@ static void alloc_fields(nsx_solver* S)
     S->shape.alloc(6 * ne); S->shape.zero(st);
     S->slot_shape.alloc(6 * ns); S->slot_shape.zero(st);
     S->slot_ec.alloc(6 * ns); S->slot_ec.zero(st);
-    S->stage.alloc(std::max(2 * nn, 6 * ne));
-    S->stage2.alloc(std::max(2 * nn, ne));
-    // Path selection: the sub-cycle working set (~300 B per element) either lives in the 126 MB L2 (direct path)
-    // or streams from HBM (TMA tile pipeline).  NSX_PATH=direct|tiles overrides.
+    NSX_CUDA(cudaMallocHost(&S->h_err, sizeof(int)));
+    *S->h_err = 0;
+    // Path selection (NsxCreateOptions.path, AUTO by size): the sub-cycle state is resident in shared memory
+    // (k_resident, decided in nsx_create_ex), or the working set (~300 B per element) lives in the 126 MB L2 (direct
+    // path), or it streams from HBM (TMA tile pipeline).
     {
-        const char* pth = getenv("NSX_PATH");
         S->direct = (double)ne * 300.0 < 90e6;
-        if (pth && !strcmp(pth, "direct")) S->direct = true;
-        if (pth && !strcmp(pth, "tiles")) S->direct = false;
+        if (S->opt.path == NSX_PATH_DIRECT) S->direct = true;
+        if (S->opt.path == NSX_PATH_TILES) S->direct = false;
         if (S->resident) S->direct = false;
         if (S->direct) { S->ec_e.alloc(6 * ne); S->ec_e.zero(st); S->contrib.alloc(6 * ne); S->contrib.zero(st); }
     }
@@ -136,7 +140,6 @@ static void alloc_fields(nsx_solver* S)
     S->d_epoch.alloc(1); S->d_done.alloc(1);
     S->d_epoch.zero(st); S->d_done.zero(st);
     S->ow_pair.alloc(64); S->ow_pair.zero(st);
-    S->ow_bar.alloc(1); S->ow_bar.zero(st);
     for (auto& e : S->ev) NSX_CUDA(cudaEventCreate(&e));
     NSX_CUDA(cudaEventCreateWithFlags(&S->ev_fork, cudaEventDisableTiming));
     NSX_CUDA(cudaEventCreateWithFlags(&S->ev_join, cudaEventDisableTiming));
@@ -202,6 +205,27 @@ static void build_halo(nsx_solver* S, const NsxHalo* H)
         S->tiles.upload(S->plan.tiles, S->stream);
     }
     S->tile_order.upload(order, S->stream);
+    if (S->resident) {
+        // resident path: which neighbour ranks (links, in S->peers order) each tile pushes to or reads ghosts of; every
+        // such tile arrives on the link once per exchange, the last arrival publishes the epoch (k_resident::signal)
+        std::vector<int> nmask(S->nn, 0);
+        int i = 0;
+        for (auto const& p : S->peers) {
+            for (int v : p.h_send_idx) nmask[v] |= 1 << i;
+            for (int v : p.h_recv_idx) nmask[v] |= 1 << i;
+            ++i;
+        }
+        for (int k = 0; k < 16; ++k) S->res_link_tiles[k] = 0;
+        for (int t = 0; t < S->plan.ntiles; ++t) {
+            nsx::TileDesc const& td = S->plan.tiles[t];
+            int m = 0;
+            for (int j = 0; j < td.n_own; ++j) m |= nmask[td.node_begin + j];
+            for (int h = 0; h < td.n_halo; ++h) m |= nmask[S->plan.halo_nodes[td.halo_off + h]];
+            S->plan.res_tiles[t].link_mask = m;
+            for (int k = 0; k < (int)S->peers.size(); ++k) S->res_link_tiles[k] += (m >> k) & 1;
+        }
+        S->res_tiles.upload(S->plan.res_tiles, S->stream);
+    }
     NSX_CUDA(cudaStreamSynchronize(S->stream));
 }
 
@@ -261,12 +285,60 @@ extern "C" int nsx_validate_mesh(const NsxMesh* mesh, const NsxHalo* halo)
     return 0;
 }
 
+// The state-resident plan: one tile per CTA, at most `ctas` tiles, everything the sub-cycle loop touches in shared
+// memory and registers.  Returns false (with the reason) when the mesh does not fit; AUTO then falls back.
+static bool try_resident_plan(const NsxMesh* mesh, const NsxHalo* halo, int ctas, MeshPlan& P, std::string& why)
+{
+    std::vector<uint8_t> xmask;
+    int nlinks = 0;
+    if (halo) {
+        xmask.assign(mesh->num_nodes, 0);
+        int const ns = halo->n_send_peers ? halo->send_ptr[halo->n_send_peers] : 0;
+        for (int q = 0; q < ns; ++q) {
+            int const v = halo->send_idx[q];
+            if (v < 0 || v >= mesh->local_ndof) { why = "send index is not an owned node"; return false; }
+            xmask[v] = 1;
+        }
+        std::vector<int> peers(halo->send_peer, halo->send_peer + halo->n_send_peers);
+        peers.insert(peers.end(), halo->recv_peer, halo->recv_peer + halo->n_recv_peers);
+        std::sort(peers.begin(), peers.end());
+        nlinks = (int)(std::unique(peers.begin(), peers.end()) - peers.begin());
+    }
+    if (nlinks > RES_MAX_LINKS) { why = "more than " + std::to_string(RES_MAX_LINKS) + " neighbour ranks"; return false; }
+    int const T = (mesh->local_ndof + ctas - 1) / ctas;
+    if (T > RES_TPB) { why = std::to_string(T) + " owned nodes per tile (limit " + std::to_string(RES_TPB) + ")"; return false; }
+    P = MeshPlan();
+    build_mesh_plan(mesh, P, std::max(32, T), 1, true, halo ? xmask.data() : nullptr);
+    size_t const smem = (size_t)(16 * P.msp + 2 * (P.max_local_nodes + 2)) * sizeof(double);     // BBM: 6 + 6 + 3 + 1 planes
+    if (P.ntiles > ctas || P.tile_nodes > RES_TPB || P.max_slots > RES_SPT * RES_TPB || smem > (size_t)RES_SMEM_MAX || P.msp >= 16384) {
+        why = "tiles " + std::to_string(P.ntiles) + ", nodes per tile " + std::to_string(P.tile_nodes) + ", max slots " +
+              std::to_string(P.max_slots) + ", shared memory " + std::to_string(smem) + " B";
+        return false;
+    }
+    return true;
+}
+
 extern "C" int nsx_create(const NsxMesh* mesh, const NsxHalo* halo, int device, nsx_handle* out)
+{
+    return nsx_create_ex(mesh, halo, device, nullptr, out);
+}
+
+extern "C" int nsx_device_sm_count(int device)
+{
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, device) != cudaSuccess) { (void)cudaGetLastError(); return -1; }
+    return n;
+}
+
+extern "C" int nsx_create_ex(const NsxMesh* mesh, const NsxHalo* halo, int device, const NsxCreateOptions* opt, nsx_handle* out)
 {
     if (!mesh || !out) { g_create_err = "nsx_create: NULL argument"; return 1; }
     *out = nullptr;
     nsx_solver* S = new nsx_solver();
     try {
+        nsx_create_options_defaults(&S->opt);
+        if (opt) S->opt = *opt;
+        if (S->opt.path < NSX_PATH_AUTO || S->opt.path > NSX_PATH_RESIDENT) throw std::invalid_argument("nsx_create: unknown path option");
         validate_inputs(mesh, halo);
         int ndev = 0;
         NSX_CUDA(cudaGetDeviceCount(&ndev));
@@ -276,35 +348,26 @@ extern "C" int nsx_create(const NsxMesh* mesh, const NsxHalo* halo, int device, 
         NSX_CUDA(cudaDeviceGetAttribute(&S->sm_count, cudaDevAttrMultiProcessorCount, device));
         NSX_CUDA(cudaStreamCreateWithFlags(&S->stream, cudaStreamNonBlocking));
         NSX_CUDA(cudaStreamCreateWithFlags(&S->stream2, cudaStreamNonBlocking));
-        NSX_CUDA(cudaStreamCreateWithFlags(&S->stream_copy, cudaStreamNonBlocking));
-        for (int b = 0; b < 2; ++b) {
-            NSX_CUDA(cudaEventCreateWithFlags(&S->ev_stage_copy[b], cudaEventDisableTiming));
-            NSX_CUDA(cudaEventCreateWithFlags(&S->ev_stage_perm[b], cudaEventDisableTiming));
+        int const ctas = (S->opt.max_sms > 0) ? std::min(S->opt.max_sms, S->sm_count) : S->sm_count;
+        // resident path: explicit request, or AUTO when the mesh fits
+        S->resident = false;
+        if (S->opt.path == NSX_PATH_RESIDENT || S->opt.path == NSX_PATH_AUTO) {
+            std::string why;
+            S->resident = try_resident_plan(mesh, halo, ctas, S->plan, why);
+            if (!S->resident && S->opt.path == NSX_PATH_RESIDENT)
+                throw std::invalid_argument("nsx_create: the resident path does not fit this mesh (" + why + ")");
         }
-        // one wave of the sub-cycle kernel = SMs x resident CTAs (2: shared memory and launch bounds); shrink the
-        // tiles until the staged working set of the largest tile fits the per-CTA shared-memory budget
-        int target = env_int("NSX_TILE_NODES", 208);
-        const char* pth0 = getenv("NSX_PATH");
-        S->resident = (pth0 && !strcmp(pth0, "resident"));
-        if (S->resident) {
-            // EXPERIMENTAL: one large tile per SM, resident for the whole sub-cycle loop (k_resident); one rank only
-            if (halo) throw std::invalid_argument("nsx_create: NSX_PATH=resident supports a single rank only");
-            int const T = (mesh->local_ndof + S->sm_count - 1) / S->sm_count;
-            S->plan = MeshPlan();
-            build_mesh_plan(mesh, S->plan, std::max(32, T), 1);
-            MeshPlan const& P = S->plan;
-            size_t const smem = (size_t)(15 * P.msp + 2 * (P.max_local_nodes + 2)) * sizeof(double);
-            if (P.ntiles > S->sm_count || P.tile_nodes > RES_TPB || P.max_slots > RES_SPT * RES_TPB || smem > 227 * 1024)
-                throw std::invalid_argument("nsx_create: NSX_PATH=resident does not fit this mesh (tiles " + std::to_string(P.ntiles) +
-                    ", nodes per tile " + std::to_string(P.tile_nodes) + ", max slots " + std::to_string(P.max_slots) +
-                    ", shared memory " + std::to_string(smem) + " B)");
-        } else
-        for (int attempt = 0;; ++attempt) {
-            S->plan = MeshPlan();
-            build_mesh_plan(mesh, S->plan, target, S->sm_count * SUB_CTAS_PER_SM);
-            if (sub_layout(S->plan, 14).total <= SUB_SMEM_CAP) break;
-            if (attempt > 12 || target <= 32) throw std::invalid_argument("nsx_create: cannot fit a tile in shared memory");
-            target = std::max(32, (int)(target * 0.88));
+        if (!S->resident) {
+            // one wave of the sub-cycle kernel = SMs x resident CTAs; shrink the tiles until the staged working set of
+            // the largest tile fits the per-CTA shared-memory budget
+            int target = S->opt.tile_nodes > 0 ? S->opt.tile_nodes : 208;
+            for (int attempt = 0;; ++attempt) {
+                S->plan = MeshPlan();
+                build_mesh_plan(mesh, S->plan, target, S->sm_count * SUB_CTAS_PER_SM);
+                if (sub_layout(S->plan, 14).total <= SUB_SMEM_CAP) break;
+                if (attempt > 12 || target <= 32) throw std::invalid_argument("nsx_create: cannot fit a tile in shared memory");
+                target = std::max(32, (int)(target * 0.88));
+            }
         }
         upload_plan(S);
         alloc_fields(S);
@@ -331,11 +394,7 @@ extern "C" int nsx_destroy(nsx_handle S)
     if (S->ev_fork) cudaEventDestroy(S->ev_fork);
     if (S->ev_join) cudaEventDestroy(S->ev_join);
     if (S->window) cudaFree(S->window);
-    if (S->stream_copy) { cudaStreamSynchronize(S->stream_copy); cudaStreamDestroy(S->stream_copy); }
-    for (int b = 0; b < 2; ++b) {
-        if (S->ev_stage_copy[b]) cudaEventDestroy(S->ev_stage_copy[b]);
-        if (S->ev_stage_perm[b]) cudaEventDestroy(S->ev_stage_perm[b]);
-    }
+    if (S->h_err) cudaFreeHost(S->h_err);
     if (S->stream2) cudaStreamDestroy(S->stream2);
     if (S->stream) cudaStreamDestroy(S->stream);
     delete S;
@@ -360,7 +419,8 @@ extern "C" int nsx_tile_info(nsx_handle S, int* out, int n)
 {
     if (!S) return 0;
     int const v[8] = {S->plan.ntiles, S->plan.tile_nodes, S->plan.nslots, S->plan.max_local_nodes, S->plan.max_slots,
-                      S->n_boundary_tiles, (int)S->sub_smem, S->direct ? 1 : 0};
+                      S->n_boundary_tiles, (int)S->sub_smem,
+                      S->resident ? NSX_PATH_RESIDENT : S->direct ? NSX_PATH_DIRECT : NSX_PATH_TILES};
     for (int i = 0; i < n && i < 8; ++i) out[i] = v[i];
     return 8;
 }
@@ -480,8 +540,55 @@ static void field_table(nsx_solver* S, const NsxFields* f, std::vector<FieldMap>
     }
 }
 
-// Field k is staged in buffer k&1: its PCIe copy (copy stream) overlaps the permutation kernel of field k-1 (main
-// stream), so the copy engine never waits for a kernel.  Every call drains both streams before returning.
+// device error word written by the bounded spins of the exchange / barrier kernels
+static std::string halo_error_text(int herr)
+{
+    if (herr >= 2000) return "open-water smoother: grid barrier timed out (the launch was not co-resident)";
+    if (herr >= 1000) return "resident solver: timed out waiting for the flag of tile " + std::to_string(herr - 1000) +
+                             " (the launch was not co-resident, or a neighbour rank died)";
+    return "halo exchange timed out waiting for rank " + std::to_string(herr - 1);
+}
+
+// One call = one device arena in host order: the PCIe copies of all fields are issued back to back on the handle's
+// stream (one cudaMemcpyAsync per caller array -- the host keeps its own vectors, pinned or not), ONE kernel permutes
+// every field between host and internal numbering, ONE stream synchronisation ends the call.
+static size_t xfer_layout(nsx_solver* S, std::vector<FieldMap> const& t, std::vector<size_t>& off)
+{
+    size_t total = 0;
+    off.resize(t.size());
+    for (size_t k = 0; k < t.size(); ++k) {
+        size_t const n = (t[k].kind == ELEM) ? S->ne : S->nn;
+        off[k] = total;
+        total += n * ((t[k].kind == NODAL2) ? 2 : 1);
+    }
+    if (S->arena.n < total) {
+        NSX_CUDA(cudaStreamSynchronize(S->stream));
+        S->arena.alloc(total + total / 8);
+    }
+    return total;
+}
+
+template <int IN>
+static void xfer_permute(nsx_solver* S, std::vector<FieldMap> const& t, std::vector<size_t> const& off)
+{
+    for (size_t k0 = 0; k0 < t.size(); k0 += XFER_MAX) {
+        XferTable T{};
+        int nmax = 0;
+        for (size_t k = k0; k < t.size() && k < k0 + XFER_MAX; ++k) {
+            XferEnt& e = T.e[T.count++];
+            e.n = (t[k].kind == ELEM) ? S->ne : S->nn;
+            e.planes = (t[k].kind == NODAL2) ? 2 : 1;
+            e.elem = (t[k].kind == ELEM) ? 1 : 0;
+            if (IN) { e.src = S->arena.p + off[k]; e.dst = t[k].dev; }
+            else { e.src = t[k].dev; e.dst = S->arena.p + off[k]; }
+            nmax = std::max(nmax, e.n);
+        }
+        dim3 const grid(std::min(nblk(nmax), 4 * S->sm_count), T.count);
+        k_permute_all<IN><<<grid, TPB, 0, S->stream>>>(T, S->node_perm.p, S->elem_perm.p);
+    }
+    NSX_CUDA(cudaGetLastError());
+}
+
 extern "C" int nsx_upload(nsx_handle S, const NsxFields* f)
 {
     NSX_API_BEGIN(S)
@@ -491,23 +598,16 @@ extern "C" int nsx_upload(nsx_handle S, const NsxFields* f)
         throw std::invalid_argument("nsx_upload: the D_* diagnostics are outputs");
     std::vector<FieldMap> t;
     field_table(S, f, t);
-    cudaStream_t st = S->stream, sc = S->stream_copy;
-    double* const stg[2] = {S->stage.p, S->stage2.p};
+    std::vector<size_t> off;
+    xfer_layout(S, t, off);
+    cudaStream_t st = S->stream;
     for (size_t k = 0; k < t.size(); ++k) {
-        auto& m = t[k];
-        int const b = (int)(k & 1);
-        int const n = (m.kind == ELEM) ? S->ne : S->nn;
-        int const planes = (m.kind == NODAL2) ? 2 : 1;
-        if (k >= 2) NSX_CUDA(cudaStreamWaitEvent(sc, S->ev_stage_perm[b], 0));      // buffer b was read by field k-2
-        NSX_CUDA(cudaMemcpyAsync(stg[b], m.host, (size_t)n * planes * sizeof(double), cudaMemcpyHostToDevice, sc));
-        NSX_CUDA(cudaEventRecord(S->ev_stage_copy[b], sc));
-        NSX_CUDA(cudaStreamWaitEvent(st, S->ev_stage_copy[b], 0));
-        k_permute_in<<<nblk(n), TPB, 0, st>>>(n, planes, m.kind == ELEM ? S->elem_perm.p : S->node_perm.p, stg[b], m.dev);
-        NSX_CUDA(cudaEventRecord(S->ev_stage_perm[b], st));
+        size_t const n = (t[k].kind == ELEM) ? S->ne : S->nn;
+        NSX_CUDA(cudaMemcpyAsync(S->arena.p + off[k], t[k].host, n * ((t[k].kind == NODAL2) ? 2 : 1) * sizeof(double),
+                                 cudaMemcpyHostToDevice, st));
     }
-    NSX_CUDA(cudaGetLastError());
+    if (!t.empty()) xfer_permute<1>(S, t, off);
     if (f->M_tau_wi && !S->have_tau_wi) { S->have_tau_wi = true; S->graph_valid = false; }
-    NSX_CUDA(cudaStreamSynchronize(sc));
     NSX_CUDA(cudaStreamSynchronize(st));
     NSX_API_END(S)
 }
@@ -518,31 +618,28 @@ extern "C" int nsx_download(nsx_handle S, NsxFields* f)
     if (!f) throw std::invalid_argument("nsx_download: NULL");
     std::vector<FieldMap> t;
     field_table(S, f, t);
-    cudaStream_t st = S->stream, sc = S->stream_copy;
-    double* const stg[2] = {S->stage.p, S->stage2.p};
-    for (size_t k = 0; k < t.size(); ++k) {
-        auto& m = t[k];
-        int const b = (int)(k & 1);
-        int const n = (m.kind == ELEM) ? S->ne : S->nn;
-        int const planes = (m.kind == NODAL2) ? 2 : 1;
-        if (k >= 2) NSX_CUDA(cudaStreamWaitEvent(st, S->ev_stage_copy[b], 0));      // buffer b was copied out for field k-2
-        k_permute_out<<<nblk(n), TPB, 0, st>>>(n, planes, m.kind == ELEM ? S->elem_perm.p : S->node_perm.p, m.dev, stg[b]);
-        NSX_CUDA(cudaEventRecord(S->ev_stage_perm[b], st));
-        NSX_CUDA(cudaStreamWaitEvent(sc, S->ev_stage_perm[b], 0));
-        NSX_CUDA(cudaMemcpyAsync(m.host, stg[b], (size_t)n * planes * sizeof(double), cudaMemcpyDeviceToHost, sc));
-        NSX_CUDA(cudaEventRecord(S->ev_stage_copy[b], sc));
+    std::vector<size_t> off;
+    size_t const total = xfer_layout(S, t, off);
+    if (f->M_shape_coeff && S->arena.n < total + 6 * (size_t)S->ne) {      // the 6 planes go behind the other fields
+        NSX_CUDA(cudaStreamSynchronize(S->stream));
+        S->arena.alloc(total + 6 * (size_t)S->ne);
     }
-    NSX_CUDA(cudaGetLastError());
-    NSX_CUDA(cudaStreamSynchronize(sc));
-    if (f->M_shape_coeff) {                       // 6 planes: needs the large staging buffer, after the pipeline drained
-        k_shape_out<<<nblk(6L * S->ne), TPB, 0, st>>>(S->ne, S->elem_perm.p, S->shape.p, S->stage.p);
-        NSX_CUDA(cudaMemcpyAsync(f->M_shape_coeff, S->stage.p, 6 * (size_t)S->ne * sizeof(double), cudaMemcpyDeviceToHost, st));
+    cudaStream_t st = S->stream;
+    if (!t.empty()) xfer_permute<0>(S, t, off);
+    for (size_t k = 0; k < t.size(); ++k) {
+        size_t const n = (t[k].kind == ELEM) ? S->ne : S->nn;
+        NSX_CUDA(cudaMemcpyAsync(t[k].host, S->arena.p + off[k], n * ((t[k].kind == NODAL2) ? 2 : 1) * sizeof(double),
+                                 cudaMemcpyDeviceToHost, st));
+    }
+    if (f->M_shape_coeff) {
+        k_shape_out<<<nblk(6L * S->ne), TPB, 0, st>>>(S->ne, S->elem_perm.p, S->shape.p, S->arena.p + total);
+        NSX_CUDA(cudaMemcpyAsync(f->M_shape_coeff, S->arena.p + total, 6 * (size_t)S->ne * sizeof(double), cudaMemcpyDeviceToHost, st));
         NSX_CUDA(cudaGetLastError());
     }
+    // the device error word (bounded spins of the exchange kernels) rides in the same stream, into pinned memory
+    NSX_CUDA(cudaMemcpyAsync(S->h_err, S->halo_err.p, sizeof(int), cudaMemcpyDeviceToHost, st));
     NSX_CUDA(cudaStreamSynchronize(st));
-    int herr = 0;
-    NSX_CUDA(cudaMemcpy(&herr, S->halo_err.p, sizeof(int), cudaMemcpyDeviceToHost));
-    if (herr) throw std::runtime_error("halo exchange timed out waiting for rank " + std::to_string(herr - 1));
+    if (*S->h_err) throw std::runtime_error(halo_error_text(*S->h_err));
     NSX_API_END(S)
 }
 
@@ -856,7 +953,7 @@ static void phase_substep(nsx_solver* S, int s, bool exchange_sync, bool overlap
         // (tiles + NVLink round trip) is latency-bound and on the critical path of both ranks of a pair: one tile per
         // CTA.  Tile path: the split that lets both kernels finish together (balanced_boundary_sms).
         int B = S->direct ? std::min(nb, 48) : balanced_boundary_sms(nb, nt, S->sm_count);
-        if (const char* e = getenv("NSX_BOUNDARY_SMS")) B = std::max(1, std::min(atoi(e), std::min(nb, S->sm_count - 1)));
+        if (S->opt.boundary_sms > 0) B = std::max(1, std::min(S->opt.boundary_sms, std::min(nb, S->sm_count - 1)));
         SubArgs Ab = A;
         Ab.fuse_halo = 1;
         Ab.H = halo_args(S, S->cur ^ 1, true);
@@ -916,8 +1013,11 @@ static void phase_ow_sweep(nsx_solver* S)
 }
 static void phase_tauw(nsx_solver* S)
 {
+    // the resident launch reads the exchange epoch at its start; the counter advances here, after it has finished
     k_tauw_owmove<<<nblk(S->nn), TPB, 0, S->stream>>>(S->K, S->nflags.p, S->node_mass.p, S->VT[S->cur], S->VTM.p,
-                                                      S->ocean.p, S->tau_w.p, S->UM.p, S->UT.p);
+                                                      S->ocean.p, S->tau_w.p, S->UM.p, S->UT.p,
+                                                      S->epoch_bump ? S->d_epoch.p : nullptr, (unsigned long long)S->epoch_bump);
+    S->epoch_bump = 0;
     S->n_launch++;
     NSX_CUDA(cudaGetLastError());
 }
@@ -933,6 +1033,76 @@ static void record(nsx_solver* S, int i)
 {
     if (S->capturing) NSX_CUDA(cudaEventRecordWithFlags(S->ev[i], S->stream, cudaEventRecordExternal));
     else NSX_CUDA(cudaEventRecord(S->ev[i], S->stream));
+}
+
+// tile flags + per-exchange link arrival counters of the resident launch; allocated outside any stream capture
+static void ensure_res_flags(nsx_solver* S)
+{
+    if (!S->resident) return;
+    size_t const words = (size_t)S->plan.ntiles * RES_FLAG_STRIDE + (size_t)(std::max(1, S->P.substeps) + 50 + 2) * RES_MAX_LINKS;
+    if (S->res_flag_words < words) {
+        NSX_CUDA(cudaStreamSynchronize(S->stream));
+        S->res_flags.alloc(words);
+        S->res_flag_words = words;
+    }
+}
+
+// The whole sub-cycle loop and the open-water smoother of one rank in ONE cooperative launch (k_resident).
+static void launch_resident(nsx_solver* S, int nrun, bool cooperative)
+{
+    KParams const& K = S->K;
+    bool const bbm = (K.dynamics_type == NSX_DYN_BBM);
+    int const nsweeps = S->P.skip_ow_smoother ? 0 : 50;            // hard-coded 50 sweeps, FE.cpp:10580
+    if (!S->peers.empty() && !S->halo_ready) throw std::runtime_error("explicit solve before nsx_halo_finalize");
+    ResidentArgs A{};
+    A.tiles = S->tiles.p; A.rtiles = S->res_tiles.p; A.nbr = S->res_nbr.p;
+    A.halo_nodes = S->halo_nodes.p; A.halo_move = S->halo_move.p; A.halo_elems = S->halo_elems.p; A.slot_conn = S->slot_conn.p;
+    A.slot_shape = S->slot_shape.p; A.slot_ec = S->slot_ec.p; A.nslots = S->plan.nslots; A.inc = S->inc.p;
+    A.n2n_loc = S->res_n2n.p; A.n2n_deg = S->res_n2n_deg.p;
+    A.s0 = S->sig[S->scur][0].p; A.s1 = S->sig[S->scur][1].p; A.s2 = S->sig[S->scur][2].p;
+    A.dm = bbm ? S->dmg[S->dcur].p : nullptr;
+    A.nflags = S->nflags.p; A.grad_ssh = S->grad_ssh.p; A.node_mass = S->node_mass.p; A.rlmass = S->rlmass.p;
+    A.cbu = S->cbu.p; A.fcor = S->fcor.p; A.tau_a = S->tau_a.p; A.tau_wi = S->have_tau_wi ? S->tau_wi.p : nullptr;
+    A.ocean = S->ocean.p; A.VTM = S->VTM.p;
+    A.VT0 = S->VT[0]; A.VT1 = S->VT[1]; A.cur = S->cur; A.UM = S->UM.p; A.UT = S->UT.p;
+    A.move_mesh = (K.dynamics_type != NSX_DYN_MEVP); A.nsub = nrun; A.nsweeps = nsweeps;
+    A.ow_count = S->ow_count.p;
+    size_t const tile_words = (size_t)S->plan.ntiles * RES_FLAG_STRIDE;
+    size_t const words = tile_words + (size_t)(nrun + nsweeps + 2) * RES_MAX_LINKS;
+    if (S->res_flag_words < words) throw std::logic_error("resident path: flag buffer too small");      // sized by ensure_res_flags
+    NSX_CUDA(cudaMemsetAsync(S->res_flags.p, 0, words * sizeof(unsigned int), S->stream));
+    A.tile_flags = S->res_flags.p; A.arrive = S->res_flags.p + tile_words;
+    A.push_ptr = S->push_ptr.p; A.push_ent = S->push_ent.p;
+    A.my_flags = S->flags; A.epoch_ctr = S->d_epoch.p; A.err = S->halo_err.p;
+    A.MS = S->plan.msp; A.MLN = S->plan.max_local_nodes + 2;
+    int slot = 0, link = 0;
+    for (auto& p : S->peers) {
+        if (!p.h_send_idx.empty()) {
+            A.P.send_vt[0][slot] = p.peer_vt[0]; A.P.send_vt[1][slot] = p.peer_vt[1]; A.P.send_nn[slot] = p.peer_nn;
+            ++slot;
+        }
+        A.P.link_flag[link] = p.peer_flags + S->rank;
+        A.P.link_rank[link] = p.rank;
+        A.P.link_tiles[link] = S->res_link_tiles[link];
+        ++link;
+    }
+    A.P.n_link = link;
+    size_t const smem = (size_t)((bbm ? 16 : 12) * A.MS + 2 * A.MLN) * sizeof(double);
+    // cooperative launch: the driver guarantees that all CTAs (one per SM) are co-resident, which the flag protocol needs
+    void* args[2] = {(void*)&K, (void*)&A};
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(S->plan.ntiles); cfg.blockDim = dim3(RES_TPB); cfg.dynamicSmemBytes = smem; cfg.stream = S->stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeCooperative; at[0].val.cooperative = 1;
+    // ranks sharing one GPU (in-process groups of the tests) launch plainly: their kernels must overlap each other, the
+    // host has checked that together they fit the device, and every spin is bounded
+    cfg.attrs = at; cfg.numAttrs = cooperative ? 1 : 0;
+    if (bbm) NSX_CUDA(cudaLaunchKernelExC(&cfg, (const void*)k_resident<1>, args));
+    else NSX_CUDA(cudaLaunchKernelExC(&cfg, (const void*)k_resident<0>, args));
+    S->n_launch++;
+    int const nex = nrun + ((link > 0) ? nsweeps : 0);
+    S->cur = (S->cur + nrun + nsweeps) & 1;          // the kernel leaves the result in that buffer whether or not it swept
+    S->epoch_bump = (link > 0) ? nex : 0;
 }
 
 static void solve_group(int n, nsx_solver** W)
@@ -951,7 +1121,8 @@ static void solve_group(int n, nsx_solver** W)
     }
     int const nrun = substeps_to_run(W[0]);
     bool const remote = (n == 1) && !W[0]->halo_local && !W[0]->peers.empty();
-    static const bool overlap_on = (env_int("NSX_OVERLAP", 1) != 0);
+    bool const overlap_on = W[0]->opt.overlap != 0;
+    bool const ow_skip = W[0]->opt.ow_skip != 0;
     auto group_exchange = [&]() {
         // in-process group: all pushes, then a cross-stream join so nobody reads ghosts too early
         for (int r = 0; r < n; ++r) { NSX_CUDA(cudaSetDevice(W[r]->device)); halo_exchange(W[r], false); NSX_CUDA(cudaEventRecord(W[r]->ev[5], W[r]->stream)); }
@@ -959,50 +1130,20 @@ static void solve_group(int n, nsx_solver** W)
             for (int q = 0; q < n; ++q)
                 if (q != r) NSX_CUDA(cudaStreamWaitEvent(W[r]->stream, W[q]->ev[5], 0));
     };
-    // measured on B200: 15.0-15.6 us per sub-cycle against 14.2 us for the graph of two launches per sub-cycle (the
-    // grid barriers cost what the launches cost, and one CTA per SM leaves half the threads idle in each phase): off
-    static const bool persist_on = (env_int("NSX_PERSIST", 0) != 0);
-    if (n == 1 && W[0]->resident && W[0]->peers.empty() && nrun > 0) {
-        // EXPERIMENTAL: the whole sub-cycle loop in one launch with the state resident in shared memory / registers
-        nsx_solver* S = W[0];
-        KParams const& K = S->K;
-        bool const bbm = (K.dynamics_type == NSX_DYN_BBM);
-        ResidentArgs A{};
-        A.tiles = S->tiles.p; A.halo_nodes = S->halo_nodes.p; A.halo_elems = S->halo_elems.p; A.slot_conn = S->slot_conn.p;
-        A.slot_shape = S->slot_shape.p; A.slot_ec = S->slot_ec.p; A.nslots = S->plan.nslots; A.inc = S->inc.p;
-        A.s0 = S->sig[S->scur][0].p; A.s1 = S->sig[S->scur][1].p; A.s2 = S->sig[S->scur][2].p;
-        A.dm = bbm ? S->dmg[S->dcur].p : nullptr;
-        A.nflags = S->nflags.p; A.grad_ssh = S->grad_ssh.p; A.node_mass = S->node_mass.p; A.rlmass = S->rlmass.p;
-        A.cbu = S->cbu.p; A.fcor = S->fcor.p; A.tau_a = S->tau_a.p; A.tau_wi = S->have_tau_wi ? S->tau_wi.p : nullptr;
-        A.ocean = S->ocean.p; A.VTM = S->VTM.p;
-        A.VT0 = S->VT[0]; A.VT1 = S->VT[1]; A.cur = S->cur; A.UM = S->UM.p; A.UT = S->UT.p;
-        A.move_mesh = (K.dynamics_type != NSX_DYN_MEVP); A.nsub = nrun;
-        A.bar = S->ow_bar.p;
-        A.MS = S->plan.msp; A.MLN = S->plan.max_local_nodes + 2;
-        size_t const smem = (size_t)((bbm ? 15 : 11) * A.MS + 2 * A.MLN) * sizeof(double);
-        S->ow_bar.zero(S->stream);
-        if (bbm) k_resident<1><<<S->plan.ntiles, RES_TPB, smem, S->stream>>>(K, A);
-        else k_resident<0><<<S->plan.ntiles, RES_TPB, smem, S->stream>>>(K, A);
-        NSX_CUDA(cudaGetLastError());
-        S->n_launch++;
-        S->cur = (S->cur + nrun) & 1;
-    } else if (n == 1 && W[0]->direct && W[0]->peers.empty() && persist_on && nrun > 0) {
-        // a rank without neighbours on an L2-resident mesh: the whole sub-cycle loop is ONE persistent launch
-        nsx_solver* S = W[0];
-        KParams const& K = S->K;
-        bool const bbm = (K.dynamics_type == NSX_DYN_BBM);
-        SubArgs A{};
-        A.s0i = A.s0o = S->sig[S->scur][0].p; A.s1i = A.s1o = S->sig[S->scur][1].p; A.s2i = A.s2o = S->sig[S->scur][2].p;
-        A.di = A.dmo = bbm ? S->dmg[S->dcur].p : nullptr;
-        A.tau_wi = S->have_tau_wi ? S->tau_wi.p : nullptr;
-        DirectArgs D = direct_args(S, A, false);
-        S->d_done.zero(S->stream);
-        int const move = (K.dynamics_type != NSX_DYN_MEVP);
-        if (bbm) k_direct_persistent<1><<<S->sm_count, PERSIST_TPB, 0, S->stream>>>(K, D, nrun, move, S->VT[0], S->VT[1], S->cur, S->d_done.p);
-        else k_direct_persistent<0><<<S->sm_count, PERSIST_TPB, 0, S->stream>>>(K, D, nrun, move, S->VT[0], S->VT[1], S->cur, S->d_done.p);
-        NSX_CUDA(cudaGetLastError());
-        S->n_launch++;
-        S->cur = (S->cur + nrun) & 1;
+    bool const resident = W[0]->resident;
+    if (resident) {
+        // state-resident path: the sub-cycle loop AND the smoother of every rank are one persistent launch each.  Ranks
+        // of an in-process group run concurrently on their own streams and synchronise through the same flags as ranks
+        // on different GPUs, so together they must fit the device (NsxCreateOptions.max_sms).
+        int tiles_on_dev = 0;
+        for (int r = 0; r < n; ++r) {
+            if (!W[r]->resident) throw std::runtime_error("group solve: every rank must use the same path");
+            if (W[r]->device == W[0]->device) tiles_on_dev += W[r]->plan.ntiles;
+        }
+        if (n > 1 && tiles_on_dev > W[0]->sm_count)
+            throw std::runtime_error("group solve: the resident launches of the ranks sharing this GPU need " + std::to_string(tiles_on_dev) +
+                                     " SMs; create the handles with NsxCreateOptions.max_sms = SMs / ranks");
+        for (int r = 0; r < n; ++r) { NSX_CUDA(cudaSetDevice(W[r]->device)); launch_resident(W[r], nrun, n == 1); }
     } else {
         for (int s = 0; s < nrun; ++s) {
             for (int r = 0; r < n; ++r) { NSX_CUDA(cudaSetDevice(W[r]->device)); phase_substep(W[r], s, remote, remote && overlap_on); }
@@ -1012,9 +1153,9 @@ static void solve_group(int n, nsx_solver** W)
     for (int r = 0; r < n; ++r) {
         NSX_CUDA(cudaSetDevice(W[r]->device));
         record(W[r], 2);
-        phase_post_move(W[r], nrun);
+        if (!resident) phase_post_move(W[r], nrun);
     }
-    if (!W[0]->P.skip_ow_smoother) {
+    if (!W[0]->P.skip_ow_smoother && !resident) {
         for (int r = 0; r < n; ++r) { NSX_CUDA(cudaSetDevice(W[r]->device)); phase_ow_begin(W[r]); }
         if (n == 1 && W[0]->peers.empty()) {
             // no neighbours: all 50 sweeps (hard-coded count, FE.cpp:10580) in one launch with a grid barrier
@@ -1022,23 +1163,9 @@ static void solve_group(int n, nsx_solver** W)
             S->d_done.zero(S->stream);
             int const grid = std::max(1, std::min(nblk(S->ndof), S->sm_count));
             k_ow_smooth_all<<<grid, TPB, 0, S->stream>>>(S->nn, 50, S->ow_list.p, S->ow_count.p, S->n2n.p, S->n2n_deg.p,
-                                                         S->VT[S->cur], S->VT[S->cur ^ 1], S->d_done.p);
+                                                         S->VT[S->cur], S->VT[S->cur ^ 1], S->d_done.p, S->halo_err.p);
             S->n_launch++;
             NSX_CUDA(cudaGetLastError());
-        } else if (n == 1 && remote && env_int("NSX_OW_PERSIST", 0) != 0) {
-            // one process per GPU: the 50 sweeps AND their ghost exchanges in a single launch.  Measured on 2 B200s
-            // (weak bench): 0.73 ms per step against 0.68 ms for 50 launches of k_ow_sweep_exchange -- a sweep + exchange
-            // is bound by the NVLink fence / flag round trip (~13 us), not by launches; off by default.
-            nsx_solver* S = W[0];
-            static const bool ow_skip = (env_int("NSX_OW_SKIP", 1) != 0);
-            S->ow_bar.zero(S->stream);
-            HaloArgs aA = halo_args(S, S->cur, true), aB = halo_args(S, S->cur ^ 1, true);
-            int const grid = std::max(1, std::min(nblk(S->ndof), S->sm_count));
-            k_ow_smooth_exchange_all<<<grid, TPB, 0, S->stream>>>(aA, aB, 50, ow_skip ? 1 : 0, S->nn, S->ow_list.p, S->ow_count.p,
-                S->n2n.p, S->n2n_deg.p, S->VT[S->cur], S->VT[S->cur ^ 1], S->d_send_src.p, S->d_send_dst.p, S->push_ptr.p,
-                S->push_ent.p, S->ow_pair.p, S->ow_pair.p + 32, S->flags, S->d_epoch.p, S->ow_bar.p, 40000000LL, S->halo_err.p);
-            S->n_launch++;
-            NSX_CUDA(cudaGetLastError());            // 50 sweeps: the result is back in VT[cur]
         } else {
             for (int nit = 0; nit < 50; ++nit) {       // hard-coded 50 sweeps, FE.cpp:10580
                 if (n == 1 && remote) {
@@ -1046,7 +1173,6 @@ static void solve_group(int n, nsx_solver** W)
                     nsx_solver* S = W[0];
                     HaloArgs a = halo_args(S, S->cur ^ 1, true);
                     int const grid = std::max(1, std::min(nblk(S->ndof), S->sm_count));
-                    static const bool ow_skip = (env_int("NSX_OW_SKIP", 1) != 0);
                     int const mode = !ow_skip ? 2 : (nit == 0) ? 0 : (nit == 49) ? 2 : 1;
                     k_ow_sweep_exchange<<<grid, TPB, 0, S->stream>>>(a, mode, S->nn, S->ow_list.p, S->ow_count.p, S->n2n.p, S->n2n_deg.p,
                         S->VT[S->cur], S->VT[S->cur ^ 1], S->d_send_src.p, S->d_send_dst.p, S->push_ptr.p, S->push_ent.p,
@@ -1075,13 +1201,13 @@ static void solve_group(int n, nsx_solver** W)
 // explicitSolve() of one rank.  The whole launch sequence (2 prep kernels, `substeps` x {tile kernel[, halo]},
 // 50 smoother sweeps, tau_w) is captured once into a CUDA graph per entry parity of the ping-pong buffers and
 // replayed afterwards: at 2e5 elements a sub-cycle is a few microseconds of device work, less than the host
-// cost of launching its kernels one by one.  NSX_NO_GRAPH=1 disables this (debugging).
+// cost of launching its kernels one by one.  NsxCreateOptions.use_graph = 0 disables this (debugging).
 extern "C" int nsx_explicit_solve(nsx_handle S)
 {
     NSX_API_BEGIN(S)
     nsx_solver* W[1] = {S};
-    static const bool no_graph = (getenv("NSX_NO_GRAPH") != nullptr);
-    if (no_graph) {
+    ensure_res_flags(S);
+    if (!S->opt.use_graph) {
         solve_group(1, W);
     } else {
         if (!S->graph_valid) {
@@ -1131,7 +1257,7 @@ extern "C" int nsx_group_explicit_solve(int n, nsx_handle* hs)
 {
     if (n <= 0 || !hs || !hs[0]) return 1;
     try {
-        for (int r = 0; r < n; ++r) hs[r]->halo_local = true;
+        for (int r = 0; r < n; ++r) { hs[r]->halo_local = true; NSX_CUDA(cudaSetDevice(hs[r]->device)); ensure_res_flags(hs[r]); }
         solve_group(n, hs);
     } catch (std::exception const& e) { hs[0]->err = e.what(); return 2; }
     return 0;
@@ -1240,8 +1366,9 @@ extern "C" int nsx_forcing_load(nsx_handle S, int var, int slot, const double* d
     int const planes = forcing_planes(var);
     auto& buf = S->forcing[var][slot];
     if (!buf.p) buf.alloc((size_t)planes * S->nn);
-    NSX_CUDA(cudaMemcpyAsync(S->stage.p, data, (size_t)planes * S->nn * sizeof(double), cudaMemcpyHostToDevice, S->stream));
-    k_permute_in<<<nblk(S->nn), TPB, 0, S->stream>>>(S->nn, planes, S->node_perm.p, S->stage.p, buf.p);
+    if (S->arena.n < (size_t)planes * S->nn) { NSX_CUDA(cudaStreamSynchronize(S->stream)); S->arena.alloc((size_t)planes * S->nn); }
+    NSX_CUDA(cudaMemcpyAsync(S->arena.p, data, (size_t)planes * S->nn * sizeof(double), cudaMemcpyHostToDevice, S->stream));
+    k_permute_in<<<nblk(S->nn), TPB, 0, S->stream>>>(S->nn, planes, S->node_perm.p, S->arena.p, buf.p);
     NSX_CUDA(cudaGetLastError());
     NSX_CUDA(cudaStreamSynchronize(S->stream));             // the caller may reuse `data` right away
     S->forcing_loaded[var][slot] = true;

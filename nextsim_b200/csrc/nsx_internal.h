@@ -140,12 +140,20 @@ struct nsx_solver {
     nsx::DBuf<double> emass, ecbu;               // element mass, element C_bu
     nsx::DBuf<double> node_mass, rlmass, cbu, fcor, grad_ssh;
     nsx::DBuf<double> ec_e, contrib;             // direct path: element-space rheology constants, staged contributions
-    bool resident = false;                       // EXPERIMENTAL state-resident persistent solver (NSX_PATH=resident)
+    NsxCreateOptions opt{};
+    bool resident = false;                       // state-resident persistent solver (k_resident)
     bool direct = false;                         // L2-resident mesh: element kernel + node kernel instead of the tile kernel
-    nsx::DBuf<double> stage;                     // transfer staging (host numbering), max(2nn, 6ne)
-    nsx::DBuf<double> stage2;                    // second staging buffer, max(2nn, ne): copies and permutations overlap
-    cudaStream_t stream_copy = nullptr;          // host<->device copies of nsx_upload / nsx_download
-    cudaEvent_t ev_stage_copy[2] = {nullptr, nullptr}, ev_stage_perm[2] = {nullptr, nullptr};
+    // resident path
+    nsx::DBuf<nsx::ResTile> res_tiles;
+    nsx::DBuf<int> res_nbr;
+    nsx::DBuf<uint16_t> res_n2n;
+    nsx::DBuf<uint8_t> res_n2n_deg, halo_move;
+    nsx::DBuf<unsigned int> res_flags;           // tile flags followed by the per-exchange link arrival counters
+    size_t res_flag_words = 0;
+    int res_link_tiles[16] = {};                 // tiles of this rank that arrive on link i per exchange
+    int epoch_bump = 0;                          // exchanges the resident launch of the current graph performs
+    nsx::DBuf<double> arena;                     // transfer arena (host numbering): all fields of one upload / download call
+    int* h_err = nullptr;                        // pinned copy of the device error word
     nsx::DBuf<int> ow_list;                      // open-water nodes to smooth
     nsx::DBuf<int> ow_count;
     nsx::DBuf<int> check_i; nsx::DBuf<double> check_d;
@@ -162,7 +170,6 @@ struct nsx_solver {
     nsx::DBuf<unsigned int> d_done;              // block completion counter of k_halo_exchange
     int n_send_total = 0;
     nsx::DBuf<int> push_ptr; nsx::DBuf<int2> push_ent;   // owned node -> (send-peer slot, holder's ghost id)
-    nsx::DBuf<unsigned int> ow_bar;              // grid-barrier counter of the single-launch multi-rank smoother
     nsx::DBuf<int> ow_pair;                      // smoother: [0..32) my open-water bit per send peer, [32..64) active links
     nsx::DBuf<uint8_t> elem_nowrite;             // element written by a boundary tile (mixed direct/tile mode)
     nsx::DBuf<int> halo_err;                     // device error word (timeouts)

@@ -459,27 +459,16 @@ constexpr int SUB_CONS = SUB_TPB - SUB_PROD;    // consumer threads
 #endif
 constexpr int SUB_GROUPS = NSX_SUB_GROUPS;      // consumer groups, each working on its own tile (latency chains overlap)
 constexpr int SUB_GS = SUB_CONS / SUB_GROUPS;   // threads per consumer group
-#ifndef NSX_SUB_NODE_THREADS
-#define NSX_SUB_NODE_THREADS 0
-#endif
-// Role split of the consumers (0 = off): the last SUB_NODE_THREADS consumer threads only run phase 2 (nodes) and the
-// others only phase 1 (elements), so that phase 2 of tile t overlaps phase 1 of tile t+1; a third mbarrier ring
-// (p1done) hands the contributions from the element warps to the node warps.
-constexpr int SUB_NODE_THREADS = NSX_SUB_NODE_THREADS;
-constexpr int SUB_ELEM_THREADS = SUB_CONS - SUB_NODE_THREADS;
-static_assert(SUB_NODE_THREADS % 32 == 0 && (SUB_NODE_THREADS == 0 || SUB_GROUPS == 1), "role split needs whole warps, one group");
 static_assert(SUB_GS % 32 == 0 && SUB_GS * SUB_GROUPS == SUB_CONS, "consumer groups must be whole warps");
 static_assert(SUB_STAGES > SUB_GROUPS || SUB_GROUPS == 1, "need one more stage than tiles in compute");
-__device__ __forceinline__ void p2_sync();      // barrier over the threads that ran phase 2 (defined below)
 __device__ __forceinline__ void cons_sync(int group)
 {
     asm volatile("bar.sync %0, %1;" ::"r"(1 + group), "n"(SUB_GS) : "memory");
 }
 
-__device__ __forceinline__ void p2_sync()
+__device__ __forceinline__ void p2_sync()       // barrier over the consumer threads of group 0 (fused halo epilogue)
 {
-    if (SUB_NODE_THREADS > 0) asm volatile("bar.sync 3, %0;" ::"n"(SUB_NODE_THREADS > 0 ? SUB_NODE_THREADS : 32) : "memory");
-    else asm volatile("bar.sync 1, %0;" ::"n"(SUB_GS) : "memory");
+    asm volatile("bar.sync 1, %0;" ::"n"(SUB_GS) : "memory");
 }
 
 // Persistent, warp-specialised, double-buffered: CTA b works on tiles b, b+grid, b+2*grid, ... of its launch
@@ -500,14 +489,11 @@ k_subcycle(KParams K, SubArgs A)
     int const tid = threadIdx.x;
     uint64_t* const full = (uint64_t*)sm_all;
     uint64_t* const empty = full + SUB_STAGES;
-    uint64_t* const p1done = empty + SUB_STAGES;
-    constexpr bool SPLIT = SUB_NODE_THREADS > 0;
     unsigned char* const stage0 = sm_all + 128;     // header: barriers [0,96), fused-halo flag at 120
     if (tid == 0) {
         for (int q = 0; q < SUB_STAGES; ++q) {
             mbar_init(full + q, SUB_PROD / 32);       // one arrival (with its TMA bytes) per producer warp
-            mbar_init(empty + q, (SPLIT ? SUB_NODE_THREADS : SUB_GS) / 32);   // one arrival per warp that reads the stage last
-            mbar_init(p1done + q, SUB_ELEM_THREADS / 32);
+            mbar_init(empty + q, SUB_GS / 32);        // one arrival per consumer warp of the group that reads the stage
         }
     }
     __syncthreads();
@@ -547,16 +533,13 @@ k_subcycle(KParams K, SubArgs A)
     }
 
     // ---- consumers ----
-    bool const node_role = SPLIT && tid >= SUB_ELEM_THREADS;
-    bool const do_p1 = !SPLIT || !node_role, do_p2 = !SPLIT || node_role;
-    int const grp = SPLIT ? 0 : tid / SUB_GS;   // consumer group; it takes tiles grp, grp + SUB_GROUPS, ...
-    int const gtid = SPLIT ? (node_role ? tid - SUB_ELEM_THREADS : tid) : tid - grp * SUB_GS;
-    int const gstride = SPLIT ? (node_role ? SUB_NODE_THREADS : SUB_ELEM_THREADS) : SUB_GS;
+    int const grp = tid / SUB_GS;               // consumer group; it takes tiles grp, grp + SUB_GROUPS, ...
+    int const gtid = tid - grp * SUB_GS;
+    int const gstride = SUB_GS;
     for (int it = grp; it < n_my; it += SUB_GROUPS) {
     int const s = it % SUB_STAGES;
     unsigned char* const sm = stage0 + (size_t)s * L.total;
-    if (node_role) mbar_wait(p1done + s, (it / SUB_STAGES) & 1);      // implies the stage is full
-    else mbar_wait(full + s, (it / SUB_STAGES) & 1);
+    mbar_wait(full + s, (it / SUB_STAGES) & 1);
     TileDesc const td = *(const TileDesc*)(sm + L.bar);
 
     // shifted views of the staged planes
@@ -579,7 +562,6 @@ k_subcycle(KParams K, SubArgs A)
 
     // ---- phase 1 ----
     int const nsl = td.n_own_slots + td.n_halo_slots;
-    if (do_p1)
     for (int k = gtid; k < nsl; k += gstride) {
         bool const own = k < td.n_own_slots;
         int const e = td.elem_begin + k;            // meaningful for writer slots only
@@ -666,11 +648,7 @@ k_subcycle(KParams K, SubArgs A)
         shp[4 * MSP + k] = vol * (s2 * dx1 + s1 * dy1);
         shp[5 * MSP + k] = vol * (s2 * dx2 + s1 * dy2);
     }
-    if (SPLIT) {
-        if (!node_role) { __syncwarp(); if ((tid & 31) == 0) mbar_arrive(p1done + s); continue; }
-    } else {
-        cons_sync(grp);
-    }
+    cons_sync(grp);
 
     // ---- phase 2 ----
     const double* const npl = (const double*)(sm + L.node);
@@ -749,7 +727,7 @@ k_subcycle(KParams K, SubArgs A)
     if ((tid & 31) == 0) mbar_arrive(empty + s);
     }   // tile loop
 
-    if (A.fuse_halo && do_p2) {
+    if (A.fuse_halo) {
         // every sent value of this CTA is on its way: count the CTA in; the last one publishes the epoch in every
         // holder's flag slot (release, system scope) and waits for the owners of this rank's ghosts (bounded spin)
         volatile int& s_last = *(volatile int*)(sm_all + 120);
@@ -959,74 +937,141 @@ k_node_direct(KParams K, DirectArgs A, int move_mesh, int lag_ghost_move, int sk
     direct_node<0>(K, A, n, move_mesh, lag_ghost_move, skip_flag_mask, VTc, VTn);
 }
 
-// Whole sub-cycle loop of a rank WITHOUT neighbours in one launch: a persistent grid (one CTA per SM, all
-// resident) alternates the element phase and the node phase, separated by a software grid barrier.  No kernel
-// boundaries (a dependent launch costs ~3 us, a sub-cycle of the 2e5-element mesh ~8 us of work), sigma/damage
-// are updated in place, VT ping-pongs between the two buffers exactly like the launch-per-phase variant.
-constexpr int PERSIST_TPB = 768;
-
-__device__ __forceinline__ void grid_barrier(unsigned int* ctr, unsigned int& target)
-{
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        target += gridDim.x;
-        __threadfence();
-        atomicAdd(ctr, 1u);
-        unsigned int v;
-        long long spins = 0;                // bounded: a grid that is not fully resident must not hang the GPU
-        do { asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory"); } while (v < target && ++spins < (1LL << 31));
-        __threadfence();                    // also drops this SM's L1 lines: the next phase reads other SMs' results
-    }
-    __syncthreads();
-}
-
-template <int BBM>
-__global__ void __launch_bounds__(PERSIST_TPB, 1)
-k_direct_persistent(KParams K, DirectArgs A, int nsub, int move_mesh, double* VT0, double* VT1, int cur, unsigned int* bar)
-{
-    unsigned int target = 0;
-    int const gt = blockIdx.x * blockDim.x + threadIdx.x, gn = gridDim.x * blockDim.x;
-    for (int s = 0; s < nsub; ++s) {
-        const double* VTc = ((cur + s) & 1) ? VT1 : VT0;
-        double* VTn = ((cur + s) & 1) ? VT0 : VT1;
-        for (int e = gt; e < K.ne; e += gn) direct_element<BBM, 1>(K, A, e, VTc);
-        grid_barrier(bar, target);
-        for (int n = gt; n < K.nn; n += gn) direct_node<1>(K, A, n, move_mesh, 0, 0, VTc, VTn);
-        grid_barrier(bar, target);
-    }
-}
-
 // ---------------------------------------------------------------------------------------------------
-// EXPERIMENTAL (NSX_PATH=resident, off by default, written at the end of round 1 and NOT yet validated on a GPU):
-// state-resident persistent solver for meshes of the headline class (<= ~2.2e5 elements on one GPU).
+// State-resident persistent solver for meshes whose sub-cycle state fits the shared memory and registers of the GPU
+// (<= ~2.2e5 elements per B200: the headline 10 km mesh, the weak-scaling points, the 3 km mesh on 8 GPUs).
 //
-// One CTA per SM owns ONE large tile (ndof / #SMs owned nodes, ~1350 elements + ~10 % redundant halo slots) for the
-// whole sub-cycle loop of a model step.  Shape coefficients, rheology constants and the stress of every slot stay in
-// shared memory (120 B per slot), damage and the slot connectivity in registers of the thread that owns the slot,
-// the velocity of the tile's local nodes in shared memory, UM / UT of the owned nodes in registers.  Per sub-cycle the
-// only global traffic is: node constants re-read from L2 (88 B per node), the owned velocities written to the
-// ping-pong VT buffer, one grid barrier, and the halo-node velocities read back (~15 % of the nodes).  HBM is not
-// touched inside the loop.  Same arithmetic and the same summation order as k_subcycle; contributions are recomputed
-// in phase 2 from the resident stress instead of being staged, so results may differ from the other paths in the
-// last bit (FMA contraction), well inside the 1e-9 tolerance.
+// ONE launch runs the whole sub-cycle loop AND the 50 open-water smoother sweeps of a model step.  One CTA per SM owns
+// one large tile (ndof / #SMs owned nodes, ~1350 elements + ~10 % redundant halo slots): shape coefficients, rheology
+// constants and the stress of every slot stay in shared memory (120 B per slot), damage and the slot connectivity in
+// registers of the thread that owns the slot, the velocity of the tile's local nodes in shared memory, UM / UT and the
+// incidence list of the owned node in registers.  HBM is not touched inside the loop.
+//
+// Synchronisation is point to point, not grid wide.  A tile publishes the velocities of its EXPORT nodes (owned nodes
+// another tile or another rank reads) in the ping-pong VT buffer and then a release flag; a tile waits only for the
+// flags of the <= ~8 tiles that own its halo nodes.  Ghost nodes work the same way across GPUs: export nodes on a
+// send list are stored straight into the holder's VT buffer over NVLink, the last tile of the rank to finish its
+// pushes for a neighbour rank publishes the exchange epoch there (st.release.sys), and only tiles that read that
+// neighbour's ghosts wait for its epoch (this is FiniteElement::updateGhosts, FE.cpp:13963-13996, per tile).
+// The per-sub-cycle schedule hides that latency behind the interior work (plan order: export nodes first, "early"
+// slots -- those touching an export or halo node -- first):
+//     1. stress of the LATE slots (interior: no halo node, no export node)            needs nothing from outside
+//     2. wait for the neighbours' flags of the previous sub-cycle, refresh the halo velocities, move the ghosts
+//     3. stress of the EARLY slots
+//     4. nodal solve of the EXPORT nodes -> VT buffer (+ NVLink pushes) -> publish
+//     5. nodal solve of the other owned nodes (shared memory only)
+// Two VT buffers are enough: a neighbour can publish sub-cycle s+1 only after it has read my sub-cycle s, which I
+// publish after my last read of sub-cycle s-1 (the neighbour relation is symmetric, between tiles and between ranks).
+// Same arithmetic and summation order as the other paths; the nodal contributions are recomputed from the resident
+// stress instead of being staged, so results may differ from them in the last bit (FMA contraction).
+// All spins are bounded and report through the halo error word.
 // ---------------------------------------------------------------------------------------------------
 #ifndef NSX_RES_TPB
 #define NSX_RES_TPB 768
 #endif
 constexpr int RES_TPB = NSX_RES_TPB;
 constexpr int RES_SPT = 3;                      // slots per thread (static unroll): tiles of up to 3 * RES_TPB slots
+constexpr int RES_MAX_LINKS = 16;               // neighbour ranks of one rank
+constexpr int RES_FLAG_STRIDE = 32;             // tile flags live 128 B apart
+
+struct ResPeers {
+    int n_link;                                 // neighbour ranks (send or receive relation)
+    double* send_vt[2][RES_MAX_LINKS];          // per send slot (push_ent.x) and parity: the holder's VT buffer
+    int send_nn[RES_MAX_LINKS];
+    unsigned long long* link_flag[RES_MAX_LINKS];   // the neighbour's flag slot for me
+    int link_rank[RES_MAX_LINKS];               // my flag slot that neighbour writes
+    int link_tiles[RES_MAX_LINKS];              // how many of my tiles arrive on that link per exchange
+};
 
 struct ResidentArgs {
-    const TileDesc* tiles; const int* halo_nodes; const int* halo_elems; const unsigned long long* slot_conn;
+    const TileDesc* tiles; const ResTile* rtiles; const int* nbr;
+    const int* halo_nodes; const uint8_t* halo_move; const int* halo_elems; const unsigned long long* slot_conn;
     const double* slot_shape; const double* slot_ec; int nslots; const uint16_t* inc;
+    const uint16_t* n2n_loc; const uint8_t* n2n_deg;
     double* s0; double* s1; double* s2; double* dm;               // updated in place at the end of the loop
     const uint8_t* nflags; const double* grad_ssh; const double* node_mass; const double* rlmass; const double* cbu;
     const double* fcor; const double* tau_a; const double* tau_wi; const double* ocean; const double* VTM;
     double* VT0; double* VT1; int cur; double* UM; double* UT;
-    int move_mesh, nsub;
-    unsigned int* bar;
+    int move_mesh, nsub, nsweeps;
+    const int* ow_count;
+    unsigned int* tile_flags;                                     // [ntiles * RES_FLAG_STRIDE], zeroed before the launch
+    unsigned int* arrive;                                         // [(nsub + nsweeps + 1) * RES_MAX_LINKS], zeroed before the launch
+    const int* push_ptr; const int2* push_ent;
+    const unsigned long long* my_flags; const unsigned long long* epoch_ctr; int* err;
     int MS, MLN;                                                  // shared-memory strides: slots per plane, local nodes
+    ResPeers P;
 };
+
+// stress (and damage) update of one resident slot; returns the new damage
+template <int BBM>
+__device__ __forceinline__ double res_slot_update(KParams const& K, int k, unsigned long long pc, double d, int MS,
+                                                  const double* shp, const double* ecp, double* sgp, const double* su, const double* sv)
+{
+    int const la = (int)(pc & 0xFFFF), lb = (int)((pc >> 16) & 0xFFFF), lc = (int)((pc >> 32) & 0xFFFF);
+    double const dx0 = shp[k], dx1 = shp[MS + k], dx2 = shp[2 * MS + k];
+    double const dy0 = shp[3 * MS + k], dy1 = shp[4 * MS + k], dy2 = shp[5 * MS + k];
+    double const c0 = ecp[k];
+    double s0, s1, s2;
+    if (BBM) {
+        double const expC = c0;
+        if (expC == 0.) {                   // conc <= 0.1 : no ice (FE.cpp:4151-4159)
+            s0 = s1 = s2 = 0.;
+            d = 0.;
+        } else {
+            double const ua = su[la], va = sv[la], ub = su[lb], vb = sv[lb], uc = su[lc], vc = sv[lc];
+            double e0 = dx0 * ua; e0 += dx1 * ub; e0 += dx2 * uc;
+            double e1 = dy0 * va; e1 += dy1 * vb; e1 += dy2 * vc;
+            double e2 = dy0 * ua; e2 += dx0 * va; e2 += dy1 * ub; e2 += dx1 * vb; e2 += dy2 * uc; e2 += dx2 * vc;
+            s0 = sgp[k]; s1 = sgp[MS + k]; s2 = sgp[2 * MS + k];
+            double const dt = K.dte;
+            double sigma_n = (s0 + s1) * 0.5;
+            double const omd = 1. - d;
+            double const time_viscous = K.lambda0 * pow_relax(omd * expC, K);
+            double tildeP = 0.;
+            if (sigma_n < 0.) tildeP = fmin(1., fast_div(-ecp[MS + k], sigma_n));
+            double const mult = fmin(1. - 1e-12, fast_div(time_viscous, time_viscous + dt * (1. - tildeP)));
+            double const elasticity = K.young * omd * expC;
+            double const dtE = dt * elasticity;
+            s0 += dtE * K.D00 * e0;  s0 += dtE * K.D01 * e1;  s0 *= mult;
+            s1 += dtE * K.D01 * e0;  s1 += dtE * K.D00 * e1;  s1 *= mult;
+            s2 += dtE * K.D22 * e2;                           s2 *= mult;
+            double const sigma_s = fast_hypot((s0 - s1) * 0.5, s2);
+            sigma_n = (s0 + s1) * 0.5;
+            double dcrit;
+            if (sigma_n < -K.compr_strength) dcrit = fast_div(-K.compr_strength, sigma_n);
+            else dcrit = fast_div(ecp[2 * MS + k], sigma_s + K.tan_phi * sigma_n);
+            if ((0. < dcrit) && (dcrit < 1.)) {
+                double const rtd = fast_sqrt(elasticity) * ecp[3 * MS + k];
+                double const f = (1. - dcrit) * dt * rtd;
+                d += omd * f;
+                s0 -= s0 * f;  s1 -= s1 * f;  s2 -= s2 * f;
+            }
+            d = fmax(0., d - ecp[4 * MS + k]);
+        }
+    } else {
+        double const Pp = c0;
+        if (Pp < 0.) {                      // thick == 0 (FE.cpp:10656-10662)
+            s0 = s1 = s2 = 0.;
+        } else {
+            double const ua = su[la], va = sv[la], ub = su[lb], vb = sv[lb], uc = su[lc], vc = sv[lc];
+            double eps11 = dx0 * ua; eps11 += dx1 * ub; eps11 += dx2 * uc;
+            double eps22 = dy0 * va; eps22 += dy1 * vb; eps22 += dy2 * vc;
+            double eps12 = 0.5 * (dx0 * va + dy0 * ua); eps12 += 0.5 * (dx1 * vb + dy1 * ub); eps12 += 0.5 * (dx2 * vc + dy2 * uc);
+            double const eps1 = eps11 + eps22, eps2 = eps11 - eps22;
+            double const delta = fast_sqrt(eps1 * eps1 + (eps2 * eps2 + 4 * eps12 * eps12) * K.re2);
+            double const zeta = fast_div(Pp, delta + K.evp_dmin);
+            s0 = sgp[k]; s1 = sgp[MS + k]; s2 = sgp[2 * MS + k];
+            double sigma1 = s0 + s1, sigma2 = s0 - s1;
+            sigma1 += K.ralpha1 * (zeta * (eps1 - delta) - sigma1);
+            sigma2 += K.ralpha2 * (zeta * eps2 * K.re2 - sigma2);
+            s2 += K.ralpha2 * (zeta * eps12 * K.re2 - s2);
+            s0 = 0.5 * (sigma1 + sigma2);
+            s1 = 0.5 * (sigma1 - sigma2);
+        }
+    }
+    sgp[k] = s0; sgp[MS + k] = s1; sgp[2 * MS + k] = s2;
+    return d;
+}
 
 template <int BBM>
 __global__ void __launch_bounds__(RES_TPB, 1)
@@ -1038,22 +1083,29 @@ k_resident(KParams K, ResidentArgs A)
     double* const shp = (double*)sm_res;                          // [6][MS]
     double* const ecp = shp + 6 * (size_t)MS;                     // [NEC][MS]
     double* const sgp = ecp + NEC * (size_t)MS;                   // [3][MS]
-    double* const su = sgp + 3 * (size_t)MS;                      // [MLN]
+    unsigned long long* const cnp = (unsigned long long*)(sgp + 3 * (size_t)MS);   // [MS] slot connectivity (3 x u16 local ids)
+    double* const su = (double*)(cnp + MS);                       // [MLN]
     double* const sv = su + MLN;                                  // [MLN]
-    TileDesc const td = A.tiles[blockIdx.x];
+    // tile descriptors live in shared memory (broadcast reads): registers are the scarce resource of this kernel
+    __shared__ TileDesc td;
+    __shared__ ResTile rt;
+    if (tid == 0) { td = A.tiles[blockIdx.x]; rt = A.rtiles[blockIdx.x]; }
+    __syncthreads();
     int const nsl = td.n_own_slots + td.n_halo_slots;
     size_t const NS = (size_t)A.nslots;
+    ResPeers const& P = A.P;
+    unsigned long long const epoch0 = P.n_link ? *A.epoch_ctr : 0ULL;
+    int const link_mask = P.n_link ? rt.link_mask : 0;
 
     // ---- load the tile once ----
-    unsigned long long conn[RES_SPT];
     double dmg[RES_SPT];
 #pragma unroll
     for (int q = 0; q < RES_SPT; ++q) {
         int const k = tid + q * RES_TPB;
-        conn[q] = 0ULL; dmg[q] = 0.;
+        dmg[q] = 0.;
         if (k < nsl) {
             size_t const g = (size_t)td.slot_begin + k;
-            conn[q] = A.slot_conn[g];
+            cnp[k] = A.slot_conn[g];
 #pragma unroll
             for (int c = 0; c < 6; ++c) shp[c * MS + k] = A.slot_shape[c * NS + g];
 #pragma unroll
@@ -1063,157 +1115,246 @@ k_resident(KParams K, ResidentArgs A)
             if (BBM) dmg[q] = A.dm[e];
         }
     }
-    double* VTr = A.cur ? A.VT1 : A.VT0;                          // buffer holding the current velocity
-    double* VTw = A.cur ? A.VT0 : A.VT1;
-    for (int j = tid; j < td.n_own; j += RES_TPB) { su[j] = VTr[td.node_begin + j]; sv[j] = VTr[td.node_begin + j + nn]; }
-    for (int h = tid; h < td.n_halo; h += RES_TPB) {
-        int const g = A.halo_nodes[td.halo_off + h];
-        su[td.n_own + HALO_GAP + h] = VTr[g]; sv[td.n_own + HALO_GAP + h] = VTr[g + nn];
+    auto VTb = [&](int parity) -> double* { return parity ? A.VT1 : A.VT0; };
+    {
+        const double* VTr = VTb(A.cur & 1);
+        for (int j = tid; j < td.n_own; j += RES_TPB) { su[j] = VTr[td.node_begin + j]; sv[j] = VTr[td.node_begin + j + nn]; }
+        for (int h = tid; h < td.n_halo; h += RES_TPB) {
+            int const g = A.halo_nodes[td.halo_off + h];
+            su[td.n_own + HALO_GAP + h] = VTr[g]; sv[td.n_own + HALO_GAP + h] = VTr[g + nn];
+        }
     }
     bool const has_node = tid < td.n_own;                         // one owned node per thread (checked by the host)
-    int const n = td.node_begin + tid;
+    int const n = td.node_begin + (has_node ? tid : 0);
     uint8_t const fl = has_node ? A.nflags[n] : (uint8_t)NF_DIRICHLET;
-    double umu = 0., umv = 0., utu = 0., utv = 0.;
-    if (has_node && A.move_mesh) { umu = A.UM[n]; umv = A.UM[n + nn]; utu = A.UT[n]; utv = A.UT[n + nn]; }
-    unsigned int bar_target = 0;
+    double const nmass = has_node ? A.node_mass[n] : 1.;
+    bool const solve_node = has_node && !(fl & NF_DIRICHLET) && nmass != 0.;
+    // displacement of the owned node over the launch: M_UM and M_UT receive the same increments dte*VT every sub-cycle
+    // (FE.cpp:10545-10549), so one accumulator serves both (added once at the end; M_UM of Neumann nodes is restored)
+    double dspu = 0., dspv = 0.;
+    // incidence list of the owned node, pre-decoded (slot | vertex << 14), 8 entries in registers
+    unsigned int incr[4] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu};
+    if (has_node) {
+        const uint16_t* ip = A.inc + td.inc_off + tid;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            if (c >= td.inc_w) break;
+            unsigned const code = ip[(size_t)c * td.n_own];
+            unsigned dec = 0xFFFFu;
+            if (code != 0xFFFFu) { unsigned const i = code / (unsigned)MS; dec = (code - i * (unsigned)MS) | (i << 14); }
+            incr[c >> 1] = (c & 1) ? ((incr[c >> 1] & 0x0000FFFFu) | (dec << 16)) : ((incr[c >> 1] & 0xFFFF0000u) | dec);
+        }
+    }
+    // the first halo node this thread refreshes, and whether this tile moves it (ghost nodes: FE.cpp:10539-10553)
+    int const hg0 = (tid < td.n_halo) ? A.halo_nodes[td.halo_off + tid] : 0;
+    bool const hmove0 = (tid < td.n_halo) && A.halo_move[td.halo_off + tid];
+    int const my_nbr = (tid < rt.n_nbr) ? A.nbr[rt.nbr_off + tid] : -1;
     __syncthreads();
 
-    for (int s = 0; s < A.nsub; ++s) {
-        // ---- phase 1: stress (and damage) of every slot of the tile ----
+    // ---- helpers ----
+    auto phase1 = [&](bool early) {
 #pragma unroll
         for (int q = 0; q < RES_SPT; ++q) {
             int const k = tid + q * RES_TPB;
-            if (k >= nsl) continue;
-            unsigned long long const pc = conn[q];
-            int const la = (int)(pc & 0xFFFF), lb = (int)((pc >> 16) & 0xFFFF), lc = (int)((pc >> 32) & 0xFFFF);
-            double const dx0 = shp[k], dx1 = shp[MS + k], dx2 = shp[2 * MS + k];
-            double const dy0 = shp[3 * MS + k], dy1 = shp[4 * MS + k], dy2 = shp[5 * MS + k];
-            double const c0 = ecp[k];
-            double s0, s1, s2;
-            if (BBM) {
-                double const expC = c0;
-                double d = dmg[q];
-                if (expC == 0.) {                   // conc <= 0.1 : no ice (FE.cpp:4151-4159)
-                    s0 = s1 = s2 = 0.;
-                    d = 0.;
-                } else {
-                    double const ua = su[la], va = sv[la], ub = su[lb], vb = sv[lb], uc = su[lc], vc = sv[lc];
-                    double e0 = dx0 * ua; e0 += dx1 * ub; e0 += dx2 * uc;
-                    double e1 = dy0 * va; e1 += dy1 * vb; e1 += dy2 * vc;
-                    double e2 = dy0 * ua; e2 += dx0 * va; e2 += dy1 * ub; e2 += dx1 * vb; e2 += dy2 * uc; e2 += dx2 * vc;
-                    s0 = sgp[k]; s1 = sgp[MS + k]; s2 = sgp[2 * MS + k];
-                    double const dt = K.dte;
-                    double sigma_n = (s0 + s1) * 0.5;
-                    double const omd = 1. - d;
-                    double const time_viscous = K.lambda0 * pow_relax(omd * expC, K);
-                    double tildeP = 0.;
-                    if (sigma_n < 0.) tildeP = fmin(1., fast_div(-ecp[MS + k], sigma_n));
-                    double const mult = fmin(1. - 1e-12, fast_div(time_viscous, time_viscous + dt * (1. - tildeP)));
-                    double const elasticity = K.young * omd * expC;
-                    double const dtE = dt * elasticity;
-                    s0 += dtE * K.D00 * e0;  s0 += dtE * K.D01 * e1;  s0 *= mult;
-                    s1 += dtE * K.D01 * e0;  s1 += dtE * K.D00 * e1;  s1 *= mult;
-                    s2 += dtE * K.D22 * e2;                           s2 *= mult;
-                    double const sigma_s = fast_hypot((s0 - s1) * 0.5, s2);
-                    sigma_n = (s0 + s1) * 0.5;
-                    double dcrit;
-                    if (sigma_n < -K.compr_strength) dcrit = fast_div(-K.compr_strength, sigma_n);
-                    else dcrit = fast_div(ecp[2 * MS + k], sigma_s + K.tan_phi * sigma_n);
-                    if ((0. < dcrit) && (dcrit < 1.)) {
-                        double const rtd = fast_sqrt(elasticity) * ecp[3 * MS + k];
-                        double const f = (1. - dcrit) * dt * rtd;
-                        d += omd * f;
-                        s0 -= s0 * f;  s1 -= s1 * f;  s2 -= s2 * f;
-                    }
-                    d = fmax(0., d - ecp[4 * MS + k]);
-                }
-                dmg[q] = d;
-            } else {
-                double const Pp = c0;
-                if (Pp < 0.) {                      // thick == 0 (FE.cpp:10656-10662)
-                    s0 = s1 = s2 = 0.;
-                } else {
-                    double const ua = su[la], va = sv[la], ub = su[lb], vb = sv[lb], uc = su[lc], vc = sv[lc];
-                    double eps11 = dx0 * ua; eps11 += dx1 * ub; eps11 += dx2 * uc;
-                    double eps22 = dy0 * va; eps22 += dy1 * vb; eps22 += dy2 * vc;
-                    double eps12 = 0.5 * (dx0 * va + dy0 * ua); eps12 += 0.5 * (dx1 * vb + dy1 * ub); eps12 += 0.5 * (dx2 * vc + dy2 * uc);
-                    double const eps1 = eps11 + eps22, eps2 = eps11 - eps22;
-                    double const delta = fast_sqrt(eps1 * eps1 + (eps2 * eps2 + 4 * eps12 * eps12) * K.re2);
-                    double const zeta = fast_div(Pp, delta + K.evp_dmin);
-                    s0 = sgp[k]; s1 = sgp[MS + k]; s2 = sgp[2 * MS + k];
-                    double sigma1 = s0 + s1, sigma2 = s0 - s1;
-                    sigma1 += K.ralpha1 * (zeta * (eps1 - delta) - sigma1);
-                    sigma2 += K.ralpha2 * (zeta * eps2 * K.re2 - sigma2);
-                    s2 += K.ralpha2 * (zeta * eps12 * K.re2 - s2);
-                    s0 = 0.5 * (sigma1 + sigma2);
-                    s1 = 0.5 * (sigma1 - sigma2);
+            bool const is_early = (k < rt.n_early_own) || (k >= td.n_own_slots);
+            if (k >= nsl || is_early != early) continue;
+            dmg[q] = res_slot_update<BBM>(K, k, cnp[k], dmg[q], MS, shp, ecp, sgp, su, sv);
+        }
+    };
+    // nodal solve of this thread's node (FE.cpp:10445-10529): contributions in ascending reference element order
+    auto node_solve = [&](double& un, double& vn) {
+        double const uice = su[tid], vice = sv[tid];
+        un = uice; vn = vice;
+        if (!solve_node) return;
+        double gu = __ldg(A.grad_ssh + n), gv = __ldg(A.grad_ssh + n + nn);
+        double const rl = __ldg(A.rlmass + n), cb = __ldg(A.cbu + n), fc = __ldg(A.fcor + n);
+        double tau_x = __ldg(A.tau_a + n), tau_y = __ldg(A.tau_a + n + nn);
+        double const ou = __ldg(A.ocean + n), ov = __ldg(A.ocean + n + nn);
+        if (A.tau_wi) { tau_x = tau_x + __ldg(A.tau_wi + n); tau_y = tau_y + __ldg(A.tau_wi + n + nn); }
+        bool more = true;
+        // keep the packed codes opaque: otherwise the compiler hoists the 8 x 3 decoded shared-memory addresses out of the
+        // sub-cycle loop and spills them (registers are the scarce resource here; the decode is two shifts)
+        asm volatile("" : "+r"(incr[0]), "+r"(incr[1]), "+r"(incr[2]), "+r"(incr[3]));
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            unsigned const code = (incr[c >> 1] >> (16 * (c & 1))) & 0xFFFFu;
+            if (code == 0xFFFFu) { more = false; break; }
+            int const i = (int)(code >> 14), k = (int)(code & 0x3FFFu);
+            double const a0 = sgp[k], a1 = sgp[MS + k], a2 = sgp[2 * MS + k];
+            double const vol = ecp[(BBM ? 5 : 1) * MS + k];
+            double const dxi = shp[i * MS + k], dyi = shp[(3 + i) * MS + k];
+            gu -= vol * (a0 * dxi + a2 * dyi);           // V*(sigma . grad N_i), FE.cpp:10464-10465
+            gv -= vol * (a2 * dxi + a1 * dyi);
+        }
+        if (more && td.inc_w > 8) {                      // nodes with more than 8 incident elements: rest from the table
+            const uint16_t* ip = A.inc + td.inc_off + tid;
+            for (int c = 8; c < td.inc_w; ++c) {
+                unsigned const code = __ldg(ip + (size_t)c * td.n_own);
+                if (code == 0xFFFFu) break;
+                int const i = (int)(code / (unsigned)MS), k = (int)(code - (unsigned)i * (unsigned)MS);
+                double const a0 = sgp[k], a1 = sgp[MS + k], a2 = sgp[2 * MS + k];
+                double const vol = ecp[(BBM ? 5 : 1) * MS + k];
+                double const dxi = shp[i * MS + k], dyi = shp[(3 + i) * MS + k];
+                gu -= vol * (a0 * dxi + a2 * dyi);
+                gv -= vol * (a2 * dxi + a1 * dyi);
+            }
+        }
+        double dtep = K.dte, delu = 0., delv = 0.;
+        if (K.dynamics_type == NSX_DYN_MEVP) {
+            delu = (__ldg(A.VTM + n) - uice) * K.mevp_rb;
+            delv = (__ldg(A.VTM + n + nn) - vice) * K.mevp_rb;
+            dtep = K.dte_mevp;
+        }
+        double const dte_over_mass = fast_div(dtep, fmax(K.min_m, nmass));
+        double const c_prime = K.rhow_cdw * fast_hypot(ou - uice, ov - vice);
+        double const tau_b = cb * fast_div(1., fast_hypot(uice, vice) + K.u0);
+        double const sin_s = (fl & NF_LATNEG) ? -K.sin_ota_abs : K.sin_ota_abs;
+        double const alpha = 1. + dte_over_mass * (c_prime * K.cos_ota + tau_b);
+        double const beta = dtep * fc + dte_over_mass * c_prime * sin_s;
+        double const rdenom = fast_div(1., alpha * alpha + beta * beta);
+        tau_x = tau_x + c_prime * (ou * K.cos_ota - ov * sin_s);
+        tau_y = tau_y + c_prime * (ov * K.cos_ota + ou * sin_s);
+        double const grad_x = gu * rl, grad_y = gv * rl;
+        un = alpha * uice + beta * vice + dte_over_mass * (alpha * (grad_x + tau_x) + beta * (grad_y + tau_y)) + alpha * delu + beta * delv;
+        un *= rdenom;
+        vn = alpha * vice - beta * uice + dte_over_mass * (alpha * (grad_y + tau_y) - beta * (grad_x + tau_x)) + alpha * delv - beta * delu;
+        vn *= rdenom;
+    };
+    // export node -> ping-pong buffer of this rank and the ghost slots of every holder (updateGhosts, FE.cpp:13963-13996)
+    auto publish_node = [&](double* VTw, int parity, double un, double vn) {
+        VTw[n] = un; VTw[n + nn] = vn;
+        if (link_mask) {
+            int const q1 = A.push_ptr[n + 1];
+            for (int q = A.push_ptr[n]; q < q1; ++q) {
+                int2 const pe = A.push_ent[q];
+                double* const dst = P.send_vt[parity][pe.x];
+                dst[pe.y] = un;
+                dst[pe.y + P.send_nn[pe.x]] = vn;
+            }
+        }
+    };
+    // exchange number ex (1-based): every export value of this tile is stored; release the tile flag, arrive on my links
+    auto signal = [&](int ex) {
+        __syncthreads();
+        if (tid == 0) {
+            if (link_mask) __threadfence_system(); else __threadfence();
+            asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(A.tile_flags + (size_t)blockIdx.x * RES_FLAG_STRIDE), "r"((unsigned)ex) : "memory");
+            for (int i = 0; i < P.n_link; ++i) {
+                if (!((link_mask >> i) & 1)) continue;
+                unsigned const old = atomicAdd(A.arrive + (size_t)ex * RES_MAX_LINKS + i, 1u);
+                if ((int)old + 1 == P.link_tiles[i]) {
+                    __threadfence_system();
+                    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(P.link_flag[i]), "l"(epoch0 + (unsigned long long)ex) : "memory");
                 }
             }
-            sgp[k] = s0; sgp[MS + k] = s1; sgp[2 * MS + k] = s2;
+        }
+    };
+    // wait until every neighbour tile / neighbour rank this tile reads has published exchange ex, then refresh the halo
+    auto wait_refresh = [&](int ex, int parity, bool move_ghosts, double dt_move) {
+        if (my_nbr >= 0) {
+            const unsigned int* f = A.tile_flags + (size_t)my_nbr * RES_FLAG_STRIDE;
+            unsigned v;
+            long long spins = 0;
+            for (;;) {
+                asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
+                if (v >= (unsigned)ex) break;
+                // bounded: a launch that is not co-resident (or a dead neighbour) must end, not hang the device; once one
+                // wait has timed out every later one gives up at once
+                if ((++spins & 1023) == 0 && (*((volatile int*)A.err) || spins > (1LL << 22))) { atomicCAS(A.err, 0, 1000 + my_nbr); break; }
+            }
+        }
+        int const li = tid - 32;
+        if (li >= 0 && li < P.n_link && ((link_mask >> li) & 1)) {
+            const unsigned long long* f = A.my_flags + P.link_rank[li];
+            unsigned long long v;
+            long long spins = 0;
+            for (;;) {
+                asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(f) : "memory");
+                if ((v & ~FLAG_OW) >= epoch0 + (unsigned long long)ex) break;
+                if ((++spins & 1023) == 0 && (*((volatile int*)A.err) || spins > (1LL << 22))) { atomicCAS(A.err, 0, 1 + P.link_rank[li]); break; }
+            }
         }
         __syncthreads();
-
-        // ---- phase 2: one owned node per thread ----
-        if (has_node) {
-            double const uice = su[tid], vice = sv[tid];
-            double un = uice, vn = vice;
-            double const nm = __ldg(A.node_mass + n);
-            if (!(fl & NF_DIRICHLET) && nm != 0.) {
-                double gu = __ldg(A.grad_ssh + n), gv = __ldg(A.grad_ssh + n + nn);
-                double const rl = __ldg(A.rlmass + n), cb = __ldg(A.cbu + n), fc = __ldg(A.fcor + n);
-                double tau_x = __ldg(A.tau_a + n), tau_y = __ldg(A.tau_a + n + nn);
-                double const ou = __ldg(A.ocean + n), ov = __ldg(A.ocean + n + nn);
-                if (A.tau_wi) { tau_x = tau_x + __ldg(A.tau_wi + n); tau_y = tau_y + __ldg(A.tau_wi + n + nn); }
-                const uint16_t* ip = A.inc + td.inc_off + tid;
-                for (int c = 0; c < td.inc_w; ++c) {
-                    unsigned const code = __ldg(ip + (size_t)c * td.n_own);
-                    if (code == 0xFFFFu) break;
-                    int const i = (int)(code / (unsigned)MS), k = (int)(code - (unsigned)i * (unsigned)MS);
-                    double const a0 = sgp[k], a1 = sgp[MS + k], a2 = sgp[2 * MS + k];
-                    double const vol = ecp[(BBM ? 5 : 1) * MS + k];
-                    double const dxi = shp[i * MS + k], dyi = shp[(3 + i) * MS + k];
-                    gu -= vol * (a0 * dxi + a2 * dyi);           // V*(sigma . grad N_i), FE.cpp:10464-10465
-                    gv -= vol * (a2 * dxi + a1 * dyi);
-                }
-                double dtep = K.dte, delu = 0., delv = 0.;
-                if (K.dynamics_type == NSX_DYN_MEVP) {
-                    delu = (__ldg(A.VTM + n) - uice) * K.mevp_rb;
-                    delv = (__ldg(A.VTM + n + nn) - vice) * K.mevp_rb;
-                    dtep = K.dte_mevp;
-                }
-                double const dte_over_mass = fast_div(dtep, fmax(K.min_m, nm));
-                double const c_prime = K.rhow_cdw * fast_hypot(ou - uice, ov - vice);
-                double const tau_b = cb * fast_div(1., fast_hypot(uice, vice) + K.u0);
-                double const sin_s = (fl & NF_LATNEG) ? -K.sin_ota_abs : K.sin_ota_abs;
-                double const alpha = 1. + dte_over_mass * (c_prime * K.cos_ota + tau_b);
-                double const beta = dtep * fc + dte_over_mass * c_prime * sin_s;
-                double const rdenom = fast_div(1., alpha * alpha + beta * beta);
-                tau_x = tau_x + c_prime * (ou * K.cos_ota - ov * sin_s);
-                tau_y = tau_y + c_prime * (ov * K.cos_ota + ou * sin_s);
-                double const grad_x = gu * rl, grad_y = gv * rl;
-                un = alpha * uice + beta * vice + dte_over_mass * (alpha * (grad_x + tau_x) + beta * (grad_y + tau_y)) + alpha * delu + beta * delv;
-                un *= rdenom;
-                vn = alpha * vice - beta * uice + dte_over_mass * (alpha * (grad_y + tau_y) - beta * (grad_x + tau_x)) + alpha * delv - beta * delu;
-                vn *= rdenom;
-            }
-            su[tid] = un; sv[tid] = vn;                          // phase 1 is over: nobody reads the old value any more
-            VTw[n] = un; VTw[n + nn] = vn;
-            if (A.move_mesh) {
-                utu = utu + K.dte * un;  utv = utv + K.dte * vn;
-                if (!(fl & NF_NEUMANN)) { umu = umu + K.dte * un;  umv = umv + K.dte * vn; }
-            }
-        }
-        // ---- every tile has published its velocities: read the halo nodes back ----
-        grid_barrier(A.bar, bar_target);
+        const double* VTr = VTb(parity);
         for (int h = tid; h < td.n_halo; h += RES_TPB) {
-            int const g = A.halo_nodes[td.halo_off + h];
-            su[td.n_own + HALO_GAP + h] = __ldcg(VTw + g); sv[td.n_own + HALO_GAP + h] = __ldcg(VTw + g + nn);
+            int const g = (h == tid) ? hg0 : A.halo_nodes[td.halo_off + h];
+            double const u = __ldcg(VTr + g), v = __ldcg(VTr + g + nn);
+            su[td.n_own + HALO_GAP + h] = u; sv[td.n_own + HALO_GAP + h] = v;
+            bool const mv = (h == tid) ? hmove0 : (A.halo_move[td.halo_off + h] != 0);
+            if (move_ghosts && mv) {                     // ghost nodes move with their owner's fresh velocity
+                A.UT[g] += dt_move * u;  A.UT[g + nn] += dt_move * v;
+                if (!(A.nflags[g] & NF_NEUMANN)) { A.UM[g] += dt_move * u;  A.UM[g + nn] += dt_move * v; }
+            }
         }
         __syncthreads();
-        double* const t = VTr; VTr = VTw; VTw = t;
+    };
+
+    // ---- the sub-cycle loop (FE.cpp:10423-10554) ----
+    int const cur = A.cur & 1;
+    for (int s = 0; s < A.nsub; ++s) {
+        int const pw = (cur + s + 1) & 1;                         // parity of the buffer this sub-cycle writes
+        phase1(false);                                            // 1. late slots
+        if (s > 0) wait_refresh(s, pw ^ 1, A.move_mesh != 0, K.dte);   // 2. (sub-cycle 0 starts from the loaded state)
+        else __syncthreads();
+        phase1(true);                                             // 3. early slots
+        __syncthreads();
+        double un = 0., vn = 0.;
+        if (has_node) node_solve(un, vn);                         // needs every incident stress: after both phase-1 parts
+        // 4./5. one node per thread: every solve has read its inputs, nobody else reads su/sv before the barrier in signal()
+        if (has_node) { su[tid] = un; sv[tid] = vn; }
+        if (tid < rt.n_x) publish_node(VTb(pw), pw, un, vn);      // export nodes -> VT buffer (+ NVLink pushes)
+        if (has_node && A.move_mesh) { dspu = dspu + K.dte * un;  dspv = dspv + K.dte * vn; }
+        signal(s + 1);                                            // barrier, then thread 0 publishes while the others go on
+    }
+    int ex = A.nsub;                                              // exchanges done so far
+    if (ex > 0) wait_refresh(ex, (cur + ex) & 1, A.move_mesh != 0, K.dte);
+    if (K.dynamics_type == NSX_DYN_MEVP && ex > 0) {
+        // mEVP: ONE mesh move with the full time step after the loop (FE.cpp:10559-10573); ghosts alike
+        if (has_node) { dspu = K.dtime_step * su[tid];  dspv = K.dtime_step * sv[tid]; }
+        for (int h = tid; h < td.n_halo; h += RES_TPB) {
+            if (!A.halo_move[td.halo_off + h]) continue;
+            int const g = A.halo_nodes[td.halo_off + h];
+            double const u = su[td.n_own + HALO_GAP + h], v = sv[td.n_own + HALO_GAP + h];
+            A.UT[g] += K.dtime_step * u;  A.UT[g + nn] += K.dtime_step * v;
+            if (!(A.nflags[g] & NF_NEUMANN)) { A.UM[g] += K.dtime_step * u;  A.UM[g + nn] += K.dtime_step * v; }
+        }
+    }
+
+    // ---- open-water smoother: 50 Jacobi sweeps over the ice-free nodes (FE.cpp:10578-10611), same exchange per sweep.
+    // A rank without neighbours and without ice-free nodes skips it; with neighbour ranks every sweep is exchanged.
+    int const nsweeps = (A.nsweeps > 0 && (P.n_link > 0 || *A.ow_count > 0)) ? A.nsweeps : 0;
+    bool const is_ow = has_node && !(fl & NF_DIRICHLET) && nmass == 0.;
+    int const deg = is_ow ? (int)A.n2n_deg[n] : 0;
+    for (int it = 0; it < nsweeps; ++it) {
+        int const pw = (cur + ex + 1) & 1;
+        double nu = 0., nv = 0.;
+        if (is_ow) {
+            const uint16_t* q = A.n2n_loc + rt.n2n_off + tid;
+            for (int j = 0; j < deg; ++j) {
+                int const l = (int)__ldg(q + (size_t)j * td.n_own);
+                nu += su[l]; nv += sv[l];
+            }
+            nu = nu / deg; nv = nv / deg;
+        }
+        __syncthreads();                                          // Jacobi: every read of the old values is done
+        if (is_ow) { su[tid] = nu; sv[tid] = nv; }
+        if (tid < rt.n_x) publish_node(VTb(pw), pw, su[tid], sv[tid]);
+        ++ex;
+        signal(ex);
+        wait_refresh(ex, pw, false, 0.);
     }
 
     // ---- write the resident state back ----
+    {
+        // always the buffer of parity cur + nsub + nsweeps: the host cannot know whether the sweeps were skipped (only a
+        // rank without neighbours, i.e. without ghosts to keep current, ever skips them)
+        double* VTf = VTb((cur + A.nsub + A.nsweeps) & 1);
+        if (has_node) {
+            VTf[n] = su[tid]; VTf[n + nn] = sv[tid];
+            A.UT[n] += dspu;  A.UT[n + nn] += dspv;
+            if (!(fl & NF_NEUMANN)) { A.UM[n] += dspu;  A.UM[n + nn] += dspv; }
+        }
+    }
 #pragma unroll
     for (int q = 0; q < RES_SPT; ++q) {
         int const k = tid + q * RES_TPB;
@@ -1223,7 +1364,6 @@ k_resident(KParams K, ResidentArgs A)
             if (BBM) A.dm[e] = dmg[q];
         }
     }
-    if (has_node && A.move_mesh) { A.UM[n] = umu; A.UM[n + nn] = umv; A.UT[n] = utu; A.UT[n + nn] = utv; }
 }
 
 // mesh move over an explicit node range with an explicit time increment:
@@ -1267,7 +1407,7 @@ k_ow_sweep(int nn, const int* __restrict__ ow_list, const int* __restrict__ ow_c
 __global__ void __launch_bounds__(TPB)
 k_ow_smooth_all(int nn, int nsweeps, const int* __restrict__ ow_list, const int* __restrict__ ow_count,
                 const int* __restrict__ n2n, const int* __restrict__ n2n_deg,
-                double* VTa, double* VTb, unsigned int* bar)
+                double* VTa, double* VTb, unsigned int* bar, int* err)
 {
     int const cnt = *ow_count;
     if (cnt == 0) return;
@@ -1289,13 +1429,22 @@ k_ow_smooth_all(int nn, int nsweeps, const int* __restrict__ ow_list, const int*
             VTout[n] = su / deg;
             VTout[n + nn] = sv / deg;
         }
-        // grid barrier
-        __threadfence();
+        // grid barrier over the nact participating CTAs: release my sweep, acquire everybody else's.  The spin is
+        // bounded (a grid that is not co-resident must not hang the device) and a timeout sets the error word that
+        // nsx_download / nsx_check report.
         __syncthreads();
         if (threadIdx.x == 0) {
+            __threadfence();
             atomicAdd(bar, 1u);
             unsigned int const target = (unsigned int)(it + 1) * (unsigned int)nact;
-            while (*((volatile unsigned int*)bar) < target) { }
+            unsigned int v;
+            long long spins = 0;
+            for (;;) {
+                asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(bar) : "memory");
+                if (v >= target) break;
+                if (++spins > (1LL << 24)) { atomicExch(err, 2000); break; }
+            }
+            __threadfence();
         }
         __syncthreads();
     }
@@ -1307,10 +1456,12 @@ k_ow_smooth_all(int nn, int nsweeps, const int* __restrict__ ow_list, const int*
 __global__ void __launch_bounds__(TPB)
 k_tauw_owmove(KParams K, const uint8_t* __restrict__ nflags, const double* __restrict__ node_mass,
               const double* __restrict__ VT, const double* __restrict__ VTM, const double* __restrict__ ocean,
-              double* __restrict__ tau_w, double* __restrict__ UM, double* __restrict__ UT)
+              double* __restrict__ tau_w, double* __restrict__ UM, double* __restrict__ UT,
+              unsigned long long* epoch_ctr, unsigned long long epoch_bump)
 {
     int const n = blockIdx.x * blockDim.x + threadIdx.x;
     int const nn = K.nn;
+    if (n == 0 && epoch_ctr) *epoch_ctr += epoch_bump;       // exchanges done by the resident launch that just finished
     if (n >= nn) return;
     double const u = VT[n], v = VT[n + nn];
     double const uice = 0.5 * (u + VTM[n]);
@@ -1483,6 +1634,25 @@ k_permute_out(int n, int planes, const int* __restrict__ perm, const double* __r
     int const q = perm[t];
     for (int p = 0; p < planes; ++p) dst[(size_t)p * n + t] = src[(size_t)p * n + q];
 }
+// All fields of one nsx_upload / nsx_download call in ONE launch: blockIdx.y selects the field.  Host order lives in
+// the transfer arena (one contiguous device buffer, one PCIe copy per field back to back, no per-field kernel).
+struct XferEnt { const double* src; double* dst; int n; int planes; int elem; int pad_; };
+constexpr int XFER_MAX = 40;
+struct XferTable { int count; int pad_; XferEnt e[XFER_MAX]; };
+template <int IN>
+__global__ void __launch_bounds__(TPB)
+k_permute_all(XferTable T, const int* __restrict__ node_perm, const int* __restrict__ elem_perm)
+{
+    XferEnt const& f = T.e[blockIdx.y];
+    int const n = f.n;
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) {
+        int const q = f.elem ? elem_perm[t] : node_perm[t];
+        for (int p = 0; p < f.planes; ++p) {
+            if (IN) f.dst[(size_t)p * n + q] = f.src[(size_t)p * n + t];
+            else f.dst[(size_t)p * n + t] = f.src[(size_t)p * n + q];
+        }
+    }
+}
 // M_shape_coeff[cpt][k] (element-major, reference numbering) from the internal SoA planes
 __global__ void __launch_bounds__(TPB)
 k_shape_out(int ne, const int* __restrict__ perm, const double* __restrict__ soa, double* __restrict__ aos)
@@ -1599,92 +1769,6 @@ k_ow_sweep_exchange(HaloArgs a, int mode, int nn, const int* __restrict__ ow_lis
     __syncthreads();
     if (threadIdx.x == 0) { *epoch_ctr = epoch; *done_ctr = 0u; }
     if (mode == 2 && i < 32) send_ow[i] = 0;                 // ready for the next model step
-}
-
-// All 50 sweeps of the multi-rank smoother in ONE launch: per sweep every CTA relaxes its share of the open-water
-// list, a software grid barrier makes the result visible, CTA 0 runs the ghost exchange (same pushes, flags and
-// open-water pair skipping as k_ow_sweep_exchange: mode 0 for the first sweep, 2 for the last, 1 in between) and a
-// second barrier releases the other CTAs into the next sweep.  Saves the launch and the last-CTA detection of 50
-// kernels (about half of the ~16 us a sweep + exchange costs as separate launches).  The grid is at most one CTA
-// per SM and nothing else runs on the stream, so every CTA is resident; all spins are bounded.
-// aA / aB: halo arguments whose peer buffers have the parity of VTa / VTb.
-__global__ void __launch_bounds__(TPB)
-k_ow_smooth_exchange_all(HaloArgs aA, HaloArgs aB, int nsweeps, int ow_skip, int nn,
-                         const int* __restrict__ ow_list, const int* __restrict__ ow_count,
-                         const int* __restrict__ n2n, const int* __restrict__ n2n_deg,
-                         double* VTa, double* VTb,
-                         const int* __restrict__ src_idx, const int* __restrict__ dst_idx,
-                         const int* __restrict__ push_ptr, const int2* __restrict__ push_ent,
-                         int* send_ow, int* pair_active, const unsigned long long* my_flags,
-                         unsigned long long* epoch_ctr, unsigned int* bar, long long max_spins, int* err)
-{
-    int const cnt = *ow_count;
-    int const nact = max(1, min((int)gridDim.x, (cnt + (int)blockDim.x - 1) / (int)blockDim.x));
-    if ((int)blockIdx.x >= nact) return;
-    __shared__ int s_act[32];
-    unsigned int target = 0;
-    auto barrier = [&]() {
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            target += (unsigned int)nact;
-            __threadfence();
-            atomicAdd(bar, 1u);
-            unsigned int v;
-            long long spins = 0;
-            do { asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(bar) : "memory"); } while (v < target && ++spins < (1LL << 26));
-            __threadfence();
-        }
-        __syncthreads();
-    };
-    int const i = (int)threadIdx.x;
-    for (int it = 0; it < nsweeps; ++it) {
-        int const mode = !ow_skip ? 2 : (it == 0) ? 0 : (it == nsweeps - 1) ? 2 : 1;
-        const double* VTin = (it & 1) ? VTb : VTa;
-        double* VTout = (it & 1) ? VTa : VTb;
-        HaloArgs const& a = (it & 1) ? aA : aB;
-        for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < cnt; t += nact * blockDim.x) {
-            int const n = ow_list[t];
-            int const deg = n2n_deg[n];
-            double su = 0., sv = 0.;
-            for (int j = 0; j < deg; ++j) {
-                int const q = n2n[(size_t)j * nn + n];
-                su += __ldcg(VTin + q);
-                sv += __ldcg(VTin + q + nn);
-            }
-            VTout[n] = su / deg;
-            VTout[n + nn] = sv / deg;
-            if (mode == 0 && ow_skip)
-                for (int q = push_ptr[n]; q < push_ptr[n + 1]; ++q) atomicOr(send_ow + push_ent[q].x, 1);
-        }
-        barrier();
-        if (blockIdx.x == 0) {
-            if (i < 32) s_act[i] = (mode != 1) ? 1 : (i < a.n_link ? __ldcg(pair_active + i) : 0);
-            __syncthreads();
-            for (int t = threadIdx.x; t < a.n_total; t += blockDim.x) {
-                int p = 0;
-                while (t >= a.peer_begin[p + 1]) ++p;
-                if (!s_act[a.peer_link[p]]) continue;
-                int const s = src_idx[t], d = dst_idx[t];
-                double* dst = a.peer_vt[p];
-                dst[d] = __ldcg(VTout + s);
-                dst[d + a.peer_nn[p]] = __ldcg(VTout + s + nn);
-            }
-            __threadfence_system();
-            __syncthreads();
-            unsigned long long const epoch = *((volatile unsigned long long*)epoch_ctr) + 1ULL;
-            int my_bit = 0;
-            if (i < a.n_link && mode != 2)
-                for (int p = 0; p < a.n_peers; ++p)
-                    if (a.peer_link[p] == i) my_bit = __ldcg(send_ow + p);
-            bool const sel = (i < a.n_link) && s_act[i];
-            unsigned long long const v = flag_signal_wait(a, i, sel, epoch | (my_bit ? FLAG_OW : 0ULL), epoch, my_flags, max_spins, err);
-            if (mode == 0 && i < a.n_link) pair_active[i] = (my_bit || (v & FLAG_OW)) ? 1 : 0;
-            __syncthreads();
-            if (i == 0) *epoch_ctr = epoch;
-            if (it == nsweeps - 1 && i < 32) send_ow[i] = 0;        // ready for the next model step
-        }
-        barrier();
-    }
 }
 
 // ---------------------------------------------------------------------------------------------------

@@ -32,7 +32,8 @@ static uint64_t hilbert_xy2d(uint32_t x, uint32_t y)        // 16-bit coordinate
     return d;
 }
 
-void build_mesh_plan(const NsxMesh* M, MeshPlan& P, int target_tile_nodes, int sm_count)
+void build_mesh_plan(const NsxMesh* M, MeshPlan& P, int target_tile_nodes, int sm_count,
+                     bool resident_order, const uint8_t* export_mask)
 {
     int const nn = M->num_nodes, ne = M->num_elements, ndof = M->local_ndof;
     if (nn <= 0 || ne <= 0 || ndof <= 0 || ndof > nn || M->local_nelements > ne)
@@ -83,6 +84,44 @@ void build_mesh_plan(const NsxMesh* M, MeshPlan& P, int target_tile_nodes, int s
     auto by_key = [&](int a, int b) { return key[a] != key[b] ? key[a] < key[b] : a < b; };
     std::sort(P.node_inv.begin(), P.node_inv.begin() + ndof, by_key);
     std::sort(P.node_inv.begin() + ndof, P.node_inv.end(), by_key);
+    // ---- tiles over the owned nodes ------------------------------------------------------------------------
+    int T = std::max(32, target_tile_nodes);
+    int ntiles = (ndof + T - 1) / T;
+    // `sm_count` here is the number of CTAs of one full wave (SMs x resident CTAs per SM): small meshes get a
+    // whole number of waves so that no SM idles during a partial last wave
+    if (sm_count > 0 && ntiles < 8 * sm_count) {
+        int const nwaves = std::max(1, (ntiles + sm_count / 2) / sm_count);
+        ntiles = nwaves * sm_count;
+    }
+    ntiles = std::max(1, std::min(ntiles, ndof));
+    T = (ndof + ntiles - 1) / ntiles;
+    ntiles = (ndof + T - 1) / T;
+    P.ntiles = ntiles; P.tile_nodes = T;
+    auto tile_of_node = [&](int internal) { return internal / T; };
+
+    // resident solver: inside every tile the EXPORT nodes come first -- owned nodes that another tile reads (they share
+    // an element with a node of another tile) or that are sent to another rank.  Tile membership does not change.
+    std::vector<uint8_t> is_x;
+    if (resident_order) {
+        std::vector<int> pos(nn);
+        for (int i = 0; i < nn; ++i) pos[P.node_inv[i]] = i;
+        is_x.assign(nn, 0);                                   // by reference id
+        for (int e = 0; e < ne; ++e) {
+            int const v[3] = {r0[e], r1[e], r2[e]};
+            for (int i = 0; i < 3; ++i) {
+                if (v[i] >= ndof) continue;
+                int const t = pos[v[i]] / T;
+                for (int j = 0; j < 3; ++j)
+                    if (j != i && v[j] < ndof && pos[v[j]] / T != t) is_x[v[i]] = 1;
+            }
+        }
+        if (export_mask)
+            for (int r = 0; r < ndof; ++r) if (export_mask[r]) is_x[r] = 1;
+        for (int t = 0; t < ntiles; ++t) {
+            auto b = P.node_inv.begin() + (size_t)t * T, e = P.node_inv.begin() + std::min(ndof, (t + 1) * T);
+            std::stable_partition(b, e, [&](int r) { return is_x[r] != 0; });
+        }
+    }
     P.node_perm.resize(nn);
     for (int i = 0; i < nn; ++i) P.node_perm[P.node_inv[i]] = i;
 
@@ -100,30 +139,42 @@ void build_mesh_plan(const NsxMesh* M, MeshPlan& P, int target_tile_nodes, int s
         P.nflags[P.node_perm[r]] |= 2;                                          // NF_NEUMANN
     }
 
-    // ---- tiles over the owned nodes ------------------------------------------------------------------------
-    int T = std::max(32, target_tile_nodes);
-    int ntiles = (ndof + T - 1) / T;
-    // `sm_count` here is the number of CTAs of one full wave (SMs x resident CTAs per SM): small meshes get a
-    // whole number of waves so that no SM idles during a partial last wave
-    if (sm_count > 0 && ntiles < 8 * sm_count) {
-        int const nwaves = std::max(1, (ntiles + sm_count / 2) / sm_count);
-        ntiles = nwaves * sm_count;
-    }
-    ntiles = std::max(1, std::min(ntiles, ndof));
-    T = (ndof + ntiles - 1) / ntiles;
-    ntiles = (ndof + T - 1) / T;
-    P.ntiles = ntiles; P.tile_nodes = T;
-    auto tile_of_node = [&](int internal) { return internal / T; };
-
     // ---- element permutation: by writer tile, then along the curve ------------------------------------------
-    std::vector<int> writer(ne);
+    std::vector<int> writer(ne, -1);
     std::vector<uint64_t> ekey(ne);
     for (int e = 0; e < ne; ++e) {
         int const v[3] = {P.node_perm[r0[e]], P.node_perm[r1[e]], P.node_perm[r2[e]]};
         int lo = nn;
         for (int i = 0; i < 3; ++i) if (v[i] < ndof) lo = std::min(lo, v[i]);
-        writer[e] = (lo < nn) ? tile_of_node(lo) : (e % ntiles);               // no owned node: any tile
-        ekey[e] = ((uint64_t)writer[e] << 32) | (uint32_t)std::min(std::min(v[0], v[1]), v[2]);
+        if (lo < nn) writer[e] = tile_of_node(lo);
+    }
+    // ghost elements without an owned node: written by a tile that already reads one of their (ghost) nodes, so that
+    // no interior tile starts depending on another rank
+    {
+        std::vector<int> tile_of_ghost(nn, -1);
+        for (int e = 0; e < ne; ++e) {
+            if (writer[e] < 0) continue;
+            int const v[3] = {r0[e], r1[e], r2[e]};
+            for (int i = 0; i < 3; ++i) if (v[i] >= ndof && tile_of_ghost[v[i]] < 0) tile_of_ghost[v[i]] = writer[e];
+        }
+        for (int e = 0; e < ne; ++e) {
+            if (writer[e] >= 0) continue;
+            int const v[3] = {r0[e], r1[e], r2[e]};
+            for (int i = 0; i < 3 && writer[e] < 0; ++i) writer[e] = tile_of_ghost[v[i]];
+            if (writer[e] < 0) writer[e] = e % ntiles;
+        }
+    }
+    std::vector<uint8_t> late(ne, 0);              // resident order: all three nodes interior to the writer tile
+    for (int e = 0; e < ne; ++e) {
+        int const v[3] = {P.node_perm[r0[e]], P.node_perm[r1[e]], P.node_perm[r2[e]]};
+        if (resident_order) {
+            int const rv[3] = {r0[e], r1[e], r2[e]};
+            bool interior = true;
+            for (int i = 0; i < 3; ++i)
+                interior = interior && rv[i] < ndof && tile_of_node(v[i]) == writer[e] && !is_x[rv[i]];
+            late[e] = interior ? 1 : 0;
+        }
+        ekey[e] = ((uint64_t)writer[e] << 32) | ((uint64_t)late[e] << 31) | (uint32_t)std::min(std::min(v[0], v[1]), v[2]);
     }
     P.elem_inv.resize(ne);
     std::iota(P.elem_inv.begin(), P.elem_inv.end(), 0);
@@ -189,6 +240,10 @@ void build_mesh_plan(const NsxMesh* M, MeshPlan& P, int target_tile_nodes, int s
 
     P.tiles.assign(ntiles, TileDesc{});
     P.halo_nodes.clear(); P.halo_elems.clear(); P.slot_elem.clear(); P.slot_conn.clear(); P.inc.clear();
+    P.res_tiles.clear(); P.res_nbr.clear(); P.res_n2n.clear(); P.res_n2n_deg.clear(); P.halo_move.clear();
+    if (resident_order) { P.res_tiles.assign(ntiles, ResTile{}); P.res_n2n_deg.assign(ndof, 0); }
+    std::vector<uint8_t> ghost_taken(nn, 0);
+    std::vector<int> nbr_stamp(ntiles, -1);
     std::vector<int> stamp_e(ne, -1), slot_of(ne, 0), stamp_n(nn, -1), lidx(nn, 0);
     P.max_local_nodes = 0; P.max_slots = 0; P.max_own_slots = 0; P.max_halo_slots = 0; P.max_halo_nodes = 0; P.max_inc = 0;
     for (int t = 0; t < ntiles; ++t) {
@@ -256,14 +311,50 @@ void build_mesh_plan(const NsxMesh* M, MeshPlan& P, int target_tile_nodes, int s
                 P.inc[td.inc_off + (size_t)c * td.n_own + j] = (uint16_t)(slot_of[ie] * 3 + i);
             }
         }
+        if (resident_order) {
+            ResTile& rt = P.res_tiles[t];
+            for (int j = 0; j < td.n_own; ++j) if (is_x[P.node_inv[td.node_begin + j]]) rt.n_x = j + 1;
+            for (int j = 0; j < rt.n_x; ++j)
+                if (!is_x[P.node_inv[td.node_begin + j]]) throw std::logic_error("nsx mesh plan: export nodes are not a prefix");
+            for (int k = 0; k < td.n_own_slots; ++k) {
+                bool const lt = late[P.elem_inv[td.elem_begin + k]] != 0;
+                if (!lt) { if (rt.n_early_own != k) throw std::logic_error("nsx mesh plan: early slots are not a prefix"); rt.n_early_own = k + 1; }
+            }
+            // neighbour tiles = owners of my halo nodes (the relation is symmetric: the shared element is a slot of both)
+            rt.nbr_off = (int)P.res_nbr.size();
+            for (int h = 0; h < nhn; ++h) {
+                int const g = P.halo_nodes[td.halo_off + h];
+                uint8_t mv = 0;
+                if (g >= ndof) { if (!ghost_taken[g]) { ghost_taken[g] = 1; mv = 1; } }
+                else {
+                    int const q = tile_of_node(g);
+                    if (nbr_stamp[q] != t) { nbr_stamp[q] = t; P.res_nbr.push_back(q); }
+                }
+                P.halo_move.push_back(mv);
+            }
+            rt.n_nbr = (int)P.res_nbr.size() - rt.nbr_off;
+            // node -> node table of the owned nodes in tile-local ids, bamg order (open-water smoother, FE.cpp:10597-10605)
+            int wmax = 0;
+            for (int j = 0; j < td.n_own; ++j) wmax = std::max(wmax, P.n2n_deg[td.node_begin + j]);
+            rt.n2n_off = (int)P.res_n2n.size();
+            rt.n2n_w = wmax;
+            P.res_n2n.resize(P.res_n2n.size() + (size_t)wmax * td.n_own, (uint16_t)0);
+            for (int j = 0; j < td.n_own; ++j) {
+                int const n = td.node_begin + j;
+                P.res_n2n_deg[n] = (uint8_t)P.n2n_deg[n];
+                for (int c = 0; c < P.n2n_deg[n]; ++c) {
+                    int const q = P.n2n[(size_t)c * nn + n];
+                    if (stamp_n[q] != t) throw std::invalid_argument("nsx_create: NodalConnectivity lists a node that shares no element with its row");
+                    P.res_n2n[rt.n2n_off + (size_t)c * td.n_own + j] = (uint16_t)lidx[q];
+                }
+            }
+        }
         P.max_local_nodes = std::max(P.max_local_nodes, td.n_own + HALO_GAP + nhn);
         P.max_slots = std::max(P.max_slots, nslots);
         P.max_own_slots = std::max(P.max_own_slots, td.n_own_slots);
         P.max_halo_slots = std::max(P.max_halo_slots, nh);
         P.max_halo_nodes = std::max(P.max_halo_nodes, nhn);
         P.max_inc = std::max(P.max_inc, dmax * td.n_own);
-        if (getenv("NSX_PLAN_DEBUG") && (nh > 250 || nhn > 250))
-            fprintf(stderr, "tile %d/%d: node_begin %d n_own %d own_slots %d halo_slots %d halo_nodes %d x=%.0f y=%.0f\n", t, ntiles, td.node_begin, td.n_own, td.n_own_slots, nh, nhn, P.x[td.node_begin], P.y[td.node_begin]);
     }
     // slot space is padded to an even count so that every slot plane (stride nslots) has the same 16-byte
     // phase; the pad slot is never computed (marked INT_MIN)

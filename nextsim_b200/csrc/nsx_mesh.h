@@ -25,6 +25,21 @@ struct TileDesc {
 };
 static_assert(sizeof(TileDesc) == 64, "TileDesc is 16 ints");
 
+// Extra per-tile data of the state-resident solver (k_resident): one tile per SM for the whole sub-cycle loop.
+// Inside a tile the owned nodes are ordered EXPORT NODES FIRST (nodes another tile reads as halo, or that are sent to
+// another rank) and the own slots EARLY SLOTS FIRST (elements with a node outside the tile's interior, i.e. an export
+// node or a halo node); halo slots are always early.  Per sub-cycle a tile can then finish its export nodes, publish
+// them, and hide the neighbours' latency behind the interior work.
+struct ResTile {
+    int n_x;                        // owned nodes [0, n_x) of the tile are export nodes
+    int n_early_own;                // own slots [0, n_early_own) are early
+    int nbr_off, n_nbr;             // neighbour tiles (owners of my halo nodes, symmetric): res_nbr[nbr_off ...]
+    int n2n_off, n2n_w;             // bamg-order node->node table of the owned nodes in tile-local ids (smoother)
+    int link_mask;                  // bit i: the tile pushes to / reads ghosts of neighbour rank (link) i   [build_halo]
+    int pad_;
+};
+static_assert(sizeof(ResTile) == 32, "ResTile is 8 ints");
+
 // The owned nodes' velocities are staged by a TMA copy that is rounded up to 16-byte granules, i.e. it may write up to
 // two doubles past the owned range; the halo nodes (written by plain stores) therefore start HALO_GAP entries later.
 constexpr int HALO_GAP = 2;
@@ -51,9 +66,18 @@ struct MeshPlan {
     std::vector<int> halo_nodes, halo_elems, slot_elem;
     std::vector<unsigned long long> slot_conn; // 3 x 16-bit tile-local node ids
     std::vector<uint16_t> inc;                 // slot*3 + vertex, 0xFFFF = padding
+    // state-resident solver only (resident_order = true)
+    std::vector<ResTile> res_tiles;
+    std::vector<int> res_nbr;                  // neighbour tile ids
+    std::vector<uint16_t> res_n2n;             // [n2n_off + c*n_own + j] tile-local node id of the c-th neighbour (bamg order)
+    std::vector<uint8_t> res_n2n_deg;          // [node_begin + j] = neighbour count
+    std::vector<uint8_t> halo_move;            // per halo_nodes entry: this tile moves that ghost node (UM / UT)
 };
 
 // throws std::invalid_argument on inconsistent input
-void build_mesh_plan(const NsxMesh* M, MeshPlan& P, int target_tile_nodes, int sm_count);
+// resident_order: export-first node order, early-first slot order and the ResTile tables; export_mask (may be NULL)
+// flags reference-numbered owned nodes that are sent to another rank.
+void build_mesh_plan(const NsxMesh* M, MeshPlan& P, int target_tile_nodes, int sm_count,
+                     bool resident_order = false, const uint8_t* export_mask = nullptr);
 
 }  // namespace nsx

@@ -19,7 +19,7 @@ pytestmark = pytest.mark.gpu
 DIAG = ("D_conc", "D_thick", "D_snow_thick", "D_sigma", "D_divergence")
 
 
-@pytest.fixture(autouse=True, params=["tiles", "direct"])
+@pytest.fixture(autouse=True, params=["tiles", "direct", "resident"])
 def solver_path(request, monkeypatch):
     monkeypatch.setenv("NSX_PATH", request.param)
     return request.param

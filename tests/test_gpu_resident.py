@@ -1,10 +1,10 @@
-"""EXPERIMENTAL state-resident persistent solver (NSX_PATH=resident, k_resident): written at the end of round 1 without
-GPU budget left to run it, so these tests are opt-in (NSX_TEST_RESIDENT=1) until the path has been validated once:
-
-    NSX_TEST_RESIDENT=1 python -m pytest tests/test_gpu_resident.py -q
+"""State-resident persistent solver (k_resident, NsxCreateOptions.path = RESIDENT; AUTO selects it whenever the mesh fits):
+one launch per model step, tile-to-tile synchronisation by release/acquire flags.
 
 Same bar as the other paths: rel-L2 <= 1e-9 against the oracle after a full model step + update(); it also has to agree
-with the direct path to rounding."""
+with the direct path to rounding.  The in-process groups below run one persistent launch PER RANK concurrently on one
+GPU (each on its share of the SMs), so the rank-to-rank flag protocol -- the same code that runs over NVLink between
+GPUs -- is exercised by the single-GPU test run."""
 import os
 
 import numpy as np
@@ -14,9 +14,7 @@ from nextsim_b200 import cases
 import oracle_bridge as ob
 from oracle import oracle as orc
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("NSX_TEST_RESIDENT") != "1",
-                                 reason="experimental path, not yet validated on a GPU (set NSX_TEST_RESIDENT=1)")]
+pytestmark = pytest.mark.gpu
 KEYS = cases.STATE_OUT
 
 
@@ -59,3 +57,46 @@ def test_resident_path(monkeypatch, name, nx, dyn, nsub):
             pairs = zip(gk, o) if k == "M_sigma" else [(gk, o)]
             for g, r in pairs:
                 assert ob.rel_l2(g, r) <= 1e-9, ("update", k)
+
+
+def test_auto_selects_resident_for_the_headline_mesh(monkeypatch):
+    monkeypatch.delenv("NSX_PATH", raising=False)
+    c = cases.make_case("10km_stable", nranks=1, dyn="bbm")
+    (s,) = cases.make_solvers(c)
+    assert s.path == "resident", s.tile_info()
+    s.close()
+
+
+@pytest.mark.parametrize("name,nx,nranks,dyn,open_east", [
+    ("toy", None, 2, "bbm", True), ("toy", None, 3, "mevp", False), ("10km_stable", 96, 4, "bbm", True),
+    ("10km_stable", 64, 8, "evp", True), ("10km_stable", 160, 2, "bbm", False)])
+def test_resident_ranks_exchange_through_flags(monkeypatch, name, nx, nranks, dyn, open_east):
+    """updateGhosts() inside the persistent launch: export nodes pushed into the holder's VT buffer, per-link arrival
+    counters, release of the exchange epoch, bounded acquire spins (FE.cpp:13963-13996)."""
+    from nextsim_b200 import capi
+    monkeypatch.setenv("NSX_PATH", "resident")
+    c = cases.make_case(name, nranks=nranks, dyn=dyn, nx=nx, open_east=open_east)
+    ranks = ob.make_ranks(c)
+    q = ob.orc_params(c.params)
+    orc.explicit_solve(ranks, q)
+    solvers = cases.make_solvers(c)
+    assert all(s.path == "resident" for s in solvers)
+    capi.group_explicit_solve(solvers)
+    for R, s in zip(ranks, solvers):
+        got = s.download(*KEYS)
+        ref = ob.get_state(R, KEYS)
+        for k in KEYS:
+            pairs = zip(got[k], ref[k]) if k == "M_sigma" else [(got[k], ref[k])]
+            for g, o in pairs:
+                assert ob.rel_l2(g, o) <= 1e-9, (k, ob.rel_l2(g, o))
+    for R, s in zip(ranks, solvers):
+        R.update(q)
+        s.update()
+        got = s.download(*cases.UPDATE_OUT)
+        ref = ob.get_state(R, cases.UPDATE_OUT)
+        for k in cases.UPDATE_OUT:
+            pairs = zip(got[k], ref[k]) if k == "M_sigma" else [(got[k], ref[k])]
+            for g, o in pairs:
+                assert ob.rel_l2(g, o) <= 1e-9, ("update", k)
+    for s in solvers:
+        s.close()
