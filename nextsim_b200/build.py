@@ -34,7 +34,7 @@ def build(force=False, verbose=False):
     if not force and not needs_build():
         return LIB
     extra = []
-    for k in ("NSX_SUB_TPB", "NSX_SUB_MINB", "NSX_SUB_STAGES", "NSX_SUB_GROUPS", "NSX_DIRECT_TPB", "NSX_DIRECT_MINB", "NSX_SUB_CTAS_PER_SM", "NSX_SUB_NODE_THREADS"):           # kernel-shape experiments
+    for k in ("NSX_SUB_TPB", "NSX_SUB_MINB", "NSX_SUB_STAGES", "NSX_SUB_GROUPS", "NSX_DIRECT_TPB", "NSX_DIRECT_MINB", "NSX_SUB_CTAS_PER_SM", "NSX_RES_TPB", "NSX_RES_CTAS"):           # kernel-shape experiments
         if os.environ.get(k):
             extra.append("-D%s=%s" % (k, os.environ[k]))
     cmd = [_nvcc()] + NVCC_FLAGS + extra + [os.path.join(CSRC, s) for s in SOURCES] + ["-o", LIB]

@@ -33,8 +33,10 @@ class Case:
     pass
 
 
-def make_params(cfg, dyn, gm, substeps=120):
-    p = capi.default_params()
+def make_params(cfg, dyn, gm, substeps=120, defaults=None):
+    """defaults: an NsxDynParams already holding the option defaults (the CPU arm of bench.py fills one from the oracle so
+    that it never loads libnsx.so); None = nsx_params_defaults."""
+    p = defaults if defaults is not None else capi.default_params()
     p.dynamics_type = capi.DYN[dyn]
     p.substeps = substeps
     p.dtime_step = cfg["dt"]
@@ -51,7 +53,7 @@ def make_params(cfg, dyn, gm, substeps=120):
 
 
 def make_case(name="toy", nranks=1, dyn="bbm", open_east=False, substeps=120, nx=None, young=True, seed=syn.SEED,
-              only_rank=None):
+              only_rank=None, defaults=None):
     cfg = dict(CONFIGS[name])
     mnx, h = syn.SIZES[cfg["mesh"]]
     if nx is not None:
@@ -61,7 +63,7 @@ def make_case(name="toy", nranks=1, dyn="bbm", open_east=False, substeps=120, nx
     c = Case()
     c.name, c.dyn, c.nranks = name, dyn, nranks
     c.gm, c.state = gm, st
-    c.params, c.C_fix, c.C_alea = make_params(cfg, dyn, gm, substeps)
+    c.params, c.C_fix, c.C_alea = make_params(cfg, dyn, gm, substeps, defaults)
     if nranks > 1:
         c.elem_part = pt.partition_elements(gm.x, gm.y, gm.tri, nranks)
         c.ghost_ptr, c.ghost_val = pt.ghost_tags(gm.tri, c.elem_part, nranks)

@@ -60,7 +60,8 @@ static SmemLayout sub_layout(MeshPlan const& P, int n_node_planes)
     L.total = (int)o;
     return L;
 }
-constexpr int RES_SMEM_MAX = 227 * 1024 - 256;        // dynamic shared memory of k_resident (its static part holds the tile descriptors)
+// dynamic shared memory of one k_resident CTA (its static part holds the tile descriptors; 1 KB per CTA is reserved by the driver)
+constexpr int RES_SMEM_MAX = (227 * 1024 - (RES_CTAS - 1) * 1024) / RES_CTAS - 256;
 constexpr int SUB_SMEM_CAP = ((227 * 1024) / SUB_CTAS_PER_SM - 1024 * (SUB_CTAS_PER_SM - 1) - 128) / SUB_STAGES;     // per stage; one persistent CTA per SM (227 KB)
 
 // ---------------------------------------------------------------------------------------------------
@@ -124,6 +125,8 @@ static void alloc_fields(nsx_solver* S)
     S->slot_ec.alloc(6 * ns); S->slot_ec.zero(st);
     NSX_CUDA(cudaMallocHost(&S->h_err, sizeof(int)));
     *S->h_err = 0;
+    NSX_CUDA(cudaMallocHost(&S->h_time, 3 * sizeof(unsigned long long)));
+    S->res_time.alloc(3); S->res_time.zero(st);
     // Path selection (NsxCreateOptions.path, AUTO by size): the sub-cycle state is resident in shared memory
     // (k_resident, decided in nsx_create_ex), or the working set (~300 B per element) lives in the 126 MB L2 (direct
     // path), or it streams from HBM (TMA tile pipeline).
@@ -348,7 +351,7 @@ extern "C" int nsx_create_ex(const NsxMesh* mesh, const NsxHalo* halo, int devic
         NSX_CUDA(cudaDeviceGetAttribute(&S->sm_count, cudaDevAttrMultiProcessorCount, device));
         NSX_CUDA(cudaStreamCreateWithFlags(&S->stream, cudaStreamNonBlocking));
         NSX_CUDA(cudaStreamCreateWithFlags(&S->stream2, cudaStreamNonBlocking));
-        int const ctas = (S->opt.max_sms > 0) ? std::min(S->opt.max_sms, S->sm_count) : S->sm_count;
+        int const ctas = RES_CTAS * ((S->opt.max_sms > 0) ? std::min(S->opt.max_sms, S->sm_count) : S->sm_count);
         // resident path: explicit request, or AUTO when the mesh fits
         S->resident = false;
         if (S->opt.path == NSX_PATH_RESIDENT || S->opt.path == NSX_PATH_AUTO) {
@@ -395,6 +398,7 @@ extern "C" int nsx_destroy(nsx_handle S)
     if (S->ev_join) cudaEventDestroy(S->ev_join);
     if (S->window) cudaFree(S->window);
     if (S->h_err) cudaFreeHost(S->h_err);
+    if (S->h_time) cudaFreeHost(S->h_time);
     if (S->stream2) cudaStreamDestroy(S->stream2);
     if (S->stream) cudaStreamDestroy(S->stream);
     delete S;
@@ -1074,6 +1078,8 @@ static void launch_resident(nsx_solver* S, int nrun, bool cooperative)
     A.tile_flags = S->res_flags.p; A.arrive = S->res_flags.p + tile_words;
     A.push_ptr = S->push_ptr.p; A.push_ent = S->push_ent.p;
     A.my_flags = S->flags; A.epoch_ctr = S->d_epoch.p; A.err = S->halo_err.p;
+    S->res_time.zero(S->stream);
+    A.tstamp = S->res_time.p;
     A.MS = S->plan.msp; A.MLN = S->plan.max_local_nodes + 2;
     int slot = 0, link = 0;
     for (auto& p : S->peers) {
@@ -1140,7 +1146,7 @@ static void solve_group(int n, nsx_solver** W)
             if (!W[r]->resident) throw std::runtime_error("group solve: every rank must use the same path");
             if (W[r]->device == W[0]->device) tiles_on_dev += W[r]->plan.ntiles;
         }
-        if (n > 1 && tiles_on_dev > W[0]->sm_count)
+        if (n > 1 && tiles_on_dev > RES_CTAS * W[0]->sm_count)
             throw std::runtime_error("group solve: the resident launches of the ranks sharing this GPU need " + std::to_string(tiles_on_dev) +
                                      " SMs; create the handles with NsxCreateOptions.max_sms = SMs / ranks");
         for (int r = 0; r < n; ++r) { NSX_CUDA(cudaSetDevice(W[r]->device)); launch_resident(W[r], nrun, n == 1); }
@@ -1287,6 +1293,17 @@ extern "C" int nsx_get_timing(nsx_handle S, NsxTiming* out)
         NSX_CUDA(cudaEventElapsedTime(&S->timing.prep_ms, S->ev[0], S->ev[1]));
         NSX_CUDA(cudaEventElapsedTime(&S->timing.subcycle_ms, S->ev[1], S->ev[2]));
         NSX_CUDA(cudaEventElapsedTime(&S->timing.ow_smoother_ms, S->ev[2], S->ev[3]));
+        if (S->resident) {
+            // one launch holds the sub-cycle loop AND the smoother: the CUDA-event time of the launch is split by the
+            // %globaltimer stamps the kernel took at its start, after its last sub-cycle and at its end (max over tiles)
+            NSX_CUDA(cudaMemcpy(S->h_time, S->res_time.p, 3 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+            double const all = (double)(S->h_time[2] - S->h_time[0]), loop = (double)(S->h_time[1] - S->h_time[0]);
+            if (S->h_time[0] && all > 0. && loop > 0. && loop <= all) {
+                float const launch_ms = S->timing.subcycle_ms;
+                S->timing.subcycle_ms = (float)(launch_ms * loop / all);
+                S->timing.ow_smoother_ms += launch_ms - S->timing.subcycle_ms;
+            }
+        }
     }
     if (S->update_timed) NSX_CUDA(cudaEventElapsedTime(&S->timing.update_ms, S->ev[3], S->ev[4]));
     *out = S->timing;

@@ -150,6 +150,8 @@ struct nsx_solver {
     nsx::DBuf<uint8_t> res_n2n_deg, halo_move;
     nsx::DBuf<unsigned int> res_flags;           // tile flags followed by the per-exchange link arrival counters
     size_t res_flag_words = 0;
+    nsx::DBuf<unsigned long long> res_time;      // %globaltimer stamps of the last resident launch: start, loop end, end
+    unsigned long long* h_time = nullptr;        // pinned copy
     int res_link_tiles[16] = {};                 // tiles of this rank that arrive on link i per exchange
     int epoch_bump = 0;                          // exchanges the resident launch of the current graph performs
     nsx::DBuf<double> arena;                     // transfer arena (host numbering): all fields of one upload / download call

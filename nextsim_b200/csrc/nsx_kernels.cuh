@@ -969,7 +969,11 @@ k_node_direct(KParams K, DirectArgs A, int move_mesh, int lag_ghost_move, int sk
 #ifndef NSX_RES_TPB
 #define NSX_RES_TPB 768
 #endif
-constexpr int RES_TPB = NSX_RES_TPB;
+#ifndef NSX_RES_CTAS
+#define NSX_RES_CTAS 1
+#endif
+constexpr int RES_TPB = NSX_RES_TPB;            // threads per tile: one owned node per thread, up to RES_SPT slots per thread
+constexpr int RES_CTAS = NSX_RES_CTAS;          // tiles (CTAs) per SM: independent tiles fill each other's barrier / latency stalls
 constexpr int RES_SPT = 3;                      // slots per thread (static unroll): tiles of up to 3 * RES_TPB slots
 constexpr int RES_MAX_LINKS = 16;               // neighbour ranks of one rank
 constexpr int RES_FLAG_STRIDE = 32;             // tile flags live 128 B apart
@@ -998,6 +1002,7 @@ struct ResidentArgs {
     unsigned int* arrive;                                         // [(nsub + nsweeps + 1) * RES_MAX_LINKS], zeroed before the launch
     const int* push_ptr; const int2* push_ent;
     const unsigned long long* my_flags; const unsigned long long* epoch_ctr; int* err;
+    unsigned long long* tstamp;                                   // [3] %globaltimer: launch start, end of the sub-cycle loop, end (max over tiles)
     int MS, MLN;                                                  // shared-memory strides: slots per plane, local nodes
     ResPeers P;
 };
@@ -1073,8 +1078,15 @@ __device__ __forceinline__ double res_slot_update(KParams const& K, int k, unsig
     return d;
 }
 
+__device__ __forceinline__ unsigned long long globaltimer_ns()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
 template <int BBM>
-__global__ void __launch_bounds__(RES_TPB, 1)
+__global__ void __launch_bounds__(RES_TPB, RES_CTAS)
 k_resident(KParams K, ResidentArgs A)
 {
     extern __shared__ __align__(16) unsigned char sm_res[];
@@ -1097,6 +1109,7 @@ k_resident(KParams K, ResidentArgs A)
     unsigned long long const epoch0 = P.n_link ? *A.epoch_ctr : 0ULL;
     int const link_mask = P.n_link ? rt.link_mask : 0;
 
+    if (tid == 0 && blockIdx.x == 0) A.tstamp[0] = globaltimer_ns();
     // ---- load the tile once ----
     double dmg[RES_SPT];
 #pragma unroll
@@ -1308,6 +1321,7 @@ k_resident(KParams K, ResidentArgs A)
     }
     int ex = A.nsub;                                              // exchanges done so far
     if (ex > 0) wait_refresh(ex, (cur + ex) & 1, A.move_mesh != 0, K.dte);
+    if (tid == 0) atomicMax(A.tstamp + 1, globaltimer_ns());
     if (K.dynamics_type == NSX_DYN_MEVP && ex > 0) {
         // mEVP: ONE mesh move with the full time step after the loop (FE.cpp:10559-10573); ghosts alike
         if (has_node) { dspu = K.dtime_step * su[tid];  dspv = K.dtime_step * sv[tid]; }
@@ -1345,6 +1359,7 @@ k_resident(KParams K, ResidentArgs A)
     }
 
     // ---- write the resident state back ----
+    if (tid == 0) atomicMax(A.tstamp + 2, globaltimer_ns());
     {
         // always the buffer of parity cur + nsub + nsweeps: the host cannot know whether the sweeps were skipped (only a
         // rank without neighbours, i.e. without ghosts to keep current, ever skips them)

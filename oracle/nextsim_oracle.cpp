@@ -1567,6 +1567,38 @@ extern "C" {
 
 const char* orc_last_error() { return g_err.c_str(); }
 
+// Defaults of the options the path reads, restated from /root/reference/model/options.cpp (line numbers in the
+// comments) so that the CPU arm of bench.py needs nothing from the product library.  cohesion[0..2] receives
+// dynamics.C_lab, dynamics.alea_factor, dynamics.time_relaxation_damage (host-side recipe, FE.cpp:6995-6999).
+void orc_params_defaults(OrcParams* p, double* cohesion)
+{
+    std::memset(p, 0, sizeof(*p));
+    p->dynamics_type = 0;                                  // setup.dynamics-type = bbm            options.cpp:111
+    p->basal_stress_type = 1;                              // setup.basal_stress-type = lemieux    options.cpp:109
+    p->newice_type = 4;                                    // thermo.newice_type                   options.cpp:397
+    p->ice_cat_type = 1;                                   // newice_type == 4 -> YOUNG_ICE        FE.cpp:1212-1215
+    p->substeps = 120;                                     // dynamics.substeps                    options.cpp:363
+    p->equal_ridging = 0;                                  // age.equal_ridging                    options.cpp:547
+    p->use_young_ice_in_myi_reset = 1;                     // age.include_young_ice                options.cpp:545
+    p->dtime_step = 200.;                                  // simul.timestep                       options.cpp:43
+    p->ocean_turning_angle_rad = (3.14159265358979323846/180.)*25.;   // dynamics.oceanic_turning_angle   options.cpp:347, FE.cpp:1172
+    p->min_h = 0.05; p->min_c = 0.01;                      // options.cpp:325-326
+    p->young = 5.9605e+08;                                 // options.cpp:313
+    p->nu0 = 1./3.;                                        // options.cpp:318
+    p->tan_phi = 0.7;                                      // options.cpp:319
+    p->compr_strength = 1e10;                              // options.cpp:320 (the host multiplies by scale_coef, FE.cpp:6998)
+    p->compaction_param = -20.;                            // options.cpp:321
+    p->undamaged_time_relaxation_sigma = 1e7;              // options.cpp:331
+    p->exponent_relaxation_sigma = 5.;                     // options.cpp:333
+    p->compression_factor = 10e3;                          // options.cpp:359
+    p->exponent_compression_factor = 1.5;                  // options.cpp:358
+    p->quad_drag_coef_water = 0.0055;                      // options.cpp:342
+    p->evp_e = 2.; p->evp_Pstar = 27.5e3; p->evp_C = 20.; p->evp_dmin = 1e-9;   // options.cpp:365-372
+    p->mevp_alpha = 500.; p->mevp_beta = 500.;             // options.cpp:375-376
+    p->basal_k1 = 10.; p->basal_k2 = 15.; p->basal_Cb = 20.; p->basal_u0 = 5e-5;   // options.cpp:350-353
+    if (cohesion) { cohesion[0] = 2.0e6; cohesion[1] = 0.; cohesion[2] = 25.; }     // options.cpp:317, 311, 329
+}
+
 void* orc_rank_create() { return new Rank(); }
 void orc_rank_destroy(void* h) { delete (Rank*)h; }
 

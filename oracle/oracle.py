@@ -60,10 +60,19 @@ def lib(fast=False):
         L.orc_rank_halo_size.restype = C.c_long
         L.orc_time_subcycles.restype = C.c_double
         L.orc_time_subcycles_mt.restype = C.c_double
-        for f in ("orc_rank_destroy", "orc_rank_sizes"):
+        for f in ("orc_rank_destroy", "orc_rank_sizes", "orc_params_defaults"):
             getattr(L, f).restype = None
         _libs[key] = L
     return _libs[key]
+
+
+def default_params():
+    """(OrcParams, C_lab, alea_factor, time_relaxation_damage_days) with the defaults of model/options.cpp, from the
+    oracle's own restatement (no product library involved)."""
+    q = OrcParams()
+    coh = (C.c_double * 3)()
+    lib().orc_params_defaults(C.byref(q), coh)
+    return q, coh[0], coh[1], coh[2]
 
 
 def _dp(a):
