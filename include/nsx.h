@@ -194,6 +194,10 @@ int nsx_tile_info(nsx_handle h, int* out, int n);
 /* host only (no GPU): the tile plan nsx_create would build for this mesh; out[0..9] = ntiles, nodes/tile, slots,
  * max local nodes, max slots, max own slots, max halo slots, max halo nodes, stage bytes, shrink attempts */
 int nsx_plan_info(const NsxMesh* mesh, int target_tile_nodes, int wave_ctas, int* out, int n);
+/* host only (no GPU): the state-resident plan nsx_create_ex would try on `sms` SMs; out[0..11] = fits, ntiles, nodes/tile,
+ * slot space, max slots per tile, max local nodes per tile, shared-memory bytes, export nodes, early own slots, halo
+ * slots, own slots, shared-memory limit.  When it does not fit, nsx_last_error(NULL) says why. */
+int nsx_resident_plan_info(const NsxMesh* mesh, const NsxHalo* halo, int sms, int* out, int n);
 const char* nsx_cfg_last_error(void);        /* message of the last failed nsx_params_from_cfg */
 
 /* ---- options ---- */

@@ -37,6 +37,8 @@ def build(force=False, verbose=False):
     for k in ("NSX_SUB_TPB", "NSX_SUB_MINB", "NSX_SUB_STAGES", "NSX_SUB_GROUPS", "NSX_DIRECT_TPB", "NSX_DIRECT_MINB", "NSX_SUB_CTAS_PER_SM", "NSX_RES_TPB", "NSX_RES_CTAS"):           # kernel-shape experiments
         if os.environ.get(k):
             extra.append("-D%s=%s" % (k, os.environ[k]))
+    if os.environ.get("NSX_DEBUG_CHECKS"):                # device-side bounds checks of the index tables (nsx_kernels.cuh)
+        extra.append("-DNSX_DEBUG_CHECKS")
     cmd = [_nvcc()] + NVCC_FLAGS + extra + [os.path.join(CSRC, s) for s in SOURCES] + ["-o", LIB]
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     log = os.path.join(HERE, "build.log")

@@ -133,7 +133,7 @@ class NsxTiming(C.Structure):
 
 
 EXPORTS = (
-    "nsx_create", "nsx_create_ex", "nsx_create_options_defaults", "nsx_device_sm_count", "nsx_destroy", "nsx_last_error", "nsx_version", "nsx_params_defaults", "nsx_params_from_cfg",
+    "nsx_resident_plan_info", "nsx_create", "nsx_create_ex", "nsx_create_options_defaults", "nsx_device_sm_count", "nsx_destroy", "nsx_last_error", "nsx_version", "nsx_params_defaults", "nsx_params_from_cfg",
     "nsx_set_params", "nsx_upload", "nsx_download", "nsx_explicit_solve", "nsx_update", "nsx_update_ghosts",
     "nsx_check", "nsx_synchronize", "nsx_get_timing", "nsx_get_stream", "nsx_halo_blob_size", "nsx_halo_blob",
     "nsx_halo_connect_blob", "nsx_halo_connect_local", "nsx_halo_finalize", "nsx_group_explicit_solve",
@@ -251,6 +251,18 @@ def mesh_structs(lm):
         a, H.send_idx = _i32(np.concatenate([lm.send_to[p] for p in sp]) if sp else np.zeros(0)); keep.append(a)
         a, H.recv_idx = _i32(np.concatenate([lm.recv_from[p] for p in rp]) if rp else np.zeros(0)); keep.append(a)
     return M, H, keep
+
+
+def resident_plan_info(lm, sms=148):
+    """Host-only statistics of the state-resident plan for this rank (see nsx.h)."""
+    M, H, keep = mesh_structs(lm)
+    out = (C.c_int * 12)()
+    L = lib()
+    if L.nsx_resident_plan_info(C.byref(M), C.byref(H) if H is not None else None, int(sms), out, 12) != 0:
+        raise RuntimeError(L.nsx_last_error(None).decode())
+    names = ("fits", "ntiles", "tile_nodes", "slot_space", "max_slots", "max_local_nodes", "smem_bytes", "export_nodes",
+             "early_own_slots", "halo_slots", "own_slots", "smem_limit")
+    return dict(zip(names, list(out)))
 
 
 def validate_mesh(lm):

@@ -88,7 +88,7 @@ static void upload_plan(nsx_solver* S)
     NSX_CUDA(cudaFuncSetAttribute(k_subcycle<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     NSX_CUDA(cudaFuncSetAttribute(k_subcycle<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     if (S->resident) {
-        S->res_tiles.upload(P.res_tiles, st); S->res_nbr.upload(P.res_nbr, st);
+        S->res_tiles.upload(P.res_tiles, st); S->halo_slot.upload(P.halo_slot, st);
         S->res_n2n.upload(P.res_n2n, st); S->res_n2n_deg.upload(P.res_n2n_deg, st); S->halo_move.upload(P.halo_move, st);
         NSX_CUDA(cudaFuncSetAttribute(k_resident<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, RES_SMEM_MAX));
         NSX_CUDA(cudaFuncSetAttribute(k_resident<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, RES_SMEM_MAX));
@@ -100,15 +100,18 @@ static void alloc_fields(nsx_solver* S)
 {
     size_t const nn = S->nn, ne = S->ne, ns = S->plan.nslots;
     cudaStream_t st = S->stream;
-    // halo window: [VT0 | VT1 | flags]
+    // halo window (one allocation, so it can be exported over CUDA IPC): [VT0 | VT1 | flags | mailbox parity 0 | parity 1]
+    // mailbox (resident path): one 32-byte {u, tag, v, tag} entry per export node, then per ghost node
     size_t const vt_bytes = 2 * nn * sizeof(double);
     size_t const flag_bytes = 256 * sizeof(unsigned long long);
-    S->window_bytes = 2 * vt_bytes + flag_bytes;
+    S->n_mb = S->resident ? S->plan.n_export + (S->nn - S->ndof) : 0;
+    S->window_bytes = 2 * vt_bytes + flag_bytes + 2 * (size_t)S->n_mb * sizeof(MbEntry);
     NSX_CUDA(cudaMalloc(&S->window, S->window_bytes));
     NSX_CUDA(cudaMemsetAsync(S->window, 0, S->window_bytes, st));
     S->VT[0] = (double*)S->window;
     S->VT[1] = S->VT[0] + 2 * nn;
     S->flags = (unsigned long long*)(S->VT[1] + 2 * nn);
+    S->mailbox = (void*)(S->flags + 256);
 
     DBuf<double>* nodal2[] = {&S->UM, &S->UT, &S->wind, &S->ocean, &S->tau_wi, &S->tau_a, &S->tau_w, &S->VTM, &S->grad_ssh};
     for (auto* b : nodal2) { b->alloc(2 * nn); b->zero(st); }
@@ -121,7 +124,8 @@ static void alloc_fields(nsx_solver* S)
                             &S->del_ci_ridge_myi, &S->emass, &S->ecbu};
     for (auto* b : elem) { b->alloc(ne); b->zero(st); }
     S->shape.alloc(6 * ne); S->shape.zero(st);
-    S->slot_shape.alloc(6 * ns); S->slot_shape.zero(st);
+    S->slot_shape.alloc(4 * ns); S->slot_shape.zero(st);
+    S->disp.alloc(2 * nn); S->disp.zero(st);
     S->slot_ec.alloc(6 * ns); S->slot_ec.zero(st);
     NSX_CUDA(cudaMallocHost(&S->h_err, sizeof(int)));
     *S->h_err = 0;
@@ -169,7 +173,7 @@ static void build_halo(nsx_solver* S, const NsxHalo* H)
                 int const v = H->send_idx[q];
                 if (v < 0 || v >= S->ndof) throw std::invalid_argument("nsx_create: send index is not an owned node");
                 p.h_send_idx.push_back(perm[v]);
-                S->plan.tiles[perm[v] / S->plan.tile_nodes].boundary = 1;
+                S->plan.tiles[S->plan.tile_of[perm[v]]].boundary = 1;
             }
         }
         for (int k = 0; k < H->n_recv_peers; ++k) {
@@ -208,27 +212,6 @@ static void build_halo(nsx_solver* S, const NsxHalo* H)
         S->tiles.upload(S->plan.tiles, S->stream);
     }
     S->tile_order.upload(order, S->stream);
-    if (S->resident) {
-        // resident path: which neighbour ranks (links, in S->peers order) each tile pushes to or reads ghosts of; every
-        // such tile arrives on the link once per exchange, the last arrival publishes the epoch (k_resident::signal)
-        std::vector<int> nmask(S->nn, 0);
-        int i = 0;
-        for (auto const& p : S->peers) {
-            for (int v : p.h_send_idx) nmask[v] |= 1 << i;
-            for (int v : p.h_recv_idx) nmask[v] |= 1 << i;
-            ++i;
-        }
-        for (int k = 0; k < 16; ++k) S->res_link_tiles[k] = 0;
-        for (int t = 0; t < S->plan.ntiles; ++t) {
-            nsx::TileDesc const& td = S->plan.tiles[t];
-            int m = 0;
-            for (int j = 0; j < td.n_own; ++j) m |= nmask[td.node_begin + j];
-            for (int h = 0; h < td.n_halo; ++h) m |= nmask[S->plan.halo_nodes[td.halo_off + h]];
-            S->plan.res_tiles[t].link_mask = m;
-            for (int k = 0; k < (int)S->peers.size(); ++k) S->res_link_tiles[k] += (m >> k) & 1;
-        }
-        S->res_tiles.upload(S->plan.res_tiles, S->stream);
-    }
     NSX_CUDA(cudaStreamSynchronize(S->stream));
 }
 
@@ -311,7 +294,7 @@ static bool try_resident_plan(const NsxMesh* mesh, const NsxHalo* halo, int ctas
     int const T = (mesh->local_ndof + ctas - 1) / ctas;
     if (T > RES_TPB) { why = std::to_string(T) + " owned nodes per tile (limit " + std::to_string(RES_TPB) + ")"; return false; }
     P = MeshPlan();
-    build_mesh_plan(mesh, P, std::max(32, T), 1, true, halo ? xmask.data() : nullptr);
+    build_mesh_plan(mesh, P, std::max(32, T), 1, true, halo ? xmask.data() : nullptr, RES_TPB);
     size_t const smem = (size_t)(16 * P.msp + 2 * (P.max_local_nodes + 2)) * sizeof(double);     // BBM: 6 + 6 + 3 + 1 planes
     if (P.ntiles > ctas || P.tile_nodes > RES_TPB || P.max_slots > RES_SPT * RES_TPB || smem > (size_t)RES_SMEM_MAX || P.msp >= 16384) {
         why = "tiles " + std::to_string(P.ntiles) + ", nodes per tile " + std::to_string(P.tile_nodes) + ", max slots " +
@@ -547,6 +530,7 @@ static void field_table(nsx_solver* S, const NsxFields* f, std::vector<FieldMap>
 // device error word written by the bounded spins of the exchange / barrier kernels
 static std::string halo_error_text(int herr)
 {
+    if (herr >= 3000) return "device-side bounds check " + std::to_string(herr - 3000) + " failed (NSX_DEBUG_CHECKS build, nsx_kernels.cuh)";
     if (herr >= 2000) return "open-water smoother: grid barrier timed out (the launch was not co-resident)";
     if (herr >= 1000) return "resident solver: timed out waiting for the flag of tile " + std::to_string(herr - 1000) +
                              " (the launch was not co-resident, or a neighbour rank died)";
@@ -665,16 +649,24 @@ extern "C" int nsx_synchronize(nsx_handle S)
 // ---------------------------------------------------------------------------------------------------
 static_assert(sizeof(cudaIpcMemHandle_t) == NSX_IPC_HANDLE_BYTES, "ipc handle size");
 
-static void finish_link(nsx_solver* S, PeerLink& p, double* base, int peer_nn, const int* peer_recv_idx_for_me, size_t n)
+// the peer's window: [VT0 | VT1 | flags | mailbox]; hdr = {num_nodes, list length, local_ndof, export nodes} of the peer
+static void finish_link(nsx_solver* S, PeerLink& p, double* base, const int* hdr, const int* peer_recv_idx_for_me, size_t n)
 {
     if (n != p.h_send_idx.size()) throw std::runtime_error("halo: peer ghost list length differs from my send list");
+    int const peer_nn = hdr[0], peer_ndof = hdr[2], peer_nx = hdr[3];
     p.peer_nn = peer_nn;
     p.peer_vt[0] = base;
     p.peer_vt[1] = base + 2 * (size_t)peer_nn;
     p.peer_flags = (unsigned long long*)(base + 4 * (size_t)peer_nn);
     p.h_send_dst.assign(peer_recv_idx_for_me, peer_recv_idx_for_me + n);
+    // resident path on the peer (peer_nx >= 0): my values go into its mailbox, ghost g -> slot export + (g - ndof)
+    p.peer_mb = (void*)(p.peer_flags + 256);
+    p.peer_nmb = peer_nx >= 0 ? peer_nx + (peer_nn - peer_ndof) : 0;
+    p.h_send_slot.clear();
+    if (peer_nx >= 0)
+        for (size_t k = 0; k < n; ++k) p.h_send_slot.push_back(peer_nx + (peer_recv_idx_for_me[k] - peer_ndof));
+    if (S->resident != (peer_nx >= 0)) throw std::runtime_error("halo: neighbour ranks must use the same sub-cycle path");
     p.connected = true;
-    (void)S;
 }
 
 extern "C" int nsx_halo_connect_local(nsx_handle S, int peer_rank, nsx_handle Q)
@@ -696,28 +688,31 @@ extern "C" int nsx_halo_connect_local(nsx_handle S, int peer_rank, nsx_handle Q)
         if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) NSX_CUDA(e);
         (void)cudaGetLastError();
     }
-    finish_link(S, *mine, Q->VT[0], Q->nn, ridx.data(), ridx.size());
+    int const hdr[4] = {Q->nn, (int)ridx.size(), Q->ndof, Q->resident ? Q->plan.n_export : -1};
+    finish_link(S, *mine, Q->VT[0], hdr, ridx.data(), ridx.size());
     NSX_API_END(S)
 }
 
-// The peer's ghost index list for me travels with the IPC handle: [64 B handle | int nn | int n | n ints]
+// The peer's ghost index list for me travels with the IPC handle:
+// [64 B handle | int num_nodes | int n | int local_ndof | int export nodes (-1: not the resident path) | n ints]
+constexpr int BLOB_HDR = 16;
 extern "C" int nsx_halo_blob_size(nsx_handle S, int peer_rank)
 {
     if (!S) return -1;
-    for (auto& p : S->peers) if (p.rank == peer_rank) return NSX_IPC_HANDLE_BYTES + 8 + 4 * (int)p.h_recv_idx.size();
-    return NSX_IPC_HANDLE_BYTES + 8;
+    for (auto& p : S->peers) if (p.rank == peer_rank) return NSX_IPC_HANDLE_BYTES + BLOB_HDR + 4 * (int)p.h_recv_idx.size();
+    return NSX_IPC_HANDLE_BYTES + BLOB_HDR;
 }
 extern "C" int nsx_halo_blob(nsx_handle S, int peer_rank, unsigned char* out)
 {
     NSX_API_BEGIN(S)
     NSX_CUDA(cudaIpcGetMemHandle(&S->ipc, S->window));
     std::memcpy(out, &S->ipc, NSX_IPC_HANDLE_BYTES);
-    int hdr[2] = {S->nn, 0};
+    int hdr[4] = {S->nn, 0, S->ndof, S->resident ? S->plan.n_export : -1};
     const PeerLink* pl = nullptr;
     for (auto& p : S->peers) if (p.rank == peer_rank) pl = &p;
     if (pl) hdr[1] = (int)pl->h_recv_idx.size();
-    std::memcpy(out + NSX_IPC_HANDLE_BYTES, hdr, 8);
-    if (pl && hdr[1]) std::memcpy(out + NSX_IPC_HANDLE_BYTES + 8, pl->h_recv_idx.data(), 4 * (size_t)hdr[1]);
+    std::memcpy(out + NSX_IPC_HANDLE_BYTES, hdr, BLOB_HDR);
+    if (pl && hdr[1]) std::memcpy(out + NSX_IPC_HANDLE_BYTES + BLOB_HDR, pl->h_recv_idx.data(), 4 * (size_t)hdr[1]);
     NSX_API_END(S)
 }
 extern "C" int nsx_halo_connect_blob(nsx_handle S, int peer_rank, const unsigned char* blob)
@@ -728,12 +723,12 @@ extern "C" int nsx_halo_connect_blob(nsx_handle S, int peer_rank, const unsigned
     if (!mine) throw std::invalid_argument("nsx_halo_connect_blob: not a neighbour rank");
     cudaIpcMemHandle_t hdl;
     std::memcpy(&hdl, blob, NSX_IPC_HANDLE_BYTES);
-    int hdr[2];
-    std::memcpy(hdr, blob + NSX_IPC_HANDLE_BYTES, 8);
+    int hdr[4];
+    std::memcpy(hdr, blob + NSX_IPC_HANDLE_BYTES, BLOB_HDR);
     void* base = nullptr;
     NSX_CUDA(cudaIpcOpenMemHandle(&base, hdl, cudaIpcMemLazyEnablePeerAccess));
     mine->ipc_base = base;
-    finish_link(S, *mine, (double*)base, hdr[0], (const int*)(blob + NSX_IPC_HANDLE_BYTES + 8), (size_t)hdr[1]);
+    finish_link(S, *mine, (double*)base, hdr, (const int*)(blob + NSX_IPC_HANDLE_BYTES + BLOB_HDR), (size_t)hdr[1]);
     NSX_API_END(S)
 }
 
@@ -769,6 +764,18 @@ extern "C" int nsx_halo_finalize(nsx_handle S)
         }
         S->push_ptr.upload(ptr, S->stream);
         S->push_ent.upload(ent, S->stream);
+        if (S->resident) {              // same lists with the holder's mailbox slot as destination
+            std::vector<int2> entm(ent.size());
+            std::vector<int> fillm(ptr.begin(), ptr.end() - 1);
+            int sl = 0;
+            for (auto& p : S->peers) {
+                if (p.h_send_idx.empty()) continue;
+                for (size_t k = 0; k < p.h_send_idx.size(); ++k) entm[fillm[p.h_send_idx[k]]++] = make_int2(sl, p.h_send_slot[k]);
+                ++sl;
+            }
+            if (sl > RES_MAX_LINKS) throw std::runtime_error("resident path: too many neighbour ranks");
+            S->push_ent_mb.upload(entm, S->stream);
+        }
         // mixed direct/tile mode: elements written by boundary tiles, nodes owned by boundary tiles
         std::vector<uint8_t> nowrite(S->ne, 0), fl = S->plan.nflags;
         for (auto const& td : S->plan.tiles) {
@@ -897,7 +904,7 @@ static DirectArgs direct_args(nsx_solver* S, SubArgs const& A, bool mixed)
     D.nflags = S->nflags.p; D.n2e = S->n2e.p; D.n2e_deg = S->n2e_deg.p;
     D.grad_ssh = S->grad_ssh.p; D.node_mass = S->node_mass.p; D.rlmass = S->rlmass.p; D.cbu = S->cbu.p; D.fcor = S->fcor.p;
     D.tau_a = S->tau_a.p; D.tau_wi = A.tau_wi; D.ocean = S->ocean.p; D.VTM = S->VTM.p;
-    D.UM = S->UM.p; D.UT = S->UT.p;
+    D.disp = S->disp.p;
     return D;
 }
 
@@ -921,13 +928,14 @@ static void phase_substep(nsx_solver* S, int s, bool exchange_sync, bool overlap
     A.nflags = S->nflags.p; A.grad_ssh = S->grad_ssh.p; A.node_mass = S->node_mass.p; A.rlmass = S->rlmass.p;
     A.cbu = S->cbu.p; A.fcor = S->fcor.p; A.tau_a = S->tau_a.p; A.tau_wi = S->have_tau_wi ? S->tau_wi.p : nullptr;
     A.ocean = S->ocean.p; A.VTM = S->VTM.p; A.VTc = S->VT[S->cur]; A.VTn = S->VT[S->cur ^ 1];
-    A.UM = S->UM.p; A.UT = S->UT.p;
+    A.disp = S->disp.p;
+    A.halo_err = S->halo_err.p;
     A.move_mesh = (K.dynamics_type != NSX_DYN_MEVP);
     A.lag_ghost_move = (A.move_mesh && s > 0);
     int npl = 0;
     for (int p = 0; p < NP_COUNT; ++p) {
-        bool use = p < NP_UMU;
-        if (p >= NP_UMU && p <= NP_UTV) use = A.move_mesh;
+        bool use = p < NP_DSU;
+        if (p == NP_DSU || p == NP_DSV) use = A.move_mesh;
         if (p == NP_VMU || p == NP_VMV) use = (K.dynamics_type == NSX_DYN_MEVP);
         if (p == NP_TWU || p == NP_TWV) use = S->have_tau_wi;
         A.np[p] = use ? npl++ : 0;
@@ -989,10 +997,10 @@ static void phase_post_move(nsx_solver* S, int nrun)
     cudaStream_t st = S->stream;
     KParams const& K = S->K;
     if (K.dynamics_type == NSX_DYN_MEVP) {
-        k_move_mesh<<<nblk(S->nn), TPB, 0, st>>>(S->nn, 0, S->nn, K.dtime_step, S->nflags.p, S->VT[S->cur], S->UM.p, S->UT.p);
+        k_move_mesh<<<nblk(S->nn), TPB, 0, st>>>(S->nn, 0, S->nn, K.dtime_step, S->VT[S->cur], S->disp.p);
         S->n_launch++;
     } else if (S->nn > S->ndof && nrun > 0) {
-        k_move_mesh<<<nblk(S->nn - S->ndof), TPB, 0, st>>>(S->nn, S->ndof, S->nn, K.dte, S->nflags.p, S->VT[S->cur], S->UM.p, S->UT.p);
+        k_move_mesh<<<nblk(S->nn - S->ndof), TPB, 0, st>>>(S->nn, S->ndof, S->nn, K.dte, S->VT[S->cur], S->disp.p);
         S->n_launch++;
     }
     NSX_CUDA(cudaGetLastError());
@@ -1019,7 +1027,7 @@ static void phase_tauw(nsx_solver* S)
 {
     // the resident launch reads the exchange epoch at its start; the counter advances here, after it has finished
     k_tauw_owmove<<<nblk(S->nn), TPB, 0, S->stream>>>(S->K, S->nflags.p, S->node_mass.p, S->VT[S->cur], S->VTM.p,
-                                                      S->ocean.p, S->tau_w.p, S->UM.p, S->UT.p,
+                                                      S->ocean.p, S->tau_w.p, S->UM.p, S->UT.p, S->resident ? nullptr : S->disp.p,
                                                       S->epoch_bump ? S->d_epoch.p : nullptr, (unsigned long long)S->epoch_bump);
     S->epoch_bump = 0;
     S->n_launch++;
@@ -1039,18 +1047,6 @@ static void record(nsx_solver* S, int i)
     else NSX_CUDA(cudaEventRecord(S->ev[i], S->stream));
 }
 
-// tile flags + per-exchange link arrival counters of the resident launch; allocated outside any stream capture
-static void ensure_res_flags(nsx_solver* S)
-{
-    if (!S->resident) return;
-    size_t const words = (size_t)S->plan.ntiles * RES_FLAG_STRIDE + (size_t)(std::max(1, S->P.substeps) + 50 + 2) * RES_MAX_LINKS;
-    if (S->res_flag_words < words) {
-        NSX_CUDA(cudaStreamSynchronize(S->stream));
-        S->res_flags.alloc(words);
-        S->res_flag_words = words;
-    }
-}
-
 // The whole sub-cycle loop and the open-water smoother of one rank in ONE cooperative launch (k_resident).
 static void launch_resident(nsx_solver* S, int nrun, bool cooperative)
 {
@@ -1059,8 +1055,9 @@ static void launch_resident(nsx_solver* S, int nrun, bool cooperative)
     int const nsweeps = S->P.skip_ow_smoother ? 0 : 50;            // hard-coded 50 sweeps, FE.cpp:10580
     if (!S->peers.empty() && !S->halo_ready) throw std::runtime_error("explicit solve before nsx_halo_finalize");
     ResidentArgs A{};
-    A.tiles = S->tiles.p; A.rtiles = S->res_tiles.p; A.nbr = S->res_nbr.p;
-    A.halo_nodes = S->halo_nodes.p; A.halo_move = S->halo_move.p; A.halo_elems = S->halo_elems.p; A.slot_conn = S->slot_conn.p;
+    A.tiles = S->tiles.p; A.rtiles = S->res_tiles.p;
+    A.halo_nodes = S->halo_nodes.p; A.halo_slot = S->halo_slot.p; A.halo_move = S->halo_move.p; A.halo_elems = S->halo_elems.p;
+    A.slot_conn = S->slot_conn.p;
     A.slot_shape = S->slot_shape.p; A.slot_ec = S->slot_ec.p; A.nslots = S->plan.nslots; A.inc = S->inc.p;
     A.n2n_loc = S->res_n2n.p; A.n2n_deg = S->res_n2n_deg.p;
     A.s0 = S->sig[S->scur][0].p; A.s1 = S->sig[S->scur][1].p; A.s2 = S->sig[S->scur][2].p;
@@ -1071,28 +1068,20 @@ static void launch_resident(nsx_solver* S, int nrun, bool cooperative)
     A.VT0 = S->VT[0]; A.VT1 = S->VT[1]; A.cur = S->cur; A.UM = S->UM.p; A.UT = S->UT.p;
     A.move_mesh = (K.dynamics_type != NSX_DYN_MEVP); A.nsub = nrun; A.nsweeps = nsweeps;
     A.ow_count = S->ow_count.p;
-    size_t const tile_words = (size_t)S->plan.ntiles * RES_FLAG_STRIDE;
-    size_t const words = tile_words + (size_t)(nrun + nsweeps + 2) * RES_MAX_LINKS;
-    if (S->res_flag_words < words) throw std::logic_error("resident path: flag buffer too small");      // sized by ensure_res_flags
-    NSX_CUDA(cudaMemsetAsync(S->res_flags.p, 0, words * sizeof(unsigned int), S->stream));
-    A.tile_flags = S->res_flags.p; A.arrive = S->res_flags.p + tile_words;
-    A.push_ptr = S->push_ptr.p; A.push_ent = S->push_ent.p;
-    A.my_flags = S->flags; A.epoch_ctr = S->d_epoch.p; A.err = S->halo_err.p;
+    A.mb = (MbEntry*)S->mailbox; A.n_mb = S->n_mb;
+    A.push_ptr = S->push_ptr.p; A.push_ent = S->push_ent_mb.p;
+    A.epoch_ctr = S->d_epoch.p; A.err = S->halo_err.p;
     S->res_time.zero(S->stream);
     A.tstamp = S->res_time.p;
     A.MS = S->plan.msp; A.MLN = S->plan.max_local_nodes + 2;
-    int slot = 0, link = 0;
+    int slot = 0;
     for (auto& p : S->peers) {
-        if (!p.h_send_idx.empty()) {
-            A.P.send_vt[0][slot] = p.peer_vt[0]; A.P.send_vt[1][slot] = p.peer_vt[1]; A.P.send_nn[slot] = p.peer_nn;
-            ++slot;
-        }
-        A.P.link_flag[link] = p.peer_flags + S->rank;
-        A.P.link_rank[link] = p.rank;
-        A.P.link_tiles[link] = S->res_link_tiles[link];
-        ++link;
+        if (p.h_send_idx.empty()) continue;
+        A.P.send_mb[slot] = (MbEntry*)p.peer_mb; A.P.send_nmb[slot] = p.peer_nmb;
+        ++slot;
     }
-    A.P.n_link = link;
+    A.P.n_send = slot;
+    A.has_peers = S->peers.empty() ? 0 : 1;
     size_t const smem = (size_t)((bbm ? 16 : 12) * A.MS + 2 * A.MLN) * sizeof(double);
     // cooperative launch: the driver guarantees that all CTAs (one per SM) are co-resident, which the flag protocol needs
     void* args[2] = {(void*)&K, (void*)&A};
@@ -1106,9 +1095,8 @@ static void launch_resident(nsx_solver* S, int nrun, bool cooperative)
     if (bbm) NSX_CUDA(cudaLaunchKernelExC(&cfg, (const void*)k_resident<1>, args));
     else NSX_CUDA(cudaLaunchKernelExC(&cfg, (const void*)k_resident<0>, args));
     S->n_launch++;
-    int const nex = nrun + ((link > 0) ? nsweeps : 0);
     S->cur = (S->cur + nrun + nsweeps) & 1;          // the kernel leaves the result in that buffer whether or not it swept
-    S->epoch_bump = (link > 0) ? nex : 0;
+    S->epoch_bump = nrun + nsweeps;                  // mailbox tags never repeat: the epoch advances after every launch
 }
 
 static void solve_group(int n, nsx_solver** W)
@@ -1212,7 +1200,6 @@ extern "C" int nsx_explicit_solve(nsx_handle S)
 {
     NSX_API_BEGIN(S)
     nsx_solver* W[1] = {S};
-    ensure_res_flags(S);
     if (!S->opt.use_graph) {
         solve_group(1, W);
     } else {
@@ -1263,7 +1250,7 @@ extern "C" int nsx_group_explicit_solve(int n, nsx_handle* hs)
 {
     if (n <= 0 || !hs || !hs[0]) return 1;
     try {
-        for (int r = 0; r < n; ++r) { hs[r]->halo_local = true; NSX_CUDA(cudaSetDevice(hs[r]->device)); ensure_res_flags(hs[r]); }
+        for (int r = 0; r < n; ++r) hs[r]->halo_local = true;
         solve_group(n, hs);
     } catch (std::exception const& e) { hs[0]->err = e.what(); return 2; }
     return 0;
@@ -1436,6 +1423,34 @@ extern "C" int nsx_plan_info(const NsxMesh* mesh, int target_tile_nodes, int wav
         int const v[11] = {P.ntiles, P.tile_nodes, P.nslots, P.max_local_nodes, P.max_slots, P.max_own_slots,
                            P.max_halo_slots, P.max_halo_nodes, sub_layout(P, 14).total, attempt, nbt};
         for (int i = 0; i < n && i < 11; ++i) out[i] = v[i];
+        return 0;
+    } catch (std::exception const& e) {
+        g_create_err = e.what();
+        return 2;
+    }
+}
+
+// host only (no GPU): the state-resident plan nsx_create_ex would try for this rank on `sms` SMs.
+// out[0..11] = fits, ntiles, nodes/tile, slot space, max slots per tile, max local nodes per tile, shared-memory bytes
+// (BBM), export nodes, early own slots (sum), halo slots (sum), own slots (sum), limit of shared-memory bytes
+extern "C" int nsx_resident_plan_info(const NsxMesh* mesh, const NsxHalo* halo, int sms, int* out, int n)
+{
+    try {
+        if (!mesh) throw std::invalid_argument("nsx_resident_plan_info: NULL mesh");
+        validate_inputs(mesh, halo);
+        MeshPlan P;
+        std::string why;
+        bool const fits = try_resident_plan(mesh, halo, RES_CTAS * std::max(1, sms), P, why);
+        if (!fits) g_create_err = why;
+        long early = 0, halo_slots = 0, own = 0;
+        for (size_t t = 0; t < P.tiles.size(); ++t) {
+            own += P.tiles[t].n_own_slots; halo_slots += P.tiles[t].n_halo_slots;
+            if (t < P.res_tiles.size()) early += P.res_tiles[t].n_early_own;
+        }
+        int const v[12] = {fits ? 1 : 0, P.ntiles, P.tile_nodes, P.nslots, P.max_slots, P.max_local_nodes,
+                           (int)((size_t)(16 * P.msp + 2 * (P.max_local_nodes + 2)) * sizeof(double)), P.n_export,
+                           (int)early, (int)halo_slots, (int)own, RES_SMEM_MAX};
+        for (int i = 0; i < n && i < 12; ++i) out[i] = v[i];
         return 0;
     } catch (std::exception const& e) {
         g_create_err = e.what();

@@ -80,6 +80,9 @@ struct PeerLink {
     std::vector<int> h_send_idx;           // my INTERNAL node ids to send (M_extract_local_index[peer], permuted)
     std::vector<int> h_recv_idx;           // my INTERNAL ghost ids filled by that peer (M_local_ghosts_local_index[peer])
     std::vector<int> h_send_dst;           // the peer's internal ghost ids for my send list (same order)
+    std::vector<int> h_send_slot;          // the peer's MAILBOX slots for my send list (resident path)
+    void* peer_mb = nullptr;               // peer's mailbox (mapped), parity 0
+    int peer_nmb = 0;                      // entries per parity of the peer's mailbox
     double* peer_vt[2] = {nullptr, nullptr};   // peer's VT ping-pong buffers (mapped)
     unsigned long long* peer_flags = nullptr;  // peer's flag array (mapped); I write slot [my rank]
     int peer_nn = 0;
@@ -117,7 +120,7 @@ struct nsx_solver {
     nsx::DBuf<int> halo_nodes, halo_elems, slot_elem;
     nsx::DBuf<unsigned long long> slot_conn;
     nsx::DBuf<uint16_t> inc;
-    nsx::DBuf<double> slot_shape, slot_ec;     // [6*nslots] each (BBM) / ec uses 2 planes for EVP, mEVP
+    nsx::DBuf<double> slot_shape, slot_ec;     // slot space: 4 shape planes, 6 rheology-constant planes (2 for EVP / mEVP)
     size_t sub_smem = 0;
 
     // ---- fields (device) ----
@@ -131,6 +134,7 @@ struct nsx_solver {
     int dcur = 0;                              // which damage plane is current (flips only under BBM)
 
     nsx::DBuf<double> UM, UT, wind, ocean, tau_wi, tau_a, tau_w, ssh, VTM;
+    nsx::DBuf<double> disp;                      // displacement accumulated over the sub-cycle loop (tile / direct paths), [2*nn]
     bool have_tau_wi = false;
     nsx::DBuf<double> sig[2][3], dmg[2];       // ping-pong (tiles recompute neighbours' elements from the old state)
     nsx::DBuf<double> conc, thick, snow, conc_young, h_young, hs_young, thick_myi, conc_myi, ridge_ratio;
@@ -145,14 +149,14 @@ struct nsx_solver {
     bool direct = false;                         // L2-resident mesh: element kernel + node kernel instead of the tile kernel
     // resident path
     nsx::DBuf<nsx::ResTile> res_tiles;
-    nsx::DBuf<int> res_nbr;
     nsx::DBuf<uint16_t> res_n2n;
     nsx::DBuf<uint8_t> res_n2n_deg, halo_move;
-    nsx::DBuf<unsigned int> res_flags;           // tile flags followed by the per-exchange link arrival counters
-    size_t res_flag_words = 0;
+    nsx::DBuf<int> halo_slot;
+    nsx::DBuf<int2> push_ent_mb;                 // owned node -> (send slot, slot in the holder's mailbox)
+    void* mailbox = nullptr;                     // inside the halo window: [2][n_mb] 32-byte entries
+    int n_mb = 0;
     nsx::DBuf<unsigned long long> res_time;      // %globaltimer stamps of the last resident launch: start, loop end, end
     unsigned long long* h_time = nullptr;        // pinned copy
-    int res_link_tiles[16] = {};                 // tiles of this rank that arrive on link i per exchange
     int epoch_bump = 0;                          // exchanges the resident launch of the current graph performs
     nsx::DBuf<double> arena;                     // transfer arena (host numbering): all fields of one upload / download call
     int* h_err = nullptr;                        // pinned copy of the device error word

@@ -17,6 +17,17 @@ namespace nsx {
 
 constexpr int TPB = 256;
 
+// Device-side bounds checks of the index tables the sub-cycle kernels trust (slot connectivity, incidence codes, halo and
+// mailbox slots, push lists).  Compiled in with -DNSX_DEBUG_CHECKS (NSX_DEBUG_CHECKS=1 python -m nextsim_b200.build): a
+// violated check writes 3000 + its id into the handle's error word, which nsx_download / nsx_check turn into an error.
+// This is the stand-in for compute-sanitizer memcheck, which is closed on the GPU pool this was developed on
+// (profiles/r2_debug_checks.txt).
+#ifdef NSX_DEBUG_CHECKS
+#define NSX_DEV_CHECK(cond, errp, id) do { if (!(cond)) atomicCAS((errp), 0, 3000 + (id)); } while (0)
+#else
+#define NSX_DEV_CHECK(cond, errp, id) do { } while (0)
+#endif
+
 __device__ __forceinline__ double ld_nc(const double* p) { return __ldg(p); }
 
 // ---------------------------------------------------------------------------------------------------
@@ -67,8 +78,10 @@ k_prep_elements(KParams K, int nslots, const int* __restrict__ slot_elem,
     double sc[6];
     sc[0] = (yb - yc) / jac;  sc[1] = (yc - ya) / jac;  sc[2] = (ya - yb) / jac;
     sc[3] = (xc - xb) / jac;  sc[4] = (xa - xc) / jac;  sc[5] = (xb - xa) / jac;
-#pragma unroll
-    for (int k = 0; k < 6; ++k) slot_shape[(size_t)k * nslots + s] = sc[k];
+    // slot space keeps FOUR planes (dN0/dx, dN1/dx, dN0/dy, dN1/dy): the gradients of the three shape functions sum to
+    // zero, the sub-cycle kernels rebuild the third pair (16 B less per slot and sub-cycle from HBM)
+    slot_shape[0 * (size_t)nslots + s] = sc[0];  slot_shape[1 * (size_t)nslots + s] = sc[1];
+    slot_shape[2 * (size_t)nslots + s] = sc[3];  slot_shape[3 * (size_t)nslots + s] = sc[4];
 
     double const cc = conc[e], hh = thick[e];
     double const vol = hh * A;                                 // FE.cpp:10450
@@ -335,7 +348,7 @@ struct SmemLayout {
     int bar, conn, shape, ec, sig, dmg, node, su, sv, hsig, inc, fl, total;
     int msp, mop, mtp, mhs;     // slot / own-slot / node / halo-slot plane strides (elements)
 };
-enum { NP_GSU, NP_GSV, NP_MASS, NP_RL, NP_CBU, NP_FCOR, NP_TAU, NP_TAV, NP_OCU, NP_OCV, NP_UMU, NP_UMV, NP_UTU, NP_UTV,
+enum { NP_GSU, NP_GSV, NP_MASS, NP_RL, NP_CBU, NP_FCOR, NP_TAU, NP_TAV, NP_OCU, NP_OCV, NP_DSU, NP_DSV,
        NP_VMU, NP_VMV, NP_TWU, NP_TWV, NP_COUNT };
 
 struct HaloArgs {
@@ -387,7 +400,7 @@ struct SubArgs {
     double* s0o; double* s1o; double* s2o; double* dmo;
     const uint8_t* nflags; const double* grad_ssh; const double* node_mass; const double* rlmass;
     const double* cbu; const double* fcor; const double* tau_a; const double* tau_wi; const double* ocean;
-    const double* VTM; const double* VTc; double* VTn; double* UM; double* UT;
+    const double* VTM; const double* VTc; double* VTn; double* disp;
     int move_mesh, lag_ghost_move, n_tiles;
     int np[NP_COUNT];           // node plane -> staging slot (compacted: only the planes this configuration reads)
     // fused ghost exchange of the boundary launch (multi-GPU): phase 2 stores sent nodes straight into the holders'
@@ -416,9 +429,11 @@ __device__ __forceinline__ uint32_t stage_tile(int g, KParams const& K, SubArgs 
     auto node_plane = [&](int p, const double* src) { return stage<1>(sm + L.node + (size_t)A.np[p] * L.mtp * 8, src + nb, no, 8, bar, ctr); };
     if (g == 0) {
         tx += stage<1>(sm + L.conn, A.slot_conn + s0, nsl, 8, bar, ctr);
+        // four staged shape planes land in planes 0, 1 (d/dx of N0, N1) and 3, 4 (d/dy); planes 2 and 5 only ever hold
+        // contributions
 #pragma unroll
-        for (int p = 0; p < 6; ++p)
-            tx += stage<1>(sm + L.shape + (size_t)p * L.msp * 8, A.slot_shape + p * NS + s0, nsl, 8, bar, ctr);
+        for (int p = 0; p < 4; ++p)
+            tx += stage<1>(sm + L.shape + (size_t)(p < 2 ? p : p + 1) * L.msp * 8, A.slot_shape + p * NS + s0, nsl, 8, bar, ctr);
         tx += stage<1>(sm + L.su, A.VTc + nb, no, 8, bar, ctr);
         tx += stage<1>(sm + L.sv, A.VTc + nn + nb, no, 8, bar, ctr);
     } else if (g == 1) {
@@ -436,10 +451,7 @@ __device__ __forceinline__ uint32_t stage_tile(int g, KParams const& K, SubArgs 
         tx += node_plane(NP_TAU, A.tau_a);      tx += node_plane(NP_TAV, A.tau_a + nn);
         tx += node_plane(NP_OCU, A.ocean);      tx += node_plane(NP_OCV, A.ocean + nn);
     } else {
-        if (A.move_mesh) {
-            tx += node_plane(NP_UMU, A.UM);     tx += node_plane(NP_UMV, A.UM + nn);
-            tx += node_plane(NP_UTU, A.UT);     tx += node_plane(NP_UTV, A.UT + nn);
-        }
+        if (A.move_mesh) { tx += node_plane(NP_DSU, A.disp); tx += node_plane(NP_DSV, A.disp + nn); }
         if (K.dynamics_type == NSX_DYN_MEVP) { tx += node_plane(NP_VMU, A.VTM); tx += node_plane(NP_VMV, A.VTM + nn); }
         if (A.tau_wi) { tx += node_plane(NP_TWU, A.tau_wi); tx += node_plane(NP_TWV, A.tau_wi + nn); }
         tx += stage<1>(sm + L.inc, A.inc + td.inc_off, td.inc_w * td.n_own, 2, bar, ctr);
@@ -568,8 +580,10 @@ k_subcycle(KParams K, SubArgs A)
         int const hk = k - td.n_own_slots;
         unsigned long long const pc = conn[k];
         int const la = (int)(pc & 0xFFFF), lb = (int)((pc >> 16) & 0xFFFF), lc = (int)((pc >> 32) & 0xFFFF);
-        double const dx0 = shp[k], dx1 = shp[MSP + k], dx2 = shp[2 * MSP + k];
-        double const dy0 = shp[3 * MSP + k], dy1 = shp[4 * MSP + k], dy2 = shp[5 * MSP + k];
+        NSX_DEV_CHECK(la < td.n_own + HALO_GAP + td.n_halo && lb < td.n_own + HALO_GAP + td.n_halo && lc < td.n_own + HALO_GAP + td.n_halo &&
+                      k < MSP && (!own || e < K.ne), A.halo_err, 11);
+        double const dx0 = shp[k], dx1 = shp[MSP + k], dy0 = shp[3 * MSP + k], dy1 = shp[4 * MSP + k];
+        double const dx2 = -(dx0 + dx1), dy2 = -(dy0 + dy1);      // sum of the shape-function gradients is zero
         double const c0 = ecp[k];
         double s0, s1, s2, vol;
         if (BBM) {
@@ -665,6 +679,7 @@ k_subcycle(KParams K, SubArgs A)
             for (int c = 0; c < td.inc_w; ++c) {
                 unsigned const code = ip[c * td.n_own];
                 if (code == 0xFFFFu) break;
+                NSX_DEV_CHECK((int)code < 3 * MSP && (int)(code % (unsigned)MSP) < nsl, A.halo_err, 12);
                 gu -= shp[code];
                 gv -= shp[code + 3 * MSP];
             }
@@ -699,18 +714,15 @@ k_subcycle(KParams K, SubArgs A)
             int const q1 = A.push_ptr[n + 1];
             for (int q = A.push_ptr[n]; q < q1; ++q) {
                 int2 const pe = A.push_ent[q];
+                NSX_DEV_CHECK(pe.x >= 0 && pe.x < A.H.n_peers && pe.y >= 0 && pe.y < A.H.peer_nn[pe.x], A.halo_err, 13);
                 double* const dst = A.H.peer_vt[pe.x];
                 dst[pe.y] = un;
                 dst[pe.y + A.H.peer_nn[pe.x]] = vn;
             }
         }
-        if (A.move_mesh) {
-            A.UT[n] = npl[A.np[NP_UTU] * MTP + shs + j] + K.dte * un;
-            A.UT[n + nn] = npl[A.np[NP_UTV] * MTP + sh_nv + j] + K.dte * vn;
-            if (!(fl & NF_NEUMANN)) {
-                A.UM[n] = npl[A.np[NP_UMU] * MTP + shs + j] + K.dte * un;
-                A.UM[n + nn] = npl[A.np[NP_UMV] * MTP + sh_nv + j] + K.dte * vn;
-            }
+        if (A.move_mesh) {      // M_UM and M_UT both receive dte*VT every sub-cycle (FE.cpp:10545-10549): one accumulator, applied
+            A.disp[n] = npl[A.np[NP_DSU] * MTP + shs + j] + K.dte * un;         // to both after the loop (k_tauw_owmove)
+            A.disp[n + nn] = npl[A.np[NP_DSV] * MTP + sh_nv + j] + K.dte * vn;
         }
     }
     // ghost nodes: moved with the velocity their owner pushed at the end of the previous sub-cycle
@@ -718,8 +730,7 @@ k_subcycle(KParams K, SubArgs A)
         for (int j = gtid; j < td.n_ghost; j += gstride) {
             int const n = td.ghost_begin + j;
             double const u = A.VTc[n], v = A.VTc[n + nn];
-            A.UT[n] += K.dte * u;  A.UT[n + nn] += K.dte * v;
-            if (!(A.nflags[n] & NF_NEUMANN)) { A.UM[n] += K.dte * u;  A.UM[n + nn] += K.dte * v; }
+            A.disp[n] += K.dte * u;  A.disp[n + nn] += K.dte * v;
         }
     }
     // every read of this stage is done: one arrival per consumer warp lets the producer refill it
@@ -771,7 +782,7 @@ struct DirectArgs {
     const uint8_t* nflags; const int* n2e; const int* n2e_deg;
     const double* grad_ssh; const double* node_mass; const double* rlmass; const double* cbu; const double* fcor;
     const double* tau_a; const double* tau_wi; const double* ocean; const double* VTM;
-    double* UM; double* UT;
+    double* disp;
 };
 
 template <int BBM, int CG>
@@ -870,10 +881,7 @@ __device__ __forceinline__ void direct_node(KParams const& K, DirectArgs const& 
     if (fl & skip_flag_mask) return;            // nodes of boundary tiles (and ghosts) belong to the boundary launch
     double const uice = ldv<CG>(VTc + n), vice = ldv<CG>(VTc + n + nn);
     if (fl & NF_GHOST) {
-        if (lag_ghost_move) {
-            A.UT[n] += K.dte * uice;  A.UT[n + nn] += K.dte * vice;
-            if (!(fl & NF_NEUMANN)) { A.UM[n] += K.dte * uice;  A.UM[n + nn] += K.dte * vice; }
-        }
+        if (lag_ghost_move) { A.disp[n] += K.dte * uice;  A.disp[n + nn] += K.dte * vice; }
         return;
     }
     double un = uice, vn = vice;
@@ -913,10 +921,7 @@ __device__ __forceinline__ void direct_node(KParams const& K, DirectArgs const& 
     }
     VTn[n] = un;
     VTn[n + nn] = vn;
-    if (move_mesh) {
-        A.UT[n] += K.dte * un;  A.UT[n + nn] += K.dte * vn;
-        if (!(fl & NF_NEUMANN)) { A.UM[n] += K.dte * un;  A.UM[n + nn] += K.dte * vn; }
-    }
+    if (move_mesh) { A.disp[n] += K.dte * un;  A.disp[n + nn] += K.dte * vn; }
 }
 
 template <int BBM>
@@ -947,12 +952,15 @@ k_node_direct(KParams K, DirectArgs A, int move_mesh, int lag_ghost_move, int sk
 // registers of the thread that owns the slot, the velocity of the tile's local nodes in shared memory, UM / UT and the
 // incidence list of the owned node in registers.  HBM is not touched inside the loop.
 //
-// Synchronisation is point to point, not grid wide.  A tile publishes the velocities of its EXPORT nodes (owned nodes
-// another tile or another rank reads) in the ping-pong VT buffer and then a release flag; a tile waits only for the
-// flags of the <= ~8 tiles that own its halo nodes.  Ghost nodes work the same way across GPUs: export nodes on a
-// send list are stored straight into the holder's VT buffer over NVLink, the last tile of the rank to finish its
-// pushes for a neighbour rank publishes the exchange epoch there (st.release.sys), and only tiles that read that
-// neighbour's ghosts wait for its epoch (this is FiniteElement::updateGhosts, FE.cpp:13963-13996, per tile).
+// Synchronisation is point to point and carried BY THE DATA (the "LL" scheme of collective libraries): no grid barrier,
+// no fence, no separate flag.  Every value another tile or another GPU reads travels as one 16-byte store
+// {value, tag} into a MAILBOX slot, tag = exchange epoch; the reader polls the slot (one 16-byte load) until the tag
+// is the epoch it expects, so a value is usable the moment it lands.  A tile stores the velocities of its EXPORT nodes
+// (owned nodes that another tile or rank reads) into its rank's mailbox, and export nodes on a send list additionally
+// straight into the holder's mailbox over NVLink -- this is FiniteElement::updateGhosts (FE.cpp:13963-13996) per
+// node; a tile waits only for the ~10 % of its nodes that are halo nodes, each thread for its own.  The mailbox is
+// double-buffered by exchange parity.  16-byte aligned vector stores / loads are single transactions on this
+// hardware (the property NCCL's LL128 protocol relies on); tags grow monotonically across launches, so no reset.
 // The per-sub-cycle schedule hides that latency behind the interior work (plan order: export nodes first, "early"
 // slots -- those touching an export or halo node -- first):
 //     1. stress of the LATE slots (interior: no halo node, no export node)            needs nothing from outside
@@ -976,20 +984,40 @@ constexpr int RES_TPB = NSX_RES_TPB;            // threads per tile: one owned n
 constexpr int RES_CTAS = NSX_RES_CTAS;          // tiles (CTAs) per SM: independent tiles fill each other's barrier / latency stalls
 constexpr int RES_SPT = 3;                      // slots per thread (static unroll): tiles of up to 3 * RES_TPB slots
 constexpr int RES_MAX_LINKS = 16;               // neighbour ranks of one rank
-constexpr int RES_FLAG_STRIDE = 32;             // tile flags live 128 B apart
+
+// mailbox entry of one node: two 16-byte {value, tag} pairs, each written / read as ONE vector transaction
+struct __align__(16) MbEntry { double u; unsigned long long tu; double v; unsigned long long tv; };
+static_assert(sizeof(MbEntry) == 32, "mailbox entry");
 
 struct ResPeers {
-    int n_link;                                 // neighbour ranks (send or receive relation)
-    double* send_vt[2][RES_MAX_LINKS];          // per send slot (push_ent.x) and parity: the holder's VT buffer
-    int send_nn[RES_MAX_LINKS];
-    unsigned long long* link_flag[RES_MAX_LINKS];   // the neighbour's flag slot for me
-    int link_rank[RES_MAX_LINKS];               // my flag slot that neighbour writes
-    int link_tiles[RES_MAX_LINKS];              // how many of my tiles arrive on that link per exchange
+    int n_send;                                 // neighbour ranks this rank sends to (send slot = push_ent.x)
+    MbEntry* send_mb[RES_MAX_LINKS];            // the holder's mailbox (parity 0; parity 1 follows send_nmb entries later)
+    int send_nmb[RES_MAX_LINKS];
 };
 
+__device__ __forceinline__ void mb_store(MbEntry* e, double u, double v, unsigned long long tag)
+{
+    asm volatile("st.volatile.global.v2.u64 [%0], {%1, %2};" ::"l"(&e->u), "l"(__double_as_longlong(u)), "l"(tag) : "memory");
+    asm volatile("st.volatile.global.v2.u64 [%0], {%1, %2};" ::"l"(&e->v), "l"(__double_as_longlong(v)), "l"(tag) : "memory");
+}
+// polls until both halves carry `tag`; bounded (sets *err and gives up, also as soon as another waiter has timed out)
+__device__ __forceinline__ void mb_wait(const MbEntry* e, unsigned long long tag, double& u, double& v, int* err, int who)
+{
+    unsigned long long a = 0, ta = 0, b = 0, tb = 0;
+    long long spins = 0;
+    for (;;) {
+        if (ta != tag) asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(ta) : "l"(&e->u) : "memory");
+        if (tb != tag) asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(b), "=l"(tb) : "l"(&e->v) : "memory");
+        if (ta == tag && tb == tag) break;
+        if ((++spins & 1023) == 0 && (*((volatile int*)err) || spins > (1LL << 22))) { atomicCAS(err, 0, who); break; }
+    }
+    u = __longlong_as_double((long long)a);
+    v = __longlong_as_double((long long)b);
+}
+
 struct ResidentArgs {
-    const TileDesc* tiles; const ResTile* rtiles; const int* nbr;
-    const int* halo_nodes; const uint8_t* halo_move; const int* halo_elems; const unsigned long long* slot_conn;
+    const TileDesc* tiles; const ResTile* rtiles;
+    const int* halo_nodes; const int* halo_slot; const uint8_t* halo_move; const int* halo_elems; const unsigned long long* slot_conn;
     const double* slot_shape; const double* slot_ec; int nslots; const uint16_t* inc;
     const uint16_t* n2n_loc; const uint8_t* n2n_deg;
     double* s0; double* s1; double* s2; double* dm;               // updated in place at the end of the loop
@@ -998,10 +1026,10 @@ struct ResidentArgs {
     double* VT0; double* VT1; int cur; double* UM; double* UT;
     int move_mesh, nsub, nsweeps;
     const int* ow_count;
-    unsigned int* tile_flags;                                     // [ntiles * RES_FLAG_STRIDE], zeroed before the launch
-    unsigned int* arrive;                                         // [(nsub + nsweeps + 1) * RES_MAX_LINKS], zeroed before the launch
-    const int* push_ptr; const int2* push_ent;
-    const unsigned long long* my_flags; const unsigned long long* epoch_ctr; int* err;
+    MbEntry* mb; int n_mb;                                        // this rank's mailbox: [2][n_mb], export nodes then ghost nodes
+    int has_peers;                                                // neighbour ranks exist: the smoother sweeps are always exchanged
+    const int* push_ptr; const int2* push_ent;                    // owned node -> (send slot, slot in the holder's mailbox)
+    const unsigned long long* epoch_ctr; int* err;
     unsigned long long* tstamp;                                   // [3] %globaltimer: launch start, end of the sub-cycle loop, end (max over tiles)
     int MS, MLN;                                                  // shared-memory strides: slots per plane, local nodes
     ResPeers P;
@@ -1106,8 +1134,7 @@ k_resident(KParams K, ResidentArgs A)
     int const nsl = td.n_own_slots + td.n_halo_slots;
     size_t const NS = (size_t)A.nslots;
     ResPeers const& P = A.P;
-    unsigned long long const epoch0 = P.n_link ? *A.epoch_ctr : 0ULL;
-    int const link_mask = P.n_link ? rt.link_mask : 0;
+    unsigned long long const epoch0 = *A.epoch_ctr;               // advanced by the host-side sequence after every launch
 
     if (tid == 0 && blockIdx.x == 0) A.tstamp[0] = globaltimer_ns();
     // ---- load the tile once ----
@@ -1119,8 +1146,12 @@ k_resident(KParams K, ResidentArgs A)
         if (k < nsl) {
             size_t const g = (size_t)td.slot_begin + k;
             cnp[k] = A.slot_conn[g];
-#pragma unroll
-            for (int c = 0; c < 6; ++c) shp[c * MS + k] = A.slot_shape[c * NS + g];
+            {   // four planes in slot space (see k_prep_elements); the resident copy keeps all six
+                double const dx0 = A.slot_shape[0 * NS + g], dx1 = A.slot_shape[1 * NS + g];
+                double const dy0 = A.slot_shape[2 * NS + g], dy1 = A.slot_shape[3 * NS + g];
+                shp[k] = dx0; shp[MS + k] = dx1; shp[2 * MS + k] = -(dx0 + dx1);
+                shp[3 * MS + k] = dy0; shp[4 * MS + k] = dy1; shp[5 * MS + k] = -(dy0 + dy1);
+            }
 #pragma unroll
             for (int c = 0; c < NEC; ++c) ecp[c * MS + k] = A.slot_ec[c * NS + g];
             int const e = (k < td.n_own_slots) ? td.elem_begin + k : A.halo_elems[td.halo_elem_off + (k - td.n_own_slots)];
@@ -1158,10 +1189,10 @@ k_resident(KParams K, ResidentArgs A)
             incr[c >> 1] = (c & 1) ? ((incr[c >> 1] & 0x0000FFFFu) | (dec << 16)) : ((incr[c >> 1] & 0xFFFF0000u) | dec);
         }
     }
-    // the first halo node this thread refreshes, and whether this tile moves it (ghost nodes: FE.cpp:10539-10553)
-    int const hg0 = (tid < td.n_halo) ? A.halo_nodes[td.halo_off + tid] : 0;
-    bool const hmove0 = (tid < td.n_halo) && A.halo_move[td.halo_off + tid];
-    int const my_nbr = (tid < rt.n_nbr) ? A.nbr[rt.nbr_off + tid] : -1;
+    // the first halo node this thread refreshes: its mailbox slot, and (ghost nodes this tile moves, FE.cpp:10539-10553)
+    // its node id, -1 otherwise
+    int const hslot0 = (tid < td.n_halo) ? A.halo_slot[td.halo_off + tid] : 0;
+    int const hmove0 = (tid < td.n_halo && A.halo_move[td.halo_off + tid]) ? A.halo_nodes[td.halo_off + tid] : -1;
     __syncthreads();
 
     // ---- helpers ----
@@ -1171,6 +1202,7 @@ k_resident(KParams K, ResidentArgs A)
             int const k = tid + q * RES_TPB;
             bool const is_early = (k < rt.n_early_own) || (k >= td.n_own_slots);
             if (k >= nsl || is_early != early) continue;
+            NSX_DEV_CHECK((int)(cnp[k] & 0xFFFF) < MLN && (int)((cnp[k] >> 16) & 0xFFFF) < MLN && (int)((cnp[k] >> 32) & 0xFFFF) < MLN && k < MS, A.err, 1);
             dmg[q] = res_slot_update<BBM>(K, k, cnp[k], dmg[q], MS, shp, ecp, sgp, su, sv);
         }
     };
@@ -1193,6 +1225,7 @@ k_resident(KParams K, ResidentArgs A)
             unsigned const code = (incr[c >> 1] >> (16 * (c & 1))) & 0xFFFFu;
             if (code == 0xFFFFu) { more = false; break; }
             int const i = (int)(code >> 14), k = (int)(code & 0x3FFFu);
+            NSX_DEV_CHECK(i < 3 && k < nsl, A.err, 2);
             double const a0 = sgp[k], a1 = sgp[MS + k], a2 = sgp[2 * MS + k];
             double const vol = ecp[(BBM ? 5 : 1) * MS + k];
             double const dxi = shp[i * MS + k], dyi = shp[(3 + i) * MS + k];
@@ -1233,71 +1266,39 @@ k_resident(KParams K, ResidentArgs A)
         vn = alpha * vice - beta * uice + dte_over_mass * (alpha * (grad_y + tau_y) - beta * (grad_x + tau_x)) + alpha * delv - beta * delu;
         vn *= rdenom;
     };
-    // export node -> ping-pong buffer of this rank and the ghost slots of every holder (updateGhosts, FE.cpp:13963-13996)
-    auto publish_node = [&](double* VTw, int parity, double un, double vn) {
-        VTw[n] = un; VTw[n + nn] = vn;
-        if (link_mask) {
+    // export node -> this rank's mailbox and, if it is on a send list, the mailbox of every holder (updateGhosts,
+    // FE.cpp:13963-13996): value and exchange epoch in one 16-byte store each
+    auto publish_node = [&](int parity, int ex, double un, double vn) {
+        unsigned long long const tag = epoch0 + (unsigned long long)ex;
+        NSX_DEV_CHECK(rt.x_off + tid < A.n_mb && n < K.ndof, A.err, 3);
+        mb_store(A.mb + (size_t)parity * A.n_mb + rt.x_off + tid, un, vn, tag);
+        if (P.n_send) {
             int const q1 = A.push_ptr[n + 1];
             for (int q = A.push_ptr[n]; q < q1; ++q) {
                 int2 const pe = A.push_ent[q];
-                double* const dst = P.send_vt[parity][pe.x];
-                dst[pe.y] = un;
-                dst[pe.y + P.send_nn[pe.x]] = vn;
+                NSX_DEV_CHECK(pe.x >= 0 && pe.x < P.n_send && pe.y >= 0 && pe.y < P.send_nmb[pe.x], A.err, 4);
+                mb_store(P.send_mb[pe.x] + (size_t)parity * P.send_nmb[pe.x] + pe.y, un, vn, tag);
             }
         }
     };
-    // exchange number ex (1-based): every export value of this tile is stored; release the tile flag, arrive on my links
-    auto signal = [&](int ex) {
-        __syncthreads();
-        if (tid == 0) {
-            if (link_mask) __threadfence_system(); else __threadfence();
-            asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(A.tile_flags + (size_t)blockIdx.x * RES_FLAG_STRIDE), "r"((unsigned)ex) : "memory");
-            for (int i = 0; i < P.n_link; ++i) {
-                if (!((link_mask >> i) & 1)) continue;
-                unsigned const old = atomicAdd(A.arrive + (size_t)ex * RES_MAX_LINKS + i, 1u);
-                if ((int)old + 1 == P.link_tiles[i]) {
-                    __threadfence_system();
-                    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(P.link_flag[i]), "l"(epoch0 + (unsigned long long)ex) : "memory");
-                }
-            }
-        }
-    };
-    // wait until every neighbour tile / neighbour rank this tile reads has published exchange ex, then refresh the halo
+    // every thread waits for ITS halo node of exchange ex (tile of this GPU or ghost of another one) and refreshes it
+    // displacement of the ghost node this thread moves (its first halo entry): accumulated like dspu / dspv, written once
+    double gdu = 0., gdv = 0.;
     auto wait_refresh = [&](int ex, int parity, bool move_ghosts, double dt_move) {
-        if (my_nbr >= 0) {
-            const unsigned int* f = A.tile_flags + (size_t)my_nbr * RES_FLAG_STRIDE;
-            unsigned v;
-            long long spins = 0;
-            for (;;) {
-                asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
-                if (v >= (unsigned)ex) break;
-                // bounded: a launch that is not co-resident (or a dead neighbour) must end, not hang the device; once one
-                // wait has timed out every later one gives up at once
-                if ((++spins & 1023) == 0 && (*((volatile int*)A.err) || spins > (1LL << 22))) { atomicCAS(A.err, 0, 1000 + my_nbr); break; }
-            }
-        }
-        int const li = tid - 32;
-        if (li >= 0 && li < P.n_link && ((link_mask >> li) & 1)) {
-            const unsigned long long* f = A.my_flags + P.link_rank[li];
-            unsigned long long v;
-            long long spins = 0;
-            for (;;) {
-                asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(f) : "memory");
-                if ((v & ~FLAG_OW) >= epoch0 + (unsigned long long)ex) break;
-                if ((++spins & 1023) == 0 && (*((volatile int*)A.err) || spins > (1LL << 22))) { atomicCAS(A.err, 0, 1 + P.link_rank[li]); break; }
-            }
-        }
-        __syncthreads();
-        const double* VTr = VTb(parity);
+        unsigned long long const tag = epoch0 + (unsigned long long)ex;
+        const MbEntry* const box = A.mb + (size_t)parity * A.n_mb;
         for (int h = tid; h < td.n_halo; h += RES_TPB) {
-            int const g = (h == tid) ? hg0 : A.halo_nodes[td.halo_off + h];
-            double const u = __ldcg(VTr + g), v = __ldcg(VTr + g + nn);
+            int const slot = (h == tid) ? hslot0 : A.halo_slot[td.halo_off + h];
+            NSX_DEV_CHECK(slot >= 0 && slot < A.n_mb && td.n_own + HALO_GAP + h < MLN, A.err, 5);
+            double u, v;
+            mb_wait(box + slot, tag, u, v, A.err, 1000 + (int)blockIdx.x);
             su[td.n_own + HALO_GAP + h] = u; sv[td.n_own + HALO_GAP + h] = v;
-            bool const mv = (h == tid) ? hmove0 : (A.halo_move[td.halo_off + h] != 0);
-            if (move_ghosts && mv) {                     // ghost nodes move with their owner's fresh velocity
-                A.UT[g] += dt_move * u;  A.UT[g + nn] += dt_move * v;
-                if (!(A.nflags[g] & NF_NEUMANN)) { A.UM[g] += dt_move * u;  A.UM[g + nn] += dt_move * v; }
-            }
+            if (!move_ghosts) continue;                  // ghost nodes move with their owner's fresh velocity
+            if (h == tid) { gdu = gdu + dt_move * u;  gdv = gdv + dt_move * v; continue; }
+            if (!A.halo_move[td.halo_off + h]) continue; // tiles with more halo nodes than threads: read-modify-write
+            int const g = A.halo_nodes[td.halo_off + h];
+            A.UT[g] += dt_move * u;  A.UT[g + nn] += dt_move * v;
+            if (!(A.nflags[g] & NF_NEUMANN)) { A.UM[g] += dt_move * u;  A.UM[g + nn] += dt_move * v; }
         }
         __syncthreads();
     };
@@ -1308,16 +1309,16 @@ k_resident(KParams K, ResidentArgs A)
         int const pw = (cur + s + 1) & 1;                         // parity of the buffer this sub-cycle writes
         phase1(false);                                            // 1. late slots
         if (s > 0) wait_refresh(s, pw ^ 1, A.move_mesh != 0, K.dte);   // 2. (sub-cycle 0 starts from the loaded state)
-        else __syncthreads();
+        else __syncthreads();                                     // (the barrier also orders phase 1 before the node solve)
         phase1(true);                                             // 3. early slots
         __syncthreads();
         double un = 0., vn = 0.;
         if (has_node) node_solve(un, vn);                         // needs every incident stress: after both phase-1 parts
-        // 4./5. one node per thread: every solve has read its inputs, nobody else reads su/sv before the barrier in signal()
+        // 4./5. one node per thread: every solve has read its inputs, nobody else reads su/sv before the barrier below
         if (has_node) { su[tid] = un; sv[tid] = vn; }
-        if (tid < rt.n_x) publish_node(VTb(pw), pw, un, vn);      // export nodes -> VT buffer (+ NVLink pushes)
+        if (tid < rt.n_x) publish_node(pw, s + 1, un, vn);        // export nodes -> mailboxes (local + NVLink), usable on arrival
         if (has_node && A.move_mesh) { dspu = dspu + K.dte * un;  dspv = dspv + K.dte * vn; }
-        signal(s + 1);                                            // barrier, then thread 0 publishes while the others go on
+        __syncthreads();                                          // su / sv complete before the next phase 1 reads them
     }
     int ex = A.nsub;                                              // exchanges done so far
     if (ex > 0) wait_refresh(ex, (cur + ex) & 1, A.move_mesh != 0, K.dte);
@@ -1326,9 +1327,10 @@ k_resident(KParams K, ResidentArgs A)
         // mEVP: ONE mesh move with the full time step after the loop (FE.cpp:10559-10573); ghosts alike
         if (has_node) { dspu = K.dtime_step * su[tid];  dspv = K.dtime_step * sv[tid]; }
         for (int h = tid; h < td.n_halo; h += RES_TPB) {
+            double const u = su[td.n_own + HALO_GAP + h], v = sv[td.n_own + HALO_GAP + h];
+            if (h == tid) { gdu = K.dtime_step * u;  gdv = K.dtime_step * v; continue; }
             if (!A.halo_move[td.halo_off + h]) continue;
             int const g = A.halo_nodes[td.halo_off + h];
-            double const u = su[td.n_own + HALO_GAP + h], v = sv[td.n_own + HALO_GAP + h];
             A.UT[g] += K.dtime_step * u;  A.UT[g + nn] += K.dtime_step * v;
             if (!(A.nflags[g] & NF_NEUMANN)) { A.UM[g] += K.dtime_step * u;  A.UM[g + nn] += K.dtime_step * v; }
         }
@@ -1336,7 +1338,7 @@ k_resident(KParams K, ResidentArgs A)
 
     // ---- open-water smoother: 50 Jacobi sweeps over the ice-free nodes (FE.cpp:10578-10611), same exchange per sweep.
     // A rank without neighbours and without ice-free nodes skips it; with neighbour ranks every sweep is exchanged.
-    int const nsweeps = (A.nsweeps > 0 && (P.n_link > 0 || *A.ow_count > 0)) ? A.nsweeps : 0;
+    int const nsweeps = (A.nsweeps > 0 && (A.has_peers || *A.ow_count > 0)) ? A.nsweeps : 0;
     bool const is_ow = has_node && !(fl & NF_DIRICHLET) && nmass == 0.;
     int const deg = is_ow ? (int)A.n2n_deg[n] : 0;
     for (int it = 0; it < nsweeps; ++it) {
@@ -1352,9 +1354,8 @@ k_resident(KParams K, ResidentArgs A)
         }
         __syncthreads();                                          // Jacobi: every read of the old values is done
         if (is_ow) { su[tid] = nu; sv[tid] = nv; }
-        if (tid < rt.n_x) publish_node(VTb(pw), pw, su[tid], sv[tid]);
         ++ex;
-        signal(ex);
+        if (tid < rt.n_x) publish_node(pw, ex, su[tid], sv[tid]);
         wait_refresh(ex, pw, false, 0.);
     }
 
@@ -1368,6 +1369,16 @@ k_resident(KParams K, ResidentArgs A)
             VTf[n] = su[tid]; VTf[n + nn] = sv[tid];
             A.UT[n] += dspu;  A.UT[n + nn] += dspv;
             if (!(fl & NF_NEUMANN)) { A.UM[n] += dspu;  A.UM[n + nn] += dspv; }
+        }
+        // ghost nodes: their last received velocity goes to the VT buffer the host-side sequence continues with
+        for (int h = tid; h < td.n_halo; h += RES_TPB) {
+            if (!A.halo_move[td.halo_off + h]) continue;
+            int const g = A.halo_nodes[td.halo_off + h];
+            VTf[g] = su[td.n_own + HALO_GAP + h]; VTf[g + nn] = sv[td.n_own + HALO_GAP + h];
+            if (h == tid) {
+                A.UT[g] += gdu;  A.UT[g + nn] += gdv;
+                if (!(A.nflags[g] & NF_NEUMANN)) { A.UM[g] += gdu;  A.UM[g + nn] += gdv; }
+            }
         }
     }
 #pragma unroll
@@ -1384,14 +1395,11 @@ k_resident(KParams K, ResidentArgs A)
 // mesh move over an explicit node range with an explicit time increment:
 //   mEVP: once after the loop with dtime_step (FE.cpp:10559-10573); ghosts: final lagged move.
 __global__ void __launch_bounds__(TPB)
-k_move_mesh(int nn, int n_begin, int n_end, double dt, const uint8_t* __restrict__ nflags,
-            const double* __restrict__ VT, double* __restrict__ UM, double* __restrict__ UT)
+k_move_mesh(int nn, int n_begin, int n_end, double dt, const double* __restrict__ VT, double* __restrict__ disp)
 {
     int const n = n_begin + blockIdx.x * blockDim.x + threadIdx.x;
     if (n >= n_end) return;
-    double const u = VT[n], v = VT[n + nn];
-    UT[n] += dt * u;  UT[n + nn] += dt * v;
-    if (!(nflags[n] & NF_NEUMANN)) { UM[n] += dt * u;  UM[n + nn] += dt * v; }
+    disp[n] += dt * VT[n];  disp[n + nn] += dt * VT[n + nn];
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -1471,13 +1479,20 @@ k_ow_smooth_all(int nn, int nsweeps, const int* __restrict__ ow_list, const int*
 __global__ void __launch_bounds__(TPB)
 k_tauw_owmove(KParams K, const uint8_t* __restrict__ nflags, const double* __restrict__ node_mass,
               const double* __restrict__ VT, const double* __restrict__ VTM, const double* __restrict__ ocean,
-              double* __restrict__ tau_w, double* __restrict__ UM, double* __restrict__ UT,
+              double* __restrict__ tau_w, double* __restrict__ UM, double* __restrict__ UT, double* __restrict__ disp,
               unsigned long long* epoch_ctr, unsigned long long epoch_bump)
 {
     int const n = blockIdx.x * blockDim.x + threadIdx.x;
     int const nn = K.nn;
     if (n == 0 && epoch_ctr) *epoch_ctr += epoch_bump;       // exchanges done by the resident launch that just finished
     if (n >= nn) return;
+    uint8_t const fl0 = nflags[n];
+    if (disp) {     // displacement accumulated by the sub-cycle loop of the tile / direct paths: M_UT and M_UM (Neumann nodes
+        double const du = disp[n], dv = disp[n + nn];          // keep their M_UM, FE.cpp:10551-10552) receive it once
+        UT[n] += du;  UT[n + nn] += dv;
+        if (!(fl0 & NF_NEUMANN)) { UM[n] += du;  UM[n + nn] += dv; }
+        disp[n] = 0.;  disp[n + nn] = 0.;
+    }
     double const u = VT[n], v = VT[n + nn];
     double const uice = 0.5 * (u + VTM[n]);
     double const vice = 0.5 * (v + VTM[n + nn]);

@@ -33,7 +33,7 @@ static uint64_t hilbert_xy2d(uint32_t x, uint32_t y)        // 16-bit coordinate
 }
 
 void build_mesh_plan(const NsxMesh* M, MeshPlan& P, int target_tile_nodes, int sm_count,
-                     bool resident_order, const uint8_t* export_mask)
+                     bool resident_order, const uint8_t* export_mask, int max_tile_nodes)
 {
     int const nn = M->num_nodes, ne = M->num_elements, ndof = M->local_ndof;
     if (nn <= 0 || ne <= 0 || ndof <= 0 || ndof > nn || M->local_nelements > ne)
@@ -96,8 +96,59 @@ void build_mesh_plan(const NsxMesh* M, MeshPlan& P, int target_tile_nodes, int s
     ntiles = std::max(1, std::min(ntiles, ndof));
     T = (ndof + ntiles - 1) / ntiles;
     ntiles = (ndof + T - 1) / T;
-    P.ntiles = ntiles; P.tile_nodes = T;
-    auto tile_of_node = [&](int internal) { return internal / T; };
+    // tile t owns the nodes [cut[t], cut[t+1]) of the curve order.  Equal node counts by default; the resident solver
+    // (one tile per SM for a whole model step, the slowest tile sets the pace) balances the SLOT counts instead: a few
+    // rounds of "measure the slots of every tile, move the cuts to equalise the cost along the curve".
+    std::vector<int> cut(ntiles + 1);
+    for (int t = 0; t <= ntiles; ++t) cut[t] = std::min(ndof, t * T);
+    if (resident_order && ntiles > 1) {
+        std::vector<std::vector<int>> inc_of(ndof);            // reference node -> incident elements
+        for (int e = 0; e < ne; ++e) {
+            int const v[3] = {r0[e], r1[e], r2[e]};
+            for (int i = 0; i < 3; ++i) if (v[i] < ndof) inc_of[v[i]].push_back(e);
+        }
+        std::vector<int> stamp(ne, -1);
+        int const max_nodes = std::max(T, max_tile_nodes);
+        // slot_cap: two slots per thread (a third round of the slot loop costs every tile that needs it a full extra
+        // slot latency): tiles above it are made a little more expensive each extra round until they fit, if they can
+        int const slot_cap = 2 * max_tile_nodes;
+        std::vector<double> penalty(ntiles, 1.0);
+        for (int round = 0; round < 24; ++round) {
+            std::vector<double> cost(ndof);                      // per curve position: slots of its tile / nodes of its tile
+            int worst = 0;
+            for (int t = 0; t < ntiles; ++t) {
+                int slots = 0;
+                for (int i = cut[t]; i < cut[t + 1]; ++i)
+                    for (int e : inc_of[P.node_inv[i]]) if (stamp[e] != round * ntiles + t) { stamp[e] = round * ntiles + t; ++slots; }
+                worst = std::max(worst, slots);
+                if (round >= 6 && max_tile_nodes > 0 && slots > slot_cap) penalty[t] *= 1.02;
+                double const c = penalty[t] * (double)slots / std::max(1, cut[t + 1] - cut[t]);
+                for (int i = cut[t]; i < cut[t + 1]; ++i) cost[i] = c;
+            }
+            if (round >= 6 && (max_tile_nodes <= 0 || worst <= slot_cap)) break;
+            double total = 0.;
+            for (int i = 0; i < ndof; ++i) total += cost[i];
+            std::vector<int> nc(ntiles + 1, 0);
+            nc[ntiles] = ndof;
+            double acc = 0.;
+            int t = 1;
+            for (int i = 0; i < ndof && t < ntiles; ++i) {
+                acc += cost[i];
+                while (t < ntiles && acc >= total * t / ntiles) nc[t++] = i + 1;
+            }
+            for (; t < ntiles; ++t) nc[t] = ndof;
+            bool ok = true;                                      // every tile non-empty and within the thread budget
+            for (int q = 0; q < ntiles; ++q) if (nc[q + 1] <= nc[q] || nc[q + 1] - nc[q] > max_nodes) ok = false;
+            if (!ok) break;
+            cut = nc;
+        }
+    }
+    T = 0;
+    for (int t = 0; t < ntiles; ++t) T = std::max(T, cut[t + 1] - cut[t]);
+    P.ntiles = ntiles; P.tile_nodes = T;                         // tile_nodes = the LARGEST tile
+    P.tile_of.assign(ndof, 0);
+    for (int t = 0; t < ntiles; ++t) for (int i = cut[t]; i < cut[t + 1]; ++i) P.tile_of[i] = t;
+    auto tile_of_node = [&](int internal) { return P.tile_of[internal]; };
 
     // resident solver: inside every tile the EXPORT nodes come first -- owned nodes that another tile reads (they share
     // an element with a node of another tile) or that are sent to another rank.  Tile membership does not change.
@@ -110,15 +161,15 @@ void build_mesh_plan(const NsxMesh* M, MeshPlan& P, int target_tile_nodes, int s
             int const v[3] = {r0[e], r1[e], r2[e]};
             for (int i = 0; i < 3; ++i) {
                 if (v[i] >= ndof) continue;
-                int const t = pos[v[i]] / T;
+                int const t = P.tile_of[pos[v[i]]];
                 for (int j = 0; j < 3; ++j)
-                    if (j != i && v[j] < ndof && pos[v[j]] / T != t) is_x[v[i]] = 1;
+                    if (j != i && v[j] < ndof && P.tile_of[pos[v[j]]] != t) is_x[v[i]] = 1;
             }
         }
         if (export_mask)
             for (int r = 0; r < ndof; ++r) if (export_mask[r]) is_x[r] = 1;
         for (int t = 0; t < ntiles; ++t) {
-            auto b = P.node_inv.begin() + (size_t)t * T, e = P.node_inv.begin() + std::min(ndof, (t + 1) * T);
+            auto b = P.node_inv.begin() + cut[t], e = P.node_inv.begin() + cut[t + 1];
             std::stable_partition(b, e, [&](int r) { return is_x[r] != 0; });
         }
     }
@@ -248,8 +299,8 @@ void build_mesh_plan(const NsxMesh* M, MeshPlan& P, int target_tile_nodes, int s
     P.max_local_nodes = 0; P.max_slots = 0; P.max_own_slots = 0; P.max_halo_slots = 0; P.max_halo_nodes = 0; P.max_inc = 0;
     for (int t = 0; t < ntiles; ++t) {
         TileDesc& td = P.tiles[t];
-        td.node_begin = t * T;
-        td.n_own = std::min(T, ndof - td.node_begin);
+        td.node_begin = cut[t];
+        td.n_own = cut[t + 1] - cut[t];
         td.elem_begin = own_begin[t];
         td.n_own_slots = own_cnt[t];
         td.slot_begin = (int)P.slot_elem.size();
@@ -355,6 +406,20 @@ void build_mesh_plan(const NsxMesh* M, MeshPlan& P, int target_tile_nodes, int s
         P.max_halo_slots = std::max(P.max_halo_slots, nh);
         P.max_halo_nodes = std::max(P.max_halo_nodes, nhn);
         P.max_inc = std::max(P.max_inc, dmax * td.n_own);
+    }
+    if (resident_order) {
+        // mailbox slots: export nodes in tile order, then the ghost nodes
+        int off = 0;
+        for (int t = 0; t < ntiles; ++t) { P.res_tiles[t].x_off = off; off += P.res_tiles[t].n_x; }
+        P.n_export = off;
+        P.halo_slot.assign(P.halo_nodes.size(), 0);
+        for (size_t h = 0; h < P.halo_nodes.size(); ++h) {
+            int const g = P.halo_nodes[h];
+            if (g >= ndof) { P.halo_slot[h] = off + (g - ndof); continue; }
+            int const q = tile_of_node(g), j = g - cut[q];
+            if (j >= P.res_tiles[q].n_x) throw std::logic_error("nsx mesh plan: a halo node is not an export node of its tile");
+            P.halo_slot[h] = P.res_tiles[q].x_off + j;
+        }
     }
     // slot space is padded to an even count so that every slot plane (stride nslots) has the same 16-byte
     // phase; the pad slot is never computed (marked INT_MIN)

@@ -35,7 +35,7 @@ struct ResTile {
     int n_early_own;                // own slots [0, n_early_own) are early
     int nbr_off, n_nbr;             // neighbour tiles (owners of my halo nodes, symmetric): res_nbr[nbr_off ...]
     int n2n_off, n2n_w;             // bamg-order node->node table of the owned nodes in tile-local ids (smoother)
-    int link_mask;                  // bit i: the tile pushes to / reads ghosts of neighbour rank (link) i   [build_halo]
+    int x_off;                      // mailbox slot of the tile's first export node (prefix sum of n_x over the tiles)
     int pad_;
 };
 static_assert(sizeof(ResTile) == 32, "ResTile is 8 ints");
@@ -60,9 +60,10 @@ struct MeshPlan {
     int nc_w = 0;                              // bamg NodalConnectivity order (FE.cpp:10597-10605)
     std::vector<int> n2n, n2n_deg;
     // tiles
-    int ntiles = 0, tile_nodes = 0, nslots = 0, max_local_nodes = 0, max_slots = 0;
+    int ntiles = 0, tile_nodes = 0 /* nodes of the largest tile */, nslots = 0, max_local_nodes = 0, max_slots = 0;
     int max_own_slots = 0, max_halo_slots = 0, max_halo_nodes = 0, max_inc = 0, msp = 0;
     std::vector<TileDesc> tiles;
+    std::vector<int> tile_of;                  // owned node (internal id) -> tile
     std::vector<int> halo_nodes, halo_elems, slot_elem;
     std::vector<unsigned long long> slot_conn; // 3 x 16-bit tile-local node ids
     std::vector<uint16_t> inc;                 // slot*3 + vertex, 0xFFFF = padding
@@ -72,12 +73,15 @@ struct MeshPlan {
     std::vector<uint16_t> res_n2n;             // [n2n_off + c*n_own + j] tile-local node id of the c-th neighbour (bamg order)
     std::vector<uint8_t> res_n2n_deg;          // [node_begin + j] = neighbour count
     std::vector<uint8_t> halo_move;            // per halo_nodes entry: this tile moves that ghost node (UM / UT)
+    std::vector<int> halo_slot;                // per halo_nodes entry: mailbox slot the value is read from
+    int n_export = 0;                          // export nodes of the rank; mailbox = [export nodes | ghost nodes]
 };
 
 // throws std::invalid_argument on inconsistent input
 // resident_order: export-first node order, early-first slot order and the ResTile tables; export_mask (may be NULL)
-// flags reference-numbered owned nodes that are sent to another rank.
+// flags reference-numbered owned nodes that are sent to another rank; max_tile_nodes bounds the tile sizes when the cuts
+// are moved to balance the slot counts.
 void build_mesh_plan(const NsxMesh* M, MeshPlan& P, int target_tile_nodes, int sm_count,
-                     bool resident_order = false, const uint8_t* export_mask = nullptr);
+                     bool resident_order = false, const uint8_t* export_mask = nullptr, int max_tile_nodes = 0);
 
 }  // namespace nsx
