@@ -256,12 +256,12 @@ def mesh_structs(lm):
 def resident_plan_info(lm, sms=148):
     """Host-only statistics of the state-resident plan for this rank (see nsx.h)."""
     M, H, keep = mesh_structs(lm)
-    out = (C.c_int * 12)()
+    out = (C.c_int * 14)()
     L = lib()
-    if L.nsx_resident_plan_info(C.byref(M), C.byref(H) if H is not None else None, int(sms), out, 12) != 0:
+    if L.nsx_resident_plan_info(C.byref(M), C.byref(H) if H is not None else None, int(sms), out, 14) != 0:
         raise RuntimeError(L.nsx_last_error(None).decode())
     names = ("fits", "ntiles", "tile_nodes", "slot_space", "max_slots", "max_local_nodes", "smem_bytes", "export_nodes",
-             "early_own_slots", "halo_slots", "own_slots", "smem_limit")
+             "early_own_slots", "halo_slots", "own_slots", "smem_limit", "gather_half_warp_wavefronts", "gather_half_warp_cells")
     return dict(zip(names, list(out)))
 
 

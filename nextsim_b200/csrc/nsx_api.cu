@@ -148,6 +148,7 @@ static void alloc_fields(nsx_solver* S)
     S->d_epoch.zero(st); S->d_done.zero(st);
     S->ow_pair.alloc(64); S->ow_pair.zero(st);
     for (auto& e : S->ev) NSX_CUDA(cudaEventCreate(&e));
+    NSX_CUDA(cudaEventCreate(&S->ev_upd));
     NSX_CUDA(cudaEventCreateWithFlags(&S->ev_fork, cudaEventDisableTiming));
     NSX_CUDA(cudaEventCreateWithFlags(&S->ev_join, cudaEventDisableTiming));
 }
@@ -377,6 +378,7 @@ extern "C" int nsx_destroy(nsx_handle S)
     for (auto& p : S->peers) if (p.ipc_base) cudaIpcCloseMemHandle(p.ipc_base);
     for (auto& g : S->graph_exec) if (g) cudaGraphExecDestroy(g);
     for (auto& e : S->ev) if (e) cudaEventDestroy(e);
+    if (S->ev_upd) cudaEventDestroy(S->ev_upd);
     if (S->ev_fork) cudaEventDestroy(S->ev_fork);
     if (S->ev_join) cudaEventDestroy(S->ev_join);
     if (S->window) cudaFree(S->window);
@@ -1260,7 +1262,7 @@ extern "C" int nsx_update(nsx_handle S)
 {
     NSX_API_BEGIN(S)
     if (!S->have_params) throw std::runtime_error("nsx_update before nsx_set_params");
-    NSX_CUDA(cudaEventRecord(S->ev[3], S->stream));
+    NSX_CUDA(cudaEventRecord(S->ev_upd, S->stream));      // own start event: ev[3] stays the end of explicitSolve()
     int const c = S->scur;
     k_update<<<nblk(S->ne), TPB, 0, S->stream>>>(S->K, S->nflags.p, S->en0.p, S->en1.p, S->en2.p, S->x.p, S->y.p, S->UM.p,
         S->surface.p, S->conc.p, S->thick.p, S->snow.p, S->thick_myi.p, S->conc_myi.p, S->ridge_ratio.p,
@@ -1292,7 +1294,7 @@ extern "C" int nsx_get_timing(nsx_handle S, NsxTiming* out)
             }
         }
     }
-    if (S->update_timed) NSX_CUDA(cudaEventElapsedTime(&S->timing.update_ms, S->ev[3], S->ev[4]));
+    if (S->update_timed) NSX_CUDA(cudaEventElapsedTime(&S->timing.update_ms, S->ev_upd, S->ev[4]));
     *out = S->timing;
     NSX_API_END(S)
 }
@@ -1447,10 +1449,10 @@ extern "C" int nsx_resident_plan_info(const NsxMesh* mesh, const NsxHalo* halo, 
             own += P.tiles[t].n_own_slots; halo_slots += P.tiles[t].n_halo_slots;
             if (t < P.res_tiles.size()) early += P.res_tiles[t].n_early_own;
         }
-        int const v[12] = {fits ? 1 : 0, P.ntiles, P.tile_nodes, P.nslots, P.max_slots, P.max_local_nodes,
+        int const v[14] = {fits ? 1 : 0, P.ntiles, P.tile_nodes, P.nslots, P.max_slots, P.max_local_nodes,
                            (int)((size_t)(16 * P.msp + 2 * (P.max_local_nodes + 2)) * sizeof(double)), P.n_export,
-                           (int)early, (int)halo_slots, (int)own, RES_SMEM_MAX};
-        for (int i = 0; i < n && i < 12; ++i) out[i] = v[i];
+                           (int)early, (int)halo_slots, (int)own, RES_SMEM_MAX, (int)P.p2_wavefronts, (int)P.p2_cells};
+        for (int i = 0; i < n && i < 14; ++i) out[i] = v[i];
         return 0;
     } catch (std::exception const& e) {
         g_create_err = e.what();

@@ -101,7 +101,14 @@ extern "C" int nsx_params_from_cfg(const char* path, NsxDynParams* p)
             dst = v;
             return true;
         };
-        auto integer = [&](int& dst) -> bool { double d; if (!num(d)) return false; dst = (int)d; return true; };
+        // po::value<int> (options.cpp:43, 363, 397) rejects anything that is not an integer literal
+        auto integer = [&](int& dst) -> bool {
+            char* end = nullptr;
+            long v = std::strtol(val.c_str(), &end, 10);
+            if (end == val.c_str() || *end != 0) { g_cfg_err = section + "." + key + ": not an integer: " + val; return false; }
+            dst = (int)v;
+            return true;
+        };
         auto boolean = [&](int& dst) -> bool {
             bool b;
             if (!to_bool(val, b)) { g_cfg_err = section + "." + key + ": not a bool: " + val; return false; }
@@ -151,7 +158,7 @@ extern "C" int nsx_params_from_cfg(const char* path, NsxDynParams* p)
                 else { g_cfg_err = "invalid option for setup.basal_stress-type: " + val; return 4; }
             }
         } else if (section == "simul") {
-            if (key == "timestep") ok = num(p->dtime_step);
+            if (key == "timestep") { int ts = 0; ok = integer(ts); if (ok) p->dtime_step = ts; }     // po::value<int>, options.cpp:43
         } else if (section == "thermo") {
             if (key == "newice_type") ok = integer(p->newice_type);
         } else if (section == "age") {

@@ -185,6 +185,7 @@ struct nsx_solver {
 
     // ---- timing ----
     cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev_upd = nullptr;                // start of nsx_update
     NsxTiming timing{};
     bool timing_valid = false;
     bool update_timed = false;

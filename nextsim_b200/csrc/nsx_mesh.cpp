@@ -227,6 +227,93 @@ void build_mesh_plan(const NsxMesh* M, MeshPlan& P, int target_tile_nodes, int s
         }
         ekey[e] = ((uint64_t)writer[e] << 32) | ((uint64_t)late[e] << 31) | (uint32_t)std::min(std::min(v[0], v[1]), v[2]);
     }
+    // Resident solver: CONFLICT-AWARE SLOT PLACEMENT.  In the nodal solve the 16 threads of a half-warp (16 consecutive
+    // owned nodes) read, for incidence column c, the stress / constants of 16 different slots with 64-bit shared-memory
+    // loads: conflict-free exactly when the 16 slot indices differ modulo 16 (the planes are a multiple of 16 apart).
+    // Slots may be placed freely inside their group (early own | late own | halo), so each slot greedily takes the
+    // residue that collides least in the (half-warp, column) cells it belongs to, within the capacity of its group.
+    std::vector<std::vector<int>> halo_order;
+    if (resident_order) {
+        halo_order.assign(ntiles, {});
+        std::vector<std::vector<int>> inc_ref(ndof);             // reference node -> incident elements, ascending
+        for (int e = 0; e < ne; ++e) {
+            int const v[3] = {r0[e], r1[e], r2[e]};
+            for (int i = 0; i < 3; ++i) if (v[i] < ndof) inc_ref[v[i]].push_back(e);
+        }
+        std::vector<std::vector<int>> own_of(ntiles);
+        for (int e = 0; e < ne; ++e) own_of[writer[e]].push_back(e);
+        std::vector<int> grp(ne, -1), seen(ne, -1), res(ne, 0), ncell(ne, 0);
+        std::vector<int> cell_of((size_t)ne * 3, 0);
+        long wf = 0, ideal = 0;
+        for (int t = 0; t < ntiles; ++t) {
+            int const no = cut[t + 1] - cut[t];
+            std::vector<int> members[3];
+            for (int e : own_of[t]) { grp[e] = late[e] ? 1 : 0; members[grp[e]].push_back(e); seen[e] = t; ncell[e] = 0; }
+            int wmax = 0;
+            for (int pj = 0; pj < no; ++pj) {
+                auto const& L = inc_ref[P.node_inv[cut[t] + pj]];
+                wmax = std::max(wmax, (int)L.size());
+                for (int e : L) if (seen[e] != t) { seen[e] = t; grp[e] = 2; ncell[e] = 0; members[2].push_back(e); }
+            }
+            int const nhw = (no + 15) / 16, ncells = nhw * std::max(1, wmax);
+            std::vector<uint8_t> cnt((size_t)ncells * 16, 0);
+            std::vector<int> order;                               // slots in the order the node loop meets them
+            order.reserve(members[0].size() + members[1].size() + members[2].size());
+            std::vector<int> queued(0);
+            for (int pj = 0; pj < no; ++pj) {
+                auto const& L = inc_ref[P.node_inv[cut[t] + pj]];
+                for (int c = 0; c < (int)L.size(); ++c) {
+                    int const e = L[c];
+                    if (ncell[e] == 0) order.push_back(e);
+                    if (ncell[e] < 3) cell_of[(size_t)e * 3 + ncell[e]++] = (pj / 16) * wmax + c;
+                }
+            }
+            for (int g = 0; g < 3; ++g) for (int e : members[g]) if (ncell[e] == 0) order.push_back(e);   // no owned node of this tile
+            int const base[4] = {0, (int)members[0].size(), (int)(members[0].size() + members[1].size()),
+                                 (int)(members[0].size() + members[1].size() + members[2].size())};
+            int cap[3][16];
+            for (int g = 0; g < 3; ++g) for (int r = 0; r < 16; ++r) cap[g][r] = 0;
+            for (int g = 0; g < 3; ++g) for (int q = base[g]; q < base[g + 1]; ++q) cap[g][q & 15]++;
+            for (int e : order) {
+                int const g = grp[e];
+                int best = -1, best_cost = 1 << 30, best_cap = -1;
+                for (int r = 0; r < 16; ++r) {
+                    if (cap[g][r] <= 0) continue;
+                    int cost = 0;
+                    for (int q = 0; q < ncell[e]; ++q) cost += cnt[(size_t)cell_of[(size_t)e * 3 + q] * 16 + r];
+                    if (cost < best_cost || (cost == best_cost && cap[g][r] > best_cap)) { best = r; best_cost = cost; best_cap = cap[g][r]; }
+                }
+                res[e] = best;
+                cap[g][best]--;
+                for (int q = 0; q < ncell[e]; ++q) cnt[(size_t)cell_of[(size_t)e * 3 + q] * 16 + best]++;
+            }
+            // positions: inside each group the free positions of residue r are handed out in placement order
+            int nextpos[3][16];
+            for (int g = 0; g < 3; ++g)
+                for (int r = 0; r < 16; ++r) {
+                    int q = base[g];
+                    while ((q & 15) != r) ++q;
+                    nextpos[g][r] = q;
+                }
+            std::vector<int> halo_pos(members[2].size());
+            std::vector<std::pair<int, int>> hp;
+            for (int e : order) {
+                int const g = grp[e], q = nextpos[g][res[e]];
+                nextpos[g][res[e]] += 16;
+                if (q >= base[g + 1]) throw std::logic_error("nsx mesh plan: slot placement ran out of positions");
+                if (g < 2) ekey[e] = ((uint64_t)writer[e] << 32) | (uint32_t)q;
+                else hp.emplace_back(q, e);
+            }
+            std::sort(hp.begin(), hp.end());
+            for (auto const& pe : hp) halo_order[t].push_back(pe.second);
+            for (int cl = 0; cl < ncells; ++cl) {
+                int mx = 0;
+                for (int r = 0; r < 16; ++r) mx = std::max(mx, (int)cnt[(size_t)cl * 16 + r]);
+                wf += mx; ideal += mx > 0;
+            }
+        }
+        P.p2_wavefronts = wf; P.p2_cells = ideal;
+    }
     P.elem_inv.resize(ne);
     std::iota(P.elem_inv.begin(), P.elem_inv.end(), 0);
     std::sort(P.elem_inv.begin(), P.elem_inv.end(), [&](int a, int b) { return ekey[a] != ekey[b] ? ekey[a] < ekey[b] : a < b; });
@@ -316,12 +403,20 @@ void build_mesh_plan(const NsxMesh* M, MeshPlan& P, int target_tile_nodes, int s
         }
         // halo slots: elements touching my owned nodes but written by another tile (reference order per node)
         int nh = 0, dmax = 0;
+        if (resident_order)                                  // placed by the conflict-aware pass above
+            for (int re : halo_order[t]) {
+                int const ie = P.elem_perm[re];
+                stamp_e[ie] = t; slot_of[ie] = td.n_own_slots + nh; ++nh;
+                P.halo_elems.push_back(ie);
+                P.slot_elem.push_back(ie);
+            }
         for (int j = 0; j < td.n_own; ++j) {
             int const n = td.node_begin + j;
             dmax = std::max(dmax, P.n2e_deg[n]);
             for (int c = 0; c < P.n2e_deg[n]; ++c) {
                 int const ie = P.n2e[(size_t)c * nn + n] % ne;
                 if (stamp_e[ie] != t) {
+                    if (resident_order) throw std::logic_error("nsx mesh plan: halo slot missing from the placement pass");
                     stamp_e[ie] = t; slot_of[ie] = td.n_own_slots + nh; ++nh;
                     P.halo_elems.push_back(ie);
                     P.slot_elem.push_back(ie);
@@ -428,6 +523,7 @@ void build_mesh_plan(const NsxMesh* M, MeshPlan& P, int target_tile_nodes, int s
 
     // post-pass: incidence codes become shared-memory offsets (vertex * msp + slot); halo slots get ~e
     P.msp = (P.max_slots + 3) & ~1;             // plane stride in shared memory: room for the alignment shift
+    if (resident_order) P.msp = (P.max_slots + 15) & ~15;      // planes a multiple of 16 slots apart: bank = slot mod 16 in every plane
     int const MS = P.msp;
     for (int t = 0; t < ntiles; ++t) {
         TileDesc const& td = P.tiles[t];

@@ -75,6 +75,7 @@ struct MeshPlan {
     std::vector<uint8_t> halo_move;            // per halo_nodes entry: this tile moves that ghost node (UM / UT)
     std::vector<int> halo_slot;                // per halo_nodes entry: mailbox slot the value is read from
     int n_export = 0;                          // export nodes of the rank; mailbox = [export nodes | ghost nodes]
+    long p2_wavefronts = 0, p2_cells = 0;      // shared-memory wavefronts of one 64-bit gather of the nodal solve / ideal
 };
 
 // throws std::invalid_argument on inconsistent input

@@ -44,8 +44,8 @@ def write_case(path, c):
 def write_cfg(path, c, dyn):
     """The options of the case as a nextsim.cfg (what cases.make_params sets through the struct)."""
     p = c.params
-    path.write_text("[setup]\ndynamics-type=%s\n[simul]\ntimestep=%r\n[dynamics]\nsubsteps=%d\nC_lab=%r\nalea_factor=%r\n"
-                    "use_coriolis=%s\n" % (dyn, p.dtime_step, p.substeps, p.C_lab, p.alea_factor,
+    path.write_text("[setup]\ndynamics-type=%s\n[simul]\ntimestep=%d\n[dynamics]\nsubsteps=%d\nC_lab=%r\nalea_factor=%r\n"
+                    "use_coriolis=%s\n" % (dyn, int(p.dtime_step), p.substeps, p.C_lab, p.alea_factor,
                                            "true" if p.use_coriolis else "false"))
 
 

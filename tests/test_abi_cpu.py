@@ -89,6 +89,27 @@ def test_cfg_reader(tmp_path):
         capi.params_from_cfg(f)
     with pytest.raises(RuntimeError, match="cannot open"):
         capi.params_from_cfg(tmp_path / "missing.cfg")
+    # po::value<int> options reject non-integers like the reference does (options.cpp:43, 363)
+    for bad in ("[simul]\ntimestep=200.5\n", "[dynamics]\nsubsteps=1e2\n"):
+        f.write_text(bad)
+        with pytest.raises(RuntimeError, match="not an integer"):
+            capi.params_from_cfg(f)
+
+
+def test_create_options_defaults_and_plan_info():
+    """NsxCreateOptions replaces the environment knobs of round 1; the resident plan can be inspected without a GPU."""
+    o = capi.create_options()
+    assert (o.path, o.use_graph, o.overlap, o.ow_skip, o.max_sms, o.tile_nodes) == (0, 1, 1, 1, 0, 0)
+    assert capi.create_options(path="resident", max_sms=37).path == 3
+    from nextsim_b200 import cases
+    c = cases.make_case("10km_stable", nranks=2, nx=96, open_east=True)
+    for lm in c.lms:
+        d = capi.resident_plan_info(lm, sms=148)
+        assert d["fits"] == 1 and d["ntiles"] <= 148 and d["tile_nodes"] <= 768 and d["max_slots"] <= 2 * 768
+        assert d["smem_bytes"] <= d["smem_limit"] and d["own_slots"] == lm.num_elements
+        assert 0 < d["export_nodes"] < lm.local_ndof and d["early_own_slots"] < d["own_slots"]
+    big = cases.make_case("10km_stable", nranks=1, nx=400)             # 320 000 elements: too many slots per SM
+    assert capi.resident_plan_info(big.lms[0])["fits"] == 0
 
 
 REF_CFG = "/root/reference/config-files"
