@@ -171,7 +171,8 @@ typedef struct NsxCreateOptions {
     int tile_nodes;     /* owned nodes per tile of the TILES path                         (0 = 208) */
     int max_sms;        /* SMs this handle may occupy; ranks sharing one GPU pass SMs/nranks (0 = all) */
     int use_graph;      /* capture explicitSolve() once into a CUDA graph and replay it   (1) */
-    int overlap;        /* multi-GPU TILES / DIRECT: fused boundary launch overlapped with the interior (1) */
+    int overlap;        /* multi-GPU TILES / DIRECT: 1 = mailbox exchange inside the sub-cycle kernels (default); 2 = round-1
+                         * fused boundary launch with epoch flags overlapped with the interior; 0 = exchange kernel after each sub-cycle */
     int boundary_sms;   /* SMs of that boundary launch                                    (0 = automatic) */
     int ow_skip;        /* multi-GPU TILES / DIRECT smoother: skip exchanges between ranks without open water (1) */
     int pad_;

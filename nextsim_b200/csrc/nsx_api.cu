@@ -100,12 +100,12 @@ static void alloc_fields(nsx_solver* S)
 {
     size_t const nn = S->nn, ne = S->ne, ns = S->plan.nslots;
     cudaStream_t st = S->stream;
-    // halo window (one allocation, so it can be exported over CUDA IPC): [VT0 | VT1 | flags | mailbox parity 0 | parity 1]
+    // halo window (one allocation, so it can be exported over CUDA IPC): [VT0 | VT1 | flags | mailbox buffers 0, 1, 2]
     // mailbox (resident path): one 32-byte {u, tag, v, tag} entry per export node, then per ghost node
     size_t const vt_bytes = 2 * nn * sizeof(double);
     size_t const flag_bytes = 256 * sizeof(unsigned long long);
-    S->n_mb = S->resident ? S->plan.n_export + (S->nn - S->ndof) : 0;
-    S->window_bytes = 2 * vt_bytes + flag_bytes + 2 * (size_t)S->n_mb * sizeof(MbEntry);
+    S->n_mb = (S->resident ? S->plan.n_export : 0) + (S->nn - S->ndof);     // [export nodes (resident path) | ghost nodes]
+    S->window_bytes = 2 * vt_bytes + flag_bytes + 3 * (size_t)S->n_mb * sizeof(MbEntry);     // 3 buffers (tile / direct paths; the resident path uses 2)
     NSX_CUDA(cudaMalloc(&S->window, S->window_bytes));
     NSX_CUDA(cudaMemsetAsync(S->window, 0, S->window_bytes, st));
     S->VT[0] = (double*)S->window;
@@ -651,23 +651,22 @@ extern "C" int nsx_synchronize(nsx_handle S)
 // ---------------------------------------------------------------------------------------------------
 static_assert(sizeof(cudaIpcMemHandle_t) == NSX_IPC_HANDLE_BYTES, "ipc handle size");
 
-// the peer's window: [VT0 | VT1 | flags | mailbox]; hdr = {num_nodes, list length, local_ndof, export nodes} of the peer
+// the peer's window: [VT0 | VT1 | flags | mailbox]; hdr = {num_nodes, list length, local_ndof, export nodes, resident} of the peer
 static void finish_link(nsx_solver* S, PeerLink& p, double* base, const int* hdr, const int* peer_recv_idx_for_me, size_t n)
 {
     if (n != p.h_send_idx.size()) throw std::runtime_error("halo: peer ghost list length differs from my send list");
-    int const peer_nn = hdr[0], peer_ndof = hdr[2], peer_nx = hdr[3];
+    int const peer_nn = hdr[0], peer_ndof = hdr[2], peer_nx = hdr[3], peer_resident = hdr[4];
     p.peer_nn = peer_nn;
     p.peer_vt[0] = base;
     p.peer_vt[1] = base + 2 * (size_t)peer_nn;
     p.peer_flags = (unsigned long long*)(base + 4 * (size_t)peer_nn);
     p.h_send_dst.assign(peer_recv_idx_for_me, peer_recv_idx_for_me + n);
-    // resident path on the peer (peer_nx >= 0): my values go into its mailbox, ghost g -> slot export + (g - ndof)
+    // my values go into the peer's mailbox: ghost g -> slot (its export nodes, resident path only) + (g - ndof)
     p.peer_mb = (void*)(p.peer_flags + 256);
-    p.peer_nmb = peer_nx >= 0 ? peer_nx + (peer_nn - peer_ndof) : 0;
+    p.peer_nmb = peer_nx + (peer_nn - peer_ndof);
     p.h_send_slot.clear();
-    if (peer_nx >= 0)
-        for (size_t k = 0; k < n; ++k) p.h_send_slot.push_back(peer_nx + (peer_recv_idx_for_me[k] - peer_ndof));
-    if (S->resident != (peer_nx >= 0)) throw std::runtime_error("halo: neighbour ranks must use the same sub-cycle path");
+    for (size_t k = 0; k < n; ++k) p.h_send_slot.push_back(peer_nx + (peer_recv_idx_for_me[k] - peer_ndof));
+    if (S->resident != (peer_resident != 0)) throw std::runtime_error("halo: neighbour ranks must use the same sub-cycle path");
     p.connected = true;
 }
 
@@ -690,14 +689,14 @@ extern "C" int nsx_halo_connect_local(nsx_handle S, int peer_rank, nsx_handle Q)
         if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) NSX_CUDA(e);
         (void)cudaGetLastError();
     }
-    int const hdr[4] = {Q->nn, (int)ridx.size(), Q->ndof, Q->resident ? Q->plan.n_export : -1};
+    int const hdr[5] = {Q->nn, (int)ridx.size(), Q->ndof, Q->resident ? Q->plan.n_export : 0, Q->resident ? 1 : 0};
     finish_link(S, *mine, Q->VT[0], hdr, ridx.data(), ridx.size());
     NSX_API_END(S)
 }
 
 // The peer's ghost index list for me travels with the IPC handle:
-// [64 B handle | int num_nodes | int n | int local_ndof | int export nodes (-1: not the resident path) | n ints]
-constexpr int BLOB_HDR = 16;
+// [64 B handle | int num_nodes | int n | int local_ndof | int export nodes | int resident path | n ints]
+constexpr int BLOB_HDR = 20;
 extern "C" int nsx_halo_blob_size(nsx_handle S, int peer_rank)
 {
     if (!S) return -1;
@@ -709,7 +708,7 @@ extern "C" int nsx_halo_blob(nsx_handle S, int peer_rank, unsigned char* out)
     NSX_API_BEGIN(S)
     NSX_CUDA(cudaIpcGetMemHandle(&S->ipc, S->window));
     std::memcpy(out, &S->ipc, NSX_IPC_HANDLE_BYTES);
-    int hdr[4] = {S->nn, 0, S->ndof, S->resident ? S->plan.n_export : -1};
+    int hdr[5] = {S->nn, 0, S->ndof, S->resident ? S->plan.n_export : 0, S->resident ? 1 : 0};
     const PeerLink* pl = nullptr;
     for (auto& p : S->peers) if (p.rank == peer_rank) pl = &p;
     if (pl) hdr[1] = (int)pl->h_recv_idx.size();
@@ -725,7 +724,7 @@ extern "C" int nsx_halo_connect_blob(nsx_handle S, int peer_rank, const unsigned
     if (!mine) throw std::invalid_argument("nsx_halo_connect_blob: not a neighbour rank");
     cudaIpcMemHandle_t hdl;
     std::memcpy(&hdl, blob, NSX_IPC_HANDLE_BYTES);
-    int hdr[4];
+    int hdr[5];
     std::memcpy(hdr, blob + NSX_IPC_HANDLE_BYTES, BLOB_HDR);
     void* base = nullptr;
     NSX_CUDA(cudaIpcOpenMemHandle(&base, hdl, cudaIpcMemLazyEnablePeerAccess));
@@ -746,6 +745,16 @@ extern "C" int nsx_halo_finalize(nsx_handle S)
     }
     S->n_send_total = (int)src.size();
     S->d_send_src.upload(src, S->stream); S->d_send_dst.upload(dst, S->stream);
+    {   // per send entry: (send slot, slot in the holder's mailbox), same order as d_send_src
+        std::vector<int2> es;
+        int sl = 0;
+        for (auto& p : S->peers) {
+            if (p.h_send_idx.empty()) continue;
+            for (size_t k = 0; k < p.h_send_idx.size(); ++k) es.push_back(make_int2(sl, p.h_send_slot[k]));
+            ++sl;
+        }
+        S->d_send_slot.upload(es, S->stream);
+    }
     // per-node push lists for the fused boundary launch: owned node -> (send-peer slot, holder's ghost id)
     {
         std::vector<int> ptr(S->ndof + 1, 0);
@@ -766,7 +775,7 @@ extern "C" int nsx_halo_finalize(nsx_handle S)
         }
         S->push_ptr.upload(ptr, S->stream);
         S->push_ent.upload(ent, S->stream);
-        if (S->resident) {              // same lists with the holder's mailbox slot as destination
+        {                               // same lists with the holder's mailbox slot as destination
             std::vector<int2> entm(ent.size());
             std::vector<int> fillm(ptr.begin(), ptr.end() - 1);
             int sl = 0;
@@ -910,6 +919,32 @@ static DirectArgs direct_args(nsx_solver* S, SubArgs const& A, bool mixed)
     return D;
 }
 
+// mailbox exchange arguments of exchange `ex` (1-based inside the model step); off for in-process groups and single ranks
+static MbExchange mb_exchange(nsx_solver* S, bool on, int ex)
+{
+    MbExchange X{};
+    X.on = on ? 1 : 0;
+    X.ex = ex;
+    X.mb = (MbEntry*)S->mailbox; X.n_mb = S->n_mb;
+    int slot = 0;
+    for (auto& p : S->peers) {
+        if (p.h_send_idx.empty()) continue;
+        if (slot >= MB_MAX_PEERS) throw std::runtime_error("mailbox exchange: too many neighbour ranks");
+        X.peer_mb[slot] = (MbEntry*)p.peer_mb; X.peer_nmb[slot] = p.peer_nmb;
+        ++slot;
+    }
+    X.push_ptr = S->push_ptr.p; X.push_ent = S->push_ent_mb.p;
+    X.epoch_ctr = S->d_epoch.p; X.err = S->halo_err.p;
+    return X;
+}
+static void ghost_import(nsx_solver* S, MbExchange const& X, double dt)
+{
+    int const nghost = S->nn - S->ndof;
+    if (!X.on || nghost <= 0) return;
+    k_ghost_import<<<nblk(nghost), TPB, 0, S->stream>>>(X, S->nn, S->ndof, dt, S->VT[S->cur], S->disp.p);
+    S->n_launch++;
+}
+
 // one sub-cycle including its ghost exchange; flips the VT and sigma parities.
 // overlap: boundary tiles first, then the halo kernel on the main stream while the interior tiles run on stream2.
 static void phase_substep(nsx_solver* S, int s, bool exchange_sync, bool overlap)
@@ -957,6 +992,31 @@ static void phase_substep(nsx_solver* S, int s, bool exchange_sync, bool overlap
         k_node_direct<<<gn, DIRECT_TPB, 0, st>>>(K, D, A.move_mesh, mixed ? 0 : A.lag_ghost_move, skip, A.VTc, A.VTn);
         S->n_launch += 2;
     };
+    // one process per GPU: mailbox exchange.  The kernels that compute the sent nodes store them straight into the holders'
+    // mailboxes (boundary tiles run first); the NEXT sub-cycle's kernels read ghost velocities from this rank's mailbox
+    // (polling the tag, which covers a neighbour that lags) -- no exchange kernel, no flags, no second launch chain.  After
+    // the loop k_ghost_import copies the last exchange into the velocity buffer.  NsxCreateOptions.overlap = 2 selects the
+    // round-1 fused boundary launch with epoch flags instead (kept for comparison).
+    bool const mailbox = exchange_sync && S->halo_ready && S->opt.overlap == 1;
+    if (mailbox) {
+        A.X = mb_exchange(S, true, s + 1);
+        if (S->direct) {
+            DirectArgs D = direct_args(S, A, false);
+            D.X = A.X;
+            int const ge = (S->ne + DIRECT_TPB - 1) / DIRECT_TPB, gn = (S->nn + DIRECT_TPB - 1) / DIRECT_TPB;
+            if (bbm) k_element_direct<1><<<ge, DIRECT_TPB, 0, S->stream>>>(K, D, A.VTc);
+            else k_element_direct<0><<<ge, DIRECT_TPB, 0, S->stream>>>(K, D, A.VTc);
+            k_node_direct<<<gn, DIRECT_TPB, 0, S->stream>>>(K, D, A.move_mesh, A.lag_ghost_move, 0, A.VTc, A.VTn);
+            S->n_launch += 2;
+        } else {
+            launch_tiles(S, A, 0, nt, S->stream, S->sm_count);
+        }
+        S->cur ^= 1;
+        S->scur = sn;
+        if (bbm) S->dcur = dn;
+        NSX_CUDA(cudaGetLastError());
+        return;
+    }
     bool const fused = overlap && exchange_sync && nb > 0 && nb < nt && S->halo_ready;
     if (fused) {
         // multi-GPU sub-cycle: [boundary tiles + NVLink push + epoch signal + wait] as ONE kernel on a few SMs of the
@@ -991,6 +1051,12 @@ static void phase_substep(nsx_solver* S, int s, bool exchange_sync, bool overlap
     S->scur = sn;
     if (bbm) S->dcur = dn;              // EVP / mEVP never touch damage (FE.cpp:10649-10699)
     NSX_CUDA(cudaGetLastError());
+}
+
+// one process per GPU on the tile / direct paths with the mailbox exchange (ghosts are imported and moved every sub-cycle)
+static bool mailbox_mode(nsx_solver const* S)
+{
+    return !S->resident && !S->halo_local && !S->peers.empty() && S->halo_ready && S->opt.overlap == 1;
 }
 
 // mesh moves that follow the loop: mEVP's single move (FE.cpp:10559-10573) or the ghosts' lagged last move
@@ -1148,6 +1214,8 @@ static void solve_group(int n, nsx_solver** W)
     }
     for (int r = 0; r < n; ++r) {
         NSX_CUDA(cudaSetDevice(W[r]->device));
+        // mailbox exchange: the ghosts of the last sub-cycle go from the mailbox into the velocity buffer
+        if (n == 1 && mailbox_mode(W[r])) ghost_import(W[r], mb_exchange(W[r], true, nrun), 0.);
         record(W[r], 2);
         if (!resident) phase_post_move(W[r], nrun);
     }
@@ -1164,8 +1232,22 @@ static void solve_group(int n, nsx_solver** W)
             NSX_CUDA(cudaGetLastError());
         } else {
             for (int nit = 0; nit < 50; ++nit) {       // hard-coded 50 sweeps, FE.cpp:10580
+                if (n == 1 && remote && mailbox_mode(W[0])) {
+                    // one process per GPU: sweep, push of every sent node, import of every ghost (mailbox exchange)
+                    nsx_solver* S = W[0];
+                    MbExchange X = mb_exchange(S, true, nrun + nit + 1);
+                    int const sweep_blocks = std::max(1, std::min(nblk(S->ndof), S->sm_count * 4));
+                    k_ow_sweep_mb<<<sweep_blocks + nblk(S->n_send_total), TPB, 0, S->stream>>>(X, nit == 0 ? 1 : 0, sweep_blocks, S->nn, S->ndof,
+                        S->ow_list.p, S->ow_count.p, S->n2n.p, S->n2n_deg.p, S->nflags.p, S->node_mass.p, S->VT[S->cur], S->VT[S->cur ^ 1],
+                        S->n_send_total, S->d_send_src.p, S->d_send_slot.p);
+                    S->n_launch++;
+                    S->cur ^= 1;
+                    if (nit == 49) ghost_import(S, X, 0.);       // the last sweep's ghosts go into the velocity buffer
+                    NSX_CUDA(cudaGetLastError());
+                    continue;
+                }
                 if (n == 1 && remote) {
-                    // one process per GPU: sweep + ghost exchange in a single launch
+                    // round-1 protocol (NsxCreateOptions.overlap = 2): sweep + ghost exchange with epoch flags in one launch
                     nsx_solver* S = W[0];
                     HaloArgs a = halo_args(S, S->cur ^ 1, true);
                     int const grid = std::max(1, std::min(nblk(S->ndof), S->sm_count));
@@ -1183,6 +1265,7 @@ static void solve_group(int n, nsx_solver** W)
             }
         }
     }
+    if (n == 1 && mailbox_mode(W[0])) W[0]->epoch_bump = nrun + (W[0]->P.skip_ow_smoother ? 0 : 50);   // tags never repeat
     for (int r = 0; r < n; ++r) {
         nsx_solver* S = W[r];
         NSX_CUDA(cudaSetDevice(S->device));

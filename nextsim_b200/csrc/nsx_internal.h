@@ -172,6 +172,7 @@ struct nsx_solver {
     // ---- halo ----
     std::deque<nsx::PeerLink> peers;             // union of send/recv peers
     nsx::DBuf<int> d_send_src, d_send_dst;       // concatenated push tables over all send peers
+    nsx::DBuf<int2> d_send_slot;                 // per send entry: (send slot, slot in the holder's mailbox)
     nsx::DBuf<unsigned long long> d_epoch;       // device-resident exchange counter (graph replay safe)
     nsx::DBuf<unsigned int> d_done;              // block completion counter of k_halo_exchange
     int n_send_total = 0;

@@ -392,6 +392,76 @@ __device__ __forceinline__ unsigned long long flag_signal_wait(HaloArgs const& a
     return v;
 }
 
+// ---- mailbox exchange (synchronisation carried by the data; see the k_resident header) ----
+constexpr int MB_MAX_PEERS = 16;
+// mailbox entry of one node: two 16-byte {value, tag} pairs, each written / read as ONE vector transaction
+struct __align__(16) MbEntry { double u; unsigned long long tu; double v; unsigned long long tv; };
+static_assert(sizeof(MbEntry) == 32, "mailbox entry");
+
+__device__ __forceinline__ void mb_store(MbEntry* e, double u, double v, unsigned long long tag)
+{
+    asm volatile("st.volatile.global.v2.u64 [%0], {%1, %2};" ::"l"(&e->u), "l"(__double_as_longlong(u)), "l"(tag) : "memory");
+    asm volatile("st.volatile.global.v2.u64 [%0], {%1, %2};" ::"l"(&e->v), "l"(__double_as_longlong(v)), "l"(tag) : "memory");
+}
+// polls until both halves carry `tag`; bounded (sets *err and gives up, also as soon as another waiter has timed out)
+__device__ __forceinline__ void mb_wait(const MbEntry* e, unsigned long long tag, double& u, double& v, int* err, int who)
+{
+    unsigned long long a = 0, ta = 0, b = 0, tb = 0;
+    long long spins = 0;
+    for (;;) {
+        if (ta != tag) asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(ta) : "l"(&e->u) : "memory");
+        if (tb != tag) asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(b), "=l"(tb) : "l"(&e->v) : "memory");
+        if (ta == tag && tb == tag) break;
+        if ((++spins & 1023) == 0 && (*((volatile int*)err) || spins > (1LL << 22))) { atomicCAS(err, 0, who); break; }
+    }
+    u = __longlong_as_double((long long)a);
+    v = __longlong_as_double((long long)b);
+}
+
+// mailbox exchange of the tile / direct paths across GPUs (one process per GPU): sent nodes go into the holders' mailboxes
+// from the kernel that computes them, the next sub-cycle's kernels read ghost velocities from this rank's mailbox (polling
+// the tag) -- no flag, no fence, no second stream.  Mailbox slot of ghost g = g - ndof; THREE buffers, exchange ex uses
+// buffer ex % 3: a neighbour can be at most one launch ahead (its launch for exchange e+1 needs this rank's pushes of e,
+// issued by a launch that started after the previous one had finished), so while some thread here still reads exchange
+// e-1 the neighbour writes at most e+1 -- never the buffer of e-1.  (Two buffers would need the tile-level symmetry the
+// resident kernel has; the ghost-move shares and the direct kernels do not have it.)
+struct MbExchange {
+    int on;                                     // 0: no neighbour ranks / in-process group (stream-ordered exchange)
+    int ex;                                     // exchange index inside the model step (1-based); tag = *epoch_ctr + ex
+    MbEntry* mb; int n_mb;                      // this rank's mailbox [2][n_mb]
+    MbEntry* peer_mb[MB_MAX_PEERS]; int peer_nmb[MB_MAX_PEERS];
+    const int* push_ptr; const int2* push_ent;  // owned node -> (send slot, slot in the holder's mailbox)
+    const unsigned long long* epoch_ctr; int* err;
+};
+__device__ __forceinline__ void mbx_push(MbExchange const& X, int n, double un, double vn)
+{
+    int const q1 = X.push_ptr[n + 1];
+    int q = X.push_ptr[n];
+    if (q == q1) return;
+    unsigned long long const tag = *X.epoch_ctr + (unsigned long long)X.ex;
+    for (; q < q1; ++q) {
+        int2 const pe = X.push_ent[q];
+        NSX_DEV_CHECK(pe.x >= 0 && pe.x < MB_MAX_PEERS && pe.y >= 0 && pe.y < X.peer_nmb[pe.x], X.err, 21);
+        mb_store(X.peer_mb[pe.x] + (size_t)(X.ex % 3) * X.peer_nmb[pe.x] + pe.y, un, vn, tag);
+    }
+}
+__device__ __forceinline__ void mbx_import(MbExchange const& X, int slot, double& u, double& v)
+{
+    NSX_DEV_CHECK(slot >= 0 && slot < X.n_mb, X.err, 22);
+    mb_wait(X.mb + (size_t)(X.ex % 3) * X.n_mb + slot, *X.epoch_ctr + (unsigned long long)X.ex, u, v, X.err, 500 + slot % 400);
+}
+// velocity of node g as the sub-cycle kernels of exchange X.ex read it: a ghost node comes from the mailbox of the PREVIOUS
+// exchange (its owner pushed it from the previous sub-cycle's launch on its GPU; polling covers a peer that lags), any
+// other node -- and every node in the first sub-cycle -- from the velocity buffer
+__device__ __forceinline__ void mbx_velocity(MbExchange const& X, int g, int ndof, int nn, const double* VT, double& u, double& v)
+{
+    if (X.on && X.ex > 1 && g >= ndof) {
+        int const slot = g - ndof, pe = X.ex - 1;
+        NSX_DEV_CHECK(slot < X.n_mb, X.err, 23);
+        mb_wait(X.mb + (size_t)(pe % 3) * X.n_mb + slot, *X.epoch_ctr + (unsigned long long)pe, u, v, X.err, 500 + slot % 400);
+    } else { u = VT[g]; v = VT[g + nn]; }
+}
+
 struct SubArgs {
     const TileDesc* tiles; const int* tile_order; int tile_base;
     const int* halo_nodes; const int* halo_elems; const unsigned long long* slot_conn;
@@ -409,6 +479,7 @@ struct SubArgs {
     const int* push_ptr; const int2* push_ent;
     const unsigned long long* my_flags; unsigned long long* epoch_ctr; unsigned int* done_ctr; int* halo_err;
     HaloArgs H;
+    MbExchange X;
     SmemLayout L;
 };
 
@@ -532,7 +603,8 @@ k_subcycle(KParams K, SubArgs A)
                 bool const hn_ok = j < td.n_halo, he_ok = j < td.n_halo_slots;
                 int const g = hn_ok ? A.halo_nodes[td.halo_off + j] : 0;
                 int const e = he_ok ? A.halo_elems[td.halo_elem_off + j] : 0;
-                double const u = A.VTc[g], v = A.VTc[g + nn];
+                double u, v;
+                mbx_velocity(A.X, g, K.ndof, nn, A.VTc, u, v);
                 double const a0 = A.s0i[e], a1 = A.s1i[e], a2 = A.s2i[e];
                 double const ad = BBM ? A.di[e] : 0.;
                 if (hn_ok) { su[td.n_own + HALO_GAP + j] = u; sv[td.n_own + HALO_GAP + j] = v; }
@@ -710,7 +782,10 @@ k_subcycle(KParams K, SubArgs A)
         }
         A.VTn[n] = un;
         A.VTn[n + nn] = vn;
-        if (A.fuse_halo) {                      // updateGhosts: owner -> every holder's ghost slot (FE.cpp:13963-13996)
+        // updateGhosts (FE.cpp:13963-13996): straight into the holders' mailboxes.  Only boundary tiles own sent nodes; the
+        // others must not even look at the push lists (a global load at the tail of phase 2 delays the stage hand-over)
+        if (A.X.on && td.boundary) mbx_push(A.X, n, un, vn);
+        if (A.fuse_halo) {                      // flag protocol of the in-kernel boundary launch (kept for reference runs)
             int const q1 = A.push_ptr[n + 1];
             for (int q = A.push_ptr[n]; q < q1; ++q) {
                 int2 const pe = A.push_ent[q];
@@ -729,7 +804,8 @@ k_subcycle(KParams K, SubArgs A)
     if (A.lag_ghost_move) {
         for (int j = gtid; j < td.n_ghost; j += gstride) {
             int const n = td.ghost_begin + j;
-            double const u = A.VTc[n], v = A.VTc[n + nn];
+            double u, v;
+            mbx_velocity(A.X, n, K.ndof, nn, A.VTc, u, v);
             A.disp[n] += K.dte * u;  A.disp[n + nn] += K.dte * v;
         }
     }
@@ -783,6 +859,7 @@ struct DirectArgs {
     const double* grad_ssh; const double* node_mass; const double* rlmass; const double* cbu; const double* fcor;
     const double* tau_a; const double* tau_wi; const double* ocean; const double* VTM;
     double* disp;
+    MbExchange X;
 };
 
 template <int BBM, int CG>
@@ -806,8 +883,10 @@ __device__ __forceinline__ void direct_element(KParams const& K, DirectArgs cons
             d = 0.;
         } else {
             int const a = A.en0[e], b = A.en1[e], c = A.en2[e];
-            double const ua = ldv<CG>(VT + a), va = ldv<CG>(VT + a + nn), ub = ldv<CG>(VT + b), vb = ldv<CG>(VT + b + nn),
-                         uc = ldv<CG>(VT + c), vc = ldv<CG>(VT + c + nn);
+            double ua, va, ub, vb, uc, vc;
+            mbx_velocity(A.X, a, K.ndof, nn, VT, ua, va);
+            mbx_velocity(A.X, b, K.ndof, nn, VT, ub, vb);
+            mbx_velocity(A.X, c, K.ndof, nn, VT, uc, vc);
             double e0 = dx0 * ua; e0 += dx1 * ub; e0 += dx2 * uc;
             double e1 = dy0 * va; e1 += dy1 * vb; e1 += dy2 * vc;
             double e2 = dy0 * ua; e2 += dx0 * va; e2 += dy1 * ub; e2 += dx1 * vb; e2 += dy2 * uc; e2 += dx2 * vc;
@@ -845,8 +924,10 @@ __device__ __forceinline__ void direct_element(KParams const& K, DirectArgs cons
             s0 = s1 = s2 = 0.;
         } else {
             int const a = A.en0[e], b = A.en1[e], c = A.en2[e];
-            double const ua = ldv<CG>(VT + a), va = ldv<CG>(VT + a + nn), ub = ldv<CG>(VT + b), vb = ldv<CG>(VT + b + nn),
-                         uc = ldv<CG>(VT + c), vc = ldv<CG>(VT + c + nn);
+            double ua, va, ub, vb, uc, vc;
+            mbx_velocity(A.X, a, K.ndof, nn, VT, ua, va);
+            mbx_velocity(A.X, b, K.ndof, nn, VT, ub, vb);
+            mbx_velocity(A.X, c, K.ndof, nn, VT, uc, vc);
             double eps11 = dx0 * ua; eps11 += dx1 * ub; eps11 += dx2 * uc;
             double eps22 = dy0 * va; eps22 += dy1 * vb; eps22 += dy2 * vc;
             double eps12 = 0.5 * (dx0 * va + dy0 * ua); eps12 += 0.5 * (dx1 * vb + dy1 * ub); eps12 += 0.5 * (dx2 * vc + dy2 * uc);
@@ -879,11 +960,15 @@ __device__ __forceinline__ void direct_node(KParams const& K, DirectArgs const& 
     int const nn = K.nn, ne = K.ne;
     uint8_t const fl = A.nflags[n];
     if (fl & skip_flag_mask) return;            // nodes of boundary tiles (and ghosts) belong to the boundary launch
-    double const uice = ldv<CG>(VTc + n), vice = ldv<CG>(VTc + n + nn);
     if (fl & NF_GHOST) {
-        if (lag_ghost_move) { A.disp[n] += K.dte * uice;  A.disp[n + nn] += K.dte * vice; }
+        if (lag_ghost_move) {
+            double u, v;
+            mbx_velocity(A.X, n, K.ndof, nn, VTc, u, v);
+            A.disp[n] += K.dte * u;  A.disp[n + nn] += K.dte * v;
+        }
         return;
     }
+    double const uice = ldv<CG>(VTc + n), vice = ldv<CG>(VTc + n + nn);
     double un = uice, vn = vice;
     double const nm = A.node_mass[n];
     if (!(fl & NF_DIRICHLET) && nm != 0.) {
@@ -921,6 +1006,7 @@ __device__ __forceinline__ void direct_node(KParams const& K, DirectArgs const& 
     }
     VTn[n] = un;
     VTn[n + nn] = vn;
+    if (A.X.on && (fl & NF_BTILE)) mbx_push(A.X, n, un, vn);      // NF_BTILE: node of a tile that owns sent nodes
     if (move_mesh) { A.disp[n] += K.dte * un;  A.disp[n + nn] += K.dte * vn; }
 }
 
@@ -983,37 +1069,13 @@ k_node_direct(KParams K, DirectArgs A, int move_mesh, int lag_ghost_move, int sk
 constexpr int RES_TPB = NSX_RES_TPB;            // threads per tile: one owned node per thread, up to RES_SPT slots per thread
 constexpr int RES_CTAS = NSX_RES_CTAS;          // tiles (CTAs) per SM: independent tiles fill each other's barrier / latency stalls
 constexpr int RES_SPT = 3;                      // slots per thread (static unroll): tiles of up to 3 * RES_TPB slots
-constexpr int RES_MAX_LINKS = 16;               // neighbour ranks of one rank
-
-// mailbox entry of one node: two 16-byte {value, tag} pairs, each written / read as ONE vector transaction
-struct __align__(16) MbEntry { double u; unsigned long long tu; double v; unsigned long long tv; };
-static_assert(sizeof(MbEntry) == 32, "mailbox entry");
+constexpr int RES_MAX_LINKS = MB_MAX_PEERS;     // neighbour ranks of one rank
 
 struct ResPeers {
     int n_send;                                 // neighbour ranks this rank sends to (send slot = push_ent.x)
     MbEntry* send_mb[RES_MAX_LINKS];            // the holder's mailbox (parity 0; parity 1 follows send_nmb entries later)
     int send_nmb[RES_MAX_LINKS];
 };
-
-__device__ __forceinline__ void mb_store(MbEntry* e, double u, double v, unsigned long long tag)
-{
-    asm volatile("st.volatile.global.v2.u64 [%0], {%1, %2};" ::"l"(&e->u), "l"(__double_as_longlong(u)), "l"(tag) : "memory");
-    asm volatile("st.volatile.global.v2.u64 [%0], {%1, %2};" ::"l"(&e->v), "l"(__double_as_longlong(v)), "l"(tag) : "memory");
-}
-// polls until both halves carry `tag`; bounded (sets *err and gives up, also as soon as another waiter has timed out)
-__device__ __forceinline__ void mb_wait(const MbEntry* e, unsigned long long tag, double& u, double& v, int* err, int who)
-{
-    unsigned long long a = 0, ta = 0, b = 0, tb = 0;
-    long long spins = 0;
-    for (;;) {
-        if (ta != tag) asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(ta) : "l"(&e->u) : "memory");
-        if (tb != tag) asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(b), "=l"(tb) : "l"(&e->v) : "memory");
-        if (ta == tag && tb == tag) break;
-        if ((++spins & 1023) == 0 && (*((volatile int*)err) || spins > (1LL << 22))) { atomicCAS(err, 0, who); break; }
-    }
-    u = __longlong_as_double((long long)a);
-    v = __longlong_as_double((long long)b);
-}
 
 struct ResidentArgs {
     const TileDesc* tiles; const ResTile* rtiles;
@@ -1728,6 +1790,71 @@ k_halo_exchange(HaloArgs a, int nn_src, const int* __restrict__ src_idx, const i
     flag_signal_wait(a, (int)threadIdx.x, true, epoch, epoch, my_flags, max_spins, err);
     __syncthreads();
     if (threadIdx.x == 0) { *epoch_ctr = epoch; *done_ctr = 0u; }
+}
+
+// Mailbox exchange of the tile / direct paths, receiving side: one thread per ghost node polls its mailbox slot for the
+// exchange `X.ex` (the owner stored it from its own sub-cycle / sweep kernel), writes it into VT and moves the ghost with
+// it (FE.cpp:10539-10553; dt = 0 for smoother sweeps).  Launched AFTER the kernel that issued this rank's pushes, so two
+// ranks can never wait for each other's unissued pushes.
+__global__ void __launch_bounds__(TPB)
+k_ghost_import(MbExchange X, int nn, int ndof, double dt, double* __restrict__ VT, double* __restrict__ disp)
+{
+    int const t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nn - ndof) return;
+    double u, v;
+    mbx_import(X, t, u, v);
+    int const n = ndof + t;
+    VT[n] = u;  VT[n + nn] = v;
+    if (dt != 0.) { disp[n] += dt * u;  disp[n + nn] += dt * v; }
+}
+// One smoother sweep with the mailbox exchange in ONE launch (one process per GPU, tile / direct paths).  Blocks
+// [0, sweep_blocks) relax the open-water list (FE.cpp:10580-10608): ghost neighbours are read from the mailbox of the
+// previous sweep (polling its tag), open-water nodes with holders push their new value.  Blocks behind them re-send the
+// sent nodes that are NOT open water (unchanged values) so that every ghost slot carries the tag its holder polls for.
+__global__ void __launch_bounds__(TPB)
+k_ow_sweep_mb(MbExchange X, int first, int sweep_blocks, int nn, int ndof, const int* __restrict__ ow_list, const int* __restrict__ ow_count,
+              const int* __restrict__ n2n, const int* __restrict__ n2n_deg, const uint8_t* __restrict__ nflags,
+              const double* __restrict__ node_mass, const double* VTin, double* VTout,
+              int n_send, const int* __restrict__ send_src, const int2* __restrict__ send_slot)
+{
+    if ((int)blockIdx.x < sweep_blocks) {
+        int const cnt = *ow_count;
+        MbExchange R = X;                   // reads refer to the previous exchange; the first sweep reads the velocity buffer
+        if (first) R.on = 0;
+        for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < cnt; t += sweep_blocks * blockDim.x) {
+            int const n = ow_list[t];
+            int const deg = n2n_deg[n];
+            double su = 0., sv = 0.;
+            for (int j = 0; j < deg; ++j) {
+                int const q = n2n[(size_t)j * nn + n];
+                double u, v;
+                mbx_velocity(R, q, ndof, nn, VTin, u, v);
+                su += u;
+                sv += v;
+            }
+            su = su / deg;  sv = sv / deg;
+            VTout[n] = su;
+            VTout[n + nn] = sv;
+            if (nflags[n] & NF_BTILE) mbx_push(X, n, su, sv);
+        }
+        return;
+    }
+    int const t = ((int)blockIdx.x - sweep_blocks) * blockDim.x + threadIdx.x;
+    if (t >= n_send) return;
+    int const n = send_src[t];
+    if (node_mass[n] == 0. && !(nflags[n] & NF_DIRICHLET)) return;       // open-water node: pushed by its sweep thread
+    int2 const pe = send_slot[t];
+    mb_store(X.peer_mb[pe.x] + (size_t)(X.ex % 3) * X.peer_nmb[pe.x] + pe.y, VTin[n], VTin[n + nn],
+             *X.epoch_ctr + (unsigned long long)X.ex);
+}
+
+// sending side of a smoother sweep: every sent node is pushed (a sweep only rewrites open-water nodes, the others are
+// re-sent unchanged so that the holder finds the tag it polls for)
+__global__ void __launch_bounds__(TPB)
+k_push_mb(MbExchange X, int nn, int ndof, const double* __restrict__ VT)
+{
+    int const t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < ndof) mbx_push(X, t, VT[t], VT[t + nn]);            // nodes without holders return at once
 }
 
 // Multi-rank smoother step: one Jacobi sweep over the open-water list AND the ghost exchange of the result in a
