@@ -188,7 +188,7 @@ int nsx_destroy(nsx_handle h);
 int nsx_validate_mesh(const NsxMesh* mesh, const NsxHalo* halo);
 const char* nsx_last_error(nsx_handle h);      /* h may be NULL: error of the last failed nsx_create */
 int nsx_version(void);
-int nsx_abi_sizes(int* out, int n);          /* sizeof NsxDynParams, NsxMesh, NsxHalo, NsxFields, NsxCheck, NsxTiming, NsxRegrid */
+int nsx_abi_sizes(int* out, int n);          /* sizeof NsxDynParams, NsxMesh, NsxHalo, NsxFields, NsxCheck, NsxTiming, NsxRegrid, NsxCreateOptions, NsxThermoParams */
 /* tile decomposition of the sub-cycle kernel: ntiles, nodes/tile, slots, max local nodes, max slots,
  * boundary tiles, dynamic shared memory bytes, selected path (NSX_PATH_TILES / DIRECT / RESIDENT) */
 int nsx_tile_info(nsx_handle h, int* out, int n);
@@ -234,6 +234,72 @@ int nsx_forcing_apply(nsx_handle h, int var, int interp_linear_time, double curr
 int nsx_synchronize(nsx_handle h);
 int nsx_get_timing(nsx_handle h, NsxTiming* out);
 void* nsx_get_stream(nsx_handle h);     /* cudaStream_t the handle launches on */
+
+/* ---- FiniteElement::thermo(dt) (FE.cpp:5170-6137) on the device-resident state ----
+ * Element-wise: bulk fluxes (OWBulkFluxes 5032-5159, IABulkFluxes 6148-6353 incl. the stability-dependent drag,
+ * specificHumidity 4966-5019, albedo 6454-6535), the slab thermodynamics (thermoWinton 6633-6853, thermoIce0 6860-6962),
+ * new-ice / lateral-melt redistribution, the slab ocean, melt ponds (6538-6627), healing time, diagnostics and the
+ * age / multi-year-ice tracers.  Not covered (the call fails): OASIS coupling (FSD, COUPLED ocean, melt_type 3) and
+ * the external AeroBulk library.  Options: model/options.cpp [thermo], [ideal_simul], [age], [dynamics] names. */
+typedef struct NsxThermoParams {
+    int thermo_type;                 /* setup.thermo-type: 0 zero-layer, 1 winton (enums.hpp:123-127)      (1) */
+    int ocean_constant;              /* M_ocean_type == CONSTANT: Qdw / Fdw constants instead of nudging   (1) */
+    int Qio_type;                    /* thermo.Qio-type: 0 basic, 1 exchange                               (0) */
+    int freezingpoint_type;          /* thermo.freezingpoint-type: 0 linear, 1 unesco                      (0) */
+    int newice_type;                 /* thermo.newice_type 1..4                                            (4) */
+    int melt_type;                   /* thermo.melt_type 1..2                                              (2) */
+    int alb_scheme;                  /* thermo.alb_scheme 1..4                                             (3) */
+    int flooding;                    /* thermo.flooding                                                    (1) */
+    int use_assim_flux;              /* thermo.use_assim_flux                                              (0) */
+    int temp_dep_healing;            /* dynamics.use_temperature_dependent_healing                         (0) */
+    int use_meltponds;               /* thermo.use_meltponds                                               (0) */
+    int force_neutral_atmosphere;    /* thermo.force_neutral_atmosphere                                    (0) */
+    int reset_by_date;               /* age.reset_by_date                                                  (0) */
+    int equal_melting;               /* age.equal_melting                                                  (1) */
+    int use_young_ice_in_myi_reset;  /* age.include_young_ice                                              (1) */
+    int ice_cat_young;               /* M_ice_cat_type == YOUNG_ICE (thermo.newice_type == 4)              (1) */
+    /* which forcing variables the atmosphere / ocean datasets provide (ExternalData::isInitialized()) */
+    int have_sphuma, have_mixrat, have_Qlw_in, have_snowfr, have_snowfall, have_mld;
+    int reset_month, reset_day;      /* age.reset_date "mmdd"                                              (9, 15) */
+    double dtime_step;               /* simul.timestep                                                     (200) */
+    double ocean_nudge_timeT_days, ocean_nudge_timeS_days;      /* (30, 30) */
+    double Qdw_const, Fdw_const;     /* ideal_simul.constant_Qdw / _Fdw                                    (0, 0) */
+    double hnull, PhiF, PhiM;        /* thermo.hnull, PhiF, PhiM                                           (0.25, 4, 0.5) */
+    double assim_flux_exponent;      /* (1) */
+    double constant_mld;             /* ideal_simul.constant_mld                                           (9) */
+    double I_0;                      /* thermo.I_0                                                         (0.30) */
+    double freeze_days_threshold;    /* age.reset_freeze_days                                              (3) */
+    double meltpond_runoff_fraction, meltpond_depth_to_fraction;   /* (0.2, 0.8) */
+    double drag_ocean_t, drag_ocean_q;                          /* (0.83e-3, 1.5e-3) */
+    double alb_ice, alb_sn, alb_ponds;                          /* (0.538, 0.8256, 0.30) */
+    double zref_wind, zref_temp, limiting_lengthscale;          /* (10, 2, 1) */
+    double quad_drag_coef_air;       /* dynamics.<atmosphere>_quad_drag_coef_air (FE.cpp:1286-1295)        (0.0049, ASR) */
+    double ocean_albedo;             /* thermo.albedoW                                                     (0.07) */
+    double ks;                       /* thermo.snow_cond                                                   (0.3096) */
+    double freezingpoint_mu;         /* thermo.freezingpoint_mu                                            (0.055) */
+    double Csens_io;                 /* thermo.Csens_io                                                    (1e-3) */
+    double time_relaxation_damage;   /* dynamics.time_relaxation_damage * 86400 (FE.cpp:1186)              (25 d) */
+    double deltaT_relaxation_damage; /* dynamics.deltaT_relaxation_damage                                  (20) */
+    double h_young_min, h_young_max; /* thermo.h_young_min, h_young_max                                    (0.05, 0.5) */
+} NsxThermoParams;
+void nsx_thermo_params_defaults(NsxThermoParams* p);
+/* Element fields of thermo() by the reference's member name, host numbering, [num_elements] each:
+ *   forcing  M_tair M_mixrat M_dair M_sphuma M_mslp M_Qsw_in M_Qlw_in M_tcc M_precip M_snowfall M_snowfr M_mld
+ *            M_ocean_temp M_ocean_salt M_conc_upd
+ *   state    M_sst M_sss M_tice0 M_tice1 M_tice2 M_tsurf_young M_del_vi_tend M_freeze_days M_freeze_onset M_conc_summer
+ *            M_thick_summer M_fyi_fraction M_age_det M_age M_pond_volume M_lid_volume M_drag_ti M_drag_ti_young
+ *            D_pond_fraction    (the ice state itself -- M_conc, M_thick, ... -- goes through NsxFields)
+ *   outputs  D_tau_ow D_Qa D_Qsw D_Qlw D_Qsh D_Qlh D_Qo D_Qnosun D_Qsw_ocean D_Qassim D_delS D_fwflux_ice D_fwflux D_brine
+ *            D_evap D_rain D_vice_melt D_del_vi_young D_del_hi D_del_hi_young D_newice D_mlt_top D_mlt_bot D_snow2ice
+ *            D_albedo D_sialb D_del_ci_mlt_myi D_del_vi_mlt_myi D_del_ci_rplnt_myi D_del_vi_rplnt_myi
+ * A field that was never uploaded reads as zero. */
+int nsx_thermo_upload(nsx_handle h, const char* name, const double* host);
+int nsx_thermo_download(nsx_handle h, const char* name, double* host);      /* any field, the ice state included */
+/* n fields in one call: one device arena, one permutation kernel, one stream synchronisation */
+int nsx_thermo_upload_many(nsx_handle h, int n, const char* const* names, const double* const* host);
+int nsx_thermo_download_many(nsx_handle h, int n, const char* const* names, double* const* host);
+/* FiniteElement::thermo(dt) at model time `current_time` (decimal days since 1900-01-01, M_current_time) */
+int nsx_thermo(nsx_handle h, const NsxThermoParams* p, int dt, double current_time);
 
 /* ---- multi-GPU halo wiring (replaces the Boost.MPI p2p of updateGhosts) ----
  * One process per GPU: every rank exports a 64-byte CUDA IPC handle of its halo window, the host

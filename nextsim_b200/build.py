@@ -7,7 +7,9 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libnsx.so")
 SOURCES = ["nsx_api.cu", "nsx_mesh.cpp", "nsx_cfg.cpp", "nsx_partmesh.cpp", "nsx_mapx.cpp"]
-HEADERS = ["nsx_kernels.cuh", "nsx_internal.h", "nsx_mesh.h", os.path.join("..", "..", "include", "nsx.h")]
+# compiled separately with -fmad=false: element-wise physics held to the reference's rounding (see nsx_thermo.cu)
+NOFMA_SOURCES = ["nsx_thermo.cu"]
+HEADERS = ["nsx_kernels.cuh", "nsx_internal.h", "nsx_mesh.h", "nsx_thermo.cuh", "nsx_thermo_api.cuh", os.path.join("..", "..", "include", "nsx.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
@@ -26,7 +28,7 @@ def needs_build():
     if not os.path.exists(LIB):
         return True
     t = os.path.getmtime(LIB)
-    deps = [os.path.join(CSRC, s) for s in SOURCES + HEADERS] + [os.path.abspath(__file__)]
+    deps = [os.path.join(CSRC, s) for s in SOURCES + NOFMA_SOURCES + HEADERS] + [os.path.abspath(__file__)]
     return any(os.path.getmtime(d) > t for d in deps)
 
 
@@ -39,16 +41,27 @@ def build(force=False, verbose=False):
             extra.append("-D%s=%s" % (k, os.environ[k]))
     if os.environ.get("NSX_DEBUG_CHECKS"):                # device-side bounds checks of the index tables (nsx_kernels.cuh)
         extra.append("-DNSX_DEBUG_CHECKS")
-    cmd = [_nvcc()] + NVCC_FLAGS + extra + [os.path.join(CSRC, s) for s in SOURCES] + ["-o", LIB]
-    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     log = os.path.join(HERE, "build.log")
-    with open(log, "w") as f:
-        f.write(" ".join(cmd) + "\n" + r.stdout)
-    if r.returncode != 0:
-        sys.stderr.write(r.stdout)
-        raise RuntimeError("nvcc failed building libnsx.so (see %s)" % log)
+    objdir = os.path.join(HERE, "_obj")
+    os.makedirs(objdir, exist_ok=True)
+    objs, text = [], ""
+    compile_flags = [f for f in NVCC_FLAGS if f != "-shared"]
+    cmds = []
+    for src in NOFMA_SOURCES:
+        obj = os.path.join(objdir, os.path.splitext(src)[0] + ".o")
+        cmds.append([_nvcc()] + compile_flags + ["-fmad=false", "-c", os.path.join(CSRC, src), "-o", obj])
+        objs.append(obj)
+    cmds.append([_nvcc()] + NVCC_FLAGS + extra + [os.path.join(CSRC, s) for s in SOURCES] + objs + ["-o", LIB])
+    for cmd in cmds:
+        r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+        text += " ".join(cmd) + "\n" + r.stdout
+        with open(log, "w") as f:
+            f.write(text)
+        if r.returncode != 0:
+            sys.stderr.write(r.stdout)
+            raise RuntimeError("nvcc failed building libnsx.so (see %s)" % log)
     if verbose:
-        print(r.stdout)
+        print(text)
     return LIB
 
 

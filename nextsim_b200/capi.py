@@ -132,6 +132,30 @@ class NsxTiming(C.Structure):
                 ("update_ms", C.c_float), ("n_launches", C.c_int), ("n_substeps", C.c_int)]
 
 
+class NsxThermoParams(C.Structure):
+    """include/nsx.h NsxThermoParams: the options of FiniteElement::thermo() (model/options.cpp [thermo], [age], ...)."""
+    _fields_ = [(n, C.c_int) for n in (
+        "thermo_type", "ocean_constant", "Qio_type", "freezingpoint_type", "newice_type", "melt_type", "alb_scheme", "flooding",
+        "use_assim_flux", "temp_dep_healing", "use_meltponds", "force_neutral_atmosphere", "reset_by_date", "equal_melting",
+        "use_young_ice_in_myi_reset", "ice_cat_young", "have_sphuma", "have_mixrat", "have_Qlw_in", "have_snowfr",
+        "have_snowfall", "have_mld", "reset_month", "reset_day")] + [(n, C.c_double) for n in (
+        "dtime_step", "ocean_nudge_timeT_days", "ocean_nudge_timeS_days", "Qdw_const", "Fdw_const", "hnull", "PhiF", "PhiM",
+        "assim_flux_exponent", "constant_mld", "I_0", "freeze_days_threshold", "meltpond_runoff_fraction",
+        "meltpond_depth_to_fraction", "drag_ocean_t", "drag_ocean_q", "alb_ice", "alb_sn", "alb_ponds", "zref_wind", "zref_temp",
+        "limiting_lengthscale", "quad_drag_coef_air", "ocean_albedo", "ks", "freezingpoint_mu", "Csens_io",
+        "time_relaxation_damage", "deltaT_relaxation_damage", "h_young_min", "h_young_max")]
+
+
+def thermo_default_params(**over):
+    p = NsxThermoParams()
+    lib().nsx_thermo_params_defaults(C.byref(p))
+    for k, v in over.items():
+        if not hasattr(p, k):
+            raise KeyError(k)
+        setattr(p, k, v)
+    return p
+
+
 EXPORTS = (
     "nsx_resident_plan_info", "nsx_create", "nsx_create_ex", "nsx_create_options_defaults", "nsx_device_sm_count", "nsx_destroy", "nsx_last_error", "nsx_version", "nsx_params_defaults", "nsx_params_from_cfg",
     "nsx_set_params", "nsx_upload", "nsx_download", "nsx_explicit_solve", "nsx_update", "nsx_update_ghosts",
@@ -139,6 +163,8 @@ EXPORTS = (
     "nsx_halo_connect_blob", "nsx_halo_connect_local", "nsx_halo_finalize", "nsx_group_explicit_solve",
     "nsx_host_register", "nsx_host_unregister", "nsx_abi_sizes", "nsx_tile_info", "nsx_plan_info", "nsx_cfg_last_error",
     "nsx_check_regridding", "nsx_update_ice_diagnostics", "nsx_forcing_load", "nsx_forcing_apply",
+    "nsx_thermo_params_defaults", "nsx_thermo_upload", "nsx_thermo_download", "nsx_thermo_upload_many", "nsx_thermo_download_many",
+    "nsx_thermo",
     "nsx_validate_mesh", "nsx_mapx_latlon", "nsx_partmesh_lat_from_mpp", "nsx_mapx_last_error", "nsx_partmesh_read", "nsx_partmesh_build", "nsx_partmesh_bc_marked_nodes", "nsx_partmesh_set_lat",
     "nsx_partmesh_views", "nsx_partmesh_ids", "nsx_partmesh_destroy", "nsx_partmesh_last_error",
 )
@@ -394,6 +420,29 @@ class Solver:
         self._chk(self.L.nsx_forcing_apply(self.h, FORCING[name], int(bool(interp_linear_time)), float(current_time),
                                            float(ftime0), float(ftime1), float(factor), float(bias_correction)),
                   "nsx_forcing_apply")
+
+    # ---- thermo() ----
+    def _thermo_xfer(self, fn, what, arrays):
+        names = list(arrays)
+        cn = (C.c_char_p * len(names))(*[n.encode() for n in names])
+        cp = (c_double_p * len(names))(*[arrays[n].ctypes.data_as(c_double_p) for n in names])
+        self._chk(fn(self.h, len(names), cn, cp), what)
+
+    def thermo_upload(self, **arrays):
+        """forcing / slab-ocean / tracer fields of thermo() by reference member name, [num_elements] each, one call"""
+        a = {k: np.ascontiguousarray(v, np.float64) for k, v in arrays.items()}
+        for k, v in a.items():
+            assert v.size == self.ne, (k, v.size, self.ne)
+        self._thermo_xfer(self.L.nsx_thermo_upload_many, "nsx_thermo_upload_many", a)
+
+    def thermo_download(self, *names):
+        out = {k: np.empty(self.ne) for k in names}
+        self._thermo_xfer(self.L.nsx_thermo_download_many, "nsx_thermo_download_many", out)
+        return out
+
+    def thermo(self, p, dt, current_time):
+        """FiniteElement::thermo(dt) at model time current_time (days since 1900-01-01) on the resident state"""
+        self._chk(self.L.nsx_thermo(self.h, C.byref(p), int(dt), C.c_double(current_time)), "nsx_thermo")
 
     def timing(self):
         t = NsxTiming()

@@ -396,10 +396,11 @@ extern "C" void* nsx_get_stream(nsx_handle h) { return h ? (void*)h->stream : nu
 // sizeof() of every struct that crosses the ABI, so a binding can detect layout drift
 extern "C" int nsx_abi_sizes(int* out, int n)
 {
-    int const s[7] = {(int)sizeof(NsxDynParams), (int)sizeof(NsxMesh), (int)sizeof(NsxHalo),
-                      (int)sizeof(NsxFields), (int)sizeof(NsxCheck), (int)sizeof(NsxTiming), (int)sizeof(NsxRegrid)};
-    for (int i = 0; i < n && i < 7; ++i) out[i] = s[i];
-    return 7;
+    int const s[9] = {(int)sizeof(NsxDynParams), (int)sizeof(NsxMesh), (int)sizeof(NsxHalo),
+                      (int)sizeof(NsxFields), (int)sizeof(NsxCheck), (int)sizeof(NsxTiming), (int)sizeof(NsxRegrid),
+                      (int)sizeof(NsxCreateOptions), (int)sizeof(NsxThermoParams)};
+    for (int i = 0; i < n && i < 9; ++i) out[i] = s[i];
+    return 9;
 }
 
 // tile decomposition summary: ntiles, nodes per tile, slots, max local nodes, max slots, boundary tiles, smem bytes,
@@ -1542,3 +1543,8 @@ extern "C" int nsx_resident_plan_info(const NsxMesh* mesh, const NsxHalo* halo, 
         return 2;
     }
 }
+
+// ---------------------------------------------------------------------------------------------------
+// thermo()
+// ---------------------------------------------------------------------------------------------------
+#include "nsx_thermo_api.cuh"

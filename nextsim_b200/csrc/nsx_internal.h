@@ -10,6 +10,7 @@
 
 #include "../../include/nsx.h"
 #include "nsx_mesh.h"
+#include "nsx_thermo.cuh"
 
 namespace nsx {
 
@@ -168,6 +169,10 @@ struct nsx_solver {
     nsx::DBuf<unsigned long long> regrid_keys;   // min-angle bits, ordered keys of min / max jacobian
     nsx::DBuf<double> forcing[3][2];             // interpolated_data[0..1] of wind, ocean (2 planes) and ssh (1 plane)
     bool forcing_loaded[3][2] = {};
+    // thermo().  th holds the device pointer of every field; th_planes owns the thermo-only ones
+    nsx::thermo::Arrays th{};
+    nsx::DBuf<double> th_planes;
+    int n_thermo_launch = 0;
 
     // ---- halo ----
     std::deque<nsx::PeerLink> peers;             // union of send/recv peers

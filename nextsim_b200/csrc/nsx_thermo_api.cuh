@@ -1,0 +1,124 @@
+// nsx_thermo_api.cuh -- FiniteElement::thermo(dt) on the device-resident state: the C ABI (included by nsx_api.cu; the
+// kernel is in nsx_thermo.cu).
+//
+// One thread per element runs nsx::thermo::thermo_element() (nsx_thermo.cuh): OWBulkFluxes + IABulkFluxes (old and young
+// ice) + the slab loop fused, so every field is read once and written once.  The kernel is HBM-bound: with the default
+// options an element reads 48 and writes 61 doubles (forcing 9, ice state 12 in/out, slab state 19 in/out -- two of them
+// the Winton layer temperatures --, diagnostics 30 out, 3 node ids) plus the L2-resident gathers of the wind at its nodes
+// = 884 algorithmic bytes.  Fields live in the handle's internal (Hilbert) element order, one plane per reference member,
+// all thermo-only planes in one allocation.
+#pragma once
+#include "nsx_thermo.cuh"
+
+namespace nsx {
+
+cudaError_t launch_thermo(thermo::Params const& P, thermo::Arrays const& A, cudaStream_t stream);      // nsx_thermo.cu
+
+// the thermo-only planes (everything but the ice state the dynamics owns), in the order of the X-lists
+inline int thermo_private_planes()
+{
+    int n = 1;      // D_pond_fraction
+#define X(f) ++n;
+    NSX_THERMO_FORCING(X) NSX_THERMO_STATE(X) NSX_THERMO_DIAG(X)
+#undef X
+    return n;
+}
+
+}  // namespace nsx
+
+// device pointers of every thermo field; allocates and zeroes the thermo-only planes on first use
+static nsx::thermo::Arrays& thermo_arrays(nsx_solver* S)
+{
+    using namespace nsx;
+    thermo::Arrays& A = S->th;
+    if (S->th_planes.p) return A;
+    size_t const ne = (size_t)S->ne;
+    S->th_planes.alloc((size_t)thermo_private_planes() * ne);
+    S->th_planes.zero(S->stream);
+    A = thermo::Arrays{};
+    A.ne = S->ne; A.nn = S->nn;
+    A.en0 = S->en0.p; A.en1 = S->en1.p; A.en2 = S->en2.p;
+    size_t k = 0;
+#define X(f) A.f = S->th_planes.p + (k++) * ne;
+    NSX_THERMO_FORCING(X) NSX_THERMO_STATE(X)
+    A.pond_fraction = S->th_planes.p + (k++) * ne;
+    NSX_THERMO_DIAG(X)
+#undef X
+    A.conc = S->conc.p; A.thick = S->thick.p; A.snow_thick = S->snow.p;
+    A.conc_young = S->conc_young.p; A.h_young = S->h_young.p; A.hs_young = S->hs_young.p;
+    A.ridge_ratio = S->ridge_ratio.p; A.conc_myi = S->conc_myi.p; A.thick_myi = S->thick_myi.p;
+    A.drag_ui = S->drag_ui.p; A.drag_ui_young = S->drag_ui_young.p; A.time_relaxation_damage = S->t_heal.p;
+    return A;
+}
+
+static void thermo_table(nsx_solver* S, int n, const char* const* names, double* const* host, std::vector<FieldMap>& t, bool upload)
+{
+    if (n < 0 || (n && (!names || !host))) throw std::invalid_argument("nsx_thermo transfer: bad argument");
+    nsx::thermo::Arrays& A = thermo_arrays(S);
+    for (int k = 0; k < n; ++k) {
+        if (!names[k] || !host[k]) throw std::invalid_argument("nsx_thermo transfer: NULL entry");
+        bool shared = false;
+        double** slot = nsx::thermo::field_slot(A, names[k], &shared);
+        if (!slot) throw std::invalid_argument(std::string("nsx_thermo transfer: unknown field ") + names[k]);
+        if (shared && upload)
+            throw std::invalid_argument(std::string("nsx_thermo_upload: ") + names[k] + " is part of the ice state, use nsx_upload (NsxFields)");
+        t.push_back({host[k], *slot, ELEM});
+    }
+}
+
+extern "C" void nsx_thermo_params_defaults(NsxThermoParams* p)
+{
+    if (p) nsx::thermo::params_defaults(*p);
+}
+
+extern "C" int nsx_thermo_upload_many(nsx_handle S, int n, const char* const* names, const double* const* host)
+{
+    NSX_API_BEGIN(S)
+    std::vector<FieldMap> t;
+    thermo_table(S, n, names, (double* const*)host, t, true);
+    std::vector<size_t> off;
+    xfer_layout(S, t, off);
+    for (size_t k = 0; k < t.size(); ++k)
+        NSX_CUDA(cudaMemcpyAsync(S->arena.p + off[k], t[k].host, (size_t)S->ne * sizeof(double), cudaMemcpyHostToDevice, S->stream));
+    if (!t.empty()) xfer_permute<1>(S, t, off);
+    NSX_CUDA(cudaStreamSynchronize(S->stream));
+    NSX_API_END(S)
+}
+
+extern "C" int nsx_thermo_download_many(nsx_handle S, int n, const char* const* names, double* const* host)
+{
+    NSX_API_BEGIN(S)
+    std::vector<FieldMap> t;
+    thermo_table(S, n, names, host, t, false);
+    std::vector<size_t> off;
+    xfer_layout(S, t, off);
+    if (!t.empty()) xfer_permute<0>(S, t, off);
+    for (size_t k = 0; k < t.size(); ++k)
+        NSX_CUDA(cudaMemcpyAsync(t[k].host, S->arena.p + off[k], (size_t)S->ne * sizeof(double), cudaMemcpyDeviceToHost, S->stream));
+    NSX_CUDA(cudaStreamSynchronize(S->stream));
+    NSX_API_END(S)
+}
+
+extern "C" int nsx_thermo_upload(nsx_handle S, const char* name, const double* host)
+{
+    return nsx_thermo_upload_many(S, 1, &name, &host);
+}
+extern "C" int nsx_thermo_download(nsx_handle S, const char* name, double* host)
+{
+    return nsx_thermo_download_many(S, 1, &name, &host);
+}
+
+extern "C" int nsx_thermo(nsx_handle S, const NsxThermoParams* p, int dt, double current_time)
+{
+    NSX_API_BEGIN(S)
+    if (!p) throw std::invalid_argument("nsx_thermo: NULL parameters");
+    if (const char* e = nsx::thermo::validate(*p, dt)) throw std::invalid_argument(e);
+    nsx::thermo::Arrays A = thermo_arrays(S);
+    A.wind = S->wind.p; A.ocean = S->ocean.p; A.VT = S->VT[S->cur];
+    nsx::thermo::Params const P = nsx::thermo::make_params(*p, dt, current_time);
+    if (S->ne > 0) {
+        NSX_CUDA(nsx::launch_thermo(P, A, S->stream));
+        ++S->n_thermo_launch;
+    }
+    NSX_API_END(S)
+}

@@ -223,3 +223,95 @@ def make_state(m, kind="large", seed=SEED, young=True):
 
 NODAL2 = ("M_VT", "M_UM", "M_UT", "M_wind", "M_ocean", "D_tau_a", "D_tau_w", "tau_wi")
 NODAL1 = ("M_ssh", "lat")
+
+
+THERMO_FORCING = ("M_tair", "M_mixrat", "M_dair", "M_sphuma", "M_mslp", "M_Qsw_in", "M_Qlw_in", "M_tcc", "M_precip", "M_snowfall",
+                  "M_snowfr", "M_mld", "M_ocean_temp", "M_ocean_salt", "M_conc_upd")
+THERMO_ICE = ("M_conc", "M_thick", "M_snow_thick", "M_conc_young", "M_h_young", "M_hs_young", "M_ridge_ratio", "M_conc_myi",
+              "M_thick_myi", "M_drag_ui", "M_drag_ui_young", "M_time_relaxation_damage")
+THERMO_STATE = ("M_sst", "M_sss", "M_tice0", "M_tice1", "M_tice2", "M_tsurf_young", "M_del_vi_tend", "M_freeze_days",
+                "M_freeze_onset", "M_conc_summer", "M_thick_summer", "M_fyi_fraction", "M_age_det", "M_age", "M_pond_volume",
+                "M_lid_volume", "M_drag_ti", "M_drag_ti_young", "D_pond_fraction")
+THERMO_DIAG = ("D_tau_ow", "D_Qa", "D_Qsw", "D_Qlw", "D_Qsh", "D_Qlh", "D_Qo", "D_Qnosun", "D_Qsw_ocean", "D_Qassim", "D_delS",
+               "D_fwflux_ice", "D_fwflux", "D_brine", "D_evap", "D_rain", "D_vice_melt", "D_del_vi_young", "D_del_hi",
+               "D_del_hi_young", "D_newice", "D_mlt_top", "D_mlt_bot", "D_snow2ice", "D_albedo", "D_sialb", "D_del_ci_mlt_myi",
+               "D_del_vi_mlt_myi", "D_del_ci_rplnt_myi", "D_del_vi_rplnt_myi")
+
+
+def make_thermo_state(ne, nn, seed=SEED, young=True, season="mixed"):
+    """Element fields of FiniteElement::thermo() (forcing, ice state, slab ocean, tracers) plus nodal wind / VT / ocean.
+
+    Built to reach every branch of thermo(): ice-free, thin (< hmin after melt), young-only and thick-ice elements; air
+    from -35 C (new ice in leads) to +8 C (surface melt, melt ponds); supercooled and warm mixed layers; snow-free and
+    snow-covered ice; multi-year-ice tracers on both sides of their clamps.  season: 'winter' / 'summer' bias the air
+    temperature and short-wave, 'mixed' spans both."""
+    rng = np.random.default_rng(seed + 77)
+    u = rng.uniform
+    S = {}
+    kind = rng.integers(0, 8, ne)                    # 0: open water, 1: trace ice, 2: thin ice, 3..7: pack ice
+    conc = np.select([kind == 0, kind == 1, kind == 2], [0.0, u(1e-13, 0.05, ne), u(0.05, 0.6, ne)], u(0.6, 1.0, ne))
+    hice = np.select([kind == 1, kind == 2], [u(0.005, 0.05, ne), u(0.008, 0.4, ne)], u(0.3, 3.5, ne))
+    hsnow = np.where(rng.random(ne) < 0.3, 0.0, u(0.0, 0.45, ne))
+    S["M_conc"] = conc
+    S["M_thick"] = conc * hice
+    S["M_snow_thick"] = conc * hsnow
+    if young:
+        cy = np.minimum(1.0 - conc, np.where(rng.random(ne) < 0.35, 0.0, u(0.0, 0.3, ne)))
+        S["M_conc_young"] = cy
+        S["M_h_young"] = cy * u(0.03, 0.6, ne)       # on both sides of h_young_min (0.05) and h_young_max_sharp (0.275)
+        S["M_hs_young"] = cy * np.where(rng.random(ne) < 0.4, 0.0, u(0.0, 0.08, ne))
+    else:
+        S["M_conc_young"] = np.zeros(ne)
+        S["M_h_young"] = np.zeros(ne)
+        S["M_hs_young"] = np.zeros(ne)
+    S["M_ridge_ratio"] = np.where(conc > 0, u(0.0, 0.6, ne), 0.0)
+    S["M_conc_myi"] = conc * u(0.0, 1.1, ne)
+    S["M_thick_myi"] = S["M_thick"] * u(0.0, 1.1, ne)
+    for k in ("M_drag_ui", "M_drag_ui_young", "M_drag_ti", "M_drag_ti_young"):
+        S[k] = u(0.8e-3, 3.0e-3, ne)
+    S["M_time_relaxation_damage"] = np.full(ne, 25.0 * 86400.0)
+
+    lo, hi = {"winter": (-35.0, -2.0), "summer": (-3.0, 8.0)}.get(season, (-35.0, 8.0))
+    tair = u(lo, hi, ne)
+    S["M_tair"] = tair
+    S["M_dair"] = tair - u(0.0, 6.0, ne)
+    S["M_mixrat"] = u(1e-4, 5e-3, ne)
+    S["M_sphuma"] = np.where(rng.random(ne) < 0.05, -1e-6, u(1e-4, 5e-3, ne))        # round-off negatives are clamped (FE.cpp:4982)
+    S["M_mslp"] = u(96500.0, 104500.0, ne)
+    S["M_Qsw_in"] = np.where(rng.random(ne) < 0.3, 0.0, u(0.0, 120.0 if season == "winter" else 420.0, ne))
+    S["M_Qlw_in"] = u(140.0, 340.0, ne)
+    S["M_tcc"] = u(0.0, 1.0, ne)
+    S["M_precip"] = np.where(rng.random(ne) < 0.3, 0.0, u(0.0, 8e-5, ne))              # kg/m^2/s
+    S["M_snowfall"] = S["M_precip"] * u(-0.02, 1.0, ne)                                # slight negatives: input round-off (FE.cpp:5343)
+    S["M_snowfr"] = u(0.0, 1.0, ne)
+    S["M_mld"] = u(5.0, 60.0, ne)
+    S["M_ocean_temp"] = u(-1.85, 4.0, ne)
+    S["M_ocean_salt"] = u(29.0, 35.5, ne)
+    S["M_conc_upd"] = np.where(rng.random(ne) < 0.5, 0.0, u(-0.3, 0.1, ne))
+
+    sss = np.where(rng.random(ne) < 0.03, u(2.0, 6.0, ne), u(27.0, 35.5, ne))          # a few brackish cells: si_eff = sss < si
+    S["M_sss"] = sss
+    tf = -0.055 * sss
+    S["M_sst"] = np.where(conc + S["M_conc_young"] > 0, tf + u(-0.02, 0.5, ne), tf + u(-0.05, 5.0, ne))
+    tfr_ice = -0.055 * 5.0
+    S["M_tice0"] = np.where(conc > 0, np.minimum(u(-32.0, 0.0, ne), np.where(hsnow > 0, 0.0, tfr_ice)), tfr_ice)
+    S["M_tice1"] = np.where(conc > 0, u(-16.0, -0.4, ne), tfr_ice)
+    S["M_tice2"] = np.where(conc > 0, u(-9.0, -0.4, ne), tfr_ice)
+    S["M_tsurf_young"] = np.where(S["M_conc_young"] > 0, u(-28.0, tfr_ice, ne), tfr_ice)
+    S["M_del_vi_tend"] = u(-0.02, 0.02, ne) * 86400.0
+    S["M_freeze_days"] = rng.integers(0, 6, ne).astype(np.float64)
+    S["M_freeze_onset"] = rng.integers(0, 2, ne).astype(np.float64)
+    S["M_conc_summer"] = u(0.0, 1.0, ne)
+    S["M_thick_summer"] = u(0.0, 3.0, ne)
+    S["M_fyi_fraction"] = u(0.0, 1.0, ne)
+    S["M_age_det"] = u(0.0, 4e7, ne)
+    S["M_age"] = u(0.0, 4e7, ne)
+    pond = (rng.random(ne) < 0.5) & (conc > 0.1)
+    S["D_pond_fraction"] = np.where(pond, u(0.0, 0.35, ne), 0.0)
+    S["M_pond_volume"] = np.where(pond, S["D_pond_fraction"] * u(0.0, 0.3, ne), 0.0)
+    S["M_lid_volume"] = np.where(pond & (rng.random(ne) < 0.5), u(0.0, 0.03, ne), 0.0)
+
+    S["M_wind"] = u(-18.0, 18.0, 2 * nn)
+    S["M_VT"] = u(-0.4, 0.4, 2 * nn)
+    S["M_ocean"] = u(-0.25, 0.25, 2 * nn)
+    return S

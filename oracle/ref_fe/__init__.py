@@ -121,3 +121,10 @@ class RefFE:
 
     def update_ice_diagnostics(self):
         self._chk(self.L.ref_fe_update_ice_diagnostics(self.h))
+
+    # ---- thermo(): `params` is a ctypes mirror of NsxThermoParams (oracle.thermo.ThermoParams) ----
+    def thermo_setup(self, params, current_time):
+        self._chk(self.L.ref_fe_thermo_setup(self.h, C.byref(params), C.c_double(current_time)))
+
+    def thermo(self, dt):
+        self._chk(self.L.ref_fe_thermo(self.h, int(dt)))

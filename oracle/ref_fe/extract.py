@@ -42,6 +42,19 @@ WANTED = [
     ("model/finiteelement.cpp", "FiniteElement::updateSigmaEVP", "", 0),
     ("model/finiteelement.cpp", "FiniteElement::updateSigmaMEVP", "", 0),
     ("model/finiteelement.cpp", "FiniteElement::updateGhosts", "", 0),
+    # thermo() and everything it calls (libm only)
+    ("model/finiteelement.cpp", "FiniteElement::specificHumidity", "", 0),
+    ("model/finiteelement.cpp", "FiniteElement::OWBulkFluxes", "", 0),
+    ("model/finiteelement.cpp", "FiniteElement::thermo", "int dt", 0),
+    ("model/finiteelement.cpp", "FiniteElement::IABulkFluxes", "", 0),
+    ("model/finiteelement.cpp", "FiniteElement::windSpeedElement", "", 0),
+    ("model/finiteelement.cpp", "FiniteElement::incomingLongwave", "", 0),
+    ("model/finiteelement.cpp", "FiniteElement::iceOceanHeatflux", "", 0),
+    ("model/finiteelement.cpp", "FiniteElement::freezingPoint", "", 0),
+    ("model/finiteelement.cpp", "FiniteElement::albedo", "", 0),
+    ("model/finiteelement.cpp", "FiniteElement::meltPonds", "", 0),
+    ("model/finiteelement.cpp", "FiniteElement::thermoWinton", "", 0),
+    ("model/finiteelement.cpp", "FiniteElement::thermoIce0", "", 0),
     ("core/src/gmshmesh.cpp", "GmshMesh::vertices", "std::vector<int> const& indices) const", 0),
     ("core/src/gmshmesh.cpp", "GmshMesh::vertices", "std::vector<double> const& um, double factor", 0),
 ]

@@ -8,6 +8,7 @@
 // Nothing here computes physics: every arithmetic statement that runs is reference text.
 #pragma once
 #include <algorithm>
+#include <cassert>
 #include <cmath>
 #include <condition_variable>
 #include <deque>
@@ -18,9 +19,11 @@
 #include <numeric>
 #include <stdexcept>
 #include <string>
+#include <tuple>
 #include <vector>
 
 #include "constants.hpp"        // the reference's own model/constants.hpp (plain C++), found through -I
+#include "enums.hpp"            // the reference's own model/enums.hpp (plain C++): setup::*, schemes::*
 
 #define PI 3.141592653589793          // contrib/mapx/include/mapx.h:47, reaches finiteelement.cpp through gmshmesh.hpp
 
@@ -39,17 +42,33 @@ namespace Nextsim {
 
 inline double real(int v) { return double(v); }      // FE.cpp:10185 `real(steps)`: std::real(int) -> double
 
-namespace setup {
-enum class DynamicsType { DEFAULT = 0, NO_MOTION = 1, EVP = 2, mEVP = 3, BBM = 4, FREE_DRIFT = 5 };
-enum class BasalStressType { NONE = 0, LEMIEUX = 1, BOUILLON = 2 };
-enum class IceCategoryType { CLASSIC = 0, YOUNG_ICE = 1 };
+using physical::sigma_sb;        // FE.cpp:6386 names it unqualified
+
+// core/include/date.hpp:116 (boost::date_time there): nextsim time = decimal days since 1900-01-01 00:00; only the
+// "%m%d" format is used on the path (FE.cpp:5216)
+inline std::string datenumToString(double const& datenum, std::string const& format)
+{
+    if (format != "%m%d") throw std::runtime_error("ref_fe stub: datenumToString format " + format);
+    long z = (long)std::floor(datenum) + 693901L - 60L;      // days since 0000-03-01 (1900-01-01 is day 693901 of the proleptic count from 0000-01-01)
+    long const era = (z >= 0 ? z : z - 146096) / 146097;
+    unsigned long const doe = (unsigned long)(z - era * 146097);
+    unsigned long const yoe = (doe - doe / 1460 + doe / 36524 - doe / 146096) / 365;
+    unsigned long const doy = doe - (365 * yoe + yoe / 4 - yoe / 100);
+    unsigned long const mp = (5 * doy + 2) / 153;
+    unsigned long const d = doy - (153 * mp + 2) / 5 + 1;
+    unsigned long const m = mp < 10 ? mp + 3 : mp - 9;
+    char buf[8];
+    std::snprintf(buf, sizeof buf, "%02lu%02lu", m, d);
+    return buf;
 }
 
 // ---- boost::program_options::variables_map stand-in ----
 struct OptValue {
     double v = 0.;
+    std::string s;
     template <class T> T as() const { return static_cast<T>(v); }
 };
+template <> inline std::string OptValue::as<std::string>() const { return s; }
 struct OptMap {
     std::map<std::string, OptValue> m;
     OptValue const& operator[](std::string const& k) const {
@@ -59,6 +78,7 @@ struct OptMap {
     }
     int count(std::string const& k) const { return (int)m.count(k); }
     void set(std::string const& k, double v) { m[k].v = v; }
+    void set(std::string const& k, std::string const& v) { m[k].s = v; }
 };
 
 struct Timer {
@@ -72,6 +92,8 @@ struct ModelVariable : std::vector<double> { using std::vector<double>::vector; 
 // ExternalData: explicitSolve only uses operator[](i) and getVector() (model/externaldata.hpp)
 struct ExternalData {
     std::vector<double> data;
+    bool initialized = false;               // thermo() branches on isInitialized() (which forcing variables the dataset has)
+    bool isInitialized() const { return initialized; }
     double operator[](int i) const { return data[i]; }
     std::vector<double> getVector() const { return data; }
 };
@@ -96,6 +118,7 @@ struct Communicator {
     World* world = nullptr;
     int me = 0;
     int size() const { return world ? world->n : 1; }
+    void barrier() const {}                 // thermo() starts with one; the harness calls it rank by rank
     int rank() const { return me; }
     void send(int dst, int /*tag*/, std::vector<double> const& v) const {
         std::lock_guard<std::mutex> g(world->mu);
@@ -176,6 +199,32 @@ public:
     inline void updateSigmaEVP(double const dte, double const e, double const Pstar, double const C, double const delta_min);
     inline void updateSigmaMEVP(double const e, double const Pstar, double const C, double const delta_min, double const alpha);
     void updateGhosts(std::vector<double>& mesh_nodal_vec);
+    // SURVEY 8(f) row 3
+    inline std::pair<double, double> specificHumidity(schemes::specificHumidity scheme, int i, double temp = -999.);
+    void OWBulkFluxes(std::vector<double>& Qow, std::vector<double>& Qlw, std::vector<double>& Qsw, std::vector<double>& Qlh,
+                      std::vector<double>& Qsh, std::vector<double>& evap, ModelVariable& tau);
+    void IABulkFluxes(const std::vector<double>& Tsurf, const std::vector<double>& snow_thick, const std::vector<double>& conc,
+                      std::vector<double>& Qia, std::vector<double>& Qlw, std::vector<double>& Qsw, std::vector<double>& Qlh,
+                      std::vector<double>& Qsh, std::vector<double>& I, std::vector<double>& subl, std::vector<double>& dQiadT,
+                      std::vector<double>& alb_tot, ModelVariable& drag_ui, ModelVariable& drag_ti, bool bulk_for_young);
+    void thermo(int dt);
+    inline double windSpeedElement(const int i);
+    inline double incomingLongwave(const int i);
+    inline double iceOceanHeatflux(const int cpt, const double sst, const double sss, const double mld, const double dt);
+    inline double freezingPoint(const double sss);
+    inline std::tuple<double, double> albedo(const double Tsurf, const double hs, const double frac_pnd, const int alb_scheme,
+                                             const double alb_ice, const double alb_sn, const double alb_pnd, const double I_0);
+    inline void meltPonds(const int cpt, const double dt, const double hi, const double hs, const double iceSurfaceMelt,
+                          const double snowMelt, const double Qia, const double rain, const double roff, const double dep2frac);
+    inline void thermoWinton(const double dt, const double conc, const double voli, const double vols, const double mld,
+                             const double snowfall, const double Qia, const double dQiadT, const double I, const double subl,
+                             const double Tbot, double& Qio, double& hi, double& hs, double& hi_old, double& del_hi,
+                             double& del_hs_mlt, double& mlt_hi_top, double& mlt_hi_bot, double& del_hi_s2i, double& Tsurf,
+                             double& T1, double& T2);
+    inline void thermoIce0(const double dt, const double conc, const double voli, const double vols, const double mld,
+                           const double snowfall, const double Qia, const double dQiadT, const double I, const double subl,
+                           const double Tbot, double& Qio, double& hi, double& hs, double& hi_old, double& del_hi,
+                           double& del_hs_mlt, double& mlt_hi_top, double& mlt_hi_bot, double& del_hi_s2i, double& Tsurf);
 
     // diffuse() gathers to the root mesh; it returns at once for diffusivity <= 0 (FE.cpp:2762-2767), the default
     void diffuse(ModelVariable&, double diffusivity, double)
@@ -211,6 +260,23 @@ public:
     ModelVariable M_random_number, M_sst, M_sss, M_tsurf_young;
     std::vector<ModelVariable> M_sigma, M_tice, D_sigma;
     ModelVariable D_tau_a, D_tau_w, D_del_ci_ridge_myi, D_conc, D_thick, D_snow_thick, D_tsurf, D_divergence, D_dmean, D_dmax;
+
+    // ---- thermo(): options, forcing, state and diagnostics (names and types of model/finiteelement.hpp) ----
+    setup::OceanType M_ocean_type = setup::OceanType::CONSTANT;
+    setup::ThermoType M_thermo_type = setup::ThermoType::WINTON;
+    setup::OceanHeatfluxScheme M_Qio_type = setup::OceanHeatfluxScheme::BASIC;
+    setup::FreezingPointType M_freezingpoint_type = setup::FreezingPointType::LINEAR;
+    double M_current_time = 0., M_ocean_albedo = 0., M_ks = 0., M_freezingpoint_mu = 0., M_Csens_io = 0.;
+    double time_relaxation_damage = 0., deltaT_relaxation_damage = 0., h_young_min = 0., h_young_max_sharp = 0., quad_drag_coef_air = 0.;
+    bool M_flooding = true;
+    ExternalData M_tair, M_mixrat, M_dair, M_sphuma, M_mslp, M_Qsw_in, M_Qlw_in, M_tcc, M_precip, M_snowfall, M_snowfr, M_mld,
+        M_ocean_temp, M_ocean_salt;
+    ModelVariable M_conc_upd, M_del_vi_tend, M_freeze_days, M_freeze_onset, M_conc_summer, M_thick_summer, M_fyi_fraction,
+        M_age_det, M_age, M_pond_volume, M_lid_volume, M_drag_ti, M_drag_ti_young;
+    ModelVariable D_tau_ow, D_pond_fraction, D_Qa, D_Qsw, D_Qlw, D_Qsh, D_Qlh, D_Qo, D_Qnosun, D_Qsw_ocean, D_Qassim, D_delS,
+        D_fwflux_ice, D_fwflux, D_brine, D_evap, D_rain, D_vice_melt, D_del_vi_young, D_del_hi, D_del_hi_young, D_newice,
+        D_mlt_top, D_mlt_bot, D_snow2ice, D_albedo, D_sialb, D_del_ci_mlt_myi, D_del_vi_mlt_myi, D_del_ci_rplnt_myi,
+        D_del_vi_rplnt_myi;
 
     // ghost exchange lists (FE.cpp:14003-14088 fills them; here the harness does)
     std::vector<std::vector<int>> M_extract_local_index, M_local_ghosts_local_index;

@@ -10,6 +10,7 @@
 #include <thread>
 
 #include "stub_fe.hpp"
+#include "../../include/nsx.h"          // NsxThermoParams: the option block both sides are driven with
 
 namespace Nextsim {
 #include "ref_fe_bodies.inc"
@@ -60,7 +61,22 @@ std::vector<double>* field(FiniteElement& fe, std::string const& n)
     F(M_conc) F(M_thick) F(M_snow_thick) F(M_damage) F(M_ridge_ratio) F(M_conc_young) F(M_h_young) F(M_hs_young)
     F(M_thick_myi) F(M_conc_myi) F(M_Cohesion) F(M_time_relaxation_damage) F(M_drag_ui) F(M_drag_ui_young)
     F(M_random_number) F(D_tau_a) F(D_tau_w) F(D_del_ci_ridge_myi) F(D_conc) F(D_thick) F(D_snow_thick) F(D_divergence)
+    // thermo(): state and diagnostics
+    F(M_sst) F(M_sss) F(M_tsurf_young) F(M_conc_upd) F(M_del_vi_tend) F(M_freeze_days) F(M_freeze_onset) F(M_conc_summer)
+    F(M_thick_summer) F(M_fyi_fraction) F(M_age_det) F(M_age) F(M_pond_volume) F(M_lid_volume) F(M_drag_ti) F(M_drag_ti_young)
+    F(D_tau_ow) F(D_pond_fraction) F(D_Qa) F(D_Qsw) F(D_Qlw) F(D_Qsh) F(D_Qlh) F(D_Qo) F(D_Qnosun) F(D_Qsw_ocean) F(D_Qassim)
+    F(D_delS) F(D_fwflux_ice) F(D_fwflux) F(D_brine) F(D_evap) F(D_rain) F(D_vice_melt) F(D_del_vi_young) F(D_del_hi)
+    F(D_del_hi_young) F(D_newice) F(D_mlt_top) F(D_mlt_bot) F(D_snow2ice) F(D_albedo) F(D_sialb) F(D_del_ci_mlt_myi)
+    F(D_del_vi_mlt_myi) F(D_del_ci_rplnt_myi) F(D_del_vi_rplnt_myi)
 #undef F
+    // thermo(): forcing (ExternalData)
+#define X(x) if (n == #x) return &fe.x.data;
+    X(M_tair) X(M_mixrat) X(M_dair) X(M_sphuma) X(M_mslp) X(M_Qsw_in) X(M_Qlw_in) X(M_tcc) X(M_precip) X(M_snowfall) X(M_snowfr)
+    X(M_mld) X(M_ocean_temp) X(M_ocean_salt)
+#undef X
+    if (n == "M_tice0") return &fe.M_tice[0];
+    if (n == "M_tice1") return fe.M_tice.size() > 1 ? &fe.M_tice[1] : nullptr;
+    if (n == "M_tice2") return fe.M_tice.size() > 2 ? &fe.M_tice[2] : nullptr;
     return nullptr;
 }
 }  // namespace
@@ -291,6 +307,95 @@ int ref_fe_update_ice_diagnostics(void* h)
 {
     Harness* H = (Harness*)h;
     try { for (auto& R : H->ranks) R->fe.updateIceDiagnostics(); }
+    catch (std::exception const& e) { H->err = e.what(); return 2; }
+    return 0;
+}
+
+// ---- thermo(): options of NsxThermoParams -> the option map and members initOptAndParam() fills (FE.cpp:1089-1300) ----
+int ref_fe_thermo_setup(void* h, const NsxThermoParams* p, double current_time)
+{
+    Harness* H = (Harness*)h;
+    char md[8];
+    std::snprintf(md, sizeof md, "%02d%02d", p->reset_month, p->reset_day);
+    for (auto& R : H->ranks) {
+        FiniteElement& fe = R->fe;
+        fe.vm.set("thermo.ocean_nudge_timeT_days", p->ocean_nudge_timeT_days);
+        fe.vm.set("thermo.ocean_nudge_timeS_days", p->ocean_nudge_timeS_days);
+        fe.vm.set("ideal_simul.constant_Qdw", p->Qdw_const);
+        fe.vm.set("ideal_simul.constant_Fdw", p->Fdw_const);
+        fe.vm.set("ideal_simul.constant_mld", p->constant_mld);
+        fe.vm.set("thermo.hnull", p->hnull);
+        fe.vm.set("thermo.PhiF", p->PhiF);
+        fe.vm.set("thermo.PhiM", p->PhiM);
+        fe.vm.set("thermo.newice_type", p->newice_type);
+        fe.vm.set("thermo.melt_type", p->melt_type);
+        fe.vm.set("thermo.use_assim_flux", p->use_assim_flux);
+        fe.vm.set("thermo.assim_flux_exponent", p->assim_flux_exponent);
+        fe.vm.set("dynamics.use_temperature_dependent_healing", p->temp_dep_healing);
+        fe.vm.set("thermo.I_0", p->I_0);
+        fe.vm.set("age.include_young_ice", p->use_young_ice_in_myi_reset);
+        fe.vm.set("age.reset_date", std::string(md));
+        fe.vm.set("age.reset_by_date", p->reset_by_date);
+        fe.vm.set("age.reset_freeze_days", p->freeze_days_threshold);
+        fe.vm.set("age.equal_melting", p->equal_melting);
+        fe.vm.set("thermo.use_meltponds", p->use_meltponds);
+        fe.vm.set("thermo.meltpond_runoff_fraction", p->meltpond_runoff_fraction);
+        fe.vm.set("thermo.meltpond_depth_to_fraction", p->meltpond_depth_to_fraction);
+        fe.vm.set("thermo.drag_ocean_t", p->drag_ocean_t);
+        fe.vm.set("thermo.drag_ocean_q", p->drag_ocean_q);
+        fe.vm.set("thermo.alb_scheme", p->alb_scheme);
+        fe.vm.set("thermo.alb_ice", p->alb_ice);
+        fe.vm.set("thermo.alb_sn", p->alb_sn);
+        fe.vm.set("thermo.alb_ponds", p->alb_ponds);
+        fe.vm.set("thermo.force_neutral_atmosphere", p->force_neutral_atmosphere);
+        fe.vm.set("thermo.zref_wind", p->zref_wind);
+        fe.vm.set("thermo.zref_temp", p->zref_temp);
+        fe.vm.set("thermo.limiting_lengthscale", p->limiting_lengthscale);
+        fe.dtime_step = p->dtime_step;
+        fe.M_current_time = current_time;
+        fe.M_ocean_albedo = p->ocean_albedo;
+        fe.M_ks = p->ks;
+        fe.M_freezingpoint_mu = p->freezingpoint_mu;
+        fe.M_Csens_io = p->Csens_io;
+        fe.M_flooding = p->flooding != 0;
+        fe.time_relaxation_damage = p->time_relaxation_damage;
+        fe.deltaT_relaxation_damage = p->deltaT_relaxation_damage;
+        fe.h_young_min = p->h_young_min;
+        fe.h_young_max_sharp = .5 * (p->h_young_min + p->h_young_max);                  // FE.cpp:1198
+        fe.quad_drag_coef_air = p->quad_drag_coef_air;
+        fe.M_thermo_type = p->thermo_type == 0 ? Nextsim::setup::ThermoType::ZERO_LAYER : Nextsim::setup::ThermoType::WINTON;
+        fe.M_ocean_type = p->ocean_constant ? Nextsim::setup::OceanType::CONSTANT : Nextsim::setup::OceanType::TOPAZ4R;
+        fe.M_Qio_type = p->Qio_type == 0 ? Nextsim::setup::OceanHeatfluxScheme::BASIC : Nextsim::setup::OceanHeatfluxScheme::EXCHANGE;
+        fe.M_freezingpoint_type = p->freezingpoint_type == 0 ? Nextsim::setup::FreezingPointType::LINEAR : Nextsim::setup::FreezingPointType::UNESCO;
+        fe.M_ice_cat_type = p->ice_cat_young ? Nextsim::setup::IceCategoryType::YOUNG_ICE : Nextsim::setup::IceCategoryType::CLASSIC;
+        fe.M_sphuma.initialized = p->have_sphuma != 0;
+        fe.M_mixrat.initialized = p->have_mixrat != 0;
+        fe.M_Qlw_in.initialized = p->have_Qlw_in != 0;
+        fe.M_snowfr.initialized = p->have_snowfr != 0;
+        fe.M_snowfall.initialized = p->have_snowfall != 0;
+        fe.M_mld.initialized = p->have_mld != 0;
+        // M_tice has one layer under the zero-layer scheme and three under Winton (FE.cpp:1330-1345)
+        size_t const ne = (size_t)fe.M_num_elements;
+        fe.M_tice.resize(p->thermo_type == 0 ? 1 : 3);
+        for (auto& t : fe.M_tice) t.resize(ne, 0.);
+        for (const char* n : {"M_sst", "M_sss", "M_tsurf_young", "M_conc_upd", "M_del_vi_tend", "M_freeze_days", "M_freeze_onset",
+                              "M_conc_summer", "M_thick_summer", "M_fyi_fraction", "M_age_det", "M_age", "M_pond_volume",
+                              "M_lid_volume", "M_drag_ti", "M_drag_ti_young", "D_tau_ow", "D_pond_fraction", "D_Qa", "D_Qsw",
+                              "D_Qlw", "D_Qsh", "D_Qlh", "D_Qo", "D_Qnosun", "D_Qsw_ocean", "D_Qassim", "D_delS", "D_fwflux_ice",
+                              "D_fwflux", "D_brine", "D_evap", "D_rain", "D_vice_melt", "D_del_vi_young", "D_del_hi",
+                              "D_del_hi_young", "D_newice", "D_mlt_top", "D_mlt_bot", "D_snow2ice", "D_albedo", "D_sialb",
+                              "D_del_ci_mlt_myi", "D_del_vi_mlt_myi", "D_del_ci_rplnt_myi", "D_del_vi_rplnt_myi", "M_tair",
+                              "M_mixrat", "M_dair", "M_sphuma", "M_mslp", "M_Qsw_in", "M_Qlw_in", "M_tcc", "M_precip",
+                              "M_snowfall", "M_snowfr", "M_mld", "M_ocean_temp", "M_ocean_salt"})
+            field(fe, n)->resize(ne, 0.);
+    }
+    return 0;
+}
+
+int ref_fe_thermo(void* h, int dt)
+{
+    Harness* H = (Harness*)h;
+    try { for (auto& R : H->ranks) R->fe.thermo(dt); }
     catch (std::exception const& e) { H->err = e.what(); return 2; }
     return 0;
 }

@@ -31,11 +31,28 @@ def test_header_symbols_exported():
 
 def test_struct_layouts_match_ctypes():
     L = capi.lib()
-    out = (C.c_int * 7)()
-    assert L.nsx_abi_sizes(out, 7) == 7
+    out = (C.c_int * 9)()
+    assert L.nsx_abi_sizes(out, 9) == 9
     expect = [C.sizeof(capi.NsxDynParams), C.sizeof(capi.NsxMesh), C.sizeof(capi.NsxHalo),
-              C.sizeof(capi.NsxFields), C.sizeof(capi.NsxCheck), C.sizeof(capi.NsxTiming), C.sizeof(capi.NsxRegrid)]
+              C.sizeof(capi.NsxFields), C.sizeof(capi.NsxCheck), C.sizeof(capi.NsxTiming), C.sizeof(capi.NsxRegrid),
+              C.sizeof(capi.NsxCreateOptions), C.sizeof(capi.NsxThermoParams)]
     assert list(out) == expect
+
+
+def test_thermo_defaults_follow_options_cpp():
+    """model/options.cpp:272-449, 543-548; the oracle's mirror of the struct holds the same values"""
+    from oracle import thermo as oth
+    p = capi.thermo_default_params()
+    q = oth.default_params()
+    assert C.sizeof(p) == C.sizeof(q)
+    for (n, _) in p._fields_:
+        assert getattr(p, n) == getattr(q, n), n
+    assert (p.thermo_type, p.newice_type, p.melt_type, p.alb_scheme, p.flooding, p.ice_cat_young) == (1, 4, 2, 3, 1, 1)
+    assert (p.alb_ice, p.alb_sn, p.alb_ponds, p.I_0, p.ocean_albedo) == (0.538, 0.8256, 0.30, 0.30, 0.07)
+    assert (p.hnull, p.PhiF, p.PhiM, p.h_young_min, p.h_young_max, p.ks) == (0.25, 4.0, 0.5, 0.05, 0.5, 0.3096)
+    assert (p.drag_ocean_t, p.drag_ocean_q, p.freezingpoint_mu, p.Csens_io) == (0.83e-3, 1.5e-3, 0.055, 1e-3)
+    assert (p.reset_month, p.reset_day, p.freeze_days_threshold, p.reset_by_date, p.equal_melting) == (9, 15, 3.0, 0, 1)
+    assert p.time_relaxation_damage == 25 * 86400.0 and p.deltaT_relaxation_damage == 20.0 and p.dtime_step == 200.0
 
 
 def test_defaults_follow_options_cpp():
