@@ -32,8 +32,10 @@ def needs_build():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False, verbose=False):
-    if not force and not needs_build():
+def build(force=False, verbose=False, out=None):
+    """out: write the library there instead of nextsim_b200/libnsx.so (kernel-shape experiments: profiles/*.sh build
+    variants with the NSX_* macros and the harness loads one through NSX_LIBRARY)."""
+    if out is None and not force and not needs_build():
         return LIB
     extra = []
     for k in ("NSX_SUB_TPB", "NSX_SUB_MINB", "NSX_SUB_STAGES", "NSX_SUB_GROUPS", "NSX_DIRECT_TPB", "NSX_DIRECT_MINB", "NSX_SUB_CTAS_PER_SM", "NSX_RES_TPB", "NSX_RES_CTAS"):           # kernel-shape experiments
@@ -44,14 +46,18 @@ def build(force=False, verbose=False):
     log = os.path.join(HERE, "build.log")
     objdir = os.path.join(HERE, "_obj")
     os.makedirs(objdir, exist_ok=True)
-    objs, text = [], ""
     compile_flags = [f for f in NVCC_FLAGS if f != "-shared"]
-    cmds = []
+    thermo = []
+    for k in ("NSX_THERMO_TPB", "NSX_THERMO_MINB"):      # launch shape of k_thermo (nsx_thermo.cu)
+        if os.environ.get(k):
+            thermo.append("-D%s=%s" % (k, os.environ[k]))
+    objs, cmds = [], []
     for src in NOFMA_SOURCES:
-        obj = os.path.join(objdir, os.path.splitext(src)[0] + ".o")
-        cmds.append([_nvcc()] + compile_flags + ["-fmad=false", "-c", os.path.join(CSRC, src), "-o", obj])
+        obj = os.path.join(objdir, os.path.splitext(src)[0] + ("" if out is None else "_" + os.path.basename(out)) + ".o")
+        cmds.append([_nvcc()] + compile_flags + thermo + ["-fmad=false", "-c", os.path.join(CSRC, src), "-o", obj])
         objs.append(obj)
-    cmds.append([_nvcc()] + NVCC_FLAGS + extra + [os.path.join(CSRC, s) for s in SOURCES] + objs + ["-o", LIB])
+    cmds.append([_nvcc()] + NVCC_FLAGS + extra + [os.path.join(CSRC, s) for s in SOURCES] + objs + ["-o", out or LIB])
+    text = ""
     for cmd in cmds:
         r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
         text += " ".join(cmd) + "\n" + r.stdout
@@ -62,8 +68,8 @@ def build(force=False, verbose=False):
             raise RuntimeError("nvcc failed building libnsx.so (see %s)" % log)
     if verbose:
         print(text)
-    return LIB
+    return out or LIB
 
 
 if __name__ == "__main__":
-    build(force=True, verbose=True)
+    build(force=True, verbose=True, out=os.environ.get("NSX_BUILD_OUT"))

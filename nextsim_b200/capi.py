@@ -176,7 +176,8 @@ def lib():
     """Load (building first if needed) libnsx.so.  Raises if it cannot be built: no fallback."""
     global _lib
     if _lib is None:
-        path = _build.build()
+        # NSX_LIBRARY: a variant built by profiles/*.sh (harness knob; the library itself reads no environment variable)
+        path = os.environ.get("NSX_LIBRARY") or _build.build()
         L = C.CDLL(path)
         L.nsx_last_error.restype = C.c_char_p
         L.nsx_last_error.argtypes = [C.c_void_p]

@@ -8,9 +8,15 @@
 
 namespace nsx {
 
-constexpr int THERMO_TPB = 128;
+#ifndef NSX_THERMO_TPB
+#define NSX_THERMO_TPB 128
+#endif
+#ifndef NSX_THERMO_MINB
+#define NSX_THERMO_MINB 1
+#endif
+constexpr int THERMO_TPB = NSX_THERMO_TPB;
 
-__global__ void __launch_bounds__(THERMO_TPB)
+__global__ void __launch_bounds__(THERMO_TPB, NSX_THERMO_MINB)
 k_thermo(const __grid_constant__ thermo::Params P, const __grid_constant__ thermo::Arrays A)
 {
     int const i = blockIdx.x * blockDim.x + threadIdx.x;

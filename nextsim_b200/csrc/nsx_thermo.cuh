@@ -31,6 +31,20 @@ constexpr double C = 2100., cmin = 1e-12, cpa = 1000.5, cpv = 1860., cpw = 4186.
 }
 constexpr double days_in_sec = 86400.;
 
+// A divisor that is the same for every element (a physical constant, the time step): the host build divides, as the
+// reference does; the device multiplies by the reciprocal computed once on the host (an IEEE double division is ~25
+// instructions, a third of the ~150 divisions of one element have such a divisor).  <= 1 ulp apart, like the libm calls.
+// -DNSX_THERMO_EXACT_DIV keeps the division on the device too.
+struct UDiv { double c, rc; };
+NSX_HD double operator/(double x, UDiv const& d)
+{
+#if defined(__CUDA_ARCH__) && !defined(NSX_THERMO_EXACT_DIV)
+    return x * d.rc;
+#else
+    return x / d.c;
+#endif
+}
+
 // options + the per-step scalars thermo() derives before its loops (FE.cpp:5180-5216, 6160-6205)
 struct Params {
     NsxThermoParams o;
@@ -40,6 +54,7 @@ struct Params {
     int midnight;                           // std::fmod(M_current_time, 1.) == 0.
     int is_0915, is_0801, is_reset_date;    // date_string_md == "0915" / "0801" / age.reset_date
     double timeT, timeS, rh0, rPhiF, qi, qs, h_young_max_sharp;
+    UDiv u_ddt, u_rhos, u_rhow, u_rhoi, u_qi, u_qs, u_ki, u_h_young_min;
     // IABulkFluxes constants (FE.cpp:6171-6205)
     double z0, Linvrange, Bm, C1, C2, C3, Bm2, C4, C5, C6, C7, D1, D2, D3, D4, D5, lambda_u, lambda_h;
 };
@@ -97,6 +112,30 @@ inline double** field_slot(Arrays& A, const char* name, bool* shared = nullptr)
 
 NSX_HD double dmax(double a, double b) { return (a < b) ? b : a; }      // std::max
 NSX_HD double dmin(double a, double b) { return (b < a) ? b : a; }      // std::min
+// std::pow(x, 2|3|4) and std::hypot of the reference.  The host build keeps the libm calls (bit for bit with the reference's
+// build); the device spells them as products: CUDA's pow(double, double) is ~350 instructions, sixteen of them per element
+// made the kernel instruction-bound (profiles/r2_thermo_v1.txt), and x*x differs from a correctly rounded pow by <= 1 ulp.
+#if defined(__CUDA_ARCH__)
+NSX_HD double pw2(double x) { return x * x; }
+NSX_HD double pw3(double x) { return x * x * x; }
+NSX_HD double pw4(double x) { double const y = x * x; return y * y; }
+NSX_HD double hyp(double u, double v) { return sqrt(u * u + v * v); }
+#else
+NSX_HD double pw2(double x) { return std::pow(x, 2); }
+NSX_HD double pw3(double x) { return std::pow(x, 3); }
+NSX_HD double pw4(double x) { return std::pow(x, 4); }
+NSX_HD double hyp(double u, double v) { return std::hypot(u, v); }
+#endif
+
+// one element's fields, held in registers between the loads at the top of thermo_element() and the stores at its end
+struct Elem {
+#define X(n) double n;
+    NSX_THERMO_FORCING(X)
+    NSX_THERMO_ICE(X)
+    NSX_THERMO_STATE(X)
+    double pond_fraction;
+#undef X
+};
 
 // FE.cpp:6432-6448
 NSX_HD double freezingPoint(Params const& P, double sss)
@@ -110,20 +149,20 @@ NSX_HD double windSpeedElement(Arrays const& A, int i)
 {
     int const n[3] = {A.en0[i], A.en1[i], A.en2[i]};
     double wspd = 0.;
-    for (int j = 0; j < 3; ++j) wspd += hypot(A.wind[n[j]], A.wind[n[j] + A.nn]);
+    for (int j = 0; j < 3; ++j) wspd += hyp(A.wind[n[j]], A.wind[n[j] + A.nn]);
     return wspd / 3.;
 }
 
 // FE.cpp:6376-6389
-NSX_HD double incomingLongwave(Params const& P, Arrays const& A, int i)
+NSX_HD double incomingLongwave(Params const& P, Elem const& E)
 {
-    if (P.o.have_Qlw_in) return A.Qlw_in[i];
-    double taa = A.tair[i] + phys::tfrwK;
-    return phys::sigma_sb * pow(taa, 4) * (1. - 0.261 * exp(-7.77e-4 * pow(taa - phys::tfrwK, 2))) * (1. + 0.275 * A.tcc[i]);
+    if (P.o.have_Qlw_in) return E.Qlw_in;
+    double taa = E.tair + phys::tfrwK;
+    return phys::sigma_sb * pw4(taa) * (1. - 0.261 * exp(-7.77e-4 * pw2(taa - phys::tfrwK))) * (1. + 0.275 * E.tcc);
 }
 
 // FE.cpp:4966-5019.  scheme 0 atmosphere, 1 water, 2 ice; returns sphum, *dsphumdT (ice only)
-NSX_HD double specificHumidity(Params const& P, Arrays const& A, int scheme, int i, double temp, double* dsphumdT)
+NSX_HD double specificHumidity(Params const& P, Elem const& E, int scheme, double temp, double* dsphumdT)
 {
     double Aa = 7.2e-4, B = 3.20e-6, Cc = 5.9e-10;
     double a = 6.1121e2, b = 18.729, c = 257.87, d = 227.3;
@@ -131,25 +170,25 @@ NSX_HD double specificHumidity(Params const& P, Arrays const& A, int scheme, int
     double salinity = 0.;
     *dsphumdT = 0.;
     if (scheme == 0) {
-        if (P.o.have_sphuma) return dmax(0., A.sphuma[i]);
-        if (P.o.have_mixrat) return A.mixrat[i] / (1. + A.mixrat[i]);
-        temp = A.dair[i];
+        if (P.o.have_sphuma) return dmax(0., E.sphuma);
+        if (P.o.have_mixrat) return E.mixrat / (1. + E.mixrat);
+        temp = E.dair;
         salinity = 0;
     } else if (scheme == 1) {
-        temp = A.sst[i];
+        temp = E.sst;
         return 640380. / phys::rhoa * exp(-5107.4 / (temp + phys::tfrwK));
     } else {
         Aa = 2.2e-4, B = 3.83e-6, Cc = 6.4e-10;
         a = 6.1115e2, b = 23.036, c = 279.82, d = 333.7;
         salinity = 0;
     }
-    double f = 1. + Aa + A.mslp[i] * 1e-2 * (B + Cc * temp * temp);
+    double f = 1. + Aa + E.mslp * 1e-2 * (B + Cc * temp * temp);
     double est = a * exp((b - temp / d) * temp / (temp + c)) * (1 - 5.37e-4 * salinity);
-    double sphum = alpha * f * est / (A.mslp[i] - beta * f * est);
+    double sphum = alpha * f * est / (E.mslp - beta * f * est);
     if (scheme == 2) {
         double dfdT = 2. * Cc * B * temp;
-        double destdT = (b * c * d - temp * (2. * c + temp)) / (d * pow(c + temp, 2)) * est;
-        *dsphumdT = alpha * A.mslp[i] * (f * destdT + est * dfdT) / pow(A.mslp[i] - beta * est * f, 2);
+        double destdT = (b * c * d - temp * (2. * c + temp)) / (d * pw2(c + temp)) * est;
+        *dsphumdT = alpha * E.mslp * (f * destdT + est * dfdT) / pw2(E.mslp - beta * est * f);
     }
     return sphum;
 }
@@ -192,23 +231,26 @@ NSX_HD double albedoFn(double Tsurf, double hs, double frac_pnd, int alb_scheme,
 }
 
 struct IceFlux { double Qia, Qlw, Qsw, Qlh, Qsh, I, subl, dQiadT, alb_tot; };
+// what OWBulkFluxes and both IABulkFluxes calls each recompute from the same inputs (pure functions of element i):
+// specificHumidity(ATMOSPHERE), the air density, windSpeedElement(), incomingLongwave()
+struct Air { double sphuma, rhoair, wspeed, Qlw_in; };
 
 // one element of IABulkFluxes (FE.cpp:6207-6352); drag_ui / drag_ti are updated in place like the reference's ModelVariables
-NSX_HD IceFlux iaBulkFluxes(Params const& P, Arrays const& A, int i, double Tsurf, double snow_thick, double conc,
+NSX_HD IceFlux iaBulkFluxes(Params const& P, Elem const& E, Air const& air, double Tsurf, double snow_thick, double conc,
                             double& drag_ui, double& drag_ti, bool bulk_for_young)
 {
     IceFlux F;
-    double Qlw_out = phys::eps * phys::sigma_sb * pow(Tsurf + phys::tfrwK, 4);
-    double dQlwdT = 4. * phys::eps * phys::sigma_sb * pow(Tsurf + phys::tfrwK, 3);
+    double Qlw_out = phys::eps * phys::sigma_sb * pw4(Tsurf + phys::tfrwK);
+    double dQlwdT = 4. * phys::eps * phys::sigma_sb * pw3(Tsurf + phys::tfrwK);
 
-    double dsphumidT, dummy;
-    double sphumi = specificHumidity(P, A, 2, i, Tsurf, &dsphumidT);
-    double sphuma = specificHumidity(P, A, 0, i, 0., &dummy);
+    double dsphumidT;
+    double sphumi = specificHumidity(P, E, 2, Tsurf, &dsphumidT);
+    double const sphuma = air.sphuma;                       // FE.cpp:6224-6225
 
-    double tairK = A.tair[i] + phys::tfrwK;
+    double tairK = E.tair + phys::tfrwK;
     double tsurfK = Tsurf + phys::tfrwK;
-    double rhoair = A.mslp[i] / (phys::Ra_dry * tairK) * (1. - sphuma * (1. - phys::Ra_vap / phys::Ra_dry));
-    double wspeed = windSpeedElement(A, i);
+    double const rhoair = air.rhoair;                       // FE.cpp:6234: same expression as FE.cpp:5115
+    double const wspeed = air.wspeed;                       // FE.cpp:6237
     const double Tpot = tairK + phys::Gamma_d * P.o.zref_temp;
     const double retv = 0.6078;
     const double ch = 3.;
@@ -254,13 +296,13 @@ NSX_HD IceFlux iaBulkFluxes(Params const& P, Arrays const& A, int i, double Tsur
     else hs = 0;
     double pen_sw;
     double pond_fraction;
-    if (A.pond_fraction[i] > 0. && A.lid_volume[i] / A.pond_fraction[i] <= 0.05) pond_fraction = A.pond_fraction[i];
+    if (E.pond_fraction > 0. && E.lid_volume / E.pond_fraction <= 0.05) pond_fraction = E.pond_fraction;
     else pond_fraction = 0.;
     if (bulk_for_young) pond_fraction = 0.;
     F.alb_tot = albedoFn(Tsurf, hs, pond_fraction, P.o.alb_scheme, P.o.alb_ice, P.o.alb_sn, P.o.alb_ponds, P.o.I_0, &pen_sw);
-    F.Qsw = -A.Qsw_in[i] * (1. - F.alb_tot) * (1. - pen_sw);
-    F.I = A.Qsw_in[i] * (1. - F.alb_tot) * pen_sw;
-    F.Qlw = Qlw_out - incomingLongwave(P, A, i);
+    F.Qsw = -E.Qsw_in * (1. - F.alb_tot) * (1. - pen_sw);
+    F.I = E.Qsw_in * (1. - F.alb_tot) * pen_sw;
+    F.Qlw = Qlw_out - air.Qlw_in;
     F.Qia = F.Qsw + F.Qlw + F.Qsh + F.Qlh;
     return F;
 }
@@ -269,11 +311,11 @@ NSX_HD IceFlux iaBulkFluxes(Params const& P, Arrays const& A, int i, double Tsur
 NSX_HD double iceOceanHeatflux(Params const& P, Arrays const& A, int cpt, double sst, double sss, double mld, double dt)
 {
     double const Tbot = freezingPoint(P, sss);
-    if (P.o.Qio_type == 0) return (sst - Tbot) * phys::rhow * phys::cpw * mld / dt;
+    if (P.o.Qio_type == 0) return (sst - Tbot) * phys::rhow * phys::cpw * mld / P.u_ddt;
     int const n[3] = {A.en0[cpt], A.en1[cpt], A.en2[cpt]};
     double welt_oce_ice = 0.;
     for (int i = 0; i < 3; ++i)
-        welt_oce_ice += hypot(A.VT[n[i]] - A.ocean[n[i]], A.VT[n[i] + A.nn] - A.ocean[n[i] + A.nn]);
+        welt_oce_ice += hyp(A.VT[n[i]] - A.ocean[n[i]], A.VT[n[i] + A.nn] - A.ocean[n[i] + A.nn]);
     double norm_Voce_ice = welt_oce_ice / 3.;
     return (sst - Tbot) * norm_Voce_ice * P.o.Csens_io * phys::rhow * phys::cpw;
 }
@@ -328,15 +370,15 @@ NSX_HD void thermoWinton(Params const& P, double dt, double conc, double voli, d
     double E1 = Crho * (T1 - Tfr_ice) - qi * (1 - Tfr_ice / T1);
     double E2 = Crho * (T2 - Tfr_ice) - qi;
 
-    hs += snowfall / phys::rhos * dt;
+    hs += snowfall / P.u_rhos * dt;
 
     if (subl * dt <= hs * phys::rhos)
-        hs -= subl * dt / phys::rhos;
+        hs -= subl * dt / P.u_rhos;
     else if (subl * dt - hs * phys::rhos <= h1 * phys::rhoi) {
-        h1 -= (subl * dt - hs * phys::rhos) / phys::rhoi;
+        h1 -= (subl * dt - hs * phys::rhos) / P.u_rhoi;
         hs = 0.;
     } else if (subl * dt - h1 * phys::rhoi - hs * phys::rhos <= h2 * phys::rhoi) {
-        h2 -= (subl * dt - h1 * phys::rhoi - hs * phys::rhos) / phys::rhoi;
+        h2 -= (subl * dt - h1 * phys::rhoi - hs * phys::rhos) / P.u_rhoi;
         h1 = 0.;
         hs = 0.;
     } else {
@@ -355,29 +397,29 @@ NSX_HD void thermoWinton(Params const& P, double dt, double conc, double voli, d
     } else {
         double delh2 = -dmin(-Mbot * dt / E2, h2);
         double delh1 = -dmin(dmax(-(Mbot * dt + E2 * h2) / E1, 0.), h1);
-        del_hs_mlt = -dmin(dmax((Mbot * dt + E2 * h2 + E1 * h1) / qs, 0.), hs);
+        del_hs_mlt = -dmin(dmax((Mbot * dt + E2 * h2 + E1 * h1) / P.u_qs, 0.), hs);
         if (h2 + h1 + hs - delh2 - delh1 - del_hs_mlt <= 0.)
-            Qio -= dmax(Mbot * dt - qs * hs + E1 * h1 + E2 * h2, 0.) / dt;
+            Qio -= dmax(Mbot * dt - qs * hs + E1 * h1 + E2 * h2, 0.) / P.u_ddt;
         hs += del_hs_mlt;
         h1 += delh1;
         h2 += delh2;
         mlt_hi_bot += delh1 + delh2;
     }
 
-    del_hs_mlt -= dmin(Msurf * dt / qs, hs);
+    del_hs_mlt -= dmin(Msurf * dt / P.u_qs, hs);
     double delh1 = -dmin(dmax(-(Msurf * dt - qs * hs) / E1, 0.), h1);
     double delh2 = -dmin(dmax(-(Msurf * dt - qs * hs + E1 * h1) / E2, 0.), h2);
     if (h2 + h1 + hs - delh2 - delh1 - del_hs_mlt <= 0.)
-        Qio -= dmax(Msurf * dt - qs * hs + E1 * h1 + E2 * h2, 0.) / dt;
+        Qio -= dmax(Msurf * dt - qs * hs + E1 * h1 + E2 * h2, 0.) / P.u_ddt;
 
     hs += del_hs_mlt;
     h1 += delh1;
     h2 += delh2;
     mlt_hi_top += delh1 + delh2;
 
-    double freeboard = (hi * (phys::rhow - phys::rhoi) - hs * phys::rhos) / phys::rhow;
+    double freeboard = (hi * (phys::rhow - phys::rhoi) - hs * phys::rhos) / P.u_rhow;
     if (P.o.flooding && freeboard < 0) {
-        hs += dmin(freeboard * phys::rhoi / phys::rhos, 0.);
+        hs += dmin(freeboard * phys::rhoi / P.u_rhos, 0.);
         double delh1b = dmax(-freeboard, 0.);
         double f1 = 1 - delh1b / (delh1b + h1);
         double Tbar = f1 * (T1 + qi * Tfr_ice / (Crho * T1)) + (1 - f1) * Tfr_ice;
@@ -404,7 +446,7 @@ NSX_HD void thermoWinton(Params const& P, double dt, double conc, double voli, d
     del_hi = hi - hi_old;
 
     if (hi < phys::hmin) {
-        Qio -= (-qs * hs + (E1 + E2) * hi / 2.) / dt;
+        Qio -= (-qs * hs + (E1 + E2) * hi / 2.) / P.u_ddt;
         if (del_hi < 0.) {
             mlt_hi_top *= -hi_old / del_hi;
             mlt_hi_bot *= -hi_old / del_hi;
@@ -441,29 +483,29 @@ NSX_HD void thermoIce0(Params const& P, double dt, double conc, double voli, dou
     double Qic, del_hb, del_ht, draft;
     double const Qia_mod = Qia + (1. - beta) * I;
 
-    Qic = M_ks * (Tbot - Tsurf) / (hs + M_ks * hi / phys::ki) * gamma;
-    Tsurf = Tsurf + (Qic - Qia_mod) / (M_ks / (hs + M_ks * hi / phys::ki) + dQiadT);
+    Qic = M_ks * (Tbot - Tsurf) / (hs + M_ks * hi / P.u_ki) * gamma;
+    Tsurf = Tsurf + (Qic - Qia_mod) / (M_ks / (hs + M_ks * hi / P.u_ki) + dQiadT);
 
     if (hs > 0.) Tsurf = dmin(0., Tsurf);
     else Tsurf = dmin(-P.o.freezingpoint_mu * phys::si, Tsurf);
 
-    del_hs_mlt = dmin(Qia_mod - Qic, 0.) * dt / qs;
-    hs += del_hs_mlt - subl * dt / phys::rhos;
-    del_ht = dmin(hs, 0.) * qs / qi;
+    del_hs_mlt = dmin(Qia_mod - Qic, 0.) * dt / P.u_qs;
+    hs += del_hs_mlt - subl * dt / P.u_rhos;
+    del_ht = dmin(hs, 0.) * qs / P.u_qi;
     hs = dmax(0., hs);
-    hs += snowfall / phys::rhos * dt;
+    hs += snowfall / P.u_rhos * dt;
 
-    del_hb = (Qic - Qio) * dt / qi;
+    del_hb = (Qic - Qio) * dt / P.u_qi;
 
     del_hi = del_ht + del_hb;
     hi = hi + del_hi;
     mlt_hi_top = dmin(del_ht, 0.);
     mlt_hi_bot = dmin(del_hb, 0.);
 
-    draft = (hi * phys::rhoi + hs * phys::rhos) / phys::rhow;
+    draft = (hi * phys::rhoi + hs * phys::rhos) / P.u_rhow;
     if (P.o.flooding && draft > hi) {
         del_hi_s2i += draft - hi;
-        hs = hs - (draft - hi) * phys::rhoi / phys::rhos;
+        hs = hs - (draft - hi) * phys::rhoi / P.u_rhos;
         hi = draft;
     }
 
@@ -474,64 +516,64 @@ NSX_HD void thermoIce0(Params const& P, double dt, double conc, double voli, dou
         }
         del_hi_s2i = 0.;
         del_hi = -hi_old;
-        Qio = Qio + hi * qi / dt + hs * qs / dt;
+        Qio = Qio + hi * qi / P.u_ddt + hs * qs / P.u_ddt;
         hi = 0.; hs = 0.;
         Tsurf = Tfr_ice;
     }
 }
 
 // FE.cpp:6538-6627
-NSX_HD void meltPonds(Params const& P, Arrays const& A, int cpt, double dt, double hi, double hs, double iceSurfaceMelt,
+NSX_HD void meltPonds(Params const& P, Elem& E, double dt, double hi, double hs, double iceSurfaceMelt,
                       double snowMelt, double Qia, double rain, double roff, double dep2frac)
 {
     const double hIceMin = 0.1;
     const double concMin = 0.1;
     const double max_lid_thickness = 0.3;
     const double min_lid_thickness = 1e-3;
-    const double ice_to_water = phys::rhoi / phys::rhow;
-    const double snow_to_water = phys::rhos / phys::rhow;
-    const double water_to_ice = phys::rhow / phys::rhoi;
+    const double ice_to_water = phys::rhoi / P.u_rhow;
+    const double snow_to_water = phys::rhos / P.u_rhow;
+    const double water_to_ice = phys::rhow / P.u_rhoi;
 
-    double const availableWater = -iceSurfaceMelt * ice_to_water - snowMelt * snow_to_water + rain / phys::rhow * dt;
-    A.pond_volume[cpt] += (1 - roff) * availableWater * A.conc[cpt];
+    double const availableWater = -iceSurfaceMelt * ice_to_water - snowMelt * snow_to_water + rain / P.u_rhow * dt;
+    E.pond_volume += (1 - roff) * availableWater * E.conc;
 
-    if (A.pond_volume[cpt] <= 0. || A.conc[cpt] <= concMin || A.thick[cpt] / A.conc[cpt] <= hIceMin) {
-        A.pond_volume[cpt] = 0.;
-        A.lid_volume[cpt] = 0.;
-        A.pond_fraction[cpt] = 0.;
+    if (E.pond_volume <= 0. || E.conc <= concMin || E.thick / E.conc <= hIceMin) {
+        E.pond_volume = 0.;
+        E.lid_volume = 0.;
+        E.pond_fraction = 0.;
         return;
     }
-    A.pond_fraction[cpt] = sqrt(A.pond_volume[cpt] / dep2frac);
-    A.pond_fraction[cpt] = dmin(A.pond_fraction[cpt], 1. - hs / (hs + 0.2));
-    double pond_depth = dmin(dep2frac * A.pond_fraction[cpt], 0.9 * hi);
-    A.pond_volume[cpt] = pond_depth * A.pond_fraction[cpt];
+    E.pond_fraction = sqrt(E.pond_volume / dep2frac);
+    E.pond_fraction = dmin(E.pond_fraction, 1. - hs / (hs + 0.2));
+    double pond_depth = dmin(dep2frac * E.pond_fraction, 0.9 * hi);
+    E.pond_volume = pond_depth * E.pond_fraction;
     pond_depth = dmax(0.05, pond_depth);
-    A.pond_fraction[cpt] = dmin(A.pond_fraction[cpt], (A.lid_volume[cpt] + A.pond_volume[cpt]) / pond_depth);
+    E.pond_fraction = dmin(E.pond_fraction, (E.lid_volume + E.pond_volume) / pond_depth);
 
     double delLidVolume = 0;
-    if (A.lid_volume[cpt] > 0. && A.pond_fraction[cpt] > 1e-11) {
+    if (E.lid_volume > 0. && E.pond_fraction > 1e-11) {
         const double TPond = -P.o.freezingpoint_mu * phys::si;
-        const double lidThickness = dmax(min_lid_thickness, dmin(max_lid_thickness, A.lid_volume[cpt] * water_to_ice / A.pond_fraction[cpt]));
-        const double Qic = (TPond - A.tice0[cpt]) / lidThickness * phys::ki;
+        const double lidThickness = dmax(min_lid_thickness, dmin(max_lid_thickness, E.lid_volume * water_to_ice / E.pond_fraction));
+        const double Qic = (TPond - E.tice0) / lidThickness * phys::ki;
         const double delLidThickness = (dmin(Qia - Qic, 0.) + Qic) * dt / (phys::rhoi * phys::Lf);
-        delLidVolume = delLidThickness * ice_to_water * A.pond_fraction[cpt];
-        delLidVolume = dmax(delLidVolume, -A.lid_volume[cpt]);
+        delLidVolume = delLidThickness * ice_to_water * E.pond_fraction;
+        delLidVolume = dmax(delLidVolume, -E.lid_volume);
     } else if (Qia > 0.) {
         delLidVolume = dt * Qia / (phys::rhoi * phys::Lf) * ice_to_water;
     }
-    A.lid_volume[cpt] += delLidVolume;
-    A.pond_volume[cpt] -= delLidVolume;
-    if (A.pond_volume[cpt] <= 0. || A.lid_volume[cpt] * water_to_ice / A.pond_fraction[cpt] >= max_lid_thickness) {
-        A.lid_volume[cpt] = 0.;
-        A.pond_volume[cpt] = 0.;
-        A.pond_fraction[cpt] = 0.;
+    E.lid_volume += delLidVolume;
+    E.pond_volume -= delLidVolume;
+    if (E.pond_volume <= 0. || E.lid_volume * water_to_ice / E.pond_fraction >= max_lid_thickness) {
+        E.lid_volume = 0.;
+        E.pond_volume = 0.;
+        E.pond_fraction = 0.;
     }
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
 // thermo() for element i
 // ---------------------------------------------------------------------------------------------------------------------
-NSX_HD void thermo_element(Params const& P, Arrays const& A, int i)
+NSX_HD void thermo_core(Params const& P, Arrays const& A, int i, Elem& E)
 {
     NsxThermoParams const& o = P.o;
     double const ddt = P.ddt;
@@ -542,32 +584,34 @@ NSX_HD void thermo_element(Params const& P, Arrays const& A, int i)
 
     // ---- OWBulkFluxes, element i (FE.cpp:5101-5158) ----
     double Qow, Qlw_ow, Qsw_ow, Qlh_ow, Qsh_ow, evap;
+    Air air;
     {
         double dummy;
-        double sphuma = specificHumidity(P, A, 0, i, 0., &dummy);
-        double sphumw = specificHumidity(P, A, 1, i, 0., &dummy);
-        double rhoair = A.mslp[i] / (phys::Ra_dry * (A.tair[i] + phys::tfrwK)) * (1. - sphuma * (1. - phys::Ra_vap / phys::Ra_dry));
+        double sphuma = specificHumidity(P, E, 0, 0., &dummy);
+        double sphumw = specificHumidity(P, E, 1, 0., &dummy);
+        double rhoair = E.mslp / (phys::Ra_dry * (E.tair + phys::tfrwK)) * (1. - sphuma * (1. - phys::Ra_vap / phys::Ra_dry));
         double wspeed = windSpeedElement(A, i);
-        Qsh_ow = o.drag_ocean_t * rhoair * (phys::cpa + sphuma * phys::cpv) * wspeed * (A.sst[i] - A.tair[i]);
-        double Lv = phys::Lv0 - 2.36418e3 * A.sst[i] + 1.58927 * A.sst[i] * A.sst[i] - 6.14342e-2 * pow(A.sst[i], 3.);
+        air.sphuma = sphuma; air.rhoair = rhoair; air.wspeed = wspeed; air.Qlw_in = incomingLongwave(P, E);
+        Qsh_ow = o.drag_ocean_t * rhoair * (phys::cpa + sphuma * phys::cpv) * wspeed * (E.sst - E.tair);
+        double Lv = phys::Lv0 - 2.36418e3 * E.sst + 1.58927 * E.sst * E.sst - 6.14342e-2 * pw3(E.sst);
         Qlh_ow = dmax(o.drag_ocean_q * phys::rhoa * Lv * wspeed * (sphumw - sphuma), 0.);
         evap = Qlh_ow / Lv;
         double drag_ocean_m = 1e-3 * dmax(1., dmin(2., 0.61 + 0.063 * wspeed));
         A.tau_ow[i] = rhoair * drag_ocean_m;
 
-        Qsw_ow = -A.Qsw_in[i] * (1. - o.ocean_albedo);
-        double Qlw_out = phys::eps * phys::sigma_sb * pow(A.sst[i] + phys::tfrwK, 4.);
-        Qlw_ow = Qlw_out - incomingLongwave(P, A, i);
+        Qsw_ow = -E.Qsw_in * (1. - o.ocean_albedo);
+        double Qlw_out = phys::eps * phys::sigma_sb * pw4(E.sst + phys::tfrwK);
+        Qlw_ow = Qlw_out - air.Qlw_in;
         Qow = Qlw_ow + Qsh_ow + Qlh_ow;
         Qow += Qsw_ow;
     }
 
     // ---- IABulkFluxes over old ice and over young ice (FE.cpp:5248-5275) ----
-    IceFlux Fi = iaBulkFluxes(P, A, i, A.tice0[i], A.snow_thick[i], A.conc[i], A.drag_ui[i], A.drag_ti[i], false);
+    IceFlux Fi = iaBulkFluxes(P, E, air, E.tice0, E.snow_thick, E.conc, E.drag_ui, E.drag_ti, false);
     IceFlux Fy;
     Fy.Qia = Fy.Qlw = Fy.Qsw = Fy.Qlh = Fy.Qsh = Fy.I = Fy.subl = Fy.dQiadT = Fy.alb_tot = 0.;
     if (young)
-        Fy = iaBulkFluxes(P, A, i, A.tsurf_young[i], A.hs_young[i], A.conc_young[i], A.drag_ui_young[i], A.drag_ti_young[i], true);
+        Fy = iaBulkFluxes(P, E, air, E.tsurf_young, E.hs_young, E.conc_young, E.drag_ui_young, E.drag_ti_young, true);
 
     // ---- the slab loop body (FE.cpp:5279-6132) ----
     double hi = 0., hi_old = 0., hs = 0.;
@@ -577,69 +621,84 @@ NSX_HD void thermo_element(Params const& P, Arrays const& A, int i)
     double Qio = 0., Qio_young = 0.;
     double Qassm = 0.;
 
-    double const old_vol = A.thick[i];
-    double const old_snow_vol = A.snow_thick[i];
+    double const old_vol = E.thick;
+    double const old_snow_vol = E.snow_thick;
     (void)old_snow_vol;
-    double const old_conc = A.conc[i];
+    double const old_conc = E.conc;
     double old_h_young = 0., old_hs_young = 0., old_conc_young = 0.;
     if (young) {
-        old_h_young = A.h_young[i];
-        old_conc_young = A.conc_young[i];
-        old_hs_young = A.hs_young[i];
+        old_h_young = E.h_young;
+        old_conc_young = E.conc_young;
+        old_hs_young = E.hs_young;
     }
     (void)old_h_young; (void)old_hs_young;
     double const old_conc_tot = old_conc + old_conc_young;
     double const old_ow_fraction = 1. - old_conc_tot;
 
+    // diagnostics that only need the fluxes and the old concentrations are written now (FE.cpp:5906-5924, 5972-5977),
+    // which ends the live range of eight flux components
+    A.Qsw[i] = Fi.Qsw * old_conc + Fy.Qsw * old_conc_young + Qsw_ow * old_ow_fraction;
+    A.Qlw[i] = Fi.Qlw * old_conc + Fy.Qlw * old_conc_young + Qlw_ow * old_ow_fraction;
+    A.Qsh[i] = Fi.Qsh * old_conc + Fy.Qsh * old_conc_young + Qsh_ow * old_ow_fraction;
+    A.Qlh[i] = Fi.Qlh * old_conc + Fy.Qlh * old_conc_young + Qlh_ow * old_ow_fraction;
+    double const Qnosun_ow = old_ow_fraction * (Qlw_ow + Qlh_ow + Qsh_ow);
+    A.Qsw_ocean[i] = old_ow_fraction * Qsw_ow;
+    {
+        double sialb = old_conc * Fi.alb_tot;
+        if (young) sialb += old_conc_young * Fy.alb_tot;
+        A.albedo[i] = sialb + dmax(0., old_ow_fraction) * o.ocean_albedo;
+        A.sialb[i] = (old_conc_tot > 0.) ? (sialb / old_conc_tot) : 0.;
+    }
+
     double tmp_snowfall = 0.;
-    if (o.have_snowfr) tmp_snowfall = A.precip[i] * A.snowfr[i];
-    else if (o.have_snowfall) tmp_snowfall = A.snowfall[i];
-    else if (A.tair[i] < 0) tmp_snowfall = A.precip[i];
+    if (o.have_snowfr) tmp_snowfall = E.precip * E.snowfr;
+    else if (o.have_snowfall) tmp_snowfall = E.snowfall;
+    else if (E.tair < 0) tmp_snowfall = E.precip;
     tmp_snowfall = dmax(0., tmp_snowfall);
 
-    if (o.have_mld) mld = A.mld[i];
+    if (o.have_mld) mld = E.mld;
 
     if (o.ocean_constant) {
         Qdw = o.Qdw_const;
         Fdw = o.Fdw_const;
     } else {
-        Qdw = -(A.sst[i] - A.ocean_temp[i]) * mld * phys::rhow * phys::cpw / P.timeT;
-        double const delS = A.sss[i] - A.ocean_salt[i];
-        Fdw = delS * mld * phys::rhow / (P.timeS * A.sss[i] - ddt * delS);
+        Qdw = -(E.sst - E.ocean_temp) * mld * phys::rhow * phys::cpw / P.timeT;
+        double const delS = E.sss - E.ocean_salt;
+        Fdw = delS * mld * phys::rhow / (P.timeS * E.sss - ddt * delS);
     }
 
-    Qio = iceOceanHeatflux(P, A, i, A.sst[i], A.sss[i], mld, dt);
+    Qio = iceOceanHeatflux(P, A, i, E.sst, E.sss, mld, dt);
     if (young) Qio_young = Qio;
-    const double tfrw = freezingPoint(P, A.sss[i]);
+    const double tfrw = freezingPoint(P, E.sss);
 
     double del_hs_mlt = 0, mlt_hi_top = 0, mlt_hi_bot = 0, del_hi_s2i = 0;
     if (o.thermo_type == 0)
-        thermoIce0(P, ddt, A.conc[i], A.thick[i], A.snow_thick[i], tmp_snowfall, Fi.Qia, Fi.dQiadT, Fi.I, Fi.subl, tfrw,
-                   Qio, hi, hs, hi_old, del_hi, del_hs_mlt, mlt_hi_top, mlt_hi_bot, del_hi_s2i, A.tice0[i]);
+        thermoIce0(P, ddt, E.conc, E.thick, E.snow_thick, tmp_snowfall, Fi.Qia, Fi.dQiadT, Fi.I, Fi.subl, tfrw,
+                   Qio, hi, hs, hi_old, del_hi, del_hs_mlt, mlt_hi_top, mlt_hi_bot, del_hi_s2i, E.tice0);
     else
-        thermoWinton(P, ddt, A.conc[i], A.thick[i], A.snow_thick[i], tmp_snowfall, Fi.Qia, Fi.dQiadT, Fi.I, Fi.subl, tfrw,
-                     Qio, hi, hs, hi_old, del_hi, del_hs_mlt, mlt_hi_top, mlt_hi_bot, del_hi_s2i, A.tice0[i], A.tice1[i], A.tice2[i]);
+        thermoWinton(P, ddt, E.conc, E.thick, E.snow_thick, tmp_snowfall, Fi.Qia, Fi.dQiadT, Fi.I, Fi.subl, tfrw,
+                     Qio, hi, hs, hi_old, del_hi, del_hs_mlt, mlt_hi_top, mlt_hi_bot, del_hi_s2i, E.tice0, E.tice1, E.tice2);
 
     double del_hs_young_mlt = 0, mlt_hi_top_young = 0, mlt_hi_bot_young = 0, del_hi_s2i_young = 0;
     if (young) {
-        thermoIce0(P, ddt, A.conc_young[i], A.h_young[i], A.hs_young[i], tmp_snowfall, Fy.Qia, Fy.dQiadT, Fy.I, Fy.subl, tfrw,
+        thermoIce0(P, ddt, E.conc_young, E.h_young, E.hs_young, tmp_snowfall, Fy.Qia, Fy.dQiadT, Fy.I, Fy.subl, tfrw,
                    Qio_young, hi_young, hs_young, hi_young_old, del_hi_young, del_hs_young_mlt, mlt_hi_top_young,
-                   mlt_hi_bot_young, del_hi_s2i_young, A.tsurf_young[i]);
-        A.h_young[i] = hi_young * old_conc_young;
-        A.hs_young[i] = hs_young * old_conc_young;
+                   mlt_hi_bot_young, del_hi_s2i_young, E.tsurf_young);
+        E.h_young = hi_young * old_conc_young;
+        E.hs_young = hs_young * old_conc_young;
     }
 
-    double conc_pre_assim = old_conc + old_conc_young - A.conc_upd[i];
-    if (o.use_assim_flux && (conc_pre_assim > 0) && (A.conc_upd[i] < 0))
+    double conc_pre_assim = old_conc + old_conc_young - E.conc_upd;
+    if (o.use_assim_flux && (conc_pre_assim > 0) && (E.conc_upd < 0))
         Qassm = (Qow * old_ow_fraction + Qio * old_conc + Qio_young * old_conc_young)
-                * (pow(A.conc_upd[i] / conc_pre_assim + 1, o.assim_flux_exponent) - 1);
+                * (pow(E.conc_upd / conc_pre_assim + 1, o.assim_flux_exponent) - 1);
 
-    double const tw_new = A.sst[i] - ddt * (Qow + Qassm) / (mld * phys::rhow * phys::cpw);
+    double const tw_new = E.sst - ddt * (Qow + Qassm) / (mld * phys::rhow * phys::cpw);
 
     double newice = 0;
     if (tw_new < tfrw) {
-        newice = old_ow_fraction * (tfrw - tw_new) * mld * phys::rhow * phys::cpw / qi;
-        Qow = -(tfrw - A.sst[i]) * mld * phys::rhow * phys::cpw / dt;
+        newice = old_ow_fraction * (tfrw - tw_new) * mld * phys::rhow * phys::cpw / P.u_qi;
+        Qow = -(tfrw - E.sst) * mld * phys::rhow * phys::cpw / P.u_ddt;
     }
     double const newice_stored = newice;
 
@@ -673,275 +732,328 @@ NSX_HD void thermo_element(Params const& P, Arrays const& A, int i)
             }
             break;
         case 3: {
-            double wspeed = windSpeedElement(A, i);
+            double wspeed = air.wspeed;                 // windSpeedElement(i), FE.cpp:5511
             double h0 = (1. + 0.1 * wspeed) / 15.;
             del_c = newice / dmax(P.rPhiF * hi_old, h0);
             break;
         }
         default:        // 4: young ice category (other values are rejected on the host)
-            A.h_young[i] += newice;
-            A.conc_young[i] = dmin(1. - A.conc[i], A.conc_young[i] + newice / o.h_young_min);
+            E.h_young += newice;
+            E.conc_young = dmin(1. - E.conc, E.conc_young + newice / P.u_h_young_min);
             newice = 0.;
             newsnow = 0.;
-            if (A.conc_young[i] > 0.) {
-                if (A.h_young[i] < o.h_young_min * A.conc_young[i]) {
-                    A.conc_young[i] = A.h_young[i] / o.h_young_min;
+            if (E.conc_young > 0.) {
+                if (E.h_young < o.h_young_min * E.conc_young) {
+                    E.conc_young = E.h_young / P.u_h_young_min;
                 } else {
-                    double const hiy = A.h_young[i] / A.conc_young[i];
+                    double const hiy = E.h_young / E.conc_young;
                     if (hiy > P.h_young_max_sharp) {
-                        double const hsy = dmax(0., A.hs_young[i] / A.conc_young[i]);
-                        double tmp = A.conc_young[i] * (P.h_young_max_sharp - o.h_young_min) / (hiy - o.h_young_min);
-                        del_c = dmax(0., A.conc_young[i] - tmp);
-                        A.conc_young[i] = tmp;
-                        tmp = A.conc_young[i] * P.h_young_max_sharp;
-                        newice = dmax(0., A.h_young[i] - tmp);
-                        A.h_young[i] = tmp;
-                        tmp = A.conc_young[i] * hsy;
-                        newsnow = dmax(0., A.hs_young[i] - tmp);
-                        A.hs_young[i] = tmp;
+                        double const hsy = dmax(0., E.hs_young / E.conc_young);
+                        double tmp = E.conc_young * (P.h_young_max_sharp - o.h_young_min) / (hiy - o.h_young_min);
+                        del_c = dmax(0., E.conc_young - tmp);
+                        E.conc_young = tmp;
+                        tmp = E.conc_young * P.h_young_max_sharp;
+                        newice = dmax(0., E.h_young - tmp);
+                        E.h_young = tmp;
+                        tmp = E.conc_young * hsy;
+                        newsnow = dmax(0., E.hs_young - tmp);
+                        E.hs_young = tmp;
                     }
                 }
             } else {
-                A.thick[i] += A.h_young[i];
-                newice = A.h_young[i];
-                newsnow = A.hs_young[i];
-                A.h_young[i] = 0.;
-                A.hs_young[i] = 0.;
+                E.thick += E.h_young;
+                newice = E.h_young;
+                newsnow = E.hs_young;
+                E.h_young = 0.;
+                E.hs_young = 0.;
             }
             break;
     }
 
-    del_c = dmin(1. - A.conc[i], del_c);
+    del_c = dmin(1. - E.conc, del_c);
 
     if (del_hi < 0.) {
         if (o.melt_type == 1) {
-            if (A.conc[i] < 1.) del_c += del_hi * A.conc[i] * o.PhiM / hi_old;
+            if (E.conc < 1.) del_c += del_hi * E.conc * o.PhiM / hi_old;
             else del_c += 0.;
         } else {        // 2: Mellor and Kantha (89) (other values are rejected on the host)
             if (hi > 0.) {
-                del_c += o.PhiM * (1. - A.conc[i]) * dmin(0., Qow) * ddt / (hi * qi + hs * qs);
+                del_c += o.PhiM * (1. - E.conc) * dmin(0., Qow) * ddt / (hi * qi + hs * qs);
                 Qow *= (1. - o.PhiM);
             } else {
-                del_c = -A.conc[i];
+                del_c = -E.conc;
             }
         }
     }
 
+    // tracer state is loaded where it is first needed: it would otherwise sit in registers through the flux and slab code
+    E.del_vi_tend = A.del_vi_tend[i]; E.freeze_days = A.freeze_days[i]; E.ridge_ratio = A.ridge_ratio[i];
+    // M_conc_summer / M_thick_summer: read by the freeze-days reset (FE.cpp:6083-6084), written on the last step of a day and
+    // at the 1 August midnight (FE.cpp:5680-5697, 6059-6077); on other steps of a reset-by-date run they are not touched
+    bool const summer_written = P.step_in_day == P.num_steps_in_day || (P.is_0801 && P.midnight);
+    if (!o.reset_by_date || summer_written) { E.conc_summer = A.conc_summer[i]; E.thick_summer = A.thick_summer[i]; }
     // ice age: freeze days (FE.cpp:5664-5699)
     bool use_young_ice_in_myi_reset = o.use_young_ice_in_myi_reset != 0;
     if (!o.reset_by_date) use_young_ice_in_myi_reset = false;
-    if (P.step_in_day == 1) A.del_vi_tend[i] = 0.;
-    A.del_vi_tend[i] += del_vi * ddt;
+    if (P.step_in_day == 1) E.del_vi_tend = 0.;
+    E.del_vi_tend += del_vi * ddt;
     if (P.step_in_day == P.num_steps_in_day) {
-        if (A.del_vi_tend[i] > 0.) {
-            A.freeze_days[i] += 1.;
-        } else if (A.del_vi_tend[i] < 0.) {
-            A.freeze_days[i] = 0.;
-            double conc_summer = A.conc[i] + dmin(0., del_c);
-            double thick_summer = A.thick[i] + dmin(0., del_vi);
+        if (E.del_vi_tend > 0.) {
+            E.freeze_days += 1.;
+        } else if (E.del_vi_tend < 0.) {
+            E.freeze_days = 0.;
+            double conc_summer = E.conc + dmin(0., del_c);
+            double thick_summer = E.thick + dmin(0., del_vi);
             if (young && use_young_ice_in_myi_reset) {
-                conc_summer += A.conc_young[i];
-                thick_summer += A.h_young[i];
+                conc_summer += E.conc_young;
+                thick_summer += E.h_young;
             }
-            A.conc_summer[i] = dmax(0., dmin(1., conc_summer));
-            A.thick_summer[i] = dmax(0., thick_summer);
+            E.conc_summer = dmax(0., dmin(1., conc_summer));
+            E.thick_summer = dmax(0., thick_summer);
         }
     }
 
-    A.conc[i] += del_c;
+    E.conc += del_c;
 
-    if (A.conc[i] >= phys::cmin) {
-        hi = (hi * old_conc + newice) / A.conc[i];
+    if (E.conc >= phys::cmin) {
+        hi = (hi * old_conc + newice) / E.conc;
         if (del_c < 0.) {
-            Qow -= del_c * hs * qs / ddt;
+            Qow -= del_c * hs * qs / P.u_ddt;
         } else {
-            hs = (hs * old_conc + newsnow) / A.conc[i];
+            hs = (hs * old_conc + newsnow) / E.conc;
         }
         if (o.thermo_type == 1) {
-            double f1 = A.thick[i] / (A.thick[i] + newice);
-            double Tbar = f1 * (A.tice1[i] - phys::Lf * o.freezingpoint_mu * phys::si / (phys::C * A.tice1[i])) + (1 - f1) * tfrw;
-            A.tice1[i] = (Tbar - sqrt(Tbar * Tbar + 4 * o.freezingpoint_mu * phys::si * phys::Lf / phys::C)) / 2.;
-            A.tice2[i] = f1 * A.tice2[i] + (1 - f1) * tfrw;
+            double f1 = E.thick / (E.thick + newice);
+            double Tbar = f1 * (E.tice1 - phys::Lf * o.freezingpoint_mu * phys::si / (phys::C * E.tice1)) + (1 - f1) * tfrw;
+            E.tice1 = (Tbar - sqrt(Tbar * Tbar + 4 * o.freezingpoint_mu * phys::si * phys::Lf / phys::C)) / 2.;
+            E.tice2 = f1 * E.tice2 + (1 - f1) * tfrw;
         }
     }
 
-    if ((A.conc[i] < phys::cmin) || (hi < phys::hmin)) {
-        Qow += A.conc[i] * hi * qi / ddt + A.conc[i] * hs * qs / ddt;
-        A.conc[i] = 0.;
-        A.tice0[i] = -o.freezingpoint_mu * phys::si;
+    if ((E.conc < phys::cmin) || (hi < phys::hmin)) {
+        Qow += E.conc * hi * qi / P.u_ddt + E.conc * hs * qs / P.u_ddt;
+        E.conc = 0.;
+        E.tice0 = -o.freezingpoint_mu * phys::si;
         if (o.thermo_type == 1) {           // M_tice has three layers under Winton, one under the zero-layer scheme
-            A.tice1[i] = -o.freezingpoint_mu * phys::si;
-            A.tice2[i] = -o.freezingpoint_mu * phys::si;
+            E.tice1 = -o.freezingpoint_mu * phys::si;
+            E.tice2 = -o.freezingpoint_mu * phys::si;
         }
         hi = 0.;
         hs = 0.;
-        A.ridge_ratio[i] = 0.;
+        E.ridge_ratio = 0.;
     }
 
-    A.thick[i] = hi * A.conc[i];
-    A.snow_thick[i] = hs * A.conc[i];
+    E.thick = hi * E.conc;
+    E.snow_thick = hs * E.conc;
 
     // ---- slab ocean (FE.cpp:5803-5846) ----
-    double const rain_on_ice = dmax(0., A.precip[i] - tmp_snowfall);
-    double rain = (1. - old_conc - old_conc_young) * A.precip[i] + (old_conc + old_conc_young) * rain_on_ice;
+    double const rain_on_ice = dmax(0., E.precip - tmp_snowfall);
+    double rain = (1. - old_conc - old_conc_young) * E.precip + (old_conc + old_conc_young) * rain_on_ice;
     double emp = evap * (1. - old_conc - old_conc_young) - rain;
 
     if (o.use_meltponds)
-        meltPonds(P, A, i, ddt, hi, hs, mlt_hi_top, del_hs_mlt, Fi.Qia, rain_on_ice, o.meltpond_runoff_fraction, o.meltpond_depth_to_fraction);
+        meltPonds(P, E, ddt, hi, hs, mlt_hi_top, del_hs_mlt, Fi.Qia, rain_on_ice, o.meltpond_runoff_fraction, o.meltpond_depth_to_fraction);
 
     double Qio_mean = Qio * old_conc + Qio_young * old_conc_young;
     double Qow_mean = Qow * old_ow_fraction;
 
-    A.sst[i] = A.sst[i] - ddt * (Qio_mean + Qow_mean - Qdw + Qassm) / (phys::rhow * phys::cpw * mld);
+    E.sst = E.sst - ddt * (Qio_mean + Qow_mean - Qdw + Qassm) / (phys::rhow * phys::cpw * mld);
 
     double denominator = (mld * phys::rhow - del_vi * phys::rhoi - (del_vs_mlt * phys::rhos + (emp - Fdw) * ddt));
     denominator = (denominator > 1. * phys::rhow) ? denominator : 1. * phys::rhow;
 
-    double const si_eff = dmin(A.sss[i], phys::si);
-    double const delsss = ((A.sss[i] - si_eff) * phys::rhoi * del_vi + A.sss[i] * (del_vs_mlt * phys::rhos + (emp - Fdw) * ddt)) / denominator;
-    A.sss[i] += delsss;
+    double const si_eff = dmin(E.sss, phys::si);
+    double const delsss = ((E.sss - si_eff) * phys::rhoi * del_vi + E.sss * (del_vs_mlt * phys::rhos + (emp - Fdw) * ddt)) / denominator;
+    E.sss += delsss;
 
-    if (A.thick[i] > old_vol) A.ridge_ratio[i] *= old_vol / A.thick[i];
+    if (E.thick > old_vol) E.ridge_ratio *= old_vol / E.thick;
 
     // ---- damage healing time (FE.cpp:5848-5882) ----
     if (o.temp_dep_healing) {
-        if (A.thick[i] > 0.) {
+        if (E.thick > 0.) {
             double deltaT;
-            double Tbot = freezingPoint(P, A.sss[i]);
+            double Tbot = freezingPoint(P, E.sss);
             double Cc;
             if (o.thermo_type == 0) {
-                Cc = phys::ki * A.snow_thick[i] / (o.ks * A.thick[i]);
-                deltaT = dmax(1e-36, Tbot - A.tice0[i]) / (1. + Cc);
+                Cc = phys::ki * E.snow_thick / (o.ks * E.thick);
+                deltaT = dmax(1e-36, Tbot - E.tice0) / (1. + Cc);
             } else {
-                Cc = phys::ki * A.snow_thick[i] / (o.ks * A.thick[i] / 4.);
-                deltaT = dmax(1e-36, Tbot + Cc * (Tbot - A.tice1[i]) - A.tice0[i]) / (1. + Cc);
+                Cc = phys::ki * E.snow_thick / (o.ks * E.thick / 4.);
+                deltaT = dmax(1e-36, Tbot + Cc * (Tbot - E.tice1) - E.tice0) / (1. + Cc);
             }
-            A.time_relaxation_damage[i] = dmax(o.time_relaxation_damage * o.deltaT_relaxation_damage / deltaT, ddt);
+            E.time_relaxation_damage = dmax(o.time_relaxation_damage * o.deltaT_relaxation_damage / deltaT, ddt);
         } else {
-            A.time_relaxation_damage[i] = 1e36;
+            E.time_relaxation_damage = 1e36;
         }
     }
 
     // ---- diagnostics (FE.cpp:5903-5984) ----
     A.Qa[i] = Fi.Qia * old_conc + Fy.Qia * old_conc_young + Qow * old_ow_fraction;
-    A.Qsw[i] = Fi.Qsw * old_conc + Fy.Qsw * old_conc_young + Qsw_ow * old_ow_fraction;
-    A.Qlw[i] = Fi.Qlw * old_conc + Fy.Qlw * old_conc_young + Qlw_ow * old_ow_fraction;
-    A.Qsh[i] = Fi.Qsh * old_conc + Fy.Qsh * old_conc_young + Qsh_ow * old_ow_fraction;
-    A.Qlh[i] = Fi.Qlh * old_conc + Fy.Qlh * old_conc_young + Qlh_ow * old_ow_fraction;
     A.Qo[i] = Qio_mean + Qow_mean;
-    A.Qnosun[i] = Qio_mean + old_ow_fraction * (Qlw_ow + Qlh_ow + Qsh_ow);
-    A.Qsw_ocean[i] = old_ow_fraction * Qsw_ow;
+    A.Qnosun[i] = Qio_mean + Qnosun_ow;
     A.Qassim[i] = Qassm;
     A.delS[i] = delsss * phys::rhow * mld * days_in_sec / o.dtime_step;
-    A.fwflux_ice[i] = -1. / ddt * ((1. - 1e-3 * si_eff) * phys::rhoi * del_vi + phys::rhos * del_vs_mlt);
+    A.fwflux_ice[i] = -1. / P.u_ddt * ((1. - 1e-3 * si_eff) * phys::rhoi * del_vi + phys::rhos * del_vs_mlt);
     A.fwflux[i] = A.fwflux_ice[i] - emp;
-    A.brine[i] = -1e-3 * si_eff * phys::rhoi * del_vi / ddt;
+    A.brine[i] = -1e-3 * si_eff * phys::rhoi * del_vi / P.u_ddt;
     A.evap[i] = evap * (1. - old_conc - old_conc_young);
     A.rain[i] = rain;
-    A.vice_melt[i] = del_vi * days_in_sec / ddt;
-    A.del_vi_young[i] = del_vi_young * days_in_sec / ddt;
-    A.del_hi[i] = del_hi * days_in_sec / ddt;
-    A.del_hi_young[i] = del_hi_young * days_in_sec / ddt;
-    A.newice[i] = newice_stored * days_in_sec / ddt;
-    A.mlt_top[i] = mlt_vi_top * days_in_sec / ddt;
-    A.mlt_bot[i] = mlt_vi_bot * days_in_sec / ddt;
-    A.snow2ice[i] = snow2ice * days_in_sec / ddt;
+    A.vice_melt[i] = del_vi * days_in_sec / P.u_ddt;
+    A.del_vi_young[i] = del_vi_young * days_in_sec / P.u_ddt;
+    A.del_hi[i] = del_hi * days_in_sec / P.u_ddt;
+    A.del_hi_young[i] = del_hi_young * days_in_sec / P.u_ddt;
+    A.newice[i] = newice_stored * days_in_sec / P.u_ddt;
+    A.mlt_top[i] = mlt_vi_top * days_in_sec / P.u_ddt;
+    A.mlt_bot[i] = mlt_vi_bot * days_in_sec / P.u_ddt;
+    A.snow2ice[i] = snow2ice * days_in_sec / P.u_ddt;
 
-    double sialb = old_conc * Fi.alb_tot;
-    if (young) sialb += old_conc_young * Fy.alb_tot;
-    A.albedo[i] = sialb + dmax(0., old_ow_fraction) * o.ocean_albedo;
-    A.sialb[i] = (old_conc_tot > 0.) ? (sialb / old_conc_tot) : 0.;
 
     // ---- age / multi-year-ice tracers (FE.cpp:5986-6131) ----
+    E.fyi_fraction = A.fyi_fraction[i]; E.age_det = A.age_det[i]; E.age = A.age[i]; E.freeze_onset = A.freeze_onset[i];
+    E.conc_myi = A.conc_myi[i]; E.thick_myi = A.thick_myi[i];
     double del_vi_rplnt_myi = 0., del_ci_rplnt_myi = 0., del_vi_mlt_myi = 0., del_ci_mlt_myi = 0.;
-    if (A.conc[i] < phys::cmin || A.thick[i] < A.conc[i] * phys::hmin) {
-        A.fyi_fraction[i] = 0.;
-        A.age_det[i] = 0.;
-        A.age[i] = 0.;
-        A.thick_myi[i] = 0.;
-        A.conc_myi[i] = 0.;
-        A.freeze_days[i] = 0.;
-        A.freeze_onset[i] = 1.;
+    if (E.conc < phys::cmin || E.thick < E.conc * phys::hmin) {
+        E.fyi_fraction = 0.;
+        E.age_det = 0.;
+        E.age = 0.;
+        E.thick_myi = 0.;
+        E.conc_myi = 0.;
+        E.freeze_days = 0.;
+        E.freeze_onset = 1.;
     } else {
         if (P.is_0915 && P.midnight) {
-            A.fyi_fraction[i] = 0.;
+            E.fyi_fraction = 0.;
         } else {
-            double conc_fyi = A.fyi_fraction[i] + del_c;
-            A.fyi_fraction[i] = dmax(0., dmin(1., conc_fyi));
+            double conc_fyi = E.fyi_fraction + del_c;
+            E.fyi_fraction = dmax(0., dmin(1., conc_fyi));
         }
-        double w_age = old_conc <= 0 ? 0. : dmin(old_conc / A.conc[i], 1.);
-        A.age_det[i] = w_age * (A.age_det[i] + dt) + dmax((1 - w_age) * dt, 0.);
-        w_age = old_vol <= 0 ? 0. : dmin(old_vol / A.thick[i], 1.);
-        A.age[i] = w_age * (A.age[i] + dt) + dmax((1 - w_age) * dt, 0.);
+        double w_age = old_conc <= 0 ? 0. : dmin(old_conc / E.conc, 1.);
+        E.age_det = w_age * (E.age_det + dt) + dmax((1 - w_age) * dt, 0.);
+        w_age = old_vol <= 0 ? 0. : dmin(old_vol / E.thick, 1.);
+        E.age = w_age * (E.age + dt) + dmax((1 - w_age) * dt, 0.);
 
         bool reset_myi = false;
         if (o.reset_by_date) {
             if (P.is_reset_date && P.midnight) reset_myi = true;
         } else {
-            if (A.freeze_days[i] >= o.freeze_days_threshold) {
-                if (A.freeze_onset[i] <= 0.5) {
+            if (E.freeze_days >= o.freeze_days_threshold) {
+                if (E.freeze_onset <= 0.5) {
                     reset_myi = true;
-                    A.freeze_onset[i] = 1.;
+                    E.freeze_onset = 1.;
                 }
             }
         }
         if (P.is_0801 && P.midnight) {
-            A.freeze_onset[i] = 0.;
-            double ctot = A.conc[i];
-            if (young) ctot += A.conc_young[i];
-            if (ctot == 0.) A.freeze_onset[i] = 1.;
-            double conc_summer = A.conc[i];
-            double thick_summer = A.thick[i];
+            E.freeze_onset = 0.;
+            double ctot = E.conc;
+            if (young) ctot += E.conc_young;
+            if (ctot == 0.) E.freeze_onset = 1.;
+            double conc_summer = E.conc;
+            double thick_summer = E.thick;
             if (young && use_young_ice_in_myi_reset) {
-                conc_summer += A.conc_young[i];
-                thick_summer += A.h_young[i];
+                conc_summer += E.conc_young;
+                thick_summer += E.h_young;
             }
-            A.conc_summer[i] = dmax(0., dmin(1., conc_summer));
-            A.thick_summer[i] = dmax(0., thick_summer);
+            E.conc_summer = dmax(0., dmin(1., conc_summer));
+            E.thick_summer = dmax(0., thick_summer);
         }
-        A.freeze_onset[i] = round(A.freeze_onset[i]);
+        E.freeze_onset = round(E.freeze_onset);
 
-        double old_conc_myi = A.conc_myi[i];
-        double old_thick_myi = A.thick_myi[i];
-        double c_myi_max = A.conc[i];
-        double v_myi_max = A.thick[i];
+        double old_conc_myi = E.conc_myi;
+        double old_thick_myi = E.thick_myi;
+        double c_myi_max = E.conc;
+        double v_myi_max = E.thick;
         if (young && use_young_ice_in_myi_reset) {
-            c_myi_max += A.conc_young[i];
-            v_myi_max += A.h_young[i];
+            c_myi_max += E.conc_young;
+            v_myi_max += E.h_young;
         }
         if (reset_myi) {
             if (!o.reset_by_date) {
-                double c_myi_reset = dmax(A.conc_summer[i], A.conc_myi[i]);
-                double v_myi_reset = dmax(A.thick_summer[i], A.thick_myi[i]);
-                A.conc_myi[i] = dmin(c_myi_max, c_myi_reset);
-                A.thick_myi[i] = dmin(v_myi_max, v_myi_reset);
+                double c_myi_reset = dmax(E.conc_summer, E.conc_myi);
+                double v_myi_reset = dmax(E.thick_summer, E.thick_myi);
+                E.conc_myi = dmin(c_myi_max, c_myi_reset);
+                E.thick_myi = dmin(v_myi_max, v_myi_reset);
             } else {
-                A.conc_myi[i] = c_myi_max;
-                A.thick_myi[i] = v_myi_max;
+                E.conc_myi = c_myi_max;
+                E.thick_myi = v_myi_max;
             }
-            A.conc_myi[i] = dmax(0., dmin(1., A.conc_myi[i]));
-            A.thick_myi[i] = dmax(0., A.thick_myi[i]);
-            del_ci_rplnt_myi = A.conc_myi[i] - old_conc_myi;
-            del_vi_rplnt_myi = A.thick_myi[i] - old_thick_myi;
+            E.conc_myi = dmax(0., dmin(1., E.conc_myi));
+            E.thick_myi = dmax(0., E.thick_myi);
+            del_ci_rplnt_myi = E.conc_myi - old_conc_myi;
+            del_vi_rplnt_myi = E.thick_myi - old_thick_myi;
         } else {
-            if ((A.thick[i] < old_vol) && (old_conc > 0) && (old_vol > 0)) {
+            if ((E.thick < old_vol) && (old_conc > 0) && (old_vol > 0)) {
                 if (o.equal_melting) {
-                    double const del_c_ratio = dmin(A.conc[i] / old_conc, 1.);
-                    double const del_v_ratio = dmin(A.thick[i] / old_vol, 1.);
-                    del_ci_mlt_myi = dmin(0., A.conc_myi[i] * (del_c_ratio - 1.));
-                    del_vi_mlt_myi = dmin(0., A.thick_myi[i] * (del_v_ratio - 1.));
+                    double const del_c_ratio = dmin(E.conc / old_conc, 1.);
+                    double const del_v_ratio = dmin(E.thick / old_vol, 1.);
+                    del_ci_mlt_myi = dmin(0., E.conc_myi * (del_c_ratio - 1.));
+                    del_vi_mlt_myi = dmin(0., E.thick_myi * (del_v_ratio - 1.));
                 }
-                A.conc_myi[i] = dmax(0., dmin(c_myi_max, A.conc_myi[i] + del_ci_mlt_myi));
-                A.thick_myi[i] = dmax(0., dmin(v_myi_max, A.thick_myi[i] + del_vi_mlt_myi));
-                del_ci_mlt_myi = A.conc_myi[i] - old_conc_myi;
-                del_vi_mlt_myi = A.thick_myi[i] - old_thick_myi;
+                E.conc_myi = dmax(0., dmin(c_myi_max, E.conc_myi + del_ci_mlt_myi));
+                E.thick_myi = dmax(0., dmin(v_myi_max, E.thick_myi + del_vi_mlt_myi));
+                del_ci_mlt_myi = E.conc_myi - old_conc_myi;
+                del_vi_mlt_myi = E.thick_myi - old_thick_myi;
             }
         }
     }
-    A.del_ci_mlt_myi[i] = del_ci_mlt_myi * days_in_sec / ddt;
-    A.del_vi_mlt_myi[i] = del_vi_mlt_myi * days_in_sec / ddt;
-    A.del_ci_rplnt_myi[i] = del_ci_rplnt_myi * days_in_sec / ddt;
-    A.del_vi_rplnt_myi[i] = del_vi_rplnt_myi * days_in_sec / ddt;
+    A.del_ci_mlt_myi[i] = del_ci_mlt_myi * days_in_sec / P.u_ddt;
+    A.del_vi_mlt_myi[i] = del_vi_mlt_myi * days_in_sec / P.u_ddt;
+    A.del_ci_rplnt_myi[i] = del_ci_rplnt_myi * days_in_sec / P.u_ddt;
+    A.del_vi_rplnt_myi[i] = del_vi_rplnt_myi * days_in_sec / P.u_ddt;
+}
+
+// thermo() for element i: the fields the options make it read are loaded once, the ones it can change are stored once.
+// Which forcing variable feeds a quantity follows ExternalData::isInitialized() exactly as in the reference
+// (specificHumidity 4980-4986, incomingLongwave 6378, the snowfall cascade 5333-5340, M_mld 5346).
+NSX_HD void thermo_element(Params const& P, Arrays const& A, int i)
+{
+    NsxThermoParams const& o = P.o;
+    bool const young = o.ice_cat_young != 0, winton = o.thermo_type == 1, ponds = o.use_meltponds != 0;
+    Elem E;
+    // forcing
+    E.tair = A.tair[i]; E.mslp = A.mslp[i]; E.Qsw_in = A.Qsw_in[i]; E.precip = A.precip[i];
+    E.sphuma = o.have_sphuma ? A.sphuma[i] : 0.;
+    E.mixrat = (!o.have_sphuma && o.have_mixrat) ? A.mixrat[i] : 0.;
+    E.dair = (!o.have_sphuma && !o.have_mixrat) ? A.dair[i] : 0.;
+    E.Qlw_in = o.have_Qlw_in ? A.Qlw_in[i] : 0.;
+    E.tcc = o.have_Qlw_in ? 0. : A.tcc[i];
+    E.snowfr = o.have_snowfr ? A.snowfr[i] : 0.;
+    E.snowfall = (!o.have_snowfr && o.have_snowfall) ? A.snowfall[i] : 0.;
+    E.mld = o.have_mld ? A.mld[i] : 0.;
+    E.ocean_temp = o.ocean_constant ? 0. : A.ocean_temp[i];
+    E.ocean_salt = o.ocean_constant ? 0. : A.ocean_salt[i];
+    E.conc_upd = o.use_assim_flux ? A.conc_upd[i] : 0.;     // only read under use_assim_flux (FE.cpp:5428)
+    // ice state
+    E.conc = A.conc[i]; E.thick = A.thick[i]; E.snow_thick = A.snow_thick[i]; E.drag_ui = A.drag_ui[i];
+    E.time_relaxation_damage = 0.;                          // written, never read
+    E.conc_young = young ? A.conc_young[i] : 0.; E.h_young = young ? A.h_young[i] : 0.; E.hs_young = young ? A.hs_young[i] : 0.;
+    E.drag_ui_young = young ? A.drag_ui_young[i] : 0.;
+    // slab ocean, ice temperatures, tracers
+    E.sst = A.sst[i]; E.sss = A.sss[i]; E.tice0 = A.tice0[i];
+    E.tice1 = winton ? A.tice1[i] : 0.; E.tice2 = winton ? A.tice2[i] : 0.;
+    E.tsurf_young = young ? A.tsurf_young[i] : 0.; E.drag_ti_young = young ? A.drag_ti_young[i] : 0.;
+    E.drag_ti = A.drag_ti[i];
+    E.conc_summer = E.thick_summer = 0.;                    // the tracer state is loaded inside thermo_core() where it is first used
+    E.pond_fraction = A.pond_fraction[i];
+    E.pond_volume = ponds ? A.pond_volume[i] : 0.;
+    E.lid_volume = (ponds || E.pond_fraction > 0.) ? A.lid_volume[i] : 0.;       // FE.cpp:6327 reads it only over a pond
+
+    thermo_core(P, A, i, E);
+
+    A.conc[i] = E.conc; A.thick[i] = E.thick; A.snow_thick[i] = E.snow_thick; A.ridge_ratio[i] = E.ridge_ratio;
+    A.conc_myi[i] = E.conc_myi; A.thick_myi[i] = E.thick_myi; A.drag_ui[i] = E.drag_ui;
+    if (o.temp_dep_healing) A.time_relaxation_damage[i] = E.time_relaxation_damage;
+    if (young) {
+        A.conc_young[i] = E.conc_young; A.h_young[i] = E.h_young; A.hs_young[i] = E.hs_young; A.drag_ui_young[i] = E.drag_ui_young;
+        A.tsurf_young[i] = E.tsurf_young; A.drag_ti_young[i] = E.drag_ti_young;
+    }
+    A.sst[i] = E.sst; A.sss[i] = E.sss; A.tice0[i] = E.tice0;
+    if (winton) { A.tice1[i] = E.tice1; A.tice2[i] = E.tice2; }
+    A.del_vi_tend[i] = E.del_vi_tend; A.freeze_days[i] = E.freeze_days; A.freeze_onset[i] = E.freeze_onset;
+    A.fyi_fraction[i] = E.fyi_fraction; A.age_det[i] = E.age_det; A.age[i] = E.age; A.drag_ti[i] = E.drag_ti;
+    // M_conc_summer / M_thick_summer change on the last step of a day and at the 1 August midnight only (FE.cpp:5680-5697, 6059-6077)
+    if (P.step_in_day == P.num_steps_in_day || (P.is_0801 && P.midnight)) { A.conc_summer[i] = E.conc_summer; A.thick_summer[i] = E.thick_summer; }
+    if (ponds) { A.pond_volume[i] = E.pond_volume; A.lid_volume[i] = E.lid_volume; A.pond_fraction[i] = E.pond_fraction; }
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -1020,6 +1132,9 @@ inline Params make_params(NsxThermoParams const& o, int dt, double current_time)
     P.qi = phys::Lf * phys::rhoi;                                                    // :5187-5188
     P.qs = phys::Lf * phys::rhos;
     P.h_young_max_sharp = .5 * (o.h_young_min + o.h_young_max);                      // :1198
+    auto ud = [](double c) { return UDiv{c, 1. / c}; };
+    P.u_ddt = ud(P.ddt); P.u_rhos = ud(phys::rhos); P.u_rhow = ud(phys::rhow); P.u_rhoi = ud(phys::rhoi);
+    P.u_qi = ud(P.qi); P.u_qs = ud(P.qs); P.u_ki = ud(phys::ki); P.u_h_young_min = ud(o.h_young_min);
     P.num_steps_in_day = (int)std::round(days_in_sec / o.dtime_step);                // :5668-5670
     P.step_in_day = 1 + (int)std::round(P.num_steps_in_day * std::fmod(current_time, 1.));
     P.midnight = std::fmod(current_time, 1.) == 0.;

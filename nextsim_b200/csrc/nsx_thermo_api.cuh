@@ -3,10 +3,10 @@
 //
 // One thread per element runs nsx::thermo::thermo_element() (nsx_thermo.cuh): OWBulkFluxes + IABulkFluxes (old and young
 // ice) + the slab loop fused, so every field is read once and written once.  The kernel is HBM-bound: with the default
-// options an element reads 48 and writes 61 doubles (forcing 9, ice state 12 in/out, slab state 19 in/out -- two of them
-// the Winton layer temperatures --, diagnostics 30 out, 3 node ids) plus the L2-resident gathers of the wind at its nodes
-// = 884 algorithmic bytes.  Fields live in the handle's internal (Hilbert) element order, one plane per reference member,
-// all thermo-only planes in one allocation.
+// options an element reads 33 doubles (7 forcing, 11 ice state, 15 slab / tracer state), its 3 node ids and the wind at
+// its nodes (a node is shared by ~6 elements: 8 B per element from DRAM), and writes 55 doubles (11 ice state, 14 slab /
+// tracer state, 30 diagnostics) = 724 algorithmic bytes.  Fields live in the handle's internal (Hilbert) element order,
+// one plane per reference member, all thermo-only planes in one allocation.
 #pragma once
 #include "nsx_thermo.cuh"
 

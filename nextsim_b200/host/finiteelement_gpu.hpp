@@ -12,6 +12,7 @@
 #include <cmath>
 #include <stdexcept>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "../../include/nsx.h"
@@ -115,6 +116,25 @@ public:
     {
         check(nsx_forcing_apply(M_handle, var, interp_linear_time ? 1 : 0, M_current_time, ftime_range0, ftime_range1,
                                 M_factor, M_bias_correction), "applyForcing");
+    }
+    //! FiniteElement::thermo(int dt) (FE.cpp:5170-6137) on the resident state.  The caller keeps the options it read from
+    //! `vm` in an NsxThermoParams (nsx_thermo_params_defaults() = model/options.cpp) and passes M_current_time.
+    void thermo(NsxThermoParams const& p, int dt, double M_current_time)
+    {
+        check(nsx_thermo(M_handle, &p, dt, M_current_time), "thermo");
+    }
+    //! forcing / slab-ocean / tracer members of thermo() by the reference's member name ("M_tair", "M_sst", "D_Qa", ...)
+    void thermoUpload(std::vector<std::pair<const char*, const double*>> const& fields)
+    {
+        std::vector<const char*> n; std::vector<const double*> v;
+        for (auto const& f : fields) { n.push_back(f.first); v.push_back(f.second); }
+        check(nsx_thermo_upload_many(M_handle, (int)n.size(), n.data(), v.data()), "thermoUpload");
+    }
+    void thermoDownload(std::vector<std::pair<const char*, double*>> const& fields)
+    {
+        std::vector<const char*> n; std::vector<double*> v;
+        for (auto const& f : fields) { n.push_back(f.first); v.push_back(f.second); }
+        check(nsx_thermo_download_many(M_handle, (int)n.size(), n.data(), v.data()), "thermoDownload");
     }
     double M_min_angle = 0.;    //!< "REGRID ANGLE" of the last checkRegridding (FE.cpp:8302)
 

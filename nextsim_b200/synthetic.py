@@ -238,17 +238,25 @@ THERMO_DIAG = ("D_tau_ow", "D_Qa", "D_Qsw", "D_Qlw", "D_Qsh", "D_Qlh", "D_Qo", "
                "D_del_vi_mlt_myi", "D_del_ci_rplnt_myi", "D_del_vi_rplnt_myi")
 
 
-def make_thermo_state(ne, nn, seed=SEED, young=True, season="mixed"):
+def make_thermo_state(ne, nn, seed=SEED, young=True, season="mixed", centroids=None):
     """Element fields of FiniteElement::thermo() (forcing, ice state, slab ocean, tracers) plus nodal wind / VT / ocean.
 
     Built to reach every branch of thermo(): ice-free, thin (< hmin after melt), young-only and thick-ice elements; air
     from -35 C (new ice in leads) to +8 C (surface melt, melt ponds); supercooled and warm mixed layers; snow-free and
     snow-covered ice; multi-year-ice tracers on both sides of their clamps.  season: 'winter' / 'summer' bias the air
-    temperature and short-wave, 'mixed' spans both."""
+    temperature and short-wave, 'mixed' spans both.  centroids=(cx, cy, L): the ice regime (open water / trace / thin /
+    pack) varies smoothly in space, as real fields do (an ice edge, leads), instead of element by element -- what the
+    timing runs use, since neighbouring elements then take the same branches."""
     rng = np.random.default_rng(seed + 77)
     u = rng.uniform
     S = {}
-    kind = rng.integers(0, 8, ne)                    # 0: open water, 1: trace ice, 2: thin ice, 3..7: pack ice
+    if centroids is None:
+        kind = rng.integers(0, 8, ne)                # 0: open water, 1: trace ice, 2: thin ice, 3..7: pack ice
+    else:
+        cx, cy, L = centroids
+        f = (np.sin(2 * np.pi * 1.5 * cx / L + 0.4) * np.sin(2 * np.pi * 1.1 * cy / L + 1.3) + 0.3 * np.sin(2 * np.pi * 3.0 * (cx - cy) / L))
+        q = np.quantile(f, [1 / 8, 2 / 8, 3 / 8])
+        kind = np.where(f < q[0], 0, np.where(f < q[1], 1, np.where(f < q[2], 2, 5)))
     conc = np.select([kind == 0, kind == 1, kind == 2], [0.0, u(1e-13, 0.05, ne), u(0.05, 0.6, ne)], u(0.6, 1.0, ne))
     hice = np.select([kind == 1, kind == 2], [u(0.005, 0.05, ne), u(0.008, 0.4, ne)], u(0.3, 3.5, ne))
     hsnow = np.where(rng.random(ne) < 0.3, 0.0, u(0.0, 0.45, ne))

@@ -4,7 +4,7 @@
     python profiles/thermo_bench.py [--mesh 3km] [--steps 20] [--warmup 5] [--cpu-elements 200000]
 
 Prints one JSON line: elements/s of k_thermo (CUDA events on the handle's stream, working set >> L2), the HBM roofline
-fraction from the algorithmic bytes per element (884 B with the default options), the end-to-end rate of a
+fraction from the algorithmic bytes per element (724 B with the default options), the end-to-end rate of a
 host-resident step (forcing upload + thermo + diagnostics download) and the single-thread CPU oracle rate on a sample.
 """
 import argparse
@@ -17,7 +17,7 @@ import numpy as np
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
-ALGO_BYTES = 884.0
+ALGO_BYTES = 724.0     # 33 doubles read + 3 node ids + 8 B of shared wind, 55 doubles written
 
 
 def main():
@@ -27,6 +27,8 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--cpu-elements", type=int, default=200000)
+    ap.add_argument("--random-regimes", action="store_true", help="ice regime drawn per element (worst case for divergence)")
+    ap.add_argument("--tag", default="")
     a = ap.parse_args()
     import torch
     from nextsim_b200 import capi, cases, partition as pt, synthetic as syn
@@ -36,7 +38,8 @@ def main():
     s = cases.make_solvers(c)[0]
     lm = c.lms[0]
     ne, nn = c.gm.ne, c.gm.nn
-    S = syn.make_thermo_state(ne, nn, seed=11, young=True)
+    cx, cy = syn.element_centroids(c.gm)
+    S = syn.make_thermo_state(ne, nn, seed=11, young=True, centroids=None if a.random_regimes else (cx, cy, c.gm.nx * c.gm.h))
     loc = {k: pt.scatter_elem(lm, S[k]) for k in syn.THERMO_FORCING + syn.THERMO_STATE + syn.THERMO_ICE}
     s.upload(**{k: loc[k] for k in syn.THERMO_ICE}, M_wind=pt.scatter_nodal2(lm, S["M_wind"], nn))
     s.thermo_upload(**{k: loc[k] for k in syn.THERMO_FORCING + syn.THERMO_STATE})
@@ -84,7 +87,8 @@ def main():
     oth.thermo(q, 200, t0, tri0, nn, S["M_wind"], S["M_VT"], S["M_ocean"], F)
     cpu_s = time.perf_counter() - w0
 
-    out = {"metric": "thermo_elements_per_second", "value": rate, "unit": "elements/s", "mesh": a.mesh, "elements": ne,
+    out = {"tag": a.tag, "regimes": "random per element" if a.random_regimes else "smooth in space",
+           "metric": "thermo_elements_per_second", "value": rate, "unit": "elements/s", "mesh": a.mesh, "elements": ne,
            "ms_per_call": {"median": float(np.median(ms)), "min": float(ms.min()), "max": float(ms.max())},
            "steps": a.steps, "warmup": a.warmup, "dtype": "f64",
            "roofline": {"bound": "hbm", "achieved": rate * ALGO_BYTES / 1e9, "peak": peak, "unit": "GB/s",
