@@ -16,6 +16,7 @@ the headline line is weak scaling (about 2e5 elements per GPU).  In the same pro
 thread) on the same workload; that arm never loads libnsx.so.  One JSON line on stdout (rank 0).
 """
 import argparse
+import ctypes
 import json
 import os
 import subprocess
@@ -456,10 +457,55 @@ def run_ours(args):
             rg = S.check_regridding(10.0)
         us_regrid = (time.perf_counter() - t0) / reps * 1e6
         nb = {"diag": 156.0 * lm.num_elements, "forcing": 48.0 * lm.num_nodes}
-        next_rows = {"update_ice_diagnostics_us": us_diag, "update_ice_diagnostics_GBps": nb["diag"] / us_diag * 1e-3,
+        # row 3: thermo() on the resident state, then FiniteElement::step() between remeshes without the per-step transfers
+        # of `e2e` (forcing time slices live on the device, thermo() runs there; the host reads the regrid decision)
+        from nextsim_b200 import synthetic as syn, partition as pt
+        cx, cy = syn.element_centroids(c.gm)
+        TS = syn.make_thermo_state(c.gm.ne, c.gm.nn, seed=11, young=True, centroids=(cx, cy, c.gm.nx * c.gm.h))
+        S.thermo_upload(**{k: pt.scatter_elem(lm, TS[k]) for k in syn.THERMO_FORCING + syn.THERMO_STATE})
+        tp = capi.thermo_default_params(dtime_step=float(c.params.dtime_step))
+        dt_i = int(c.params.dtime_step)
+        tnow = [43133.25]
+        us_thermo = timed(lambda: S.thermo(tp, dt_i, tnow[0]))
+        TH_FORCING = ("M_tair", "M_dair", "M_mslp", "M_Qsw_in", "M_tcc", "M_precip")
+        for k in TH_FORCING:
+            a = pt.scatter_elem(lm, TS[k])
+            S.thermo_forcing_load(k, 0, a); S.thermo_forcing_load(k, 1, a)
+        for k in ("M_ocean", "M_ssh"):
+            S.forcing_load(k, 0, f[k]); S.forcing_load(k, 1, f[k])
+        S.upload(**{k: f[k] for k in cases.UPLOAD_KEYS})          # back to the case's initial state
+
+        def resident_step(k):
+            t = 43133.25 + k * dt_i / 86400.0
+            for name in ("M_wind", "M_ocean", "M_ssh"):
+                S.forcing_apply(name, True, t, 43133.25, 43133.5)
+            for name in TH_FORCING:
+                S.thermo_forcing_apply(name, True, t, 43133.25, 43133.5)
+            S.thermo(tp, dt_i, t)
+            S.explicit_solve()
+            S.update()
+            return S.check_regridding(10.0)                      # synchronises and reads the decision back
+        resident_step(0)
+        t0 = time.perf_counter()
+        for k in range(args.steps):
+            resident_step(1 + k)
+        rs_s = (time.perf_counter() - t0) / args.steps
+        chk_rs = S.check()
+        resident = {"value": ne_global * nsub / rs_s, "unit": UNIT, "ms_per_step": rs_s * 1e3,
+                    "fraction_of_device_rate": ne_global * nsub / rs_s / m["value"],
+                    "h2d_bytes_per_step": 0, "d2h_bytes_per_step": ctypes.sizeof(capi.NsxRegrid),
+                    "per_step": "time interpolation of wind / ocean / ssh and of 6 element forcing fields on the device, thermo(dt), "
+                                "explicitSolve(), update(), checkRegridding() with its result read back; forcing time slices were "
+                                "loaded once (they change every few hours of model time), the state never leaves the GPU",
+                    "check": {"n_nan": chk_rs.n_nan, "n_range": chk_rs.n_range, "max_speed": chk_rs.max_speed}}
+        next_rows = {"thermo_us": us_thermo, "thermo_elements_per_s": lm.num_elements / us_thermo * 1e6,
+                     "thermo_GBps_of_724B_per_element": 724.0 * lm.num_elements / us_thermo * 1e-3,
+                     "thermo_note": "instruction-bound FP64 kernel (divisions, exp / log / cbrt / atan), see profiles/r2_thermo_v2.txt",
+                     "resident_step": resident,
+                     "update_ice_diagnostics_us": us_diag, "update_ice_diagnostics_GBps": nb["diag"] / us_diag * 1e-3,
                      "forcing_apply_wind_us": us_forc, "forcing_apply_wind_GBps": nb["forcing"] / us_forc * 1e-3,
                      "check_regridding_us_incl_sync_and_readback": us_regrid, "min_angle_deg": rg.min_angle,
-                     "launches": 3 * reps + 3}
+                     "launches": 3 * reps + 3 + (reps + 1) + (args.steps + 1) * 10}
     traffic = None
     try:                                  # ncu dram__bytes of one launch; only meaningful for the HBM-streaming tile path
         tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))

@@ -298,6 +298,12 @@ int nsx_thermo_download(nsx_handle h, const char* name, double* host);      /* a
 /* n fields in one call: one device arena, one permutation kernel, one stream synchronisation */
 int nsx_thermo_upload_many(nsx_handle h, int n, const char* const* names, const double* const* host);
 int nsx_thermo_download_many(nsx_handle h, int n, const char* const* names, double* const* host);
+/* The forcing members are ExternalData (two time slices, externaldata.cpp:366-455): like nsx_forcing_load / _apply for
+ * the nodal forcing, `load` keeps interpolated_data[slot] of one variable on the device and `apply` evaluates
+ * M_factor*(fcoeff[0]*d0[i] + fcoeff[1]*d1[i]) + M_bias_correction into the resident member every step. */
+int nsx_thermo_forcing_load(nsx_handle h, const char* name, int slot, const double* interpolated_data);
+int nsx_thermo_forcing_apply(nsx_handle h, const char* name, int interp_linear_time, double current_time, double ftime0,
+                             double ftime1, double factor, double bias_correction);
 /* FiniteElement::thermo(dt) at model time `current_time` (decimal days since 1900-01-01, M_current_time) */
 int nsx_thermo(nsx_handle h, const NsxThermoParams* p, int dt, double current_time);
 

@@ -164,7 +164,7 @@ EXPORTS = (
     "nsx_host_register", "nsx_host_unregister", "nsx_abi_sizes", "nsx_tile_info", "nsx_plan_info", "nsx_cfg_last_error",
     "nsx_check_regridding", "nsx_update_ice_diagnostics", "nsx_forcing_load", "nsx_forcing_apply",
     "nsx_thermo_params_defaults", "nsx_thermo_upload", "nsx_thermo_download", "nsx_thermo_upload_many", "nsx_thermo_download_many",
-    "nsx_thermo",
+    "nsx_thermo", "nsx_thermo_forcing_load", "nsx_thermo_forcing_apply",
     "nsx_validate_mesh", "nsx_mapx_latlon", "nsx_partmesh_lat_from_mpp", "nsx_mapx_last_error", "nsx_partmesh_read", "nsx_partmesh_build", "nsx_partmesh_bc_marked_nodes", "nsx_partmesh_set_lat",
     "nsx_partmesh_views", "nsx_partmesh_ids", "nsx_partmesh_destroy", "nsx_partmesh_last_error",
 )
@@ -440,6 +440,17 @@ class Solver:
         out = {k: np.empty(self.ne) for k in names}
         self._thermo_xfer(self.L.nsx_thermo_download_many, "nsx_thermo_download_many", out)
         return out
+
+    def thermo_forcing_load(self, name, slot, data):
+        """ExternalData time slice `slot` (0/1) of one element forcing variable of thermo() ("M_tair", ...)"""
+        a, p = _f64(data)
+        assert a.size == self.ne, (name, a.size)
+        self._chk(self.L.nsx_thermo_forcing_load(self.h, name.encode(), int(slot), p), "nsx_thermo_forcing_load")
+
+    def thermo_forcing_apply(self, name, interp_linear_time, current_time, ftime0, ftime1, factor=1., bias_correction=0.):
+        self._chk(self.L.nsx_thermo_forcing_apply(self.h, name.encode(), int(bool(interp_linear_time)), C.c_double(current_time),
+                                                  C.c_double(ftime0), C.c_double(ftime1), C.c_double(factor),
+                                                  C.c_double(bias_correction)), "nsx_thermo_forcing_apply")
 
     def thermo(self, p, dt, current_time):
         """FiniteElement::thermo(dt) at model time current_time (days since 1900-01-01) on the resident state"""

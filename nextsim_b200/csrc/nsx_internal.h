@@ -4,6 +4,8 @@
 #include <cstdint>
 #include <cstdio>
 #include <deque>
+#include <map>
+#include <memory>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -173,6 +175,8 @@ struct nsx_solver {
     nsx::thermo::Arrays th{};
     nsx::DBuf<double> th_planes;
     int n_thermo_launch = 0;
+    struct ThermoForcing { nsx::DBuf<double> d[2]; bool loaded[2] = {false, false}; };
+    std::map<std::string, std::unique_ptr<ThermoForcing>> th_forcing;    // time slices of the element forcing (ExternalData)
 
     // ---- halo ----
     std::deque<nsx::PeerLink> peers;             // union of send/recv peers

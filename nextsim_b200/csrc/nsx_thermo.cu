@@ -12,7 +12,7 @@ namespace nsx {
 #define NSX_THERMO_TPB 128
 #endif
 #ifndef NSX_THERMO_MINB
-#define NSX_THERMO_MINB 1
+#define NSX_THERMO_MINB 4
 #endif
 constexpr int THERMO_TPB = NSX_THERMO_TPB;
 

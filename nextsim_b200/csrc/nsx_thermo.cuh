@@ -127,6 +127,20 @@ NSX_HD double pw4(double x) { return std::pow(x, 4); }
 NSX_HD double hyp(double u, double v) { return std::hypot(u, v); }
 #endif
 
+// exp / log / atan / cbrt: one out-of-line copy each on the device.  Inlined at their 9 call sites (x2 for the two
+// IABulkFluxes instances) they made the kernel body larger than the SM's instruction cache (stall "no instruction" was the
+// top stall reason, profiles/r2_thermo_v3.txt); arguments and results travel in registers, so the call costs a few cycles.
+#if defined(__CUDA_ARCH__)
+#define NSX_LIBM_WRAP(name) __device__ __noinline__ static double m_##name(double x) { return ::name(x); }
+#else
+#define NSX_LIBM_WRAP(name) inline double m_##name(double x) { return std::name(x); }
+#endif
+NSX_LIBM_WRAP(exp)
+NSX_LIBM_WRAP(log)
+NSX_LIBM_WRAP(atan)
+NSX_LIBM_WRAP(cbrt)
+#undef NSX_LIBM_WRAP
+
 // one element's fields, held in registers between the loads at the top of thermo_element() and the stores at its end
 struct Elem {
 #define X(n) double n;
@@ -158,7 +172,7 @@ NSX_HD double incomingLongwave(Params const& P, Elem const& E)
 {
     if (P.o.have_Qlw_in) return E.Qlw_in;
     double taa = E.tair + phys::tfrwK;
-    return phys::sigma_sb * pw4(taa) * (1. - 0.261 * exp(-7.77e-4 * pw2(taa - phys::tfrwK))) * (1. + 0.275 * E.tcc);
+    return phys::sigma_sb * pw4(taa) * (1. - 0.261 * m_exp(-7.77e-4 * pw2(taa - phys::tfrwK))) * (1. + 0.275 * E.tcc);
 }
 
 // FE.cpp:4966-5019.  scheme 0 atmosphere, 1 water, 2 ice; returns sphum, *dsphumdT (ice only)
@@ -176,14 +190,14 @@ NSX_HD double specificHumidity(Params const& P, Elem const& E, int scheme, doubl
         salinity = 0;
     } else if (scheme == 1) {
         temp = E.sst;
-        return 640380. / phys::rhoa * exp(-5107.4 / (temp + phys::tfrwK));
+        return 640380. / phys::rhoa * m_exp(-5107.4 / (temp + phys::tfrwK));
     } else {
         Aa = 2.2e-4, B = 3.83e-6, Cc = 6.4e-10;
         a = 6.1115e2, b = 23.036, c = 279.82, d = 333.7;
         salinity = 0;
     }
     double f = 1. + Aa + E.mslp * 1e-2 * (B + Cc * temp * temp);
-    double est = a * exp((b - temp / d) * temp / (temp + c)) * (1 - 5.37e-4 * salinity);
+    double est = a * m_exp((b - temp / d) * temp / (temp + c)) * (1 - 5.37e-4 * salinity);
     double sphum = alpha * f * est / (E.mslp - beta * f * est);
     if (scheme == 2) {
         double dfdT = 2. * Cc * B * temp;
@@ -267,15 +281,15 @@ NSX_HD IceFlux iaBulkFluxes(Params const& P, Elem const& E, Air const& air, doub
         const double zetah = P.o.zref_temp * Linv;
         double psim, psih;
         if (Linv >= 0) {
-            const double x = cbrt(1. + zetam);
-            psim = P.C1 * (x - 1.) + P.C2 * (2. * log((x + P.Bm) * P.C3) - log((x * x - x * P.Bm + P.Bm2) * P.C4)
-                                              + P.C5 * (atan((2. * x - P.Bm) * P.C6) - P.C7));
-            psih = P.D1 * log(1. + ch * zetah + zetah * zetah) + P.D2 * (log((2. * zetah + P.D3) / (2. * zetah + P.D4)) - P.D5);
+            const double x = m_cbrt(1. + zetam);
+            psim = P.C1 * (x - 1.) + P.C2 * (2. * m_log((x + P.Bm) * P.C3) - m_log((x * x - x * P.Bm + P.Bm2) * P.C4)
+                                              + P.C5 * (m_atan((2. * x - P.Bm) * P.C6) - P.C7));
+            psih = P.D1 * m_log(1. + ch * zetah + zetah * zetah) + P.D2 * (m_log((2. * zetah + P.D3) / (2. * zetah + P.D4)) - P.D5);
         } else {
             double x = sqrt(sqrt(1. - 16. * zetam));
-            psim = 2. * log(0.5 * (1. + x)) + log(0.5 * (1. + x * x)) - 2. * atan(x) + 0.5 * 3.14159265358979323846;
+            psim = 2. * m_log(0.5 * (1. + x)) + m_log(0.5 * (1. + x * x)) - 2. * m_atan(x) + 0.5 * 3.14159265358979323846;
             x = sqrt(sqrt(1. - 16. * zetah));
-            psih = 2. * log(0.5 * (1. + x * x));
+            psih = 2. * m_log(0.5 * (1. + x * x));
         }
         drag_ui = phys::vonKarman / (P.lambda_u - psim);
         drag_ui *= drag_ui;

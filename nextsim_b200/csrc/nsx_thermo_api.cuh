@@ -108,6 +108,61 @@ extern "C" int nsx_thermo_download(nsx_handle S, const char* name, double* host)
     return nsx_thermo_download_many(S, 1, &name, &host);
 }
 
+// the element forcing of thermo() is ExternalData too (FE.cpp:8063 checkReloadDatasets): same two-slice time interpolation
+// as nsx_forcing_load / nsx_forcing_apply, evaluated into the resident M_tair, M_mslp, ...
+static double* thermo_forcing_plane(nsx_solver* S, const char* name, const char* who)
+{
+    if (!name) throw std::invalid_argument(std::string(who) + ": NULL name");
+    nsx::thermo::Arrays& A = thermo_arrays(S);
+    double** slot = nullptr;
+#define X(f) if (!slot && std::string(name) == "M_" #f) slot = &A.f;
+    NSX_THERMO_FORCING(X)
+#undef X
+    if (!slot || std::string(name) == "M_conc_upd")
+        throw std::invalid_argument(std::string(who) + ": " + name + " is not an ExternalData forcing variable of thermo()");
+    return *slot;
+}
+
+extern "C" int nsx_thermo_forcing_load(nsx_handle S, const char* name, int slot, const double* data)
+{
+    NSX_API_BEGIN(S)
+    thermo_forcing_plane(S, name, "nsx_thermo_forcing_load");
+    if (slot < 0 || slot > 1 || !data) throw std::invalid_argument("nsx_thermo_forcing_load: bad argument");
+    auto& f = S->th_forcing[name];
+    if (!f) f.reset(new nsx_solver::ThermoForcing());
+    size_t const ne = (size_t)S->ne;
+    if (!f->d[slot].p) f->d[slot].alloc(ne);
+    if (S->arena.n < ne) { NSX_CUDA(cudaStreamSynchronize(S->stream)); S->arena.alloc(ne); }
+    NSX_CUDA(cudaMemcpyAsync(S->arena.p, data, ne * sizeof(double), cudaMemcpyHostToDevice, S->stream));
+    std::vector<FieldMap> t{{const_cast<double*>(data), f->d[slot].p, ELEM}};
+    std::vector<size_t> off{0};
+    xfer_permute<1>(S, t, off);
+    NSX_CUDA(cudaStreamSynchronize(S->stream));             // the caller may reuse `data` right away
+    f->loaded[slot] = true;
+    NSX_API_END(S)
+}
+
+extern "C" int nsx_thermo_forcing_apply(nsx_handle S, const char* name, int interp_linear_time, double current_time, double ftime0,
+                                        double ftime1, double factor, double bias_correction)
+{
+    NSX_API_BEGIN(S)
+    double* const dst = thermo_forcing_plane(S, name, "nsx_thermo_forcing_apply");
+    auto it = S->th_forcing.find(name);
+    if (it == S->th_forcing.end() || !it->second->loaded[0] || (interp_linear_time && !it->second->loaded[1]))
+        throw std::runtime_error("nsx_thermo_forcing_apply: time slice not loaded (nsx_thermo_forcing_load)");
+    double c0 = 1., c1 = 0.;
+    if (interp_linear_time) {                               // externaldata.cpp:368-370
+        double const fdt = std::fabs(ftime1 - ftime0);
+        c0 = std::fabs(current_time - ftime1) / fdt;
+        c1 = std::fabs(current_time - ftime0) / fdt;
+    }
+    double const* const d0 = it->second->d[0].p;
+    double const* const d1 = interp_linear_time ? it->second->d[1].p : d0;
+    k_forcing_apply<<<nblk(S->ne), TPB, 0, S->stream>>>((long)S->ne, interp_linear_time, c0, c1, factor, bias_correction, d0, d1, dst);
+    NSX_CUDA(cudaGetLastError());
+    NSX_API_END(S)
+}
+
 extern "C" int nsx_thermo(nsx_handle S, const NsxThermoParams* p, int dt, double current_time)
 {
     NSX_API_BEGIN(S)

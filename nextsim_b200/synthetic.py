@@ -244,30 +244,48 @@ def make_thermo_state(ne, nn, seed=SEED, young=True, season="mixed", centroids=N
     Built to reach every branch of thermo(): ice-free, thin (< hmin after melt), young-only and thick-ice elements; air
     from -35 C (new ice in leads) to +8 C (surface melt, melt ponds); supercooled and warm mixed layers; snow-free and
     snow-covered ice; multi-year-ice tracers on both sides of their clamps.  season: 'winter' / 'summer' bias the air
-    temperature and short-wave, 'mixed' spans both.  centroids=(cx, cy, L): the ice regime (open water / trace / thin /
-    pack) varies smoothly in space, as real fields do (an ice edge, leads), instead of element by element -- what the
-    timing runs use, since neighbouring elements then take the same branches."""
+    temperature and short-wave, 'mixed' spans both.  centroids=(cx, cy, L): every field varies smoothly in space, as
+    real fields do (an ice edge, a front), instead of independently element by element -- what the timing runs use,
+    since neighbouring elements then mostly take the same branches; the value distributions are the same."""
     rng = np.random.default_rng(seed + 77)
-    u = rng.uniform
-    S = {}
     if centroids is None:
+        u = rng.uniform
+        rnd = lambda: rng.random(ne)
         kind = rng.integers(0, 8, ne)                # 0: open water, 1: trace ice, 2: thin ice, 3..7: pack ice
     else:
+        # every variate is a smooth random field of the element centroid, rank-transformed so that its marginal is
+        # still exactly uniform: same value distribution as above, but spatially coherent
         cx, cy, L = centroids
-        f = (np.sin(2 * np.pi * 1.5 * cx / L + 0.4) * np.sin(2 * np.pi * 1.1 * cy / L + 1.3) + 0.3 * np.sin(2 * np.pi * 3.0 * (cx - cy) / L))
-        q = np.quantile(f, [1 / 8, 2 / 8, 3 / 8])
-        kind = np.where(f < q[0], 0, np.where(f < q[1], 1, np.where(f < q[2], 2, 5)))
+        xs, ys = 2 * np.pi * cx / L, 2 * np.pi * cy / L
+
+        def rnd(n=ne):
+            f = np.zeros(ne)
+            for _ in range(4):
+                kx, ky = rng.uniform(-3.0, 3.0, 2)
+                f += rng.uniform(0.3, 1.0) * np.sin(kx * xs + ky * ys + rng.uniform(0, 2 * np.pi))
+            f += 0.02 * rng.standard_normal(ne)
+            r = np.empty(ne)
+            r[np.argsort(f, kind="stable")] = (np.arange(ne) + 0.5) / ne
+            return r
+
+        def u(lo, hi, n=ne):
+            if n != ne:
+                return rng.uniform(lo, hi, n)        # nodal vectors
+            return lo + (hi - lo) * rnd()
+
+        kind = np.minimum((8 * rnd()).astype(np.int64), 7)
+    S = {}
     conc = np.select([kind == 0, kind == 1, kind == 2], [0.0, u(1e-13, 0.05, ne), u(0.05, 0.6, ne)], u(0.6, 1.0, ne))
     hice = np.select([kind == 1, kind == 2], [u(0.005, 0.05, ne), u(0.008, 0.4, ne)], u(0.3, 3.5, ne))
-    hsnow = np.where(rng.random(ne) < 0.3, 0.0, u(0.0, 0.45, ne))
+    hsnow = np.where(rnd() < 0.3, 0.0, u(0.0, 0.45, ne))
     S["M_conc"] = conc
     S["M_thick"] = conc * hice
     S["M_snow_thick"] = conc * hsnow
     if young:
-        cy = np.minimum(1.0 - conc, np.where(rng.random(ne) < 0.35, 0.0, u(0.0, 0.3, ne)))
+        cy = np.minimum(1.0 - conc, np.where(rnd() < 0.35, 0.0, u(0.0, 0.3, ne)))
         S["M_conc_young"] = cy
         S["M_h_young"] = cy * u(0.03, 0.6, ne)       # on both sides of h_young_min (0.05) and h_young_max_sharp (0.275)
-        S["M_hs_young"] = cy * np.where(rng.random(ne) < 0.4, 0.0, u(0.0, 0.08, ne))
+        S["M_hs_young"] = cy * np.where(rnd() < 0.4, 0.0, u(0.0, 0.08, ne))
     else:
         S["M_conc_young"] = np.zeros(ne)
         S["M_h_young"] = np.zeros(ne)
@@ -284,20 +302,20 @@ def make_thermo_state(ne, nn, seed=SEED, young=True, season="mixed", centroids=N
     S["M_tair"] = tair
     S["M_dair"] = tair - u(0.0, 6.0, ne)
     S["M_mixrat"] = u(1e-4, 5e-3, ne)
-    S["M_sphuma"] = np.where(rng.random(ne) < 0.05, -1e-6, u(1e-4, 5e-3, ne))        # round-off negatives are clamped (FE.cpp:4982)
+    S["M_sphuma"] = np.where(rnd() < 0.05, -1e-6, u(1e-4, 5e-3, ne))        # round-off negatives are clamped (FE.cpp:4982)
     S["M_mslp"] = u(96500.0, 104500.0, ne)
-    S["M_Qsw_in"] = np.where(rng.random(ne) < 0.3, 0.0, u(0.0, 120.0 if season == "winter" else 420.0, ne))
+    S["M_Qsw_in"] = np.where(rnd() < 0.3, 0.0, u(0.0, 120.0 if season == "winter" else 420.0, ne))
     S["M_Qlw_in"] = u(140.0, 340.0, ne)
     S["M_tcc"] = u(0.0, 1.0, ne)
-    S["M_precip"] = np.where(rng.random(ne) < 0.3, 0.0, u(0.0, 8e-5, ne))              # kg/m^2/s
+    S["M_precip"] = np.where(rnd() < 0.3, 0.0, u(0.0, 8e-5, ne))              # kg/m^2/s
     S["M_snowfall"] = S["M_precip"] * u(-0.02, 1.0, ne)                                # slight negatives: input round-off (FE.cpp:5343)
     S["M_snowfr"] = u(0.0, 1.0, ne)
     S["M_mld"] = u(5.0, 60.0, ne)
     S["M_ocean_temp"] = u(-1.85, 4.0, ne)
     S["M_ocean_salt"] = u(29.0, 35.5, ne)
-    S["M_conc_upd"] = np.where(rng.random(ne) < 0.5, 0.0, u(-0.3, 0.1, ne))
+    S["M_conc_upd"] = np.where(rnd() < 0.5, 0.0, u(-0.3, 0.1, ne))
 
-    sss = np.where(rng.random(ne) < 0.03, u(2.0, 6.0, ne), u(27.0, 35.5, ne))          # a few brackish cells: si_eff = sss < si
+    sss = np.where(rnd() < 0.03, u(2.0, 6.0, ne), u(27.0, 35.5, ne))          # a few brackish cells: si_eff = sss < si
     S["M_sss"] = sss
     tf = -0.055 * sss
     S["M_sst"] = np.where(conc + S["M_conc_young"] > 0, tf + u(-0.02, 0.5, ne), tf + u(-0.05, 5.0, ne))
@@ -307,17 +325,17 @@ def make_thermo_state(ne, nn, seed=SEED, young=True, season="mixed", centroids=N
     S["M_tice2"] = np.where(conc > 0, u(-9.0, -0.4, ne), tfr_ice)
     S["M_tsurf_young"] = np.where(S["M_conc_young"] > 0, u(-28.0, tfr_ice, ne), tfr_ice)
     S["M_del_vi_tend"] = u(-0.02, 0.02, ne) * 86400.0
-    S["M_freeze_days"] = rng.integers(0, 6, ne).astype(np.float64)
-    S["M_freeze_onset"] = rng.integers(0, 2, ne).astype(np.float64)
+    S["M_freeze_days"] = np.floor(6 * rnd())
+    S["M_freeze_onset"] = np.floor(2 * rnd())
     S["M_conc_summer"] = u(0.0, 1.0, ne)
     S["M_thick_summer"] = u(0.0, 3.0, ne)
     S["M_fyi_fraction"] = u(0.0, 1.0, ne)
     S["M_age_det"] = u(0.0, 4e7, ne)
     S["M_age"] = u(0.0, 4e7, ne)
-    pond = (rng.random(ne) < 0.5) & (conc > 0.1)
+    pond = (rnd() < 0.5) & (conc > 0.1)
     S["D_pond_fraction"] = np.where(pond, u(0.0, 0.35, ne), 0.0)
     S["M_pond_volume"] = np.where(pond, S["D_pond_fraction"] * u(0.0, 0.3, ne), 0.0)
-    S["M_lid_volume"] = np.where(pond & (rng.random(ne) < 0.5), u(0.0, 0.03, ne), 0.0)
+    S["M_lid_volume"] = np.where(pond & (rnd() < 0.5), u(0.0, 0.03, ne), 0.0)
 
     S["M_wind"] = u(-18.0, 18.0, 2 * nn)
     S["M_VT"] = u(-0.4, 0.4, 2 * nn)

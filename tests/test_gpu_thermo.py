@@ -47,8 +47,9 @@ def run_gpu(p, t, dt, S, nx, nranks=1, steps=1, path="tiles"):
     return out
 
 
-def assert_close(ref, got, what, tol=TOL):
+def assert_close(ref, got, what, tol=TOL, report=False):
     worst = 0.0
+    errs = {}
     for k, a in ref.items():
         b = got[k]
         assert np.isfinite(b).all(), (what, k)
@@ -61,7 +62,11 @@ def assert_close(ref, got, what, tol=TOL):
             assert err == 0.0, (what, k, err)
             continue
         worst = max(worst, err / na)
+        errs[k] = (err / na, int(np.count_nonzero(np.abs(a - b) > 1e-12 * (np.abs(a) + 1e-300))))
         assert err / na <= tol, "%s: %s rel-L2 %.3e > %.1e" % (what, k, err / na, tol)
+    if report:
+        top = sorted(errs.items(), key=lambda kv: -kv[1][0])[:6]
+        print("  largest: " + ", ".join("%s %.1e (%d entries off by > 1e-12)" % (k, e, n) for k, (e, n) in top))
     return worst
 
 
@@ -100,7 +105,7 @@ def test_large_mesh_five_steps():
     p, t, dt, gm, S = tc.make_inputs(name, nx=283)
     ref = tc.run_oracle(p, t, dt, gm, S, steps=5)
     got = run_gpu(p, t, dt, S, nx=283, steps=5, path="resident")
-    w = assert_close({k: ref[k] for k in tc.OUT_FIELDS}, got, name)
+    w = assert_close({k: ref[k] for k in tc.OUT_FIELDS}, got, name, report=True)
     print("thermo 160k x5: worst rel-L2 %.2e" % w)
 
 
@@ -141,4 +146,102 @@ def test_rejected_options_and_names():
         s.thermo_upload(M_no_such_field=np.zeros(s.ne))
     with pytest.raises(RuntimeError):
         s.thermo_upload(M_conc=np.zeros(s.ne))          # ice state goes through NsxFields
+    s.close()
+
+
+@pytest.mark.parametrize("linear", [True, False])
+def test_element_forcing_interpolation_bit_exact(linear):
+    """ExternalData::get() of the element forcing (externaldata.cpp:366-455) evaluated on the device: bit-exact"""
+    from oracle import oracle as orc
+    c = cases.make_case("10km_stable", nx=40)
+    s = cases.make_solvers(c)[0]
+    rng = np.random.default_rng(5)
+    t0, t1, t = 43133.25, 43133.5, 43133.25 + 0.25 * 0.6113
+    for name, factor, bias in (("M_tair", 1.0, -273.15), ("M_mslp", 1.0, 0.0), ("M_precip", 1.0 / 3600.0, 0.0), ("M_Qsw_in", 0.97, 0.0)):
+        d0, d1 = rng.normal(250.0, 30.0, s.ne), rng.normal(250.0, 30.0, s.ne)
+        s.thermo_forcing_load(name, 0, d0)
+        if linear:
+            s.thermo_forcing_load(name, 1, d1)
+        s.thermo_forcing_apply(name, linear, t, t0, t1, factor, bias)
+        ref = orc.external_data_get_vector(d0, d1, linear, t, t0, t1, factor, bias)
+        assert np.array_equal(s.thermo_download(name)[name], ref), name
+    with pytest.raises(RuntimeError):
+        s.thermo_forcing_apply("M_dair", True, t, t0, t1)           # never loaded
+    with pytest.raises(RuntimeError):
+        s.thermo_forcing_load("M_conc_upd", 0, np.zeros(s.ne))        # a ModelVariable, not ExternalData
+    s.close()
+
+
+@pytest.mark.parametrize("path", ["resident", "tiles"])
+def test_coupled_model_steps(path):
+    """FiniteElement::step() between remeshes, device-resident: per step the time interpolation of the air temperature,
+    thermo(dt), explicitSolve(), update() -- against the same sequence of the CPU oracles (ExternalData, thermo, dynamics).
+    The ice-ocean heat flux uses the exchange scheme, so thermo() reads the velocities the dynamics produced, and the
+    dynamics reads the concentration / thickness / healing time thermo() produced."""
+    from oracle import oracle as orc
+    from oracle import thermo as oth
+    import oracle_bridge as ob
+    nsteps = 3
+    c = cases.make_case("10km_stable", nx=40)
+    lm, f = c.lms[0], c.local[0]
+    ne, nn = lm.num_elements, lm.num_nodes
+    dt = int(c.params.dtime_step)
+    over = dict(Qio_type=1, temp_dep_healing=1, dtime_step=float(dt))
+    S = syn.make_thermo_state(ne, nn, seed=21, young=True, season="winter")
+    # a consistent start: the case's pack ice with the synthetic slab ocean / atmosphere
+    for k in syn.THERMO_ICE:
+        S[k] = f[k].copy()
+    tfr = -0.055 * S["M_sss"]
+    S["M_sst"] = tfr + 0.02
+    for k in ("M_tice0", "M_tice1", "M_tice2", "M_tsurf_young"):
+        S[k] = np.minimum(S[k], -1.0)
+    t0, t1, tstart = 43133.0, 43133.25, 43133.0 + 100 * dt / 86400.0
+    tair0, tair1 = S["M_tair"].copy(), S["M_tair"] - 3.0
+
+    # ---- CPU ----
+    R = ob.make_ranks(c)[0]
+    q = ob.orc_params(c.params)
+    p = oth.default_params(**over)
+    F = {k: S[k].copy() for k in syn.THERMO_FORCING + syn.THERMO_STATE + syn.THERMO_ICE}
+    tri0 = np.asarray(lm.indices, np.int64).reshape(-1, 3) - 1
+    for k in range(nsteps):
+        t = tstart + k * dt / 86400.0
+        F["M_tair"] = orc.external_data_get_vector(tair0, tair1, True, t, t0, t1, 1.0, 0.0)
+        for name in syn.THERMO_ICE:
+            F[name] = R.get(name)
+        out = oth.thermo(p, dt, t, tri0, nn, R.get("M_wind"), R.get("M_VT"), R.get("M_ocean"), F)
+        F = {name: out[name] for name in F}
+        for name in syn.THERMO_ICE:
+            R.set(name, out[name])
+        orc.explicit_solve([R], q)
+        R.update(q)
+
+    # ---- GPU ----
+    s = cases.make_solvers(c, path=path)[0]
+    pg = capi.thermo_default_params(**over)
+    s.thermo_upload(**{k: S[k] for k in syn.THERMO_FORCING + syn.THERMO_STATE})
+    s.thermo_forcing_load("M_tair", 0, tair0)
+    s.thermo_forcing_load("M_tair", 1, tair1)
+    for k in range(nsteps):
+        t = tstart + k * dt / 86400.0
+        s.thermo_forcing_apply("M_tair", True, t, t0, t1)
+        s.thermo(pg, dt, t)
+        s.explicit_solve()
+        s.update()
+    assert s.path == path
+    got = s.download("M_VT", "M_conc", "M_thick", "M_damage", "M_sigma", "M_time_relaxation_damage")
+    gth = s.thermo_download("M_sst", "M_sss", "M_tice0", "M_tice1", "M_age", "D_Qa", "D_Qo", "M_fyi_fraction")
+    worst = 0.0
+    for name, a in list(got.items()) + list(gth.items()):
+        if name == "M_sigma":
+            pairs = [(a[i], R.get("M_sigma%d" % i)) for i in range(3)]
+        elif name in gth:
+            pairs = [(a, F[name] if name in F else out[name])]
+        else:
+            pairs = [(a, R.get(name))]
+        for x, y in pairs:
+            e = ob.rel_l2(x, y)
+            worst = max(worst, e)
+            assert e <= TOL, "%s after %d coupled steps: rel-L2 %.3e" % (name, nsteps, e)
+    print("coupled steps (%s): worst rel-L2 %.2e" % (path, worst))
     s.close()
