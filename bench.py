@@ -500,7 +500,7 @@ def run_ours(args):
                     "check": {"n_nan": chk_rs.n_nan, "n_range": chk_rs.n_range, "max_speed": chk_rs.max_speed}}
         next_rows = {"thermo_us": us_thermo, "thermo_elements_per_s": lm.num_elements / us_thermo * 1e6,
                      "thermo_GBps_of_724B_per_element": 724.0 * lm.num_elements / us_thermo * 1e-3,
-                     "thermo_note": "instruction-bound FP64 kernel (divisions, exp / log / cbrt / atan), see profiles/r2_thermo_v2.txt",
+                     "thermo_note": "instruction-bound FP64 kernel (divisions, exp / log / cbrt / atan), see profiles/r2_thermo_v4.txt",
                      "resident_step": resident,
                      "update_ice_diagnostics_us": us_diag, "update_ice_diagnostics_GBps": nb["diag"] / us_diag * 1e-3,
                      "forcing_apply_wind_us": us_forc, "forcing_apply_wind_GBps": nb["forcing"] / us_forc * 1e-3,

@@ -3,7 +3,7 @@
 //
 // One thread per element runs nsx::thermo::thermo_element() (nsx_thermo.cuh): OWBulkFluxes + IABulkFluxes (old and young
 // ice) + the slab loop fused, so every field is read once and written once.  The kernel is HBM-bound: with the default
-// options an element reads 33 doubles (7 forcing, 11 ice state, 15 slab / tracer state), its 3 node ids and the wind at
+// options an element reads 34 doubles (6 forcing, 11 ice state, 17 slab / tracer state), its 3 node ids and the wind at
 // its nodes (a node is shared by ~6 elements: 8 B per element from DRAM), and writes 55 doubles (11 ice state, 14 slab /
 // tracer state, 30 diagnostics) = 724 algorithmic bytes.  Fields live in the handle's internal (Hilbert) element order,
 // one plane per reference member, all thermo-only planes in one allocation.

@@ -17,7 +17,7 @@ import numpy as np
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
-ALGO_BYTES = 724.0     # 33 doubles read + 3 node ids + 8 B of shared wind, 55 doubles written
+ALGO_BYTES = 724.0     # 34 doubles read + 3 node ids + 8 B of shared wind, 55 doubles written
 
 
 def main():
