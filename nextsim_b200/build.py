@@ -51,10 +51,14 @@ def build(force=False, verbose=False, out=None):
     for k in ("NSX_THERMO_TPB", "NSX_THERMO_MINB"):      # launch shape of k_thermo (nsx_thermo.cu)
         if os.environ.get(k):
             thermo.append("-D%s=%s" % (k, os.environ[k]))
+    for k in ("NSX_THERMO_FAST_MINMAX", "NSX_THERMO_EXACT_DIV"):     # arithmetic experiments of k_thermo
+        if os.environ.get(k):
+            thermo.append("-D%s" % k)
     objs, cmds = [], []
     for src in NOFMA_SOURCES:
         obj = os.path.join(objdir, os.path.splitext(src)[0] + ("" if out is None else "_" + os.path.basename(out)) + ".o")
-        cmds.append([_nvcc()] + compile_flags + thermo + ["-fmad=false", "-c", os.path.join(CSRC, src), "-o", obj])
+        fmad = [] if os.environ.get("NSX_THERMO_FMAD") else ["-fmad=false"]
+        cmds.append([_nvcc()] + compile_flags + thermo + fmad + ["-c", os.path.join(CSRC, src), "-o", obj])
         objs.append(obj)
     cmds.append([_nvcc()] + NVCC_FLAGS + extra + [os.path.join(CSRC, s) for s in SOURCES] + objs + ["-o", out or LIB])
     text = ""

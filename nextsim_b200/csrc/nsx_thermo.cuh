@@ -45,6 +45,17 @@ NSX_HD double operator/(double x, UDiv const& d)
 #endif
 }
 
+// The same for a divisor that belongs to the element but divides several quantities (the concentration, the denominators of
+// the Winton temperature solve): one reciprocal on the device, plain divisions on the host.
+NSX_HD UDiv recip(double c)
+{
+#if defined(__CUDA_ARCH__) && !defined(NSX_THERMO_EXACT_DIV)
+    return UDiv{c, 1. / c};
+#else
+    return UDiv{c, 0.};
+#endif
+}
+
 // options + the per-step scalars thermo() derives before its loops (FE.cpp:5180-5216, 6160-6205)
 struct Params {
     NsxThermoParams o;
@@ -54,7 +65,7 @@ struct Params {
     int midnight;                           // std::fmod(M_current_time, 1.) == 0.
     int is_0915, is_0801, is_reset_date;    // date_string_md == "0915" / "0801" / age.reset_date
     double timeT, timeS, rh0, rPhiF, qi, qs, h_young_max_sharp;
-    UDiv u_ddt, u_rhos, u_rhow, u_rhoi, u_qi, u_qs, u_ki, u_h_young_min;
+    UDiv u_ddt, u_2ddt, u_rhos, u_rhow, u_rhoi, u_qi, u_qs, u_ki, u_h_young_min, u_Crho;
     // IABulkFluxes constants (FE.cpp:6171-6205)
     double z0, Linvrange, Bm, C1, C2, C3, Bm2, C4, C5, C6, C7, D1, D2, D3, D4, D5, lambda_u, lambda_h;
 };
@@ -110,8 +121,13 @@ inline double** field_slot(Arrays& A, const char* name, bool* shared = nullptr)
     return nullptr;
 }
 
+#if defined(__CUDA_ARCH__) && defined(NSX_THERMO_FAST_MINMAX)
+NSX_HD double dmax(double a, double b) { return fmax(a, b); }           // one DMNMX; differs from std::max for NaN and +-0 only
+NSX_HD double dmin(double a, double b) { return fmin(a, b); }
+#else
 NSX_HD double dmax(double a, double b) { return (a < b) ? b : a; }      // std::max
 NSX_HD double dmin(double a, double b) { return (b < a) ? b : a; }      // std::min
+#endif
 // std::pow(x, 2|3|4) and std::hypot of the reference.  The host build keeps the libm calls (bit for bit with the reference's
 // build); the device spells them as products: CUDA's pow(double, double) is ~350 instructions, sixteen of them per element
 // made the kernel instruction-bound (profiles/r2_thermo_v1.txt), and x*x differs from a correctly rounded pow by <= 1 ulp.
@@ -351,33 +367,36 @@ NSX_HD void thermoWinton(Params const& P, double dt, double conc, double voli, d
         Tsurf = Tfr_ice; T1 = Tfr_ice; T2 = Tfr_ice;
         return;
     }
-    hi = voli / conc;
+    UDiv const u_conc = recip(conc);
+    hi = voli / u_conc;
     hi_old = hi;
-    hs = vols / conc;
+    hs = vols / u_conc;
     double const Tfr_surf = (hs > 0) ? 0. : Tfr_ice;
 
     double K12 = 4 * phys::ki * M_ks / (M_ks * hi + 4 * phys::ki * hs);
     double A = Qia - Tsurf * dQiadT;
     double B = dQiadT;
-    double K32 = 2 * phys::ki / hi;
+    UDiv const u_hi = recip(hi);
+    double K32 = 2 * phys::ki / u_hi;
 
-    double A1 = hi * Crho / (2 * dt) + K32 * (4 * dt * K32 + hi * Crho) / (6 * dt * K32 + hi * Crho) + K12 * B / (K12 + B);
-    double B1 = -hi / (2 * dt) * (Crho * T1 + qi * Tfr_ice / T1) - I
-                - K32 * (4 * dt * K32 * Tbot + hi * Crho * T2) / (6 * dt * K32 + hi * Crho) + A * K12 / (K12 + B);
-    double C1 = hi * qi * Tfr_ice / (2 * dt);
+    UDiv const u_D6 = recip(6 * dt * K32 + hi * Crho), u_KB = recip(K12 + B);
+    double A1 = hi * Crho / P.u_2ddt + K32 * (4 * dt * K32 + hi * Crho) / u_D6 + K12 * B / u_KB;
+    double B1 = -hi / P.u_2ddt * (Crho * T1 + qi * Tfr_ice / T1) - I
+                - K32 * (4 * dt * K32 * Tbot + hi * Crho * T2) / u_D6 + A * K12 / u_KB;
+    double C1 = hi * qi * Tfr_ice / P.u_2ddt;
 
     T1 = -(B1 + sqrt(B1 * B1 - 4 * A1 * C1)) / (2 * A1);
-    Tsurf = (K12 * T1 - A) / (K12 + B);
+    Tsurf = (K12 * T1 - A) / u_KB;
 
     double Msurf = 0.;
     if (Tsurf > Tfr_surf) {
         Tsurf = Tfr_surf;
-        A1 += K12 - K12 * B / (K12 + B);
-        B1 -= K12 * Tsurf + A * K12 / (K12 + B);
+        A1 += K12 - K12 * B / u_KB;
+        B1 -= K12 * Tsurf + A * K12 / u_KB;
         T1 = -(B1 + sqrt(B1 * B1 - 4 * A1 * C1)) / (2 * A1);
         Msurf = K12 * (T1 - Tsurf) - (A + B * Tsurf);
     }
-    T2 = (2 * dt * K32 * (T1 + 2 * Tbot) + hi * Crho * T2) / (6 * dt * K32 + hi * Crho);
+    T2 = (2 * dt * K32 * (T1 + 2 * Tbot) + hi * Crho * T2) / u_D6;
 
     double h1 = hi / 2.;
     double h2 = hi / 2.;
@@ -400,7 +419,7 @@ NSX_HD void thermoWinton(Params const& P, double dt, double conc, double voli, d
     }
     mlt_hi_top = dmax(0., h1 + h2 - hi_old);
 
-    double Mbot = Qio - 4 * phys::ki * (Tbot - T2) / hi;
+    double Mbot = Qio - 4 * phys::ki * (Tbot - T2) / u_hi;
 
     del_hs_mlt = 0;
     if (Mbot <= 0.) {
@@ -437,7 +456,7 @@ NSX_HD void thermoWinton(Params const& P, double dt, double conc, double voli, d
         double delh1b = dmax(-freeboard, 0.);
         double f1 = 1 - delh1b / (delh1b + h1);
         double Tbar = f1 * (T1 + qi * Tfr_ice / (Crho * T1)) + (1 - f1) * Tfr_ice;
-        T1 = (Tbar - sqrt(Tbar * Tbar - 4 * Tfr_ice * qi / Crho)) / 2.;
+        T1 = (Tbar - sqrt(Tbar * Tbar - 4 * Tfr_ice * qi / P.u_Crho)) / 2.;
         h1 += delh1b;
         del_hi_s2i += delh1b;
     }
@@ -446,7 +465,7 @@ NSX_HD void thermoWinton(Params const& P, double dt, double conc, double voli, d
     if (h2 > h1) {
         double f1 = h1 / hi * 2.;
         double Tbar = f1 * (T1 + qi * Tfr_ice / (Crho * T1)) + (1 - f1) * T2;
-        T1 = (Tbar - sqrt(Tbar * Tbar - 4 * Tfr_ice * qi / Crho)) / 2.;
+        T1 = (Tbar - sqrt(Tbar * Tbar - 4 * Tfr_ice * qi / P.u_Crho)) / 2.;
     } else if (hi > 0.) {
         double f1 = (2. * h1 - hi) / hi;
         T2 = f1 * (T1 + qi * Tfr_ice / (Crho * T1)) + (1 - f1) * T2;
@@ -490,15 +509,17 @@ NSX_HD void thermoIce0(Params const& P, double dt, double conc, double voli, dou
         del_hi = 0.;
         return;
     }
-    hi = voli / conc;
+    UDiv const u_conc = recip(conc);
+    hi = voli / u_conc;
     hi_old = hi;
-    hs = vols / conc;
+    hs = vols / u_conc;
 
     double Qic, del_hb, del_ht, draft;
     double const Qia_mod = Qia + (1. - beta) * I;
 
-    Qic = M_ks * (Tbot - Tsurf) / (hs + M_ks * hi / P.u_ki) * gamma;
-    Tsurf = Tsurf + (Qic - Qia_mod) / (M_ks / (hs + M_ks * hi / P.u_ki) + dQiadT);
+    UDiv const u_res = recip(hs + M_ks * hi / P.u_ki);
+    Qic = M_ks * (Tbot - Tsurf) / u_res * gamma;
+    Tsurf = Tsurf + (Qic - Qia_mod) / (M_ks / u_res + dQiadT);
 
     if (hs > 0.) Tsurf = dmin(0., Tsurf);
     else Tsurf = dmin(-P.o.freezingpoint_mu * phys::si, Tsurf);
@@ -830,11 +851,12 @@ NSX_HD void thermo_core(Params const& P, Arrays const& A, int i, Elem& E)
     E.conc += del_c;
 
     if (E.conc >= phys::cmin) {
-        hi = (hi * old_conc + newice) / E.conc;
+        UDiv const u_c = recip(E.conc);
+        hi = (hi * old_conc + newice) / u_c;
         if (del_c < 0.) {
             Qow -= del_c * hs * qs / P.u_ddt;
         } else {
-            hs = (hs * old_conc + newsnow) / E.conc;
+            hs = (hs * old_conc + newsnow) / u_c;
         }
         if (o.thermo_type == 1) {
             double f1 = E.thick / (E.thick + newice);
@@ -1149,6 +1171,7 @@ inline Params make_params(NsxThermoParams const& o, int dt, double current_time)
     auto ud = [](double c) { return UDiv{c, 1. / c}; };
     P.u_ddt = ud(P.ddt); P.u_rhos = ud(phys::rhos); P.u_rhow = ud(phys::rhow); P.u_rhoi = ud(phys::rhoi);
     P.u_qi = ud(P.qi); P.u_qs = ud(P.qs); P.u_ki = ud(phys::ki); P.u_h_young_min = ud(o.h_young_min);
+    P.u_2ddt = ud(2 * P.ddt); P.u_Crho = ud(phys::C * phys::rhoi);
     P.num_steps_in_day = (int)std::round(days_in_sec / o.dtime_step);                // :5668-5670
     P.step_in_day = 1 + (int)std::round(P.num_steps_in_day * std::fmod(current_time, 1.));
     P.midnight = std::fmod(current_time, 1.) == 0.;

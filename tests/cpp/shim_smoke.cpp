@@ -27,6 +27,18 @@ int main(int argc, char** argv)
         fe.applyForcing(NSX_FORCING_WIND, false, 0., 0., 1.);
         bool const regrid = fe.checkRegridding(10., [](bool b) { return b; }) || fe.checkRegridding(10.);
         std::printf("regrid=%d min angle=%g\n", (int)regrid, fe.M_min_angle);
+        // row 3: thermo() on the one element (cold air over open water at the freezing point: new ice must form)
+        NsxThermoParams tp;
+        nsx_thermo_params_defaults(&tp);
+        std::vector<double> tair{-20.}, dair{-22.}, mslp{101000.}, qsw{0.}, tcc{0.5}, precip{1e-5}, sst{-1.8}, sss{33.}, t0{-0.275};
+        fe.thermoUpload({{"M_tair", tair.data()}, {"M_dair", dair.data()}, {"M_mslp", mslp.data()}, {"M_Qsw_in", qsw.data()},
+                         {"M_tcc", tcc.data()}, {"M_precip", precip.data()}, {"M_sst", sst.data()}, {"M_sss", sss.data()},
+                         {"M_tice0", t0.data()}, {"M_tice1", t0.data()}, {"M_tice2", t0.data()}, {"M_tsurf_young", t0.data()}});
+        fe.thermo(tp, 200, 43133.25);
+        std::vector<double> newice(1), hy(1);
+        fe.thermoDownload({{"D_newice", newice.data()}, {"M_h_young", hy.data()}});
+        std::printf("thermo: D_newice=%g m/day, M_h_young=%g m\n", newice[0], hy[0]);
+        if (!(newice[0] > 0.) || !(hy[0] > 0.)) return 1;
     } catch (std::runtime_error const& e) {
         std::printf("threw: %s\n", e.what());
         return std::strstr(e.what(), "nsx_create") ? 0 : 1;

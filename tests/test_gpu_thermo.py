@@ -245,3 +245,17 @@ def test_coupled_model_steps(path):
             assert e <= TOL, "%s after %d coupled steps: rel-L2 %.3e" % (name, nsteps, e)
     print("coupled steps (%s): worst rel-L2 %.2e" % (path, worst))
     s.close()
+
+
+def test_cpp_shim_thermo(tmp_path):
+    """the C++ host shim (FiniteElementGPU::thermo / thermoUpload / thermoDownload) on a one-element mesh: cold air over
+    open water at the freezing point forms young ice"""
+    import subprocess
+    root = os.path.dirname(HERE)
+    libdir = os.path.join(root, "nextsim_b200")
+    exe = tmp_path / "shim_smoke"
+    subprocess.check_call(["g++", "-std=c++17", "-I", root, os.path.join(root, "tests", "cpp", "shim_smoke.cpp"),
+                           "-o", str(exe), "-L", libdir, "-lnsx", "-Wl,-rpath," + libdir])
+    r = subprocess.run([str(exe)], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert r.returncode == 0, r.stdout
+    assert "handle created" in r.stdout and "thermo: D_newice=" in r.stdout, r.stdout
