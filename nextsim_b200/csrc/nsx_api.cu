@@ -302,6 +302,16 @@ static bool try_resident_plan(const NsxMesh* mesh, const NsxHalo* halo, int ctas
               std::to_string(P.max_slots) + ", shared memory " + std::to_string(smem) + " B";
         return false;
     }
+    // k_resident updates one late slot per thread before the halo wait and at most two slots per thread after it
+    for (size_t t = 0; t < P.tiles.size() && t < P.res_tiles.size(); ++t) {
+        int const E = P.res_tiles[t].n_early_own, O = P.tiles[t].n_own_slots, nsl = O + P.tiles[t].n_halo_slots;
+        int const after = E + nsl - std::min(O, E + RES_TPB);
+        if (after > (RES_SPT - 1) * RES_TPB) {
+            why = "tile " + std::to_string(t) + ": " + std::to_string(after) + " slots after the halo wait (limit " +
+                  std::to_string((RES_SPT - 1) * RES_TPB) + ")";
+            return false;
+        }
+    }
     return true;
 }
 

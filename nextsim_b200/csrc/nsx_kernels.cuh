@@ -1199,12 +1199,31 @@ k_resident(KParams K, ResidentArgs A)
     unsigned long long const epoch0 = *A.epoch_ctr;               // advanced by the host-side sequence after every launch
 
     if (tid == 0 && blockIdx.x == 0) A.tstamp[0] = globaltimer_ns();
+    // Which slots a thread updates.  Round 0 runs BEFORE the halo of the previous sub-cycle is awaited: one late slot (no
+    // halo node, no export node) per thread, k = n_early_own + tid.  Rounds 1, 2 run after it and take everything else in
+    // order -- early own slots, the late slots beyond the first RES_TPB, halo slots.  A balanced tile (<= 2 * RES_TPB slots,
+    // at least nsl - RES_TPB late ones) needs one round on either side of the wait, and every warp has work in both.
+    int const late_end = min(td.n_own_slots, rt.n_early_own + RES_TPB);
+    int const n_after = rt.n_early_own + nsl - late_end;          // <= 2 * RES_TPB, checked by the host
+    auto slot_of = [&](int round) -> int {
+        if (round == 0) { int const k = rt.n_early_own + tid; return k < late_end ? k : -1; }
+        int const idx = tid + (round - 1) * RES_TPB;
+        if (idx >= n_after) return -1;
+        return idx < rt.n_early_own ? idx : late_end + (idx - rt.n_early_own);
+    };
     // ---- load the tile once ----
     double dmg[RES_SPT];
 #pragma unroll
     for (int q = 0; q < RES_SPT; ++q) {
-        int const k = tid + q * RES_TPB;
         dmg[q] = 0.;
+        if (BBM) {
+            int const k = slot_of(q);
+            if (k >= 0) dmg[q] = A.dm[(k < td.n_own_slots) ? td.elem_begin + k : A.halo_elems[td.halo_elem_off + (k - td.n_own_slots)]];
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < RES_SPT; ++q) {
+        int const k = tid + q * RES_TPB;
         if (k < nsl) {
             size_t const g = (size_t)td.slot_begin + k;
             cnp[k] = A.slot_conn[g];
@@ -1218,7 +1237,6 @@ k_resident(KParams K, ResidentArgs A)
             for (int c = 0; c < NEC; ++c) ecp[c * MS + k] = A.slot_ec[c * NS + g];
             int const e = (k < td.n_own_slots) ? td.elem_begin + k : A.halo_elems[td.halo_elem_off + (k - td.n_own_slots)];
             sgp[k] = A.s0[e]; sgp[MS + k] = A.s1[e]; sgp[2 * MS + k] = A.s2[e];
-            if (BBM) dmg[q] = A.dm[e];
         }
     }
     auto VTb = [&](int parity) -> double* { return parity ? A.VT1 : A.VT0; };
@@ -1258,26 +1276,39 @@ k_resident(KParams K, ResidentArgs A)
     __syncthreads();
 
     // ---- helpers ----
-    auto phase1 = [&](bool early) {
+    auto phase1 = [&](bool after_wait) {
 #pragma unroll
         for (int q = 0; q < RES_SPT; ++q) {
-            int const k = tid + q * RES_TPB;
-            bool const is_early = (k < rt.n_early_own) || (k >= td.n_own_slots);
-            if (k >= nsl || is_early != early) continue;
+            if ((q > 0) != after_wait) continue;
+            int const k = slot_of(q);
+            if (k < 0) continue;
             NSX_DEV_CHECK((int)(cnp[k] & 0xFFFF) < MLN && (int)((cnp[k] >> 16) & 0xFFFF) < MLN && (int)((cnp[k] >> 32) & 0xFFFF) < MLN && k < MS, A.err, 1);
             dmg[q] = res_slot_update<BBM>(K, k, cnp[k], dmg[q], MS, shp, ecp, sgp, su, sv);
         }
     };
     // nodal solve of this thread's node (FE.cpp:10445-10529): contributions in ascending reference element order
-    auto node_solve = [&](double& un, double& vn) {
+    // the nine step-constant values of the owned node come from L2 every sub-cycle (no register or shared-memory room to
+    // keep them): the loads are issued BEFORE the barrier that precedes the solve, so their latency overlaps the wait
+    struct NodeConst { double gu, gv, rl, cb, fc, tau_x, tau_y, ou, ov; };
+    auto node_consts = [&]() {
+        NodeConst c;
+        c.gu = c.gv = c.rl = c.cb = c.fc = c.tau_x = c.tau_y = c.ou = c.ov = 0.;
+        if (!solve_node) return c;
+        c.gu = __ldg(A.grad_ssh + n); c.gv = __ldg(A.grad_ssh + n + nn);
+        c.rl = __ldg(A.rlmass + n); c.cb = __ldg(A.cbu + n); c.fc = __ldg(A.fcor + n);
+        c.tau_x = __ldg(A.tau_a + n); c.tau_y = __ldg(A.tau_a + n + nn);
+        c.ou = __ldg(A.ocean + n); c.ov = __ldg(A.ocean + n + nn);
+        if (A.tau_wi) { c.tau_x = c.tau_x + __ldg(A.tau_wi + n); c.tau_y = c.tau_y + __ldg(A.tau_wi + n + nn); }
+        return c;
+    };
+    auto node_solve = [&](NodeConst const& nc, double& un, double& vn) {
         double const uice = su[tid], vice = sv[tid];
         un = uice; vn = vice;
         if (!solve_node) return;
-        double gu = __ldg(A.grad_ssh + n), gv = __ldg(A.grad_ssh + n + nn);
-        double const rl = __ldg(A.rlmass + n), cb = __ldg(A.cbu + n), fc = __ldg(A.fcor + n);
-        double tau_x = __ldg(A.tau_a + n), tau_y = __ldg(A.tau_a + n + nn);
-        double const ou = __ldg(A.ocean + n), ov = __ldg(A.ocean + n + nn);
-        if (A.tau_wi) { tau_x = tau_x + __ldg(A.tau_wi + n); tau_y = tau_y + __ldg(A.tau_wi + n + nn); }
+        double gu = nc.gu, gv = nc.gv;
+        double const rl = nc.rl, cb = nc.cb, fc = nc.fc;
+        double tau_x = nc.tau_x, tau_y = nc.tau_y;
+        double const ou = nc.ou, ov = nc.ov;
         bool more = true;
         // keep the packed codes opaque: otherwise the compiler hoists the 8 x 3 decoded shared-memory addresses out of the
         // sub-cycle loop and spills them (registers are the scarce resource here; the decode is two shifts)
@@ -1369,13 +1400,14 @@ k_resident(KParams K, ResidentArgs A)
     int const cur = A.cur & 1;
     for (int s = 0; s < A.nsub; ++s) {
         int const pw = (cur + s + 1) & 1;                         // parity of the buffer this sub-cycle writes
-        phase1(false);                                            // 1. late slots
+        phase1(false);                                            // 1. one late slot per thread
         if (s > 0) wait_refresh(s, pw ^ 1, A.move_mesh != 0, K.dte);   // 2. (sub-cycle 0 starts from the loaded state)
         else __syncthreads();                                     // (the barrier also orders phase 1 before the node solve)
-        phase1(true);                                             // 3. early slots
+        phase1(true);                                             // 3. early, remaining late and halo slots
+        NodeConst const nc = node_consts();
         __syncthreads();
         double un = 0., vn = 0.;
-        if (has_node) node_solve(un, vn);                         // needs every incident stress: after both phase-1 parts
+        if (has_node) node_solve(nc, un, vn);                     // needs every incident stress: after both phase-1 parts
         // 4./5. one node per thread: every solve has read its inputs, nobody else reads su/sv before the barrier below
         if (has_node) { su[tid] = un; sv[tid] = vn; }
         if (tid < rt.n_x) publish_node(pw, s + 1, un, vn);        // export nodes -> mailboxes (local + NVLink), usable on arrival
@@ -1449,7 +1481,13 @@ k_resident(KParams K, ResidentArgs A)
         if (k < td.n_own_slots) {
             int const e = td.elem_begin + k;
             A.s0[e] = sgp[k]; A.s1[e] = sgp[MS + k]; A.s2[e] = sgp[2 * MS + k];
-            if (BBM) A.dm[e] = dmg[q];
+        }
+    }
+    if (BBM) {
+#pragma unroll
+        for (int q = 0; q < RES_SPT; ++q) {
+            int const k = slot_of(q);
+            if (k >= 0 && k < td.n_own_slots) A.dm[td.elem_begin + k] = dmg[q];
         }
     }
 }

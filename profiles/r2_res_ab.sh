@@ -1,0 +1,15 @@
+#!/bin/bash
+# round 2: k_resident with one late slot per thread before the halo wait / the rest after it, node constants prefetched
+# above the barrier: parity of the resident path, then the N=1 bench
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests/test_gpu_resident.py tests/test_gpu_golden.py -x -q 2>&1 | tail -4
+timeout 900 python -m pytest tests/test_gpu_parity.py -x -q -k "resident" 2>&1 | tail -4
+NSX_PATH=resident timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu-baseline 2>gpurun_out/bench_err_res.log > gpurun_out/bench_10km_resident_ab.json
+python - <<PY
+import json
+for l in open("gpurun_out/bench_10km_resident_ab.json"):
+    if l.startswith("{"):
+        d = json.loads(l)
+        print("resident", "%.4g" % d["value"], d["roofline"]["us_per_subcycle"], d["roofline"]["frac"], d["phase_ms"], d["check"], "e2e %.4g" % d["e2e"]["value"], d.get("parity"))
+PY
+tail -3 gpurun_out/bench_err_res.log
