@@ -45,7 +45,7 @@ KERNEL_OF_PATH = {
     "direct": "one sub-cycle = k_element_direct + k_node_direct (working set resident in L2)",
     "tiles": "one sub-cycle = k_subcycle (persistent TMA tile pipeline streaming from HBM)",
     "resident": "k_resident: ONE launch per model step = all sub-cycles + the 50 smoother sweeps, state resident in shared "
-                "memory / registers, release/acquire flags between tiles and between GPUs",
+                "memory / registers, 16-byte {value, epoch} mailbox stores between tiles and between GPUs",
 }
 
 

@@ -1253,6 +1253,9 @@ k_resident(KParams K, ResidentArgs A)
     uint8_t const fl = has_node ? A.nflags[n] : (uint8_t)NF_DIRICHLET;
     double const nmass = has_node ? A.node_mass[n] : 1.;
     bool const solve_node = has_node && !(fl & NF_DIRICHLET) && nmass != 0.;
+    // dte / max(min_m, mass) of the owned node is the same in every sub-cycle (FE.cpp:10483): one division per launch
+    double const dte_over_mass_c = fast_div(K.dynamics_type == NSX_DYN_MEVP ? K.dte_mevp : K.dte, fmax(K.min_m, nmass));
+    bool const mass_is_zero = nmass == 0.;
     // displacement of the owned node over the launch: M_UM and M_UT receive the same increments dte*VT every sub-cycle
     // (FE.cpp:10545-10549), so one accumulator serves both (added once at the end; M_UM of Neumann nodes is restored)
     double dspu = 0., dspv = 0.;
@@ -1344,7 +1347,7 @@ k_resident(KParams K, ResidentArgs A)
             delv = (__ldg(A.VTM + n + nn) - vice) * K.mevp_rb;
             dtep = K.dte_mevp;
         }
-        double const dte_over_mass = fast_div(dtep, fmax(K.min_m, nmass));
+        double const dte_over_mass = dte_over_mass_c;
         double const c_prime = K.rhow_cdw * fast_hypot(ou - uice, ov - vice);
         double const tau_b = cb * fast_div(1., fast_hypot(uice, vice) + K.u0);
         double const sin_s = (fl & NF_LATNEG) ? -K.sin_ota_abs : K.sin_ota_abs;
@@ -1433,7 +1436,7 @@ k_resident(KParams K, ResidentArgs A)
     // ---- open-water smoother: 50 Jacobi sweeps over the ice-free nodes (FE.cpp:10578-10611), same exchange per sweep.
     // A rank without neighbours and without ice-free nodes skips it; with neighbour ranks every sweep is exchanged.
     int const nsweeps = (A.nsweeps > 0 && (A.has_peers || *A.ow_count > 0)) ? A.nsweeps : 0;
-    bool const is_ow = has_node && !(fl & NF_DIRICHLET) && nmass == 0.;
+    bool const is_ow = has_node && !(fl & NF_DIRICHLET) && mass_is_zero;
     int const deg = is_ow ? (int)A.n2n_deg[n] : 0;
     for (int it = 0; it < nsweeps; ++it) {
         int const pw = (cur + ex + 1) & 1;

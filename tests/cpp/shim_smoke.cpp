@@ -30,7 +30,7 @@ int main(int argc, char** argv)
         // row 3: thermo() on the one element (cold air over open water at the freezing point: new ice must form)
         NsxThermoParams tp;
         nsx_thermo_params_defaults(&tp);
-        std::vector<double> tair{-20.}, dair{-22.}, mslp{101000.}, qsw{0.}, tcc{0.5}, precip{1e-5}, sst{-1.8}, sss{33.}, t0{-0.275};
+        std::vector<double> tair{-20.}, dair{-22.}, mslp{101000.}, qsw{0.}, tcc{0.5}, precip{1e-5}, sst{-1.815}, sss{33.}, t0{-0.275};
         fe.thermoUpload({{"M_tair", tair.data()}, {"M_dair", dair.data()}, {"M_mslp", mslp.data()}, {"M_Qsw_in", qsw.data()},
                          {"M_tcc", tcc.data()}, {"M_precip", precip.data()}, {"M_sst", sst.data()}, {"M_sss", sss.data()},
                          {"M_tice0", t0.data()}, {"M_tice1", t0.data()}, {"M_tice2", t0.data()}, {"M_tsurf_young", t0.data()}});
