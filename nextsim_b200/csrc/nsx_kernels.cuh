@@ -1316,17 +1316,30 @@ k_resident(KParams K, ResidentArgs A)
         // keep the packed codes opaque: otherwise the compiler hoists the 8 x 3 decoded shared-memory addresses out of the
         // sub-cycle loop and spills them (registers are the scarce resource here; the decode is two shifts)
         asm volatile("" : "+r"(incr[0]), "+r"(incr[1]), "+r"(incr[2]), "+r"(incr[3]));
+        // two incidences at a time: their twelve shared-memory loads and their products are independent, only the two
+        // subtractions keep the reference's order (an invalid second entry reads the first one's slot and is dropped)
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {
-            unsigned const code = (incr[c >> 1] >> (16 * (c & 1))) & 0xFFFFu;
-            if (code == 0xFFFFu) { more = false; break; }
-            int const i = (int)(code >> 14), k = (int)(code & 0x3FFFu);
-            NSX_DEV_CHECK(i < 3 && k < nsl, A.err, 2);
-            double const a0 = sgp[k], a1 = sgp[MS + k], a2 = sgp[2 * MS + k];
-            double const vol = ecp[(BBM ? 5 : 1) * MS + k];
-            double const dxi = shp[i * MS + k], dyi = shp[(3 + i) * MS + k];
-            gu -= vol * (a0 * dxi + a2 * dyi);           // V*(sigma . grad N_i), FE.cpp:10464-10465
-            gv -= vol * (a2 * dxi + a1 * dyi);
+        for (int c = 0; c < 8; c += 2) {
+            unsigned const code0 = incr[c >> 1] & 0xFFFFu, code1 = incr[c >> 1] >> 16;
+            if (code0 == 0xFFFFu) { more = false; break; }
+            bool const two = code1 != 0xFFFFu;
+            unsigned const cd1 = two ? code1 : code0;
+            int const i0 = (int)(code0 >> 14), k0 = (int)(code0 & 0x3FFFu);
+            int const i1 = (int)(cd1 >> 14), k1 = (int)(cd1 & 0x3FFFu);
+            NSX_DEV_CHECK(i0 < 3 && k0 < nsl && i1 < 3 && k1 < nsl, A.err, 2);
+            double const a0 = sgp[k0], a1 = sgp[MS + k0], a2 = sgp[2 * MS + k0];
+            double const vol = ecp[(BBM ? 5 : 1) * MS + k0];
+            double const dxi = shp[i0 * MS + k0], dyi = shp[(3 + i0) * MS + k0];
+            double const b0 = sgp[k1], b1 = sgp[MS + k1], b2 = sgp[2 * MS + k1];
+            double const wol = ecp[(BBM ? 5 : 1) * MS + k1];
+            double const exi = shp[i1 * MS + k1], eyi = shp[(3 + i1) * MS + k1];
+            double const pu0 = a0 * dxi + a2 * dyi, pv0 = a2 * dxi + a1 * dyi;       // sigma . grad N_i, FE.cpp:10464-10465
+            double const pu1 = b0 * exi + b2 * eyi, pv1 = b2 * exi + b1 * eyi;
+            gu = fma(-vol, pu0, gu);                      // gu -= V * (...): the fused form the single-entry loop compiled to
+            gv = fma(-vol, pv0, gv);
+            if (!two) { more = false; break; }
+            gu = fma(-wol, pu1, gu);
+            gv = fma(-wol, pv1, gv);
         }
         if (more && td.inc_w > 8) {                      // nodes with more than 8 incident elements: rest from the table
             const uint16_t* ip = A.inc + td.inc_off + tid;
