@@ -1451,14 +1451,32 @@ k_resident(KParams K, ResidentArgs A)
     int const nsweeps = (A.nsweeps > 0 && (A.has_peers || *A.ow_count > 0)) ? A.nsweeps : 0;
     bool const is_ow = has_node && !(fl & NF_DIRICHLET) && mass_is_zero;
     int const deg = is_ow ? (int)A.n2n_deg[n] : 0;
+    // the first eight neighbour ids of an open-water node move into the registers that held the incidence codes: the
+    // sweeps then read no global memory (an L2 round trip per sweep otherwise)
+    if (nsweeps > 0 && is_ow) {
+        const uint16_t* q = A.n2n_loc + rt.n2n_off + tid;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            unsigned const l = j < deg ? (unsigned)__ldg(q + (size_t)j * td.n_own) : 0xFFFFu;
+            incr[j >> 1] = (j & 1) ? ((incr[j >> 1] & 0x0000FFFFu) | (l << 16)) : ((incr[j >> 1] & 0xFFFF0000u) | l);
+        }
+    }
     for (int it = 0; it < nsweeps; ++it) {
         int const pw = (cur + ex + 1) & 1;
         double nu = 0., nv = 0.;
         if (is_ow) {
-            const uint16_t* q = A.n2n_loc + rt.n2n_off + tid;
-            for (int j = 0; j < deg; ++j) {
-                int const l = (int)__ldg(q + (size_t)j * td.n_own);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                unsigned const l = (incr[j >> 1] >> (16 * (j & 1))) & 0xFFFFu;
+                if (j >= deg) break;
                 nu += su[l]; nv += sv[l];
+            }
+            if (deg > 8) {
+                const uint16_t* q = A.n2n_loc + rt.n2n_off + tid;
+                for (int j = 8; j < deg; ++j) {
+                    int const l = (int)__ldg(q + (size_t)j * td.n_own);
+                    nu += su[l]; nv += sv[l];
+                }
             }
             nu = nu / deg; nv = nv / deg;
         }
