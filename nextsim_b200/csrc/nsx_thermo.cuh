@@ -3,10 +3,16 @@
 // The reference runs three loops over the elements -- OWBulkFluxes (FE.cpp:5032-5159), IABulkFluxes for old and for young
 // ice (6148-6353), then the slab loop of thermo() (5278-6133) -- but every statement only touches element i (plus the
 // three nodes of element i for the wind and ice-ocean speed), so they fuse into one pass: one thread per element, every
-// field read once and written once.  Statement order, constants and libm calls follow the reference text line by line
-// (citations in the comments); nothing is re-associated, so that the SAME function compiled for the host
-// (tests/cpp/thermo_host.cpp) reproduces the reference's own compiled bodies (oracle/ref_fe) bit for bit, and the device
-// instance differs from it only by the accuracy of CUDA's exp / pow / log / cbrt / atan (1-2 ulp).
+// field read once and written once.  Statement order and constants follow the reference text line by line (citations in
+// the comments) and nothing is re-associated, so that the HOST build of this function (oracle/thermo_oracle.cpp) reproduces
+// the reference's own compiled bodies (oracle/ref_fe) bit for bit (tests/test_thermo_cpu.py).
+//
+// The DEVICE build deviates from that text in four marked places, each worth <= 1-2 ulp per operation: CUDA's libm for
+// exp / log / cbrt / atan; pow(x, 2|3|4) spelled as products and hypot as sqrt(u*u + v*v) (pw2..pw4, hyp); division by a
+// divisor that is the same for all elements as multiplication by its host-computed reciprocal (UDiv); one reciprocal per
+// element for divisors that divide several quantities (recip).  The kernel is built -fmad=false (nsx_thermo.cu).
+// Quantities all three bulk-flux loops recompute from the same inputs (atmospheric humidity, air density, wind speed,
+// incoming long-wave) are computed once -- same values, no rounding change.
 //
 // NSX_HD marks host+device functions; the header has no other CUDA dependency.
 #pragma once
@@ -338,7 +344,7 @@ NSX_HD IceFlux iaBulkFluxes(Params const& P, Elem const& E, Air const& air, doub
 }
 
 // FE.cpp:6396-6428
-NSX_HD double iceOceanHeatflux(Params const& P, Arrays const& A, int cpt, double sst, double sss, double mld, double dt)
+NSX_HD double iceOceanHeatflux(Params const& P, Arrays const& A, int cpt, double sst, double sss, double mld, double /*dt: P.u_ddt*/)
 {
     double const Tbot = freezingPoint(P, sss);
     if (P.o.Qio_type == 0) return (sst - Tbot) * phys::rhow * phys::cpw * mld / P.u_ddt;

@@ -3,7 +3,8 @@
 // thermo() is one element-wise function, so the restatement of FE.cpp:4966-6962 exists ONCE, as the host+device function
 // nsx::thermo::thermo_element() of nextsim_b200/csrc/nsx_thermo.cuh; this file compiles that function for the host (g++,
 // -ffp-contract=off like the rest of the oracle) and loops it over the elements.  It is the checker of the device build
-// of the same text: the two differ only by the device libm.  What pins the TEXT to the reference is not this file but
+// of the same text: the two differ by the device libm and by the marked reciprocal / integer-power shortcuts of the device
+// build (<= 1-2 ulp each, header of nsx_thermo.cuh).  What pins the TEXT to the reference is not this file but
 // oracle/ref_fe -- the reference's own thermo(), OWBulkFluxes(), IABulkFluxes(), thermoWinton(), thermoIce0(), ... bodies cut
 // from /root/reference at build time -- against which tests/test_thermo_cpu.py holds this build BIT FOR BIT over every
 // option branch, and from which tests/golden/thermo/*.npz were generated.  PARITY PINNED.
