@@ -1101,10 +1101,15 @@ NSX_HD void thermo_element(Params const& P, Arrays const& A, int i)
 // ---------------------------------------------------------------------------------------------------------------------
 // host side: options -> Params (the scalars thermo() and IABulkFluxes derive before their loops)
 // ---------------------------------------------------------------------------------------------------------------------
-// nextsim time (decimal days since 1900-01-01 00:00, core/include/date.hpp) -> month, day
+// nextsim time (decimal days since 1900-01-01 00:00) -> month, day of datenumToString(t, "%m%d") (core/include/date.hpp:87-120):
+// the date is 1900-01-01 + static_cast<long>(t) days, the time of day is rounded to milliseconds, and a time of day that rounds
+// to 24:00:00.000 carries into the next date (boost::posix_time::ptime(date, time_duration)).
 inline void month_day(double datenum, int& month, int& day)
 {
-    long z = (long)std::floor(datenum) + 693901L - 60L;
+    long days = static_cast<long>(datenum);
+    double const frac = datenum - std::floor(datenum);
+    if (static_cast<long>(std::floor(frac * 24.0 * 60.0 * 60.0 * 1000.0 + 0.5)) >= 86400000L) ++days;
+    long const z = days + 693901L;                          // days since 0000-03-01 (1970-01-01 is day 719468, 1900-01-01 is 25567 earlier)
     long const era = (z >= 0 ? z : z - 146096) / 146097;
     unsigned long const doe = (unsigned long)(z - era * 146097);
     unsigned long const yoe = (doe - doe / 1460 + doe / 36524 - doe / 146096) / 365;

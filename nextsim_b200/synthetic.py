@@ -238,7 +238,7 @@ THERMO_DIAG = ("D_tau_ow", "D_Qa", "D_Qsw", "D_Qlw", "D_Qsh", "D_Qlh", "D_Qo", "
                "D_del_vi_mlt_myi", "D_del_ci_rplnt_myi", "D_del_vi_rplnt_myi")
 
 
-def make_thermo_state(ne, nn, seed=SEED, young=True, season="mixed", centroids=None):
+def make_thermo_state(ne, nn, seed=SEED, young=True, season="mixed", centroids=None, films=True):
     """Element fields of FiniteElement::thermo() (forcing, ice state, slab ocean, tracers) plus nodal wind / VT / ocean.
 
     Built to reach every branch of thermo(): ice-free, thin (< hmin after melt), young-only and thick-ice elements; air
@@ -246,7 +246,10 @@ def make_thermo_state(ne, nn, seed=SEED, young=True, season="mixed", centroids=N
     snow-covered ice; multi-year-ice tracers on both sides of their clamps.  season: 'winter' / 'summer' bias the air
     temperature and short-wave, 'mixed' spans both.  centroids=(cx, cy, L): every field varies smoothly in space, as
     real fields do (an ice edge, a front), instead of independently element by element -- what the timing runs use,
-    since neighbouring elements then mostly take the same branches; the value distributions are the same."""
+    since neighbouring elements then mostly take the same branches; the value distributions are the same.
+    films=False leaves out the micrometre-thin ice films: the Winton temperature solve of such a film cancels eight digits
+    (K32 = 2 ki / hi ~ 1e7), so one ulp of difference becomes 1e-8 -- fine for the bit-for-bit CPU comparison and for single
+    calls, not for a 1e-9 comparison of two libm's over several calls."""
     rng = np.random.default_rng(seed + 77)
     if centroids is None:
         u = rng.uniform
@@ -278,6 +281,12 @@ def make_thermo_state(ne, nn, seed=SEED, young=True, season="mixed", centroids=N
     conc = np.select([kind == 0, kind == 1, kind == 2], [0.0, u(1e-13, 0.05, ne), u(0.05, 0.6, ne)], u(0.6, 1.0, ne))
     hice = np.select([kind == 1, kind == 2], [u(0.005, 0.05, ne), u(0.008, 0.4, ne)], u(0.3, 3.5, ne))
     hsnow = np.where(rnd() < 0.3, 0.0, u(0.0, 0.45, ne))
+    # rare corners: films of ice thin enough to sublimate or melt away within one step (thermoWinton's layer cascade,
+    # FE.cpp:6721-6744, 6760-6764), and cells that are exactly full (lateral melt of melt_type 1, FE.cpp:5577-5580)
+    film = (rng.random(ne) < 0.012) & bool(films)
+    hice = np.where(film & (conc > 0), 10.0 ** rng.uniform(-7.5, -5.0, ne), hice)
+    hsnow = np.where(film, 0.0, hsnow)
+    conc = np.where((rng.random(ne) < 0.01) & (conc > 0.6), 1.0, conc)
     S["M_conc"] = conc
     S["M_thick"] = conc * hice
     S["M_snow_thick"] = conc * hsnow

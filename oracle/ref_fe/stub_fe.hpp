@@ -44,21 +44,25 @@ inline double real(int v) { return double(v); }      // FE.cpp:10185 `real(steps
 
 using physical::sigma_sb;        // FE.cpp:6386 names it unqualified
 
-// core/include/date.hpp:116 (boost::date_time there): nextsim time = decimal days since 1900-01-01 00:00; only the
-// "%m%d" format is used on the path (FE.cpp:5216)
+// core/include/date.hpp:87-120 (boost::date_time there): nextsim time = decimal days since 1900-01-01 00:00; the date is the
+// epoch + static_cast<long>(t) days, the time of day is rounded to milliseconds and 24:00:00.000 carries into the next date.
+// Only the "%m%d" format is used on the path (FE.cpp:5216).  Written independently of the product's month_day(): a table walk
+// over the years instead of the era arithmetic, so that the two check each other (tests/test_thermo_cpu.py::test_dates).
 inline std::string datenumToString(double const& datenum, std::string const& format)
 {
     if (format != "%m%d") throw std::runtime_error("ref_fe stub: datenumToString format " + format);
-    long z = (long)std::floor(datenum) + 693901L - 60L;      // days since 0000-03-01 (1900-01-01 is day 693901 of the proleptic count from 0000-01-01)
-    long const era = (z >= 0 ? z : z - 146096) / 146097;
-    unsigned long const doe = (unsigned long)(z - era * 146097);
-    unsigned long const yoe = (doe - doe / 1460 + doe / 36524 - doe / 146096) / 365;
-    unsigned long const doy = doe - (365 * yoe + yoe / 4 - yoe / 100);
-    unsigned long const mp = (5 * doy + 2) / 153;
-    unsigned long const d = doy - (153 * mp + 2) / 5 + 1;
-    unsigned long const m = mp < 10 ? mp + 3 : mp - 9;
+    long days = static_cast<long>(datenum);
+    double const fractionalDay = datenum - std::floor(datenum);
+    if (static_cast<long>(std::floor(fractionalDay * 24.0 * 60.0 * 60.0 * 1000.0 + 0.5)) >= 86400000L) ++days;
+    if (days < 0) throw std::runtime_error("ref_fe stub: time before 1900-01-01");
+    int year = 1900;
+    auto leap = [](int y) { return (y % 4 == 0 && y % 100 != 0) || y % 400 == 0; };
+    while (days >= (leap(year) ? 366 : 365)) { days -= leap(year) ? 366 : 365; ++year; }
+    static const int mlen[12] = {31, 28, 31, 30, 31, 30, 31, 31, 30, 31, 30, 31};
+    int month = 0;
+    while (days >= mlen[month] + (month == 1 && leap(year) ? 1 : 0)) { days -= mlen[month] + (month == 1 && leap(year) ? 1 : 0); ++month; }
     char buf[8];
-    std::snprintf(buf, sizeof buf, "%02lu%02lu", m, d);
+    std::snprintf(buf, sizeof buf, "%02d%02d", month + 1, (int)days + 1);
     return buf;
 }
 

@@ -5,6 +5,7 @@
 // updateIceDiagnostics, ...) against stub_fe.hpp and exposes set / run / get entry points for ctypes.  The harness
 // only fills members and calls the reference functions; P ranks run explicitSolve() on P threads so that the
 // reference's updateGhosts() exchanges through the in-process Communicator stand-in.
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <thread>
@@ -391,6 +392,9 @@ int ref_fe_thermo_setup(void* h, const NsxThermoParams* p, double current_time)
     }
     return 0;
 }
+
+// month * 100 + day of the stand-in for datenumToString(t, "%m%d") the reference bodies are compiled against
+int ref_fe_month_day(double datenum) { return std::atoi(Nextsim::datenumToString(datenum, "%m%d").c_str()); }
 
 int ref_fe_thermo(void* h, int dt)
 {

@@ -43,8 +43,12 @@ def build():
 def lib():
     global _lib
     if _lib is None:
-        build()
-        _lib = C.CDLL(_LIB)
+        # THERMO_ORACLE_LIB: an instrumented build (oracle/thermo_coverage.sh measures the branch coverage of the tests with gcov)
+        path = os.environ.get("THERMO_ORACLE_LIB")
+        if not path:
+            build()
+            path = _LIB
+        _lib = C.CDLL(path)
         _lib.orc_thermo_field_names.restype = C.c_char_p
         _lib.orc_thermo_last_error.restype = C.c_char_p
         assert _lib.orc_thermo_params_size() == C.sizeof(ThermoParams), "ThermoParams out of step with NsxThermoParams"

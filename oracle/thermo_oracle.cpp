@@ -42,6 +42,8 @@ const char* orc_thermo_last_error() { return g_err.c_str(); }
 
 void orc_thermo_params_defaults(NsxThermoParams* p) { nsx::thermo::params_defaults(*p); }
 int orc_thermo_params_size() { return (int)sizeof(NsxThermoParams); }
+// month * 100 + day of datenumToString(t, "%m%d") as the product decodes it (nsx::thermo::month_day)
+int orc_thermo_month_day(double datenum) { int m, d; nsx::thermo::month_day(datenum, m, d); return 100 * m + d; }
 
 // tri0: [3*ne] 0-based node ids, element-major; wind / VT / ocean: [2*nn]; names[k] -> ptrs[k] ([ne] doubles, updated in place)
 int orc_thermo(const NsxThermoParams* o, int dt, double current_time, int ne, int nn, const int* tri0, const double* wind,

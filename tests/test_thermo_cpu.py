@@ -70,6 +70,56 @@ def test_branch_coverage_of_the_inputs():
     assert ((out["M_freeze_days"] == 0) & (S["M_freeze_days"] > 0) & (out["M_conc"] > 0)).sum() > 10
 
 
+def test_dates():
+    """datenumToString(M_current_time, "%m%d") (core/include/date.hpp:87-120): the product's decoder (era arithmetic) and the
+    stand-in the reference bodies are compiled against (a walk over the calendar) against Python's datetime, day by day
+    from 1900 to 2100, plus the carry of a time of day that rounds to 24:00:00.000"""
+    import ctypes as C
+    import datetime
+    from oracle import thermo as oth
+    L = oth.lib()
+    L.orc_thermo_month_day.argtypes = [C.c_double]
+    fns = [L.orc_thermo_month_day]
+    if ref_fe.available():
+        R = ref_fe.lib()
+        R.ref_fe_month_day.argtypes = [C.c_double]
+        fns.append(R.ref_fe_month_day)
+    epoch = datetime.date(1900, 1, 1)
+    for n in list(range(0, 73415, 1)):
+        d = epoch + datetime.timedelta(days=n)
+        want = 100 * d.month + d.day
+        for f in fns:
+            assert f(float(n)) == want, (n, d)
+    for f in fns:
+        assert f(tc.datenum(2018, 9, 15, 0.75)) == 915
+        assert f(tc.datenum(2018, 9, 14, 0.999999)) == 914
+        assert f(tc.datenum(2018, 9, 14) + (1.0 - 2e-9)) == 915       # 23:59:59.9998 rounds to 24:00:00.000
+        assert f(tc.datenum(2020, 2, 28) + (1.0 - 2e-9)) == 229
+        assert f(tc.datenum(1900, 2, 28) + 1.0) == 301                 # 1900 is not a leap year
+
+
+def test_date_branches_fire():
+    """the midnights of 15 September / 1 August / the reset date really take their branches (FE.cpp:6003-6007, 6051-6077, 6029-6034)"""
+    p, t, dt, gm, S = tc.make_inputs("sept15_midnight")
+    out = tc.run_oracle(p, t, dt, gm, S)
+    ice = out["M_conc"] > 0
+    assert ice.sum() > 200 and (out["M_fyi_fraction"][ice] == 0).all() and (S["M_fyi_fraction"][ice] > 0).any()
+    p, t, dt, gm, S = tc.make_inputs("aug01_midnight")
+    out = tc.run_oracle(p, t, dt, gm, S)
+    ice = out["M_conc"] > 0
+    changed = out["M_conc_summer"][ice] != S["M_conc_summer"][ice]
+    assert changed.mean() > 0.9                                   # every ice element resets its summer minimum
+    assert set(np.unique(out["M_freeze_onset"][ice])) <= {0.0, 1.0} and (out["M_freeze_onset"][ice] == 0).sum() > 100
+    p, t, dt, gm, S = tc.make_inputs("reset_by_date_hit")
+    out = tc.run_oracle(p, t, dt, gm, S)
+    ice = out["M_conc"] > 0
+    cmax = np.minimum(1.0, out["M_conc"] + out["M_conc_young"])
+    assert np.allclose(out["M_conc_myi"][ice], cmax[ice], rtol=0, atol=0) and (out["D_del_ci_rplnt_myi"][ice] != 0).sum() > 100
+    p, t, dt, gm, S = tc.make_inputs("reset_by_date_miss")
+    out = tc.run_oracle(p, t, dt, gm, S)
+    assert (out["D_del_ci_rplnt_myi"] == 0).all()
+
+
 def test_rejected_options():
     """the values the reference throws std::logic_error on (FE.cpp:5562, 5653, 6527), and melt_type 3 (OASIS-only)"""
     for over in (dict(newice_type=5, ice_cat_young=0), dict(melt_type=3), dict(melt_type=0), dict(alb_scheme=7),

@@ -41,6 +41,8 @@ OPTION_SETS = {
     "aug01_midnight": ({}, datenum(2018, 8, 1, 0.0), 200, "summer"),
     "reset_by_date_hit": (dict(reset_by_date=1, reset_month=10, reset_day=2), datenum(2018, 10, 2, 0.0), 200, "mixed"),
     "reset_by_date_miss": (dict(reset_by_date=1), datenum(2018, 10, 2, 0.5), 200, "mixed"),
+    "reset_by_date_last_step": (dict(reset_by_date=1), datenum(2018, 7, 20, LAST_STEP), 200, "summer"),
+    "reset_by_date_aug01": (dict(reset_by_date=1), datenum(2018, 8, 1, 0.0), 200, "summer"),
     "dt900": (dict(dtime_step=900.0), datenum(2020, 2, 29, 0.5), 900, "mixed"),
     "classic_winton_newice1": (dict(newice_type=1, ice_cat_young=0, hnull=0.4, PhiM=0.3), datenum(2018, 4, 3, 0.6), 200, "mixed"),
 }
@@ -51,11 +53,11 @@ def mesh(nx=24):
     return gm
 
 
-def make_inputs(name, nx=24, seed=syn.SEED):
+def make_inputs(name, nx=24, seed=syn.SEED, films=True):
     over, t, dt, season = OPTION_SETS[name]
     p = oth.default_params(**over)
     gm = mesh(nx)
-    S = syn.make_thermo_state(gm.ne, gm.nn, seed=seed, young=bool(p.ice_cat_young), season=season)
+    S = syn.make_thermo_state(gm.ne, gm.nn, seed=seed, young=bool(p.ice_cat_young), season=season, films=films)
     return p, t, dt, gm, S
 
 
