@@ -78,6 +78,11 @@ CASES = [
     ("10km", 64, "bbm", 2, False, True, 120, {}),
     ("10km_stable", 40, "bbm", 2, True, True, 30, {"basal_stress_type": 1, "equal_ridging": 1}),
     ("10km_stable", 40, "bbm", 1, True, True, 30, {"exponent_relaxation_sigma": 4.5, "ocean_turning_angle_rad": 0.4363}),
+    # branches gcov showed no other case reaches: the compression cap of the damage criterion (FE.cpp:4218-4221; ~7 % of the
+    # elements with this strength), no basal stress (setup.basal_stress-type = none), the classic ice category in update()
+    ("10km_stable", 40, "bbm", 2, True, True, 30, {"compr_strength": 2.0e4}),
+    ("10km_stable", 40, "bbm", 1, True, True, 30, {"basal_stress_type": 0}),
+    ("10km_stable", 40, "bbm", 1, False, False, 30, {"newice_type": 1, "ice_cat_type": 0}),
 ]
 
 
