@@ -662,17 +662,9 @@ NSX_HD void thermo_core(Params const& P, Arrays const& A, int i, Elem& E)
     double Qio = 0., Qio_young = 0.;
     double Qassm = 0.;
 
-    double const old_vol = E.thick;
-    double const old_snow_vol = E.snow_thick;
-    (void)old_snow_vol;
+    double const old_vol = E.thick;                         // (old_snow_vol, old_h_young, old_hs_young of FE.cpp:5307-5317 are never read)
     double const old_conc = E.conc;
-    double old_h_young = 0., old_hs_young = 0., old_conc_young = 0.;
-    if (young) {
-        old_h_young = E.h_young;
-        old_conc_young = E.conc_young;
-        old_hs_young = E.hs_young;
-    }
-    (void)old_h_young; (void)old_hs_young;
+    double const old_conc_young = young ? E.conc_young : 0.;
     double const old_conc_tot = old_conc + old_conc_young;
     double const old_ow_fraction = 1. - old_conc_tot;
 
